@@ -1,0 +1,152 @@
+"""ctypes binding of ``libfsg_dense.so`` (C ABI: ``include/fsg_dense.h``).
+
+The shared library is the product; this module only marshals ``tensor.data_ptr()`` values, sizes and the
+current CUDA stream across the boundary.  There is **no CPU fallback**: if the library is missing or a
+tensor is not a CUDA tensor the call raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfsg_dense.so")
+ABI_VERSION = 1
+STATS_HEADER = 2
+SCALARS_HEADER = 10
+
+c_i32, c_i64, c_f32, c_f64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+c_ptr, c_size = ctypes.c_void_p, ctypes.c_size_t
+
+
+class LossParams(ctypes.Structure):
+    """``struct fsg_loss_params``."""
+
+    _fields_ = [
+        ("num_classes", c_i32),
+        ("gambler_mode", c_i32),
+        ("norm_mode", c_i32),
+        ("reserved", c_i32),
+        ("focal_alpha", c_f32),
+        ("focal_gamma", c_f32),
+        ("smooth_l1_beta", c_f32),
+        ("temperature", c_f32),
+        ("gambler_gamma", c_f32),
+        ("c_cls", c_f32),
+        ("c_reg", c_f32),
+        ("c_gam", c_f32),
+        ("box_weights", c_f32 * 4),
+    ]
+
+
+CLS_MODES = {"focal": 0, "sigmoid": 1}
+NORM_NONE, NORM_IMAGE, NORM_BATCH = 0, 1, 2
+
+# name -> (restype, argtypes); must list every symbol include/fsg_dense.h declares
+PROTOTYPES = {
+    "fsg_abi_version": (c_i32, []),
+    "fsg_status_string": (ctypes.c_char_p, [c_i32]),
+    "fsg_pairwise_iou": (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr]),
+    "fsg_matcher": (c_i32, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "fsg_match_workspace_bytes": (c_size, [c_i32, c_i64, c_i64]),
+    "fsg_match_anchors": (
+        c_i32,
+        [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr,
+         c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_ptr, c_size, c_ptr],
+    ),
+    "fsg_box2box_get_deltas": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "fsg_box2box_apply_deltas": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_f32, c_ptr, c_ptr]),
+    "fsg_loss_prepass_workspace_bytes": (c_size, [c_i32, c_i64]),
+    "fsg_loss_prepass": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_f32, c_ptr, c_ptr, c_size, c_ptr]),
+    "fsg_loss_main_workspace_bytes": (c_size, [c_i32, c_i64, c_i32]),
+    "fsg_loss_main": (
+        c_i32,
+        [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64,
+         ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
+    ),
+    "fsg_loss_post": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i64, ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr, c_ptr]),
+    "fsg_scale_inplace": (c_i32, [c_ptr, c_i64, c_ptr, c_f32, c_ptr]),
+    "fsg_nms_workspace_bytes": (c_size, [c_i64]),
+    "fsg_nms": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_f64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "fsg_detect_workspace_bytes": (c_size, [c_i32, c_i64, c_i32, c_i32, c_i32]),
+    "fsg_detect": (
+        c_i32,
+        [c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i64, c_i32, c_ptr, c_i32, c_f32, c_i32, c_f64, c_i32, c_ptr, c_f32,
+         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
+    ),
+    "fsg_permute_level": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i64, c_i64, c_i64, c_i32, c_ptr]),
+}
+
+_LIB = None
+LAUNCHES = 0  # kernels enqueued through this binding (bench.py reports it as gpu_launches)
+
+
+def build(verbose=False):
+    """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = [os.path.join(_HERE, "csrc", "build.sh")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libfsg_dense.so failed:\n" + res.stderr[-4000:])
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library.  Fails loudly when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "libfsg_dense.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or csrc/build.sh. There is no CPU fallback for this path." % LIB_PATH
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if the header and the library diverge
+            fn.restype = res
+            fn.argtypes = args
+        if L.fsg_abi_version() != ABI_VERSION:
+            raise RuntimeError("libfsg_dense.so ABI %d != binding ABI %d" % (L.fsg_abi_version(), ABI_VERSION))
+        _LIB = L
+    return _LIB
+
+
+def check(status):
+    if status != 0:
+        msg = lib().fsg_status_string(status).decode()
+        raise RuntimeError("fsg_dense: %s (status %d)" % (msg, status))
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("fsg_dense kernels take CUDA tensors only (no CPU path); got %s" % t.device)
+    if not t.is_contiguous():
+        raise RuntimeError("fsg_dense kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def host_f32(vals):
+    return (c_f32 * len(vals))(*[float(v) for v in vals])
+
+
+def host_i8(vals):
+    return (ctypes.c_int8 * len(vals))(*[int(v) for v in vals])
+
+
+def host_i64(vals):
+    return (c_i64 * len(vals))(*[int(v) for v in vals])
+
+
+def count_launches(n):
+    global LAUNCHES
+    LAUNCHES += n

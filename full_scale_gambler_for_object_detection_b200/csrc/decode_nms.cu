@@ -1,0 +1,703 @@
+// K3: score scan + per-level top-k + threshold + box decode + per-class NMS + top detections.
+//
+// Reference semantics (paths relative to the reference tree):
+//   detectron2/modeling/meta_arch/retinanet.py:460-520  RetinaNet.inference_single_image
+//   detectron2/modeling/box_regression.py:69-107        Box2BoxTransform.apply_deltas
+//   detectron2/layers/nms.py:6,9-26                     nms / batched_nms (torchvision greedy NMS,
+//                                                        per-class un-offset form)
+//
+// Where the reference sorts every level's H*W*A*K scores to keep 1000, the scan kernel streams the
+// logits once (coalesced 16-byte loads), keeps a running exact top-k candidate buffer in shared memory
+// per CTA (radix-select pruning raises a logit pre-filter as it goes), and the last CTA of each
+// (image, level) slab merges, sorts and decodes.  One CTA per image then runs the per-class greedy
+// NMS entirely in shared memory (bitonic sort on composite keys, warp-per-class suppression) and
+// emits the final detections -- no host round trip, no n^2 mask in global memory.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace fsg {
+
+constexpr int kSelThreads = 512;
+constexpr int kSelCap = 8192;                       // candidate buffer entries (u64 keys)
+constexpr int kSelIter = kSelThreads * 8;           // elements consumed per block iteration
+constexpr int kSelTrigger = kSelCap - kSelIter;     // prune when the buffer may overflow next iteration
+constexpr int kMaxLevels = 8;
+constexpr int kNmsThreads = 1024;
+constexpr int kNmsCap = 8192;                       // candidates per image the NMS kernel holds
+
+struct DetectLevels {
+  int64_t off[kMaxLevels + 1];  // anchor offsets of the levels
+  int nparts[kMaxLevels];       // CTAs per (image, level) slab
+  int part_base[kMaxLevels];    // first blockIdx.x of the level
+  int k[kMaxLevels];            // min(topk, HWA_l)
+  int64_t part_len[kMaxLevels]; // elements per part (multiple of kSelIter)
+  int num_levels;
+  int total_parts;
+  int max_parts;                // slot stride (parts) per level in the scratch arrays
+};
+
+__device__ __forceinline__ float sigmoid_score(float x) { return __fdiv_rn(1.f, 1.f + expf(-x)); }
+
+// key: score bits in the high word, inverted slab index in the low word => descending key order is
+// (score descending, index ascending), the reference's stable descending sort (retinanet.py:489).
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
+  return ((uint64_t)__float_as_uint(score) << 32) | (uint64_t)(0xffffffffu - idx);
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return __uint_as_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_index(uint64_t k) { return 0xffffffffu - (uint32_t)k; }
+
+// ---- block-wide exact k-th largest over 64-bit keys in shared memory (8-bit radix select) ----------
+// returns T such that exactly k keys are >= T (keys are distinct).  Requires count >= k >= 1.
+template <int NT>
+__device__ uint64_t select_kth(const uint64_t* buf, int count, int k, unsigned* hist /*256*/, int* s_tmp /*4*/) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint64_t prefix = 0;
+  int need = k;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    for (int i = tid; i < count; i += NT) {
+      const uint64_t key = buf[i];
+      const bool match = (shift == 56) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+      if (match) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // lane L owns bins 255-8L .. 248-8L (descending)
+      unsigned loc[8];
+      unsigned sum = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { loc[b] = hist[255 - 8 * lane - b]; sum += loc[b]; }
+      unsigned inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned v = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const unsigned before = inc - sum;
+      if (before < (unsigned)need && inc >= (unsigned)need) {
+        unsigned cum = before;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (cum < (unsigned)need && cum + loc[b] >= (unsigned)need) {
+            s_tmp[0] = 255 - 8 * lane - b;  // digit
+            s_tmp[1] = (int)cum;            // keys strictly above this digit (within prefix)
+            s_tmp[2] = (int)loc[b];         // keys in this digit's bin
+          }
+          cum += loc[b];
+        }
+      }
+    }
+    __syncthreads();
+    const int digit = s_tmp[0], above = s_tmp[1], inbin = s_tmp[2];
+    need -= above;
+    prefix |= (uint64_t)digit << shift;
+    __syncthreads();
+    if (inbin == need) break;  // the whole bin is taken: low bits of the threshold stay zero
+  }
+  return prefix;
+}
+
+// keep only keys >= T (order not preserved).  count <= kSelCap.
+template <int NT>
+__device__ void compact_ge(uint64_t* buf, int* s_count, uint64_t T) {
+  constexpr int PER = (kSelCap + NT - 1) / NT;
+  const int tid = threadIdx.x;
+  const int count = *s_count;
+  uint64_t mine[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = tid + j * NT;
+    mine[j] = (i < count) ? buf[i] : 0ull;
+  }
+  __syncthreads();
+  if (tid == 0) *s_count = 0;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = tid + j * NT;
+    if (i < count && mine[j] >= T) buf[atomicAdd(s_count, 1)] = mine[j];
+  }
+  __syncthreads();
+}
+
+// block-wide minimum of buf[0..count); result valid in every thread
+template <int NT>
+__device__ uint64_t block_min_u64(const uint64_t* buf, int count, uint64_t* s_red /*NT/32*/) {
+  uint64_t mn = ~0ull;
+  for (int i = threadIdx.x; i < count; i += NT) mn = min(mn, buf[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = min(mn, (uint64_t)__shfl_xor_sync(kFull, (unsigned long long)mn, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  mn = s_red[0];
+  for (int w = 1; w < NT / 32; ++w) mn = min(mn, s_red[w]);
+  __syncthreads();
+  return mn;
+}
+
+template <int NT>
+__device__ void prune_topk(uint64_t* buf, int* s_count, int k, unsigned* hist, int* s_tmp) {
+  const int count = *s_count;  // caller synchronised
+  if (count <= k) return;
+  const uint64_t T = select_kth<NT>(buf, count, k, hist, s_tmp);
+  compact_ge<NT>(buf, s_count, T);
+}
+
+// descending bitonic sort of m (power of two) keys in shared memory
+template <int NT>
+__device__ void bitonic_desc(uint64_t* a, int m) {
+  for (int size = 2; size <= m; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (m >> 1); t += NT) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t x = a[lo], y = a[hi];
+        if (desc ? (x < y) : (x > y)) { a[lo] = y; a[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ float4 decode_box3(float4 d, float4 b, float wx, float wy, float ww, float wh,
+                                              float clampv) {  // box_regression.py:81-106
+  float w = __fsub_rn(b.z, b.x), h = __fsub_rn(b.w, b.y);
+  float cx = __fadd_rn(b.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(b.y, __fmul_rn(0.5f, h));
+  float dx = __fdiv_rn(d.x, wx), dy = __fdiv_rn(d.y, wy);
+  float dw = fminf(__fdiv_rn(d.z, ww), clampv), dh = fminf(__fdiv_rn(d.w, wh), clampv);
+  float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+  float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+  return make_float4(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), __fsub_rn(pcy, __fmul_rn(0.5f, ph)),
+                     __fadd_rn(pcx, __fmul_rn(0.5f, pw)), __fadd_rn(pcy, __fmul_rn(0.5f, ph)));
+}
+
+struct SelectArgs {
+  const float* logits;
+  const float4* deltas;
+  const float4* anchors;
+  int64_t anchor_stride4;
+  int64_t R;
+  int K;
+  int topk;       // slot stride per level in the candidate arrays
+  float thr;      // SCORE_THRESH_TEST
+  float xpre;     // conservative logit pre-filter for thr
+  float wx, wy, ww, wh, clampv;
+  uint64_t* part_keys;   // (N, L, max_parts, topk)
+  int* part_count;       // (N, L, max_parts)
+  unsigned* done;        // (N, L)
+  float4* cand_box;      // (N, L*topk)
+  float* cand_score;     // (N, L*topk)
+  int64_t* cand_class;   // (N, L*topk)
+  int* lvl_count;        // (N, L)
+};
+
+__device__ __forceinline__ void try_append(float x, uint32_t idx, float xb, float ts, uint64_t* buf, int* s_count) {
+  // warp-aggregated append; all 32 lanes call this together
+  bool p = x > xb;
+  float s = 0.f;
+  if (p) { s = sigmoid_score(x); p = s > ts; }
+  const unsigned m = __ballot_sync(kFull, p);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == (__ffs(m) - 1)) base = atomicAdd(s_count, __popc(m));
+  base = __shfl_sync(kFull, base, __ffs(m) - 1);
+  if (p) buf[base + __popc(m & ((1u << lane) - 1u))] = make_key(s, idx);
+}
+
+__global__ void __launch_bounds__(kSelThreads) detect_select_kernel(const SelectArgs A, const DetectLevels LV) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);  // kSelCap
+  __shared__ unsigned hist[256];
+  __shared__ int s_tmp[4];
+  __shared__ int s_count;
+  __shared__ float s_xb, s_ts;
+  __shared__ bool s_last;
+  __shared__ uint64_t s_red64[kSelThreads / 32];
+
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y;
+  int l = 0;
+  while (l + 1 < LV.num_levels && (int)blockIdx.x >= LV.part_base[l + 1]) ++l;
+  const int part = blockIdx.x - LV.part_base[l];
+  const int k = LV.k[l];
+  const int64_t hwa = LV.off[l + 1] - LV.off[l];
+  const int64_t E = hwa * A.K;                         // elements in the slab
+  const float* slab = A.logits + ((int64_t)n * A.R + LV.off[l]) * A.K;
+  const int64_t e0 = (int64_t)part * LV.part_len[l];
+  const int64_t e1 = min(E, e0 + LV.part_len[l]);
+
+  if (tid == 0) { s_count = 0; s_xb = A.xpre; s_ts = A.thr; }
+  __syncthreads();
+
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(slab) & 15) == 0);
+  for (int64_t base = e0; base < e1; base += kSelIter) {
+    const float xb = s_xb, ts = s_ts;
+    float v[8];
+    const int64_t p0 = base + (int64_t)tid * 4;
+    const int64_t p1 = p0 + kSelThreads * 4;
+    if (vec_ok && p0 + 4 <= e1) {
+      float4 t = ldg_stream4(slab + p0); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (p0 + j < e1) ? ldg_stream1(slab + p0 + j) : -INFINITY;
+    }
+    if (vec_ok && p1 + 4 <= e1) {
+      float4 t = ldg_stream4(slab + p1); v[4] = t.x; v[5] = t.y; v[6] = t.z; v[7] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[4 + j] = (p1 + j < e1) ? ldg_stream1(slab + p1 + j) : -INFINITY;
+    }
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) any |= (v[j] > xb);
+    if (__any_sync(kFull, any)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) try_append(v[j], (uint32_t)(p0 + j), xb, ts, buf, &s_count);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) try_append(v[4 + j], (uint32_t)(p1 + j), xb, ts, buf, &s_count);
+    }
+    __syncthreads();
+    if (s_count > kSelTrigger) {   // uniform: read after the barrier
+      prune_topk<kSelThreads>(buf, &s_count, k, hist, s_tmp);
+      const int now = s_count;
+      if (now >= k) {
+        // buffer now holds exactly the k best so far: raise the bar.  A later element (higher index)
+        // must beat the current minimum strictly (ties lose on index).
+        const uint64_t mn = block_min_u64<kSelThreads>(buf, now, s_red64);
+        if (tid == 0) {
+          const float t = key_score(mn);
+          s_ts = t;
+          const float lg = logf(t / (1.f - t));            // +inf when t == 1: nothing can beat it
+          s_xb = fmaxf(A.xpre, lg - 1e-4f * (1.f + fabsf(lg)));
+        }
+      }
+      __syncthreads();
+    }
+  }
+  prune_topk<kSelThreads>(buf, &s_count, k, hist, s_tmp);
+  __syncthreads();
+
+  // ---- publish this part's candidates
+  const int cnt = s_count;
+  const int64_t slot = (((int64_t)n * LV.num_levels + l) * LV.max_parts + part);
+  uint64_t* gk = A.part_keys + slot * A.topk;
+  for (int i = tid; i < cnt; i += kSelThreads) gk[i] = buf[i];
+  __syncthreads();
+  if (tid == 0) {
+    A.part_count[slot] = cnt;
+    __threadfence();
+    s_last = (atomicAdd(&A.done[n * LV.num_levels + l], 1u) == (unsigned)LV.nparts[l] - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // ---- last CTA of the slab: merge parts, exact top-k, sort, decode
+  if (tid == 0) { s_count = 0; A.done[n * LV.num_levels + l] = 0u; }
+  __syncthreads();
+  const int nparts = LV.nparts[l];
+  if (nparts > 1) {
+    for (int p = 0; p < nparts; ++p) {
+      const int64_t sl = (((int64_t)n * LV.num_levels + l) * LV.max_parts + p);
+      const int c = __ldcg(&A.part_count[sl]);
+      const uint64_t* src = A.part_keys + sl * A.topk;
+      __shared__ int s_base;
+      if (tid == 0) { s_base = s_count; s_count += c; }
+      __syncthreads();
+      for (int i = tid; i < c; i += kSelThreads) buf[s_base + i] = __ldcg(&src[i]);
+      __syncthreads();
+    }
+    prune_topk<kSelThreads>(buf, &s_count, k, hist, s_tmp);
+    __syncthreads();
+  } else {
+    if (tid == 0) s_count = cnt;
+    __syncthreads();
+  }
+  const int fin = s_count;
+  int m = 1;
+  while (m < fin) m <<= 1;
+  for (int i = fin + tid; i < m; i += kSelThreads) buf[i] = 0ull;
+  __syncthreads();
+  bitonic_desc<kSelThreads>(buf, m);
+  const int64_t cbase = (int64_t)n * LV.num_levels * A.topk + (int64_t)l * A.topk;
+  for (int t = tid; t < fin; t += kSelThreads) {
+    const uint64_t key = buf[t];
+    const uint32_t idx = key_index(key);
+    const int64_t a = idx / (uint32_t)A.K;          // retinanet.py:498-499
+    const int c = (int)(idx - (uint32_t)a * (uint32_t)A.K);
+    const int64_t r = LV.off[l] + a;
+    const float4 d = A.deltas[(int64_t)n * A.R + r];
+    const float4 an = A.anchors[(int64_t)n * A.anchor_stride4 + r];
+    A.cand_box[cbase + t] = decode_box3(d, an, A.wx, A.wy, A.ww, A.wh, A.clampv);
+    A.cand_score[cbase + t] = key_score(key);
+    A.cand_class[cbase + t] = c;
+  }
+  if (tid == 0) A.lvl_count[n * LV.num_levels + l] = fin;
+}
+
+// ------------------------------------------------------------------------------------------
+// NMS: one CTA per image (or per stand-alone call)
+// ------------------------------------------------------------------------------------------
+struct NmsArgs {
+  const float4* boxes;      // per image: slots_per_image entries
+  const float* scores;
+  const int64_t* classes;   // may be NULL (single class)
+  int64_t slots_per_image;
+  const int* lvl_count;     // (N, L) or NULL -> fixed_count
+  int L;
+  int topk;                 // slot stride per level
+  int fixed_count;
+  float thr;                // largest float <= the double threshold (strict > compare, see fsg_nms)
+  int max_out;              // truncate to this many (DETECTIONS_PER_IMAGE); <= 0: all
+  // outputs
+  int64_t* keep;            // (N, keep_stride) candidate indices in concatenation order
+  int64_t keep_stride;
+  int32_t* num_keep;        // (N)
+  float4* out_boxes;        // (N, max_out) or NULL
+  float* out_scores;
+  int64_t* out_classes;
+  // optional compact export of the candidates
+  float4* exp_boxes;        // (N, L*topk)
+  float* exp_scores;
+  int64_t* exp_classes;
+  int32_t* exp_count;
+};
+
+// ascending bitonic sort
+template <int NT>
+__device__ void bitonic_asc(uint64_t* a, int m) {
+  for (int size = 2; size <= m; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (m >> 1); t += NT) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool asc = ((lo & size) == 0);
+        const uint64_t x = a[lo], y = a[hi];
+        if (asc ? (x > y) : (x < y)) { a[lo] = y; a[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                      // kNmsCap * 8
+  float4* sbox = reinterpret_cast<float4*>(smem_raw + (size_t)kNmsCap * 8);     // kNmsCap * 16
+  uint16_t* seg = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kNmsCap * 24); // kNmsCap * 2
+  unsigned char* dead = smem_raw + (size_t)kNmsCap * 26;                        // kNmsCap
+  __shared__ int s_pref[kMaxLevels + 1];
+  __shared__ int s_warp[kNmsThreads / 32];
+  __shared__ int s_nseg, s_next, s_nkeep;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = blockIdx.x;
+  if (tid == 0) {
+    s_pref[0] = 0;
+    if (A.lvl_count) {
+      for (int l = 0; l < A.L; ++l) s_pref[l + 1] = s_pref[l] + A.lvl_count[n * A.L + l];
+    } else {
+      s_pref[1] = A.fixed_count;
+    }
+    s_nseg = 0; s_next = 0; s_nkeep = 0;
+  }
+  __syncthreads();
+  const int L = A.lvl_count ? A.L : 1;
+  const int nc = s_pref[L];
+  const float4* gbox = A.boxes + (int64_t)n * A.slots_per_image;
+  const float* gscore = A.scores + (int64_t)n * A.slots_per_image;
+  const int64_t* gcls = A.classes ? A.classes + (int64_t)n * A.slots_per_image : nullptr;
+  int m = 1;
+  while (m < nc) m <<= 1;
+
+  // slot of concatenation index i
+  auto slot_of = [&](int i) -> int {
+    int l = 0;
+    while (l + 1 < L && i >= s_pref[l + 1]) ++l;
+    return l * A.topk + (i - s_pref[l]);
+  };
+
+  // ---- 1. composite keys: class (19 bits) | inverted score (32) | concat index (13)
+  //         ascending => class, score descending, index ascending
+  for (int i = tid; i < m; i += kNmsThreads) {
+    uint64_t key = ~0ull;
+    if (i < nc) {
+      const int s = slot_of(i);
+      const uint64_t c = gcls ? (uint64_t)(gcls[s] & 0x7ffff) : 0ull;
+      const uint32_t sb = __float_as_uint(gscore[s]);
+      // order-preserving map for any float (negative scores can reach the stand-alone nms)
+      const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
+      key = (c << 45) | ((uint64_t)(0xffffffffu - ord) << 13) | (uint64_t)i;
+      if (A.exp_boxes) {
+        const int64_t eo = (int64_t)n * A.L * A.topk + i;
+        A.exp_boxes[eo] = gbox[s];
+        A.exp_scores[eo] = gscore[s];
+        A.exp_classes[eo] = gcls ? gcls[s] : 0;
+      }
+    }
+    keys[i] = key;
+  }
+  if (tid == 0 && A.exp_count) A.exp_count[n] = nc;
+  __syncthreads();
+  bitonic_asc<kNmsThreads>(keys, m);
+
+  // ---- 2. boxes in sorted order, segment starts
+  for (int i = tid; i < nc; i += kNmsThreads) {
+    sbox[i] = gbox[slot_of((int)(keys[i] & 0x1fff))];
+    dead[i] = 0;
+  }
+  __syncthreads();
+  for (int i0 = 0; i0 < nc; i0 += kNmsThreads) {
+    const int i = i0 + tid;
+    const bool start = (i < nc) && (i == 0 || (keys[i] >> 45) != (keys[i - 1] >> 45));
+    const unsigned bm = __ballot_sync(kFull, start);
+    if (lane == 0) s_warp[wid] = __popc(bm);
+    __syncthreads();
+    int before = s_nseg;
+    for (int w = 0; w < wid; ++w) before += s_warp[w];
+    if (start) seg[before + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)i;
+    int tot = 0;
+    if (tid == 0)
+      for (int w = 0; w < kNmsThreads / 32; ++w) tot += s_warp[w];
+    __syncthreads();
+    if (tid == 0) s_nseg += tot;
+    __syncthreads();
+  }
+  const int nseg = s_nseg;
+
+  // ---- 3. greedy NMS, one warp per class segment (torchvision nms_kernel semantics)
+  for (;;) {
+    int s = 0;
+    if (lane == 0) s = atomicAdd(&s_next, 1);
+    s = __shfl_sync(kFull, s, 0);
+    if (s >= nseg) break;
+    const int b = seg[s];
+    const int e = (s + 1 < nseg) ? (int)seg[s + 1] : nc;
+    for (int i = b; i < e; ++i) {
+      if (dead[i]) continue;   // warp-uniform (shared memory, synchronised below)
+      const float4 bi = sbox[i];
+      const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+      for (int j = i + 1 + lane; j < e; j += 32) {
+        if (dead[j]) continue;
+        const float4 bj = sbox[j];
+        const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+        const float w = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+        const float h = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+        const float inter = __fmul_rn(w, h);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+        if (ovr > A.thr) dead[j] = 1;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- 4. survivors by score descending (ties: lower concat index first), truncate
+  uint64_t* k2 = reinterpret_cast<uint64_t*>(sbox);  // the sorted boxes are no longer needed
+  for (int i = tid; i < m; i += kNmsThreads) {
+    uint64_t key = ~0ull;
+    if (i < nc && !dead[i]) key = keys[i] & ((1ull << 45) - 1ull);  // drop the class field
+    k2[i] = key;
+  }
+  __syncthreads();
+  {
+    int c = 0;
+    for (int i = tid; i < nc; i += kNmsThreads) c += (k2[i] != ~0ull) ? 1 : 0;
+    c = __reduce_add_sync(kFull, c);
+    if (lane == 0 && c) atomicAdd(&s_nkeep, c);
+  }
+  __syncthreads();
+  bitonic_asc<kNmsThreads>(k2, m);
+  int nk = s_nkeep;
+  if (A.max_out > 0 && nk > A.max_out) nk = A.max_out;
+  if (tid == 0 && A.num_keep) A.num_keep[n] = nk;
+  const int out_rows = (A.max_out > 0) ? A.max_out : nk;
+  for (int t = tid; t < out_rows; t += kNmsThreads) {
+    if (t < nk) {
+      const int ci = (int)(k2[t] & 0x1fff);
+      const int s = slot_of(ci);
+      if (A.keep) A.keep[(int64_t)n * A.keep_stride + t] = ci;
+      if (A.out_boxes) {
+        A.out_boxes[(int64_t)n * A.max_out + t] = gbox[s];
+        A.out_scores[(int64_t)n * A.max_out + t] = gscore[s];
+        A.out_classes[(int64_t)n * A.max_out + t] = gcls ? gcls[s] : 0;
+      }
+    } else {
+      if (A.keep && t < A.keep_stride) A.keep[(int64_t)n * A.keep_stride + t] = -1;
+      if (A.out_boxes) {
+        A.out_boxes[(int64_t)n * A.max_out + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        A.out_scores[(int64_t)n * A.max_out + t] = 0.f;
+        A.out_classes[(int64_t)n * A.max_out + t] = 0;
+      }
+    }
+  }
+}
+
+static float threshold_floor(double thr) {
+  // fp32 IoU `ovr > (double)thr`  <=>  `ovr > f` with f the largest float <= thr
+  float f = (float)thr;
+  if ((double)f > thr) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
+constexpr size_t kNmsSmem = (size_t)kNmsCap * 27;
+constexpr size_t kSelSmem = (size_t)kSelCap * 8;
+
+static DetectLevels plan_levels(const int64_t* off, int num_levels, int K, int topk) {
+  DetectLevels lv;
+  lv.num_levels = num_levels;
+  int base = 0, maxp = 1;
+  const int cap_parts = kSelCap / (topk > 0 ? topk : 1);
+  for (int l = 0; l < num_levels; ++l) {
+    lv.off[l] = off[l];
+    const int64_t hwa = off[l + 1] - off[l];
+    const int64_t E = hwa * K;
+    lv.k[l] = (int)(hwa < topk ? hwa : topk);
+    int parts = (int)ceil_div(E > 0 ? E : 1, (int64_t)64 * kSelIter);  // ~256K elements per CTA
+    if (parts > 16) parts = 16;
+    if (parts > cap_parts) parts = cap_parts;
+    if (parts < 1) parts = 1;
+    int64_t plen = ceil_div(ceil_div(E > 0 ? E : 1, parts), kSelIter) * kSelIter;
+    parts = (int)ceil_div(E > 0 ? E : 1, plen);
+    lv.nparts[l] = parts;
+    lv.part_len[l] = plen;
+    lv.part_base[l] = base;
+    base += parts;
+    if (parts > maxp) maxp = parts;
+  }
+  lv.off[num_levels] = off[num_levels];
+  for (int l = num_levels; l < kMaxLevels; ++l) { lv.nparts[l] = 0; lv.part_base[l] = base; lv.k[l] = 0; lv.part_len[l] = 0; }
+  lv.total_parts = base;
+  lv.max_parts = maxp;
+  return lv;
+}
+
+struct DetectWs {
+  size_t off_done, off_pcount, off_pkeys, off_lvl, off_cbox, off_cscore, off_ccls, total;
+};
+static DetectWs detect_ws_layout(int N, int num_levels, int topk, int max_parts) {
+  DetectWs w;
+  size_t o = 0;
+  const size_t slabs = (size_t)N * num_levels;
+  w.off_done = o;   o += align_up(sizeof(unsigned) * slabs, 16);
+  w.off_lvl = o;    o += align_up(sizeof(int) * slabs, 16);
+  w.off_pcount = o; o += align_up(sizeof(int) * slabs * max_parts, 16);
+  w.off_pkeys = o;  o += align_up(sizeof(uint64_t) * slabs * max_parts * topk, 16);
+  w.off_cbox = o;   o += align_up(sizeof(float4) * slabs * topk, 16);
+  w.off_cscore = o; o += align_up(sizeof(float) * slabs * topk, 16);
+  w.off_ccls = o;   o += align_up(sizeof(int64_t) * slabs * topk, 16);
+  w.total = o;
+  return w;
+}
+
+}  // namespace fsg
+
+using namespace fsg;
+
+extern "C" size_t fsg_nms_workspace_bytes(int64_t n) { return 16; }
+
+extern "C" int fsg_nms(const float* boxes, const float* scores, const int64_t* class_ids, int64_t n,
+                       double iou_threshold, int64_t* keep, int32_t* num_keep, void* workspace,
+                       size_t workspace_bytes, fsg_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (n < 0 || !num_keep) return FSG_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) {
+    FSG_CUDA_TRY(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), s));
+    return FSG_OK;
+  }
+  if (!boxes || !scores || !keep) return FSG_ERR_INVALID_ARG;
+  if (n > kNmsCap) return FSG_ERR_UNSUPPORTED;
+  NmsArgs a = {};
+  a.boxes = (const float4*)boxes; a.scores = scores; a.classes = class_ids;
+  a.slots_per_image = n; a.lvl_count = nullptr; a.L = 1; a.topk = (int)n; a.fixed_count = (int)n;
+  a.thr = threshold_floor(iou_threshold); a.max_out = 0;
+  a.keep = keep; a.keep_stride = n; a.num_keep = num_keep;
+  FSG_CUDA_TRY(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmem));
+  nms_image_kernel<<<1, kNmsThreads, kNmsSmem, s>>>(a);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" size_t fsg_detect_workspace_bytes(int N, int64_t R, int K, int num_levels, int topk) {
+  if (N <= 0 || num_levels <= 0 || num_levels > kMaxLevels || topk <= 0 || K <= 0) return 0;
+  (void)R;
+  int maxp = kSelCap / topk;
+  if (maxp > 16) maxp = 16;
+  if (maxp < 1) maxp = 1;
+  return detect_ws_layout(N, num_levels, topk, maxp).total;
+}
+
+extern "C" int fsg_detect(const float* logits, const float* deltas, const float* anchors,
+                          int64_t anchor_image_stride, int N, int64_t R, int K, const int64_t* h_level_offsets,
+                          int num_levels, float score_threshold, int topk, double nms_threshold, int max_det,
+                          const float* h_box_weights, float scale_clamp, float* out_boxes, float* out_scores,
+                          int64_t* out_classes, int32_t* out_count, float* cand_boxes, float* cand_scores,
+                          int64_t* cand_classes, int32_t* cand_count, int64_t* keep_idx, void* workspace,
+                          size_t workspace_bytes, fsg_stream_t stream) {
+  if (N <= 0 || R <= 0 || K <= 0 || !h_level_offsets || num_levels <= 0 || num_levels > kMaxLevels)
+    return FSG_ERR_INVALID_ARG;
+  if (!logits || !deltas || !anchors || !out_boxes || !out_scores || !out_classes || !out_count || !h_box_weights)
+    return FSG_ERR_INVALID_ARG;
+  if (topk <= 0 || max_det <= 0) return FSG_ERR_INVALID_ARG;
+  if (anchor_image_stride % 4 != 0) return FSG_ERR_INVALID_ARG;
+  if (h_level_offsets[0] != 0 || h_level_offsets[num_levels] != R) return FSG_ERR_INVALID_ARG;
+  if (topk > kSelTrigger || (int64_t)num_levels * topk > kNmsCap || K > 65535 || N > 65535)
+    return FSG_ERR_UNSUPPORTED;
+  for (int l = 0; l < num_levels; ++l) {
+    const int64_t hwa = h_level_offsets[l + 1] - h_level_offsets[l];
+    if (hwa < 0 || hwa * K >= ((int64_t)1 << 32)) return FSG_ERR_UNSUPPORTED;
+  }
+  if ((cand_boxes || cand_scores || cand_classes) && !(cand_boxes && cand_scores && cand_classes))
+    return FSG_ERR_INVALID_ARG;
+  const DetectLevels lv = plan_levels(h_level_offsets, num_levels, K, topk);
+  int maxp = kSelCap / topk;
+  if (maxp > 16) maxp = 16;
+  if (maxp < 1) maxp = 1;
+  DetectLevels lv2 = lv;
+  lv2.max_parts = maxp;
+  const DetectWs w = detect_ws_layout(N, num_levels, topk, maxp);
+  if (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  FSG_CUDA_TRY(cudaMemsetAsync(ws + w.off_done, 0, w.off_pcount - w.off_done, s));  // done + lvl_count
+
+  SelectArgs sa;
+  sa.logits = logits; sa.deltas = (const float4*)deltas; sa.anchors = (const float4*)anchors;
+  sa.anchor_stride4 = anchor_image_stride / 4; sa.R = R; sa.K = K; sa.topk = topk;
+  sa.thr = score_threshold;
+  {
+    // logit of the score threshold, minus a safety margin (the exact `score > thr` test follows)
+    const double t = (double)score_threshold;
+    double lg = (t <= 0.0) ? -INFINITY : ((t >= 1.0) ? INFINITY : log(t / (1.0 - t)));
+    sa.xpre = (float)(lg - 1e-3 * (1.0 + fabs(lg)));
+    if (t <= 0.0) sa.xpre = -INFINITY;
+  }
+  sa.wx = h_box_weights[0]; sa.wy = h_box_weights[1]; sa.ww = h_box_weights[2]; sa.wh = h_box_weights[3];
+  sa.clampv = scale_clamp;
+  sa.part_keys = (uint64_t*)(ws + w.off_pkeys); sa.part_count = (int*)(ws + w.off_pcount);
+  sa.done = (unsigned*)(ws + w.off_done);
+  sa.cand_box = (float4*)(ws + w.off_cbox); sa.cand_score = (float*)(ws + w.off_cscore);
+  sa.cand_class = (int64_t*)(ws + w.off_ccls); sa.lvl_count = (int*)(ws + w.off_lvl);
+  FSG_CUDA_TRY(cudaFuncSetAttribute(detect_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmem));
+  dim3 grid((unsigned)lv2.total_parts, (unsigned)N);
+  detect_select_kernel<<<grid, kSelThreads, kSelSmem, s>>>(sa, lv2);
+  FSG_LAUNCH_CHECK();
+
+  NmsArgs a = {};
+  a.boxes = sa.cand_box; a.scores = sa.cand_score; a.classes = sa.cand_class;
+  a.slots_per_image = (int64_t)num_levels * topk; a.lvl_count = sa.lvl_count; a.L = num_levels; a.topk = topk;
+  a.fixed_count = 0; a.thr = threshold_floor(nms_threshold); a.max_out = max_det;
+  a.keep = keep_idx; a.keep_stride = max_det; a.num_keep = out_count;
+  a.out_boxes = (float4*)out_boxes; a.out_scores = out_scores; a.out_classes = out_classes;
+  a.exp_boxes = (float4*)cand_boxes; a.exp_scores = cand_scores; a.exp_classes = cand_classes;
+  a.exp_count = cand_count;
+  FSG_CUDA_TRY(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmem));
+  nms_image_kernel<<<(unsigned)N, kNmsThreads, kNmsSmem, s>>>(a);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}

@@ -1,0 +1,653 @@
+// K2: fused Box2Box encode + gambler-weighted sigmoid-focal / smooth-L1 loss, forward + backward.
+//
+// Reference semantics (paths relative to the reference tree):
+//   detectron2/modeling/meta_arch/retinanet.py:201-248      RetinaNet.losses
+//   ImbalanceDetection/imbalancedetection/gambler_heads.py:104-128  calc_cls_loss
+//                                                    :131-253  calc_gambler_loss (L_BAHW, L_BAHW_extendtobatch)
+//                                                    :291-318  bet normalisation
+//                                                    :502-602  LayeredUnetGambler.gambler_loss
+//   ImbalanceDetection/train_net.py:1089-1098               loss combination
+//
+// One pass over the (N, R, K) logits: each anchor row is owned by a group of G lanes that read it
+// with 16-byte streaming loads, evaluate focal loss and its derivative sharing one exp2 and one
+// reciprocal per element (log1p by a degree-7 polynomial, so the per-element relative error stays
+// ~3e-7 instead of MUFU.LG2's 1e-5 near 1), write the gradient once, and reduce the per-anchor loss
+// with shuffles.  The gradient scale needs max(1, num_foreground) and the per-image bet normaliser
+// S[n] up front (pre-pass over (N,R)-sized data, fused into K1's second pass), and d/d bets needs
+// A[n] = sum_r w_hat*l afterwards (post pass over (N,R)-sized data).
+#include "common.cuh"
+
+namespace fsg {
+
+constexpr int kLossBlock = 256;
+constexpr int kAnchorsPerGroup = 4;
+constexpr int kPartialStride = 8;  // floats per tile partial: cls, reg, wl, l, maxl
+
+enum LossVariant { kFastWrite = 0, kFastNoWrite = 1, kGeneric = 2 };
+
+struct LossArgs {
+  const float* logits;
+  const float* pred_deltas;
+  const float* gt_deltas;
+  const float4* anchors;
+  int64_t anchor_stride4;
+  const float4* gt_boxes;
+  const int32_t* gt_offsets;
+  const int32_t* matched;
+  const int64_t* gt_classes;
+  const int64_t* mask;
+  const float* bets;
+  int N;
+  int64_t R;
+  int K;
+  int nvec;       // K / V
+  int G;          // lanes per anchor (power of two)
+  int logG;
+  int tiles_per_image;
+  int anchors_per_tile;
+  float a0, a1;   // alpha_t for t=0 / t=1 (1,1 when alpha < 0)
+  float gamma, beta, T, ggamma;
+  int gmode, nmode;
+  float c_cls, c_reg, c_gam;
+  float wx, wy, ww, wh;
+  const double* stats;
+  float* grad_logits;
+  float* grad_deltas;
+  float* ell;
+  float* wout;
+  float* partials;
+  unsigned* counter;
+  double* scalars;
+};
+
+// ---- vector load/store by width -------------------------------------------------------------
+template <int V> struct Vec;
+template <> struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) { float4 t = ldg_stream4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ __forceinline__ void store(float* p) const { stg_stream4(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <> struct Vec<2> {
+  float v[2];
+  __device__ __forceinline__ void load(const float* p) { float2 t = ldg_stream2(p); v[0] = t.x; v[1] = t.y; }
+  __device__ __forceinline__ void store(float* p) const { stg_stream2(p, make_float2(v[0], v[1])); }
+};
+template <> struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = ldg_stream1(p); }
+  __device__ __forceinline__ void store(float* p) const { stg_stream1(p, v[0]); }
+};
+
+// log1p(e) for e in [0,1]: e * P7(e), max relative error 3.3e-7 (fit in DESIGN.md)
+__device__ __forceinline__ float log1p_unit(float e) {
+  float p = -8.539245470e-03f;
+  p = fmaf(p, e, 4.408976170e-02f);
+  p = fmaf(p, e, -1.076818928e-01f);
+  p = fmaf(p, e, 1.774525379e-01f);
+  p = fmaf(p, e, -2.449546718e-01f);
+  p = fmaf(p, e, 3.327548051e-01f);
+  p = fmaf(p, e, -4.999740544e-01f);
+  p = fmaf(p, e, 9.999998057e-01f);
+  return p * e;
+}
+
+// shared sub-expressions of sigmoid / BCE for one logit (t = 0 side):
+//   p = sigmoid(x), omp = 1 - p (computed as sigmoid(-x), no cancellation), ce0 = softplus(x)
+__device__ __forceinline__ void sigmoid_parts(float x, float& p, float& omp, float& ce0) {
+  const float e = exp2f(-fabsf(x) * 1.4426950408889634f);  // MUFU.EX2
+  const float r = __frcp_rn(1.f + e);
+  const float er = e * r;
+  const float l1p = log1p_unit(e);
+  const bool pos = x >= 0.f;
+  p = pos ? r : er;
+  omp = pos ? er : r;
+  ce0 = pos ? x + l1p : l1p;
+}
+
+// one element with target t = 0, gamma = 2:  loss/(1-alpha) and dloss/dx/(1-alpha)
+__device__ __forceinline__ void focal_neg_g2(float x, float& loss, float& grad) {
+  float p, omp, ce;
+  sigmoid_parts(x, p, omp, ce);
+  const float p2 = p * p;
+  loss = p2 * ce;
+  grad = p2 * fmaf(2.f * omp, ce, p);
+}
+
+// general element (any t, any gamma, either mode); unscaled by alpha_t
+__device__ __forceinline__ void cls_elem_general(float x, bool t, float gamma, float& focal, float& fgrad,
+                                                 float& bce, float& bgrad) {
+  float p, omp, ce0;
+  sigmoid_parts(x, p, omp, ce0);
+  const float ce = t ? ce0 - x : ce0;   // BCE-with-logits
+  const float q = t ? omp : p;          // 1 - p_t
+  const float pt = t ? p : omp;
+  const float qg = (gamma == 2.f) ? q * q : ((gamma == 0.f) ? 1.f : powf(q, gamma));
+  focal = qg * ce;
+  const float inner = fmaf(gamma * pt, ce, q);
+  fgrad = t ? -qg * inner : qg * inner;
+  bce = ce;
+  bgrad = t ? -omp : p;
+}
+
+__device__ __forceinline__ float4 encode_deltas_loss(float4 s, float4 t, float wx, float wy, float ww, float wh) {
+  float sw = __fsub_rn(s.z, s.x), sh = __fsub_rn(s.w, s.y);
+  float sx = __fadd_rn(s.x, __fmul_rn(0.5f, sw)), sy = __fadd_rn(s.y, __fmul_rn(0.5f, sh));
+  float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
+  float tx = __fadd_rn(t.x, __fmul_rn(0.5f, tw)), ty = __fadd_rn(t.y, __fmul_rn(0.5f, th));
+  float4 d;
+  d.x = __fdiv_rn(__fmul_rn(wx, __fsub_rn(tx, sx)), sw);
+  d.y = __fdiv_rn(__fmul_rn(wy, __fsub_rn(ty, sy)), sh);
+  d.z = __fmul_rn(ww, logf(__fdiv_rn(tw, sw)));
+  d.w = __fmul_rn(wh, logf(__fdiv_rn(th, sh)));
+  return d;
+}
+
+__device__ __forceinline__ void smooth_l1_elem(float pd, float gd, float beta, float& loss, float& grad) {
+  const float d = pd - gd;
+  const float n = fabsf(d);
+  if (beta < 1e-5f) {
+    loss = n;
+    grad = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+  } else if (n < beta) {
+    loss = 0.5f * n * n / beta;
+    grad = d / beta;
+  } else {
+    loss = n - 0.5f * beta;
+    grad = (d > 0.f) ? 1.f : -1.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pre-pass (stand-alone form; K1's pass B carries the same reduction fused)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_prepass_kernel(const int64_t* __restrict__ gt_classes,
+                                                           const int64_t* __restrict__ mask,
+                                                           const float* __restrict__ bets, int N, int64_t R,
+                                                           int num_classes, float temperature,
+                                                           int* __restrict__ part_cnt, float* __restrict__ part_s,
+                                                           unsigned* __restrict__ counter, double* __restrict__ stats) {
+  __shared__ float s_red[8];
+  __shared__ int s_redi[8];
+  __shared__ double s_tc[8], s_ts[8];
+  __shared__ bool s_last;
+  const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t r = (int64_t)blockIdx.x * 256 + tid;
+  int fg = 0;
+  float w = 0.f;
+  if (r < R) {
+    const int64_t o = (int64_t)n * R + r;
+    const int64_t c = gt_classes[o];
+    fg = (c >= 0 && c != num_classes) ? 1 : 0;
+    if (bets) w = __fadd_rn(__fmul_rn(bets[o], mask ? (float)mask[o] : 1.f), temperature);
+  }
+  int fgw = __reduce_add_sync(kFull, fg);
+  float sw = warp_sum(w);
+  if (lane == 0) { s_redi[wid] = fgw; s_red[wid] = sw; }
+  __syncthreads();
+  const int nb = gridDim.x;
+  if (tid == 0) {
+    int ci = 0; float cs = 0.f;
+    for (int k = 0; k < 8; ++k) { ci += s_redi[k]; cs += s_red[k]; }
+    part_cnt[n * nb + blockIdx.x] = ci;
+    part_s[n * nb + blockIdx.x] = cs;
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == (unsigned)(nb * N) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double tc = 0.0, ts = 0.0;
+  for (int img = wid; img < N; img += 8) {
+    double c = 0.0, s = 0.0;
+    for (int b = lane; b < nb; b += 32) {
+      c += (double)__ldcg(&part_cnt[img * nb + b]);
+      s += (double)__ldcg(&part_s[img * nb + b]);
+    }
+    c = warp_sum_d(c); s = warp_sum_d(s);
+    if (lane == 0) { stats[FSG_STATS_HEADER + img] = s; tc += c; ts += s; }
+  }
+  if (lane == 0) { s_tc[wid] = tc; s_ts[wid] = ts; }
+  __syncthreads();
+  if (tid == 0) {
+    double c = 0.0, s = 0.0;
+    for (int k = 0; k < 8; ++k) { c += s_tc[k]; s += s_ts[k]; }
+    stats[0] = c; stats[1] = s;
+    *counter = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// main pass
+// ------------------------------------------------------------------------------------------
+template <int V, int BATCH, int VARIANT>
+__global__ void __launch_bounds__(kLossBlock) loss_main_kernel(const LossArgs A) {
+  constexpr bool kWrite = (VARIANT != kFastNoWrite);
+  constexpr bool kFast = (VARIANT != kGeneric);
+  __shared__ float s_part[kLossBlock / 32][5];
+  __shared__ bool s_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = blockIdx.y;
+  const int G = A.G;
+  const int gl = tid & (G - 1);           // lane within the anchor group
+  const int grp = tid >> A.logG;          // group within the block
+  const int ngrp = kLossBlock >> A.logG;
+  const int64_t tile_base = (int64_t)blockIdx.x * A.anchors_per_tile;
+
+  __shared__ float s_inv[2];
+  const double nf_d = A.stats[0];
+  if (tid == 0) {
+    s_inv[0] = (float)(1.0 / (nf_d > 1.0 ? nf_d : 1.0));
+    float is = 1.f;
+    if (A.nmode == FSG_NORM_IMAGE) is = (float)(1.0 / A.stats[FSG_STATS_HEADER + n]);
+    else if (A.nmode == FSG_NORM_BATCH) is = (float)(1.0 / A.stats[1]);
+    s_inv[1] = is;
+  }
+  __syncthreads();
+  const float inv_nf = s_inv[0];
+  const float inv_S = s_inv[1];
+  const int m0 = A.gt_offsets ? A.gt_offsets[n] : 0;
+  const bool write_grad = kWrite && (A.grad_logits != nullptr);
+
+  float acc_cls = 0.f, acc_reg = 0.f, acc_wl = 0.f, acc_l = 0.f, max_l = 0.f;
+
+#pragma unroll 1
+  for (int it = 0; it < kAnchorsPerGroup; ++it) {
+    const int64_t r = tile_base + (int64_t)it * ngrp + grp;
+    const bool live = r < A.R;   // uniform within the group
+    const int64_t o = (int64_t)n * A.R + (live ? r : 0);
+
+    // ---- per-anchor metadata (same address for the G lanes of a group: one broadcast request)
+    int cls = -1;
+    float w_hat = 0.f;
+    if (live) {
+      cls = (int)A.gt_classes[o];
+      if (A.bets) {
+        const float m = A.mask ? (float)A.mask[o] : 1.f;
+        const float w = __fadd_rn(__fmul_rn(A.bets[o], m), A.T);   // gambler_heads.py:569,304
+        w_hat = w * inv_S;                                        // :308-311
+      }
+    }
+    const bool valid = cls >= 0;
+    const bool fgc = valid && cls != A.K;
+    const float wg = (A.ggamma == 1.f) ? w_hat : powf(w_hat, A.ggamma);
+    // d total / d x = f'(x) * coef_f + bce'(x) * coef_b
+    float coef_f = 0.f, coef_b = 0.f;
+    if (valid) {
+      coef_f = A.c_cls * inv_nf;
+      if (A.gmode == FSG_CLS_FOCAL) coef_f = fmaf(-A.c_gam, wg, coef_f);
+      else coef_b = -A.c_gam * wg;
+    }
+    const int jpos = fgc ? cls / V : -1;   // vector that holds the positive class
+    const int kpos = fgc ? cls - jpos * V : 0;
+
+    float sum_f = 0.f, sum_b = 0.f;       // per-lane partial of sum_k focal / sum_k bce (unscaled for t=0)
+    float pos_fix = 0.f;                  // (alpha_1 f_1 - alpha_0 f_0) of the positive element
+    const float* xrow = A.logits + o * A.K;
+    float* grow = write_grad ? A.grad_logits + o * A.K : nullptr;
+
+    if (live && !valid) {
+      // ignored anchor: zero loss, zero gradient (gambler_heads.py:554-555, retinanet.py:233)
+      if (write_grad) {
+        Vec<V> z;
+#pragma unroll
+        for (int k = 0; k < V; ++k) z.v[k] = 0.f;
+        for (int j = gl; j < A.nvec; j += G) z.store(grow + (int64_t)j * V);
+      }
+    } else if (live) {
+      for (int j0 = gl; j0 < A.nvec; j0 += G * BATCH) {
+        Vec<V> x[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int j = j0 + b * G;
+          if (j < A.nvec) x[b].load(xrow + (int64_t)j * V);
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int j = j0 + b * G;
+          if (j < A.nvec) {
+            Vec<V> g;
+            if (kFast) {
+#pragma unroll
+              for (int k = 0; k < V; ++k) {
+                float l, d;
+                focal_neg_g2(x[b].v[k], l, d);
+                sum_f += l;
+                g.v[k] = d * (coef_f * A.a0);
+              }
+              if (j == jpos) {   // rare: patch the single positive element of this anchor
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                  if (k == kpos) {
+                    float l0, d0, f1, fg1, b1, bg1;
+                    focal_neg_g2(x[b].v[k], l0, d0);
+                    cls_elem_general(x[b].v[k], true, 2.f, f1, fg1, b1, bg1);
+                    pos_fix = f1 * A.a1 - l0 * A.a0;
+                    g.v[k] = fg1 * (coef_f * A.a1);
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < V; ++k) {
+                const bool t = (j == jpos) && (k == kpos);
+                float f, fgd, bc, bgd;
+                cls_elem_general(x[b].v[k], t, A.gamma, f, fgd, bc, bgd);
+                const float at = t ? A.a1 : A.a0;
+                sum_f += f * at;
+                sum_b += bc;
+                g.v[k] = fmaf(fgd * at, coef_f, bgd * coef_b);
+              }
+            }
+            if (write_grad) g.store(grow + (int64_t)j * V);
+          }
+        }
+      }
+    }
+    if (kFast) sum_f = fmaf(sum_f, A.a0, pos_fix);
+    // ---- reduce over the group's lanes
+    for (int s = G >> 1; s > 0; s >>= 1) {
+      sum_f += __shfl_xor_sync(kFull, sum_f, s);
+      if (!kFast) sum_b += __shfl_xor_sync(kFull, sum_b, s);
+    }
+    if (live && gl == 0) {
+      const float lf = valid ? sum_f : 0.f;                                   // gambler_heads.py:554-555
+      const float lg = (A.gmode == FSG_CLS_FOCAL) ? lf : (valid ? sum_b : 0.f);
+      if (A.ell) A.ell[o] = lg;
+      if (A.wout) A.wout[o] = w_hat;
+      acc_cls += lf;
+      acc_wl = fmaf(wg, lg, acc_wl);
+      acc_l += lg;
+      max_l = fmaxf(max_l, lg);
+    }
+    // ---- regression: one lane per anchor (the group's last lane, to spread the work)
+    if (live && gl == G - 1 && A.pred_deltas) {
+      float4 gout = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fgc) {
+        const float4 pd = reinterpret_cast<const float4*>(A.pred_deltas)[o];
+        float4 gd;
+        if (A.gt_deltas) gd = reinterpret_cast<const float4*>(A.gt_deltas)[o];
+        else gd = encode_deltas_loss(A.anchors[(int64_t)n * A.anchor_stride4 + r],
+                                     A.gt_boxes[m0 + A.matched[o]], A.wx, A.wy, A.ww, A.wh);
+        const float sc = A.c_reg * inv_nf;
+        float l, g;
+        smooth_l1_elem(pd.x, gd.x, A.beta, l, g); acc_reg += l; gout.x = g * sc;
+        smooth_l1_elem(pd.y, gd.y, A.beta, l, g); acc_reg += l; gout.y = g * sc;
+        smooth_l1_elem(pd.z, gd.z, A.beta, l, g); acc_reg += l; gout.z = g * sc;
+        smooth_l1_elem(pd.w, gd.w, A.beta, l, g); acc_reg += l; gout.w = g * sc;
+      }
+      if (A.grad_deltas) reinterpret_cast<float4*>(A.grad_deltas)[o] = gout;
+    }
+  }
+
+  // ---- tile partials (deterministic: one slot per tile, fixed reduction order)
+  acc_cls = warp_sum(acc_cls); acc_reg = warp_sum(acc_reg); acc_wl = warp_sum(acc_wl);
+  acc_l = warp_sum(acc_l); max_l = warp_max(max_l);
+  if (lane == 0) {
+    s_part[wid][0] = acc_cls; s_part[wid][1] = acc_reg; s_part[wid][2] = acc_wl;
+    s_part[wid][3] = acc_l; s_part[wid][4] = max_l;
+  }
+  __syncthreads();
+  const int T = A.tiles_per_image;
+  if (tid == 0) {
+    float c = 0.f, g = 0.f, w = 0.f, l = 0.f, mx = 0.f;
+    for (int k = 0; k < kLossBlock / 32; ++k) {
+      c += s_part[k][0]; g += s_part[k][1]; w += s_part[k][2]; l += s_part[k][3];
+      mx = fmaxf(mx, s_part[k][4]);
+    }
+    float* P = A.partials + ((int64_t)n * T + blockIdx.x) * kPartialStride;
+    P[0] = c; P[1] = g; P[2] = w; P[3] = l; P[4] = mx;
+    __threadfence();
+    s_last = (atomicAdd(A.counter, 1u) == (unsigned)(T * A.N) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+
+  // ---- last block: reduce all tile partials -> scalars (fixed order => run-to-run deterministic)
+  __threadfence();
+  __shared__ double s_tot[kLossBlock / 32][5];
+  double t_cls = 0.0, t_reg = 0.0, t_wl = 0.0, t_l = 0.0, t_mx = 0.0;
+  for (int img = wid; img < A.N; img += kLossBlock / 32) {
+    double c = 0.0, g = 0.0, w = 0.0, l = 0.0;
+    float mx = 0.f;
+    for (int b = lane; b < T; b += 32) {
+      const float* P = A.partials + ((int64_t)img * T + b) * kPartialStride;
+      c += (double)__ldcg(P + 0); g += (double)__ldcg(P + 1); w += (double)__ldcg(P + 2);
+      l += (double)__ldcg(P + 3); mx = fmaxf(mx, __ldcg(P + 4));
+    }
+    c = warp_sum_d(c); g = warp_sum_d(g); w = warp_sum_d(w); l = warp_sum_d(l); mx = warp_max(mx);
+    if (lane == 0) {
+      A.scalars[FSG_SCALARS_HEADER + img] = w;
+      t_cls += c; t_reg += g; t_wl += w; t_l += l; t_mx += (double)mx;
+    }
+  }
+  if (lane == 0) {
+    s_tot[wid][0] = t_cls; s_tot[wid][1] = t_reg; s_tot[wid][2] = t_wl; s_tot[wid][3] = t_l; s_tot[wid][4] = t_mx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int k = 0; k < kLossBlock / 32; ++k)
+      for (int q = 0; q < 5; ++q) v[q] += s_tot[k][q];
+    const double nfc = nf_d > 1.0 ? nf_d : 1.0;
+    for (int q = 0; q < 5; ++q) A.scalars[q] = v[q];
+    A.scalars[5] = v[0] / nfc;
+    A.scalars[6] = v[1] / nfc;
+    A.scalars[7] = -v[2];
+    A.scalars[8] = (double)A.c_cls * A.scalars[5] + (double)A.c_reg * A.scalars[6] + (double)A.c_gam * A.scalars[7];
+    A.scalars[9] = nf_d;
+    *A.counter = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// post pass: d(c_gam * G)/d bets
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_post_kernel(const float* __restrict__ bets,
+                                                        const int64_t* __restrict__ mask,
+                                                        const float* __restrict__ ell, int N, int64_t R, float T,
+                                                        float ggamma, int nmode, float c_gam,
+                                                        const double* __restrict__ stats,
+                                                        const double* __restrict__ scalars,
+                                                        float* __restrict__ grad_bets) {
+  const int n = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= R) return;
+  const int64_t o = (int64_t)n * R + r;
+  const float m = mask ? (float)mask[o] : 1.f;
+  const float l = ell[o];
+  const float w = __fadd_rn(__fmul_rn(bets[o], m), T);
+  float g;
+  if (nmode == FSG_NORM_NONE) {
+    const float pw = (ggamma == 1.f) ? 1.f : powf(w, ggamma - 1.f);
+    g = -m * ggamma * pw * l;
+  } else {
+    const double S = (nmode == FSG_NORM_IMAGE) ? stats[FSG_STATS_HEADER + n] : stats[1];
+    const double Asum = (nmode == FSG_NORM_IMAGE) ? scalars[FSG_SCALARS_HEADER + n] : scalars[2];
+    const float inv_S = (float)(1.0 / S);
+    const float w_hat = w * inv_S;
+    const float pw = (ggamma == 1.f) ? 1.f : powf(w_hat, ggamma - 1.f);
+    g = -(m * inv_S) * ggamma * (pw * l - (float)Asum);
+  }
+  grad_bets[o] = c_gam * g;
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, int64_t n4, int64_t n,
+                                                    const float* __restrict__ sdev, float shost) {
+  const float s = sdev ? *sdev * shost : shost;
+  if (s == 1.f) return;  // unit upstream gradient: nothing to do (checked on the device, no host sync)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) x[i] *= s;
+  }
+}
+
+struct LossPlan {
+  int V, G, logG, batch, nvec, anchors_per_tile, tiles_per_image;
+};
+
+static LossPlan plan_loss(int64_t R, int K) {
+  LossPlan p;
+  p.V = (K % 4 == 0) ? 4 : ((K % 2 == 0) ? 2 : 1);
+  p.nvec = K / p.V;
+  // pick lanes-per-anchor G (power of two) and the unroll batch to minimise predicated-off work;
+  // prefer G >= 4 so a group's request covers at least two full 32-byte sectors
+  double best = 1e30;
+  p.G = 32; p.batch = 4;
+  for (int g = 1; g <= 32; g <<= 1) {
+    if (g < 4 && p.nvec >= 4) continue;
+    for (int b = 4; b <= 5; ++b) {
+      const int64_t span = (int64_t)g * b;
+      const double waste = (double)(ceil_div(p.nvec, span) * span) / p.nvec;
+      const double cost = waste + 0.002 * g + (ceil_div(p.nvec, span) > 8 ? 0.5 : 0.0);
+      if (cost < best - 1e-9) { best = cost; p.G = g; p.batch = b; }
+    }
+  }
+  p.logG = 0;
+  while ((1 << p.logG) < p.G) ++p.logG;
+  p.anchors_per_tile = (kLossBlock / p.G) * kAnchorsPerGroup;
+  p.tiles_per_image = (int)ceil_div(R > 0 ? R : 1, p.anchors_per_tile);
+  return p;
+}
+
+struct LossWs {
+  size_t off_counter, off_partials, total;
+};
+static LossWs loss_ws_layout(int N, const LossPlan& p) {
+  LossWs w;
+  size_t o = 0;
+  w.off_counter = o; o += 16;
+  w.off_partials = o; o += align_up(sizeof(float) * kPartialStride * (size_t)N * p.tiles_per_image, 16);
+  w.total = o;
+  return w;
+}
+
+template <int V, int BATCH>
+static void launch_main(int variant, dim3 grid, cudaStream_t s, const LossArgs& a) {
+  if (variant == kFastWrite) loss_main_kernel<V, BATCH, kFastWrite><<<grid, kLossBlock, 0, s>>>(a);
+  else if (variant == kFastNoWrite) loss_main_kernel<V, BATCH, kFastNoWrite><<<grid, kLossBlock, 0, s>>>(a);
+  else loss_main_kernel<V, BATCH, kGeneric><<<grid, kLossBlock, 0, s>>>(a);
+}
+
+}  // namespace fsg
+
+using namespace fsg;
+
+extern "C" size_t fsg_loss_prepass_workspace_bytes(int N, int64_t R) {
+  if (N <= 0 || R < 0) return 0;
+  const size_t nb = (size_t)ceil_div(R > 0 ? R : 1, 256);
+  return 16 + align_up(sizeof(int) * N * nb, 16) + align_up(sizeof(float) * N * nb, 16);
+}
+
+extern "C" int fsg_loss_prepass(const int64_t* gt_classes, const int64_t* mask, const float* bets, int N,
+                                int64_t R, int num_classes, float temperature, double* stats, void* workspace,
+                                size_t workspace_bytes, fsg_stream_t stream) {
+  if (N <= 0 || R <= 0 || !gt_classes || !stats) return FSG_ERR_INVALID_ARG;
+  if (N > 65535) return FSG_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < fsg_loss_prepass_workspace_bytes(N, R) || ((uintptr_t)workspace & 15))
+    return FSG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nb = (size_t)ceil_div(R, 256);
+  char* ws = (char*)workspace;
+  unsigned* counter = (unsigned*)ws;
+  int* pc = (int*)(ws + 16);
+  float* ps = (float*)(ws + 16 + align_up(sizeof(int) * N * nb, 16));
+  FSG_CUDA_TRY(cudaMemsetAsync(counter, 0, 16, s));
+  dim3 grid((unsigned)nb, (unsigned)N);
+  loss_prepass_kernel<<<grid, 256, 0, s>>>(gt_classes, mask, bets, N, R, num_classes, temperature, pc, ps,
+                                           counter, stats);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" size_t fsg_loss_main_workspace_bytes(int N, int64_t R, int K) {
+  if (N <= 0 || R < 0 || K <= 0) return 0;
+  return loss_ws_layout(N, plan_loss(R, K)).total;
+}
+
+extern "C" int fsg_loss_main(const float* logits, const float* pred_deltas, const float* gt_deltas,
+                             const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
+                             const int32_t* gt_offsets, const int32_t* matched_idx32, const int64_t* gt_classes,
+                             const int64_t* mask, const float* bets, int N, int64_t R,
+                             const fsg_loss_params* hp, const double* stats, float* grad_logits,
+                             float* grad_deltas, float* per_anchor_loss, float* weights_out, double* scalars,
+                             void* workspace, size_t workspace_bytes, fsg_stream_t stream) {
+  if (!hp || N <= 0 || R <= 0 || hp->num_classes <= 0) return FSG_ERR_INVALID_ARG;
+  if (!logits || !gt_classes || !stats || !scalars) return FSG_ERR_INVALID_ARG;
+  if (N > 65535) return FSG_ERR_UNSUPPORTED;
+  if (anchor_image_stride % 4 != 0) return FSG_ERR_INVALID_ARG;
+  if (pred_deltas && !gt_deltas && (!anchors || !gt_boxes || !gt_offsets || !matched_idx32))
+    return FSG_ERR_INVALID_ARG;
+  if (grad_deltas && !pred_deltas) return FSG_ERR_INVALID_ARG;
+  if (!bets && (hp->c_gam != 0.f || weights_out)) return FSG_ERR_INVALID_ARG;
+  if (hp->gambler_mode != FSG_CLS_FOCAL && hp->gambler_mode != FSG_CLS_SIGMOID) return FSG_ERR_INVALID_ARG;
+  if (hp->norm_mode < FSG_NORM_NONE || hp->norm_mode > FSG_NORM_BATCH) return FSG_ERR_INVALID_ARG;
+  const int K = hp->num_classes;
+  const LossPlan p = plan_loss(R, K);
+  const LossWs w = loss_ws_layout(N, p);
+  if (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  if (p.V == 4 && (((uintptr_t)logits | (uintptr_t)grad_logits) & 15)) return FSG_ERR_INVALID_ARG;
+  if (p.V == 2 && (((uintptr_t)logits | (uintptr_t)grad_logits) & 7)) return FSG_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+
+  LossArgs a;
+  a.logits = logits; a.pred_deltas = pred_deltas; a.gt_deltas = gt_deltas;
+  a.anchors = (const float4*)anchors; a.anchor_stride4 = anchor_image_stride / 4;
+  a.gt_boxes = (const float4*)gt_boxes; a.gt_offsets = gt_offsets; a.matched = matched_idx32;
+  a.gt_classes = gt_classes; a.mask = mask; a.bets = bets;
+  a.N = N; a.R = R; a.K = K; a.nvec = p.nvec; a.G = p.G; a.logG = p.logG;
+  a.tiles_per_image = p.tiles_per_image; a.anchors_per_tile = p.anchors_per_tile;
+  a.a0 = hp->focal_alpha >= 0.f ? 1.f - hp->focal_alpha : 1.f;
+  a.a1 = hp->focal_alpha >= 0.f ? hp->focal_alpha : 1.f;
+  a.gamma = hp->focal_gamma; a.beta = hp->smooth_l1_beta; a.T = hp->temperature; a.ggamma = hp->gambler_gamma;
+  a.gmode = hp->gambler_mode; a.nmode = bets ? hp->norm_mode : FSG_NORM_NONE;
+  a.c_cls = hp->c_cls; a.c_reg = hp->c_reg; a.c_gam = hp->c_gam;
+  a.wx = hp->box_weights[0]; a.wy = hp->box_weights[1]; a.ww = hp->box_weights[2]; a.wh = hp->box_weights[3];
+  a.stats = stats; a.grad_logits = grad_logits; a.grad_deltas = grad_deltas; a.ell = per_anchor_loss;
+  a.wout = weights_out; a.partials = (float*)(ws + w.off_partials); a.counter = (unsigned*)(ws + w.off_counter);
+  a.scalars = scalars;
+
+  FSG_CUDA_TRY(cudaMemsetAsync(a.counter, 0, 16, s));
+  const bool fast = (hp->focal_gamma == 2.f) && (hp->gambler_mode == FSG_CLS_FOCAL);
+  const int variant = fast ? (grad_logits ? kFastWrite : kFastNoWrite) : kGeneric;
+  dim3 grid((unsigned)p.tiles_per_image, (unsigned)N);
+  if (p.V == 4) { if (p.batch == 5) launch_main<4, 5>(variant, grid, s, a); else launch_main<4, 4>(variant, grid, s, a); }
+  else if (p.V == 2) { if (p.batch == 5) launch_main<2, 5>(variant, grid, s, a); else launch_main<2, 4>(variant, grid, s, a); }
+  else { if (p.batch == 5) launch_main<1, 5>(variant, grid, s, a); else launch_main<1, 4>(variant, grid, s, a); }
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" int fsg_loss_post(const float* bets, const int64_t* mask, const float* per_anchor_loss, int N,
+                             int64_t R, const fsg_loss_params* hp, const double* stats, const double* scalars,
+                             float* grad_bets, fsg_stream_t stream) {
+  if (!hp || N <= 0 || R <= 0 || !bets || !per_anchor_loss || !stats || !scalars || !grad_bets)
+    return FSG_ERR_INVALID_ARG;
+  if (N > 65535) return FSG_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(R, 256), (unsigned)N);
+  loss_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bets, mask, per_anchor_loss, N, R, hp->temperature,
+                                                           hp->gambler_gamma, hp->norm_mode, hp->c_gam, stats,
+                                                           scalars, grad_bets);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" int fsg_scale_inplace(float* x, int64_t n, const float* scale_dev, float scale_host,
+                                 fsg_stream_t stream) {
+  if (n < 0) return FSG_ERR_INVALID_ARG;
+  if (n == 0) return FSG_OK;
+  if (!x) return FSG_ERR_INVALID_ARG;
+  const bool aligned = (((uintptr_t)x) & 15) == 0;
+  const int64_t n4 = aligned ? n / 4 : 0;
+  int64_t blocks = ceil_div(n4 > 0 ? n4 : 1, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n4, n, scale_dev, scale_host);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}

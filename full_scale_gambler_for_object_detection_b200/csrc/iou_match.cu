@@ -1,0 +1,590 @@
+// K1: pairwise IoU, Matcher, and the fused IoU+Matcher+GT-assignment path (sm_100a).
+//
+// Reference semantics (paths relative to the reference tree):
+//   detectron2/structures/boxes.py:243-275   pairwise_iou (fp32 op order reproduced exactly:
+//                                            no FMA contraction, IEEE division)
+//   detectron2/modeling/matcher.py:55-132    Matcher.__call__ / set_low_quality_matches_
+//   detectron2/modeling/box_regression.py:34-67  get_deltas
+//   detectron2/modeling/meta_arch/retinanet.py:339-363, 400-425  GT assignment + picky mask
+//
+// Layout: anchors (R,4) float4-aligned, streamed with one coalesced 16-byte load per anchor;
+// the image's GT boxes are staged into shared memory by a TMA bulk copy (cp.async.bulk +
+// mbarrier); every thread owns U anchors and walks the GT table with shared-memory broadcast
+// reads; per-GT maxima are reduced with redux.sync and merged with atomicMax on the
+// float-as-uint pattern (valid because IoU >= 0).
+#include "common.cuh"
+
+namespace fsg {
+
+constexpr int kMaxThr = 4;       // thresholds per matcher
+constexpr int kMatchBlock = 256;
+constexpr int kGtChunk = 1024;   // GT boxes staged per shared-memory chunk
+
+struct MatcherBands {
+  float lo[kMaxThr + 1];
+  float hi[kMaxThr + 1];
+  int8_t lab[kMaxThr + 1];
+  int n;  // number of bands (= thresholds + 1); 0 = matcher disabled
+};
+
+__device__ __forceinline__ float box_area(float4 b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));  // boxes.py:119
+}
+
+// boxes.py:261-274, b1 = ground truth (area1), b2 = anchor (area2)
+__device__ __forceinline__ float iou_exact(float4 a, float area_a, float4 b, float area_b) {
+  float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+  float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+  float inter = __fmul_rn(w, h);
+  float r = 0.f;
+  if (inter > 0.f) r = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return r;
+}
+
+__device__ __forceinline__ int8_t band_label(const MatcherBands& mb, float v) {
+  int8_t l = 1;  // matcher.py:88
+#pragma unroll
+  for (int i = 0; i <= kMaxThr; ++i)
+    if (i < mb.n && v >= mb.lo[i] && v < mb.hi[i]) l = mb.lab[i];
+  return l;
+}
+
+// box_regression.py:49-63 (mul-then-add order kept; 0.5*w is exact so the fused form is identical)
+__device__ __forceinline__ float4 encode_deltas(float4 s, float4 t, float wx, float wy, float ww, float wh) {
+  float sw = __fsub_rn(s.z, s.x), sh = __fsub_rn(s.w, s.y);
+  float sx = __fadd_rn(s.x, __fmul_rn(0.5f, sw)), sy = __fadd_rn(s.y, __fmul_rn(0.5f, sh));
+  float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
+  float tx = __fadd_rn(t.x, __fmul_rn(0.5f, tw)), ty = __fadd_rn(t.y, __fmul_rn(0.5f, th));
+  float4 d;
+  d.x = __fdiv_rn(__fmul_rn(wx, __fsub_rn(tx, sx)), sw);
+  d.y = __fdiv_rn(__fmul_rn(wy, __fsub_rn(ty, sy)), sh);
+  d.z = __fmul_rn(ww, logf(__fdiv_rn(tw, sw)));
+  d.w = __fmul_rn(wh, logf(__fdiv_rn(th, sh)));
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// pairwise_iou drop-in: materialises the (n1, n2) matrix
+// ------------------------------------------------------------------------------------------
+constexpr int kIouRows = 8;
+__global__ void __launch_bounds__(256) pairwise_iou_kernel(const float4* __restrict__ b1, int64_t n1,
+                                                           const float4* __restrict__ b2, int64_t n2,
+                                                           float* __restrict__ out) {
+  __shared__ float4 rows[kIouRows];
+  __shared__ float areas[kIouRows];
+  const int64_t i0 = (int64_t)blockIdx.y * kIouRows;
+  if (threadIdx.x < kIouRows && i0 + threadIdx.x < n1) {
+    float4 r = b1[i0 + threadIdx.x];
+    rows[threadIdx.x] = r;
+    areas[threadIdx.x] = box_area(r);
+  }
+  __syncthreads();
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n2) return;
+  const float4 c = b2[j];
+  const float ac = box_area(c);
+#pragma unroll
+  for (int k = 0; k < kIouRows; ++k) {
+    if (i0 + k < n1) out[(i0 + k) * n2 + j] = iou_exact(rows[k], areas[k], c, ac);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Matcher drop-in on a materialised matrix
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) matrix_rowmax_kernel(const float* __restrict__ q, int64_t M, int64_t N,
+                                                            unsigned* __restrict__ rowmax) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t g0 = (int64_t)blockIdx.y * 64;
+  const int64_t g1 = min(M, g0 + 64);
+  for (int64_t g = g0; g < g1; ++g) {
+    float v = (n < N) ? q[g * N + n] : 0.f;
+    unsigned m = __reduce_max_sync(kFull, __float_as_uint(v));
+    if ((threadIdx.x & 31) == 0 && m > 0u) atomicMax(&rowmax[g], m);
+  }
+}
+
+__global__ void __launch_bounds__(256) matrix_match_kernel(const float* __restrict__ q, int64_t M, int64_t N,
+                                                           MatcherBands mb, int allow_lq,
+                                                           const float* __restrict__ rowmax,
+                                                           int64_t* __restrict__ matches,
+                                                           int8_t* __restrict__ labels) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (M == 0) {  // matcher.py:70-80
+    matches[n] = 0;
+    labels[n] = mb.lab[0];
+    return;
+  }
+  float best = q[n];
+  int64_t bi = 0;
+  bool lq = allow_lq && (best == rowmax[0]);
+  for (int64_t g = 1; g < M; ++g) {
+    float v = q[g * N + n];
+    if (v > best) { best = v; bi = g; }
+    if (allow_lq && v == rowmax[g]) lq = true;
+  }
+  matches[n] = bi;
+  labels[n] = lq ? (int8_t)1 : band_label(mb, best);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused path, pass A: per-anchor max/argmax over the image's GT + per-GT max over anchors
+// ------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(kMatchBlock) match_pass_a_kernel(
+    const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
+    const float4* __restrict__ gt_boxes, const int32_t* __restrict__ gt_offsets,
+    float* __restrict__ best_val, int32_t* __restrict__ best_idx, unsigned* __restrict__ gt_max) {
+  __shared__ __align__(16) float4 s_gt[kGtChunk];
+  __shared__ float s_area[kGtChunk];
+  __shared__ unsigned s_max[kGtChunk];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int n = blockIdx.y;
+  const int m0 = gt_offsets[n];
+  const int M = gt_offsets[n + 1] - m0;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int64_t base = (int64_t)blockIdx.x * (kMatchBlock * U);
+  const float4* a_img = anchors + (int64_t)n * anchor_stride4;
+
+  float4 a[U];
+  float aa[U], bv[U];
+  int bi[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    int64_t r = base + u * kMatchBlock + tid;
+    a[u] = (r < R) ? a_img[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+    aa[u] = box_area(a[u]);
+    bv[u] = -1.f;  // first GT always wins the initial compare -> argmax of an all-zero column is 0
+    bi[u] = 0;
+  }
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  uint32_t phase = 0;
+  for (int c = 0; c < M; c += kGtChunk) {
+    const int cnt = min(kGtChunk, M - c);
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&s_bar, (uint32_t)cnt * 16u);
+      tma_bulk_g2s(s_gt, gt_boxes + m0 + c, (uint32_t)cnt * 16u, &s_bar);
+    }
+    mbar_wait(&s_bar, phase);
+    phase ^= 1u;
+    for (int g = tid; g < cnt; g += kMatchBlock) {
+      s_area[g] = box_area(s_gt[g]);
+      s_max[g] = 0u;
+    }
+    __syncthreads();
+
+    for (int g = 0; g < cnt; ++g) {
+      const float4 G = s_gt[g];
+      const float ga = s_area[g];
+      float m = 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float v = iou_exact(G, ga, a[u], aa[u]);
+        if (v > bv[u]) { bv[u] = v; bi[u] = c + g; }
+        m = fmaxf(m, v);
+      }
+      // padding lanes (r >= R) hold a zero box: inter == 0 -> v == 0, harmless for the max
+      unsigned wm = __reduce_max_sync(kFull, __float_as_uint(m));
+      if (lane == 0 && wm > 0u) atomicMax(&s_max[g], wm);
+    }
+    __syncthreads();
+    for (int g = tid; g < cnt; g += kMatchBlock) {
+      unsigned v = s_max[g];
+      if (v > 0u) atomicMax(&gt_max[m0 + c + g], v);
+    }
+    __syncthreads();  // s_gt / s_max are rewritten by the next chunk
+  }
+
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    int64_t r = base + u * kMatchBlock + tid;
+    if (r < R) {
+      best_val[(int64_t)n * R + r] = (M > 0) ? bv[u] : 0.f;
+      best_idx[(int64_t)n * R + r] = bi[u];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused path, pass B: low-quality pass, labels, class relabel, picky mask, encode, loss pre-pass
+// ------------------------------------------------------------------------------------------
+struct MatchOut {
+  int64_t* matches;
+  int8_t* match_labels;
+  int8_t* picky_labels;
+  int64_t* gt_classes;
+  int64_t* mask;
+  float4* gt_deltas;
+  int32_t* matched_idx32;
+};
+
+__global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
+    const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
+    const float4* __restrict__ gt_boxes, const int64_t* __restrict__ gt_class_ids,
+    const int32_t* __restrict__ gt_offsets, int N, int num_classes, MatcherBands mb, MatcherBands pmb, int allow_lq,
+    float wx, float wy, float ww, float wh, const float* __restrict__ best_val,
+    const int32_t* __restrict__ best_idx, const unsigned* __restrict__ gt_max, MatchOut out,
+    const float* __restrict__ bets, float temperature, int* __restrict__ part_cnt,
+    float* __restrict__ part_s, unsigned* __restrict__ done_counter, double* __restrict__ stats) {
+  __shared__ __align__(16) float4 s_gt[kGtChunk];
+  __shared__ float s_area[kGtChunk];
+  __shared__ float s_max[kGtChunk];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ float s_red[kMatchBlock / 32];
+  __shared__ int s_redi[kMatchBlock / 32];
+  __shared__ float s_min;
+  __shared__ bool s_last;
+
+  const int n = blockIdx.y;
+  const int m0 = gt_offsets[n];
+  const int M = gt_offsets[n + 1] - m0;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t r = (int64_t)blockIdx.x * kMatchBlock + tid;
+  const bool live = r < R;
+  const int64_t o = (int64_t)n * R + r;
+
+  float val = 0.f;
+  int idx = 0;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    val = best_val[o];
+    idx = best_idx[o];
+    a = anchors[(int64_t)n * anchor_stride4 + r];
+  }
+
+  // minimum over the image's per-GT maxima: an anchor can only equal some GT's maximum if its own
+  // best IoU reaches that minimum (IoU(g,a) <= best(a)), which prunes almost every anchor.
+  float mn = __int_as_float(0x7f800000);
+  for (int g = tid; g < M; g += kMatchBlock) mn = fminf(mn, __uint_as_float(gt_max[m0 + g]));
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, s));
+  if (lane == 0) s_red[wid] = mn;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float v = s_red[0];
+    for (int w = 1; w < kMatchBlock / 32; ++w) v = fminf(v, s_red[w]);
+    s_min = v;
+  }
+  __syncthreads();
+  const float min_gt_max = s_min;
+
+  bool lq = false;
+  const bool cand = allow_lq && live && M > 0 && val >= min_gt_max;
+  if (__syncthreads_or(cand)) {
+    const float aa = box_area(a);
+    uint32_t phase = 0;
+    for (int c = 0; c < M; c += kGtChunk) {
+      const int cnt = min(kGtChunk, M - c);
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar, (uint32_t)cnt * 16u);
+        tma_bulk_g2s(s_gt, gt_boxes + m0 + c, (uint32_t)cnt * 16u, &s_bar);
+      }
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+      for (int g = tid; g < cnt; g += kMatchBlock) {
+        s_area[g] = box_area(s_gt[g]);
+        s_max[g] = __uint_as_float(gt_max[m0 + c + g]);
+      }
+      __syncthreads();
+      if (__any_sync(kFull, cand)) {
+        for (int g = 0; g < cnt; ++g) {
+          const float gm = s_max[g];
+          if (cand && gm <= val) {
+            float v = iou_exact(s_gt[g], s_area[g], a, aa);
+            if (v == gm) lq = true;  // matcher.py:114-116 (ties included)
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  int fg = 0;
+  float w_part = 0.f;
+  if (live) {
+    int8_t l1, l2 = 0;
+    int64_t cls, msk = 0;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (M > 0) {
+      l1 = lq ? (int8_t)1 : band_label(mb, val);
+      if (pmb.n) l2 = lq ? (int8_t)1 : band_label(pmb, val);
+      cls = gt_class_ids ? gt_class_ids[m0 + idx] : 0;
+      if (l1 == 0) cls = num_classes;   // retinanet.py:356
+      if (l1 == -1) cls = -1;           // :360
+      msk = (l2 == 1) ? 1 : 0;          // :417-423
+      if (out.gt_deltas) d = encode_deltas(a, gt_boxes[m0 + idx], wx, wy, ww, wh);
+    } else {                            // matcher.py:70-80, retinanet.py:362-363, :425
+      l1 = mb.lab[0];
+      l2 = pmb.n ? pmb.lab[0] : 0;
+      cls = num_classes;
+      msk = num_classes;
+      idx = 0;
+    }
+    if (out.matches) out.matches[o] = idx;
+    if (out.match_labels) out.match_labels[o] = l1;
+    if (out.picky_labels) out.picky_labels[o] = l2;
+    if (out.gt_classes) out.gt_classes[o] = cls;
+    if (out.mask) out.mask[o] = msk;
+    if (out.gt_deltas) out.gt_deltas[o] = d;
+    if (out.matched_idx32) out.matched_idx32[o] = idx;
+    fg = (cls >= 0 && cls != num_classes) ? 1 : 0;
+    if (bets) w_part = __fadd_rn(__fmul_rn(bets[o], (float)msk), temperature);  // gambler_heads.py:569,304
+  }
+
+  if (stats == nullptr) return;
+  // ---- loss pre-pass: num_foreground and S[n] = sum_r (bet*mask + T), deterministic two-level sum
+  int fg_w = __reduce_add_sync(kFull, fg);
+  float s_w = warp_sum(w_part);
+  if (lane == 0) { s_redi[wid] = fg_w; s_red[wid] = s_w; }
+  __syncthreads();
+  const int nb = gridDim.x;
+  if (tid == 0) {
+    int ci = 0;
+    float cs = 0.f;
+    for (int w = 0; w < kMatchBlock / 32; ++w) { ci += s_redi[w]; cs += s_red[w]; }
+    part_cnt[n * nb + blockIdx.x] = ci;
+    part_s[n * nb + blockIdx.x] = cs;
+    __threadfence();
+    unsigned prev = atomicAdd(done_counter, 1u);
+    s_last = (prev == (unsigned)(nb * N) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double tot_cnt = 0.0, tot_s = 0.0;  // meaningful in warp 0 lane 0 after the loop below
+  for (int img = wid; img < N; img += kMatchBlock / 32) {
+    double c = 0.0, s = 0.0;
+    for (int b = lane; b < nb; b += 32) {
+      c += (double)__ldcg(&part_cnt[img * nb + b]);
+      s += (double)__ldcg(&part_s[img * nb + b]);
+    }
+    c = warp_sum_d(c);
+    s = warp_sum_d(s);
+    if (lane == 0) {
+      stats[FSG_STATS_HEADER + img] = s;
+      tot_cnt += c;
+      tot_s += s;
+    }
+  }
+  __shared__ double s_tc[kMatchBlock / 32], s_ts[kMatchBlock / 32];
+  if (lane == 0) { s_tc[wid] = tot_cnt; s_ts[wid] = tot_s; }
+  __syncthreads();
+  if (tid == 0) {
+    double c = 0.0, s = 0.0;
+    for (int w = 0; w < kMatchBlock / 32; ++w) { c += s_tc[w]; s += s_ts[w]; }
+    stats[0] = c;
+    stats[1] = s;
+    *done_counter = 0u;  // self-reset for the next call
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Box2BoxTransform drop-ins
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) get_deltas_kernel(const float4* __restrict__ src,
+                                                         const float4* __restrict__ tgt, int64_t n, float wx,
+                                                         float wy, float ww, float wh, float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = encode_deltas(src[i], tgt[i], wx, wy, ww, wh);
+}
+
+// box_regression.py:81-106
+__device__ __forceinline__ float4 decode_box(float4 d, float4 b, float wx, float wy, float ww, float wh,
+                                             float clampv) {
+  float w = __fsub_rn(b.z, b.x), h = __fsub_rn(b.w, b.y);
+  float cx = __fadd_rn(b.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(b.y, __fmul_rn(0.5f, h));
+  float dx = __fdiv_rn(d.x, wx), dy = __fdiv_rn(d.y, wy);
+  float dw = fminf(__fdiv_rn(d.z, ww), clampv), dh = fminf(__fdiv_rn(d.w, wh), clampv);
+  float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+  float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+  float4 o;
+  o.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+  o.y = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  o.z = __fadd_rn(pcx, __fmul_rn(0.5f, pw));
+  o.w = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+  return o;
+}
+
+__global__ void __launch_bounds__(256) apply_deltas_kernel(const float4* __restrict__ deltas,
+                                                           const float4* __restrict__ boxes, int64_t n, int k,
+                                                           float wx, float wy, float ww, float wh, float clampv,
+                                                           float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * k) return;
+  out[i] = decode_box(deltas[i], boxes[i / k], wx, wy, ww, wh, clampv);
+}
+
+static int make_bands(const float* thr, const int8_t* lab, int nthr, MatcherBands* mb) {
+  if (nthr < 1 || nthr > kMaxThr || !thr || !lab) return FSG_ERR_INVALID_ARG;
+  mb->n = nthr + 1;
+  for (int i = 0; i <= nthr; ++i) {
+    mb->lo[i] = (i == 0) ? -__builtin_huge_valf() : thr[i - 1];
+    mb->hi[i] = (i == nthr) ? __builtin_huge_valf() : thr[i];
+    if (lab[i] < -1 || lab[i] > 1) return FSG_ERR_INVALID_ARG;
+    mb->lab[i] = lab[i];
+    if (i > 0 && i < nthr && !(thr[i - 1] <= thr[i])) return FSG_ERR_INVALID_ARG;
+  }
+  for (int i = nthr + 1; i <= kMaxThr; ++i) { mb->lo[i] = 0; mb->hi[i] = 0; mb->lab[i] = 0; }
+  return FSG_OK;
+}
+
+}  // namespace fsg
+
+using namespace fsg;
+
+extern "C" int fsg_pairwise_iou(const float* boxes1, int64_t n1, const float* boxes2, int64_t n2, float* iou,
+                                fsg_stream_t stream) {
+  if (n1 < 0 || n2 < 0) return FSG_ERR_INVALID_ARG;
+  if (n1 == 0 || n2 == 0) return FSG_OK;
+  if (!boxes1 || !boxes2 || !iou) return FSG_ERR_INVALID_ARG;
+  dim3 grid((unsigned)ceil_div(n2, 256), (unsigned)ceil_div(n1, kIouRows));
+  if (ceil_div(n1, kIouRows) > 65535) return FSG_ERR_UNSUPPORTED;
+  pairwise_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes1, n1, (const float4*)boxes2,
+                                                              n2, iou);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" int fsg_matcher(const float* mqm, int64_t M, int64_t N, const float* h_thresholds,
+                           const int8_t* h_labels, int num_thresholds, int allow_lq, int64_t* matches,
+                           int8_t* match_labels, float* ws_rowmax, fsg_stream_t stream) {
+  MatcherBands mb;
+  int st = make_bands(h_thresholds, h_labels, num_thresholds, &mb);
+  if (st) return st;
+  if (M < 0 || N < 0) return FSG_ERR_INVALID_ARG;
+  if (N == 0) return FSG_OK;
+  if (!matches || !match_labels || (M > 0 && !mqm)) return FSG_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M > 0 && allow_lq) {
+    if (!ws_rowmax) return FSG_ERR_WORKSPACE;
+    FSG_CUDA_TRY(cudaMemsetAsync(ws_rowmax, 0, sizeof(float) * M, s));
+    dim3 grid((unsigned)ceil_div(N, 256), (unsigned)ceil_div(M, 64));
+    if (ceil_div(M, 64) > 65535) return FSG_ERR_UNSUPPORTED;
+    matrix_rowmax_kernel<<<grid, 256, 0, s>>>(mqm, M, N, (unsigned*)ws_rowmax);
+    FSG_LAUNCH_CHECK();
+  }
+  matrix_match_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, s>>>(mqm, M, N, mb, (M > 0 && allow_lq) ? 1 : 0,
+                                                                 ws_rowmax, matches, match_labels);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+namespace {
+struct MatchWs {
+  size_t off_counter, off_gtmax, off_val, off_idx, off_pcnt, off_ps, total;
+  int nb;
+};
+MatchWs match_ws_layout(int N, int64_t R, int64_t sum_M) {
+  MatchWs w;
+  w.nb = (int)ceil_div(R > 0 ? R : 1, kMatchBlock);
+  size_t o = 0;
+  w.off_counter = o; o += 16;
+  w.off_gtmax = o;   o += align_up(sizeof(unsigned) * (size_t)(sum_M > 0 ? sum_M : 1), 16);
+  w.off_val = o;     o += align_up(sizeof(float) * (size_t)N * (size_t)R, 16);
+  w.off_idx = o;     o += align_up(sizeof(int32_t) * (size_t)N * (size_t)R, 16);
+  w.off_pcnt = o;    o += align_up(sizeof(int) * (size_t)N * w.nb, 16);
+  w.off_ps = o;      o += align_up(sizeof(float) * (size_t)N * w.nb, 16);
+  w.total = o;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t fsg_match_workspace_bytes(int N, int64_t R, int64_t sum_M) {
+  if (N <= 0 || R < 0 || sum_M < 0) return 0;
+  return match_ws_layout(N, R, sum_M).total;
+}
+
+extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor_image_stride,
+                                 const float* gt_boxes, const int64_t* gt_class_ids, const int32_t* gt_offsets,
+                                 int N, int64_t sum_M, int num_classes, const float* h_thresholds,
+                                 const int8_t* h_labels, int num_thresholds, int allow_lq,
+                                 const float* h_picky_thresholds, const int8_t* h_picky_labels,
+                                 int num_picky_thresholds,
+                                 const float* h_box_weights, int64_t* matches, int8_t* match_labels,
+                                 int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
+                                 float* gt_deltas, int32_t* matched_idx32, const float* bets, float temperature,
+                                 double* stats, void* workspace, size_t workspace_bytes, fsg_stream_t stream) {
+  if (N <= 0 || R < 0 || sum_M < 0 || !gt_offsets) return FSG_ERR_INVALID_ARG;
+  if (R == 0) return FSG_OK;
+  if (!anchors || (sum_M > 0 && !gt_boxes)) return FSG_ERR_INVALID_ARG;
+  if (N > 65535) return FSG_ERR_UNSUPPORTED;
+  if (anchor_image_stride % 4 != 0) return FSG_ERR_INVALID_ARG;
+  if (gt_classes_out && sum_M > 0 && !gt_class_ids) return FSG_ERR_INVALID_ARG;
+  MatcherBands mb, pmb;
+  int st = make_bands(h_thresholds, h_labels, num_thresholds, &mb);
+  if (st) return st;
+  if (h_picky_thresholds) {
+    st = make_bands(h_picky_thresholds, h_picky_labels, num_picky_thresholds, &pmb);
+    if (st) return st;
+  } else {
+    if (mask_out || picky_labels) return FSG_ERR_INVALID_ARG;
+    pmb.n = 0;
+  }
+  if (bets && !stats) return FSG_ERR_INVALID_ARG;
+  const MatchWs w = match_ws_layout(N, R, sum_M);
+  if (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned* counter = (unsigned*)(ws + w.off_counter);
+  unsigned* gtmax = (unsigned*)(ws + w.off_gtmax);
+  float* bval = (float*)(ws + w.off_val);
+  int32_t* bidx = (int32_t*)(ws + w.off_idx);
+  // counter + gt_max are contiguous: one memset node
+  FSG_CUDA_TRY(cudaMemsetAsync(ws, 0, w.off_val, s));
+  const float wx = h_box_weights ? h_box_weights[0] : 1.f, wy = h_box_weights ? h_box_weights[1] : 1.f;
+  const float ww = h_box_weights ? h_box_weights[2] : 1.f, wh = h_box_weights ? h_box_weights[3] : 1.f;
+
+  constexpr int U = 2;
+  dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
+  match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
+                                                        (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
+  FSG_LAUNCH_CHECK();
+  MatchOut out{matches, match_labels, picky_labels, gt_classes_out, mask_out, (float4*)gt_deltas, matched_idx32};
+  dim3 grid_b((unsigned)w.nb, (unsigned)N);
+  match_pass_b_kernel<<<grid_b, kMatchBlock, 0, s>>>(
+      (const float4*)anchors, R, anchor_image_stride / 4, (const float4*)gt_boxes, gt_class_ids, gt_offsets, N,
+      num_classes, mb, pmb, allow_lq ? 1 : 0, wx, wy, ww, wh, bval, bidx, gtmax, out, bets, temperature,
+      (int*)(ws + w.off_pcnt), (float*)(ws + w.off_ps), counter, stats);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" int fsg_box2box_get_deltas(const float* src_boxes, const float* target_boxes, int64_t n,
+                                      const float* h_weights, float* deltas, fsg_stream_t stream) {
+  if (n < 0 || !h_weights) return FSG_ERR_INVALID_ARG;
+  if (n == 0) return FSG_OK;
+  if (!src_boxes || !target_boxes || !deltas) return FSG_ERR_INVALID_ARG;
+  get_deltas_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)src_boxes, (const float4*)target_boxes, n, h_weights[0], h_weights[1], h_weights[2],
+      h_weights[3], (float4*)deltas);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" int fsg_box2box_apply_deltas(const float* deltas, const float* boxes, int64_t n, int k,
+                                        const float* h_weights, float scale_clamp, float* out,
+                                        fsg_stream_t stream) {
+  if (n < 0 || k < 1 || !h_weights) return FSG_ERR_INVALID_ARG;
+  if (n == 0) return FSG_OK;
+  if (!deltas || !boxes || !out) return FSG_ERR_INVALID_ARG;
+  apply_deltas_kernel<<<(unsigned)ceil_div(n * k, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)deltas, (const float4*)boxes, n, k, h_weights[0], h_weights[1], h_weights[2], h_weights[3],
+      scale_clamp, (float4*)out);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}

@@ -1,0 +1,342 @@
+"""Functional wrappers, one per C-ABI entry point of ``libfsg_dense.so``.
+
+Everything here takes and returns CUDA tensors; torch is used only to allocate outputs/workspaces and to
+supply the current stream.  The reference-shaped classes (``Matcher``, ``Box2BoxTransform``, ...) and the
+fused training / inference steps are thin layers over these functions.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import LossParams, check, count_launches, host_f32, host_i8, host_i64, lib, ptr, stream
+
+SCALE_CLAMP = math.log(1000.0 / 16)  # box_regression.py:8
+
+
+def _f32c(t):
+    return t.to(torch.float32).contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1
+# ------------------------------------------------------------------------------------------------
+def pairwise_iou(boxes1, boxes2):
+    """(n1,4),(n2,4) fp32 XYXY -> (n1,n2) IoU (boxes.py:243-275)."""
+    b1, b2 = _f32c(boxes1).reshape(-1, 4), _f32c(boxes2).reshape(-1, 4)
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
+    if out.numel():
+        check(lib().fsg_pairwise_iou(ptr(b1), b1.shape[0], ptr(b2), b2.shape[0], ptr(out), stream()))
+        count_launches(1)
+    return out
+
+
+def matcher(mqm, thresholds, labels, allow_low_quality_matches):
+    """matcher.py:55-132 on a materialised (M,N) matrix -> (matches int64 (N), match_labels int8 (N))."""
+    assert mqm.dim() == 2
+    q = _f32c(mqm)
+    M, N = q.shape
+    matches = torch.empty(N, dtype=torch.int64, device=q.device)
+    out_labels = torch.empty(N, dtype=torch.int8, device=q.device)
+    if N == 0:
+        return matches, out_labels
+    rowmax = torch.empty(max(M, 1), dtype=torch.float32, device=q.device)
+    check(lib().fsg_matcher(ptr(q) if M > 0 else None, M, N, host_f32(thresholds), host_i8(labels), len(thresholds),
+                            int(bool(allow_low_quality_matches)), ptr(matches), ptr(out_labels), ptr(rowmax),
+                            stream()))
+    count_launches(2 if (M > 0 and allow_low_quality_matches) else 1)
+    return matches, out_labels
+
+
+class PackedGT:
+    """Ground truth of a batch in the packed layout the fused kernels read: boxes (sum_M,4) fp32, classes
+    (sum_M) int64, offsets (N+1) int32 (device) + the same offsets on the host."""
+
+    def __init__(self, boxes, classes, offsets_dev, offsets_host):
+        self.boxes, self.classes, self.offsets, self.offsets_host = boxes, classes, offsets_dev, offsets_host
+
+    @property
+    def num_images(self):
+        return len(self.offsets_host) - 1
+
+    @property
+    def total(self):
+        return int(self.offsets_host[-1])
+
+    @staticmethod
+    def from_lists(gt_boxes, gt_classes, device):
+        """gt_boxes: list of (M_i,4); gt_classes: list of (M_i) int64.  One H2D copy per array."""
+        counts = [int(b.shape[0]) for b in gt_boxes]
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        if offs[-1] > 0:
+            boxes = torch.cat([b.reshape(-1, 4).to(torch.float32) for b in gt_boxes]).to(device).contiguous()
+            classes = torch.cat([c.reshape(-1).to(torch.int64) for c in gt_classes]).to(device).contiguous()
+        else:
+            boxes = torch.zeros((1, 4), dtype=torch.float32, device=device)
+            classes = torch.zeros((1,), dtype=torch.int64, device=device)
+        offsets = torch.tensor(offs, dtype=torch.int32).to(device)
+        return PackedGT(boxes, classes, offsets, offs)
+
+
+def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1, 1),
+                  picky_thresholds=(0.4, 0.9), picky_labels=None, box_weights=(1.0, 1.0, 1.0, 1.0),
+                  want=("gt_classes", "mask", "matched_idx32"), bets=None, temperature=0.0,
+                  allow_low_quality_matches=True):
+    """Fused IoU + Matcher(s) + GT assignment (retinanet.py:339-363, 400-425) for a batch.
+
+    anchors: (R,4) shared by all images or (N,R,4) per image.  gt: PackedGT.
+    want: subset of {matches, match_labels, picky_labels, gt_classes, mask, gt_deltas, matched_idx32}.
+    bets (N,R): when given, the loss pre-pass is fused in and ``stats`` is returned too.
+    Returns a dict of the requested (N,R[,4]) tensors (+ "stats").
+    """
+    a = _f32c(anchors)
+    dev = a.device
+    N = gt.num_images
+    if a.dim() == 3:
+        assert a.shape[0] == N
+        R, stride = a.shape[1], a.shape[1] * 4
+    else:
+        R, stride = a.shape[0], 0
+    if picky_thresholds is not None and picky_labels is None:
+        picky_labels = labels
+    kinds = {
+        "matches": (torch.int64, ()), "match_labels": (torch.int8, ()), "picky_labels": (torch.int8, ()),
+        "gt_classes": (torch.int64, ()), "mask": (torch.int64, ()), "gt_deltas": (torch.float32, (4,)),
+        "matched_idx32": (torch.int32, ()),
+    }
+    out = {}
+    for k in want:
+        dt, tail = kinds[k]
+        out[k] = torch.empty((N, R) + tail, dtype=dt, device=dev)
+    stats = None
+    if bets is not None:
+        bets = _f32c(bets)
+        assert bets.shape == (N, R)
+    if bets is not None or "stats" in want:
+        stats = torch.empty(_lib.STATS_HEADER + N, dtype=torch.float64, device=dev)
+    L = lib()
+    ws = _ws(L.fsg_match_workspace_bytes(N, R, gt.total), dev)
+    if R > 0:
+        check(L.fsg_match_anchors(
+            ptr(a), R, stride, ptr(gt.boxes), ptr(gt.classes), ptr(gt.offsets), N, gt.total, int(num_classes),
+            host_f32(thresholds), host_i8(labels), len(thresholds), int(bool(allow_low_quality_matches)),
+            host_f32(picky_thresholds) if picky_thresholds is not None else None,
+            host_i8(picky_labels) if picky_thresholds is not None else None,
+            len(picky_thresholds) if picky_thresholds is not None else 0,
+            host_f32(box_weights), ptr(out.get("matches")), ptr(out.get("match_labels")),
+            ptr(out.get("picky_labels")), ptr(out.get("gt_classes")), ptr(out.get("mask")),
+            ptr(out.get("gt_deltas")), ptr(out.get("matched_idx32")), ptr(bets), float(temperature), ptr(stats),
+            ptr(ws), ws.numel(), stream()))
+        count_launches(2)
+    if stats is not None:
+        out["stats"] = stats
+    return out
+
+
+def get_deltas(src_boxes, target_boxes, weights):
+    s, t = _f32c(src_boxes), _f32c(target_boxes)
+    assert s.shape == t.shape and s.shape[-1] == 4
+    out = torch.empty_like(s)
+    n = s.shape[0]
+    if n:
+        check(lib().fsg_box2box_get_deltas(ptr(s), ptr(t), n, host_f32(weights), ptr(out), stream()))
+        count_launches(1)
+    return out
+
+
+def apply_deltas(deltas, boxes, weights, scale_clamp=SCALE_CLAMP):
+    d, b = _f32c(deltas), _f32c(boxes)
+    n = b.shape[0]
+    assert d.shape[0] == n and d.shape[1] % 4 == 0
+    out = torch.empty_like(d)
+    if d.numel():
+        check(lib().fsg_box2box_apply_deltas(ptr(d), ptr(b), n, d.shape[1] // 4, host_f32(weights),
+                                             float(scale_clamp), ptr(out), stream()))
+        count_launches(1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# layout adapter
+# ------------------------------------------------------------------------------------------------
+def levels_to_flat(levels, K, out=None):
+    """list[(N, A*K, H, W)] -> (N, sum HWA, K) (retinanet.py:24-54).  One transpose launch per level."""
+    N = levels[0].shape[0]
+    dev = levels[0].device
+    rows = [x.shape[1] // K * x.shape[2] * x.shape[3] for x in levels]
+    R = sum(rows)
+    if out is None:
+        out = torch.empty((N, R, K), dtype=torch.float32, device=dev)
+    off = 0
+    for x, r in zip(levels, rows):
+        x = _f32c(x)
+        C, HW = x.shape[1], x.shape[2] * x.shape[3]
+        check(lib().fsg_permute_level(ptr(x), ptr(out), N, C, HW, R * K, off * K, 0, stream()))
+        off += r
+    count_launches(len(levels))
+    return out
+
+
+def flat_to_levels(flat, shapes):
+    """(N, R, K) -> list[(N, A*K, H, W)] for ``shapes`` = [(C, H, W), ...] (the gradient direction)."""
+    flat = _f32c(flat)
+    N, R, K = flat.shape
+    outs, off = [], 0
+    for C, H, W in shapes:
+        o = torch.empty((N, C, H, W), dtype=torch.float32, device=flat.device)
+        check(lib().fsg_permute_level(ptr(o), ptr(flat), N, C, H * W, R * K, off * K, 1, stream()))
+        off += (C // K) * H * W
+        outs.append(o)
+    count_launches(len(shapes))
+    return outs
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+def make_loss_params(num_classes, alpha=0.25, gamma=2.0, beta=0.1, temperature=0.1, gambler_gamma=1.0,
+                     mode="focal", norm_mode=_lib.NORM_IMAGE, c_cls=1.0, c_reg=1.0, c_gam=0.0,
+                     box_weights=(1.0, 1.0, 1.0, 1.0)):
+    p = LossParams()
+    p.num_classes = int(num_classes)
+    p.gambler_mode = _lib.CLS_MODES[mode]
+    p.norm_mode = int(norm_mode)
+    p.focal_alpha, p.focal_gamma, p.smooth_l1_beta = float(alpha), float(gamma), float(beta)
+    p.temperature, p.gambler_gamma = float(temperature), float(gambler_gamma)
+    p.c_cls, p.c_reg, p.c_gam = float(c_cls), float(c_reg), float(c_gam)
+    for i in range(4):
+        p.box_weights[i] = float(box_weights[i])
+    return p
+
+
+def loss_prepass(gt_classes, mask, bets, num_classes, temperature):
+    """stats = [num_foreground, S_batch, S[0..N-1]] (double), see include/fsg_dense.h."""
+    N, R = gt_classes.shape
+    dev = gt_classes.device
+    stats = torch.empty(_lib.STATS_HEADER + N, dtype=torch.float64, device=dev)
+    L = lib()
+    ws = _ws(L.fsg_loss_prepass_workspace_bytes(N, R), dev)
+    check(L.fsg_loss_prepass(ptr(gt_classes), ptr(mask), ptr(bets), N, R, int(num_classes), float(temperature),
+                             ptr(stats), ptr(ws), ws.numel(), stream()))
+    count_launches(1)
+    return stats
+
+
+def loss_main(logits, gt_classes, params, stats, pred_deltas=None, gt_deltas=None, anchors=None, gt=None,
+              matched_idx32=None, mask=None, bets=None, want_grad_logits=True, want_grad_deltas=True,
+              want_weights=False, grad_logits_out=None):
+    """The fused main pass.  Returns dict(grad_logits, grad_deltas, per_anchor_loss, weights, scalars)."""
+    x = logits
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    N, R, K = x.shape
+    dev = x.device
+    assert K == params.num_classes
+    out = {}
+    if want_grad_logits:
+        out["grad_logits"] = grad_logits_out if grad_logits_out is not None else torch.empty_like(x)
+    if pred_deltas is not None and want_grad_deltas:
+        out["grad_deltas"] = torch.empty_like(pred_deltas)
+    out["per_anchor_loss"] = torch.empty((N, R), dtype=torch.float32, device=dev)
+    if want_weights:
+        out["weights"] = torch.empty((N, R), dtype=torch.float32, device=dev)
+    scalars = torch.empty(_lib.SCALARS_HEADER + N, dtype=torch.float64, device=dev)
+    out["scalars"] = scalars
+    a_ptr, a_stride = None, 0
+    if anchors is not None:
+        a_ptr = ptr(anchors)
+        a_stride = anchors.shape[1] * 4 if anchors.dim() == 3 else 0
+    L = lib()
+    ws = _ws(L.fsg_loss_main_workspace_bytes(N, R, K), dev)
+    check(L.fsg_loss_main(
+        ptr(x), ptr(pred_deltas), ptr(gt_deltas), a_ptr, a_stride, ptr(gt.boxes) if gt is not None else None,
+        ptr(gt.offsets) if gt is not None else None, ptr(matched_idx32), ptr(gt_classes), ptr(mask), ptr(bets),
+        N, R, params, ptr(stats), ptr(out.get("grad_logits")), ptr(out.get("grad_deltas")),
+        ptr(out["per_anchor_loss"]), ptr(out.get("weights")), ptr(scalars), ptr(ws), ws.numel(), stream()))
+    count_launches(1)
+    return out
+
+
+def loss_post(bets, mask, per_anchor_loss, params, stats, scalars):
+    N, R = bets.shape
+    g = torch.empty_like(bets)
+    check(lib().fsg_loss_post(ptr(bets), ptr(mask), ptr(per_anchor_loss), N, R, params, ptr(stats), ptr(scalars),
+                              ptr(g), stream()))
+    count_launches(1)
+    return g
+
+
+def scale_(x, scale):
+    """In-place x *= scale; scale is a python float or a 0-d CUDA tensor (no host sync)."""
+    if isinstance(scale, torch.Tensor):
+        s = scale.detach().to(torch.float32).reshape(1).contiguous()
+        check(lib().fsg_scale_inplace(ptr(x), x.numel(), ptr(s), 1.0, stream()))
+    else:
+        if float(scale) == 1.0:
+            return x
+        check(lib().fsg_scale_inplace(ptr(x), x.numel(), None, float(scale), stream()))
+    count_launches(1)
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# K3
+# ------------------------------------------------------------------------------------------------
+NMS_MAX_BOXES = 8192
+
+
+def nms_raw(boxes, scores, class_ids, iou_threshold):
+    """Device-side result: (keep int64 (n) padded, num_keep int32 (1)).  n <= NMS_MAX_BOXES."""
+    b, s = _f32c(boxes).reshape(-1, 4), _f32c(scores).reshape(-1)
+    n = b.shape[0]
+    if n > NMS_MAX_BOXES:
+        raise RuntimeError("fsg_nms holds at most %d boxes per call in shared memory; got %d" % (NMS_MAX_BOXES, n))
+    keep = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
+    num = torch.zeros(1, dtype=torch.int32, device=b.device)
+    c = class_ids.to(torch.int64).contiguous() if class_ids is not None else None
+    check(lib().fsg_nms(ptr(b) if n else None, ptr(s) if n else None, ptr(c), n, float(iou_threshold), ptr(keep),
+                        ptr(num), None, 0, stream()))
+    count_launches(1)
+    return keep, num
+
+
+def detect(logits, deltas, anchors, level_offsets, score_threshold=0.05, topk=1000, nms_threshold=0.5,
+           max_det=100, box_weights=(1.0, 1.0, 1.0, 1.0), scale_clamp=SCALE_CLAMP, want_candidates=False):
+    """Batched RetinaNet.inference (retinanet.py:431-520) on flattened predictions.
+
+    logits (N,R,K), deltas (N,R,4), anchors (R,4) or (N,R,4); level_offsets: list of L+1 anchor offsets.
+    Returns dict(boxes (N,max_det,4), scores (N,max_det), classes (N,max_det) int64, count (N) int32
+    [, cand_boxes, cand_scores, cand_classes, cand_count, keep_idx])."""
+    x, d, a = logits, _f32c(deltas), _f32c(anchors)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    N, R, K = x.shape
+    dev = x.device
+    nl = len(level_offsets) - 1
+    out = {
+        "boxes": torch.empty((N, max_det, 4), dtype=torch.float32, device=dev),
+        "scores": torch.empty((N, max_det), dtype=torch.float32, device=dev),
+        "classes": torch.empty((N, max_det), dtype=torch.int64, device=dev),
+        "count": torch.empty((N,), dtype=torch.int32, device=dev),
+    }
+    if want_candidates:
+        cap = nl * topk
+        out["cand_boxes"] = torch.zeros((N, cap, 4), dtype=torch.float32, device=dev)
+        out["cand_scores"] = torch.zeros((N, cap), dtype=torch.float32, device=dev)
+        out["cand_classes"] = torch.zeros((N, cap), dtype=torch.int64, device=dev)
+        out["cand_count"] = torch.empty((N,), dtype=torch.int32, device=dev)
+        out["keep_idx"] = torch.empty((N, max_det), dtype=torch.int64, device=dev)
+    L = lib()
+    ws = _ws(L.fsg_detect_workspace_bytes(N, R, K, nl, topk), dev)
+    check(L.fsg_detect(
+        ptr(x), ptr(d), ptr(a), a.shape[1] * 4 if a.dim() == 3 else 0, N, R, K, host_i64(level_offsets), nl,
+        float(score_threshold), int(topk), float(nms_threshold), int(max_det), host_f32(box_weights),
+        float(scale_clamp), ptr(out["boxes"]), ptr(out["scores"]), ptr(out["classes"]), ptr(out["count"]),
+        ptr(out.get("cand_boxes")), ptr(out.get("cand_scores")), ptr(out.get("cand_classes")),
+        ptr(out.get("cand_count")), ptr(out.get("keep_idx")), ptr(ws), ws.numel(), stream()))
+    count_launches(2)
+    return out

@@ -1,0 +1,167 @@
+"""The per-anchor method bodies of the reference's RetinaNet meta-architecture
+(detectron2/modeling/meta_arch/retinanet.py), with the same names, arguments and return values:
+
+    get_ground_truth(anchors, targets)           :309-368
+    get_picky_ground_truth(anchors, targets)     :370-429   (fork)
+    losses(gt_classes, gt_anchors_deltas, pred_class_logits, pred_anchor_deltas)   :201-248
+    inference(box_cls, box_delta, anchors, image_sizes) / inference_single_image   :431-520
+
+Backbone, head convolutions and the gambler U-Net are out of scope (cuDNN territory); this class is what a
+maintainer binds those methods to.  All arithmetic runs in ``libfsg_dense.so``.
+"""
+from typing import List
+
+import torch
+
+from . import _lib, ops
+from .box_regression import Box2BoxTransform
+from .matcher import Matcher
+from .structures import Boxes, Instances
+
+
+class _LevelsToFlat(torch.autograd.Function):
+    """permute_to_N_HWA_K + cat over levels (retinanet.py:24-54) as transpose kernels, differentiable."""
+
+    @staticmethod
+    def forward(ctx, K, *levels):
+        ctx.K = K
+        ctx.shapes = [tuple(x.shape[1:]) for x in levels]
+        return ops.levels_to_flat([x.detach() for x in levels], K)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + tuple(ops.flat_to_levels(g.contiguous(), ctx.shapes))
+
+
+def levels_to_flat(levels, K):
+    return _LevelsToFlat.apply(K, *levels)
+
+
+class _RetinaLosses(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, deltas, gt_classes, gt_deltas, params):
+        x = logits.detach().to(torch.float32).contiguous()
+        d = deltas.detach().to(torch.float32).contiguous()
+        stats = ops.loss_prepass(gt_classes, None, None, params.num_classes, 0.0)
+        out = ops.loss_main(x, gt_classes, params, stats, pred_deltas=d, gt_deltas=gt_deltas)
+        ctx.save_for_backward(out["grad_logits"], out["grad_deltas"])
+        s = out["scalars"]
+        return s[5].to(torch.float32), s[6].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g_cls, g_reg):
+        gl, gd = ctx.saved_tensors
+        # loss_cls depends only on the logits and loss_box_reg only on the deltas, so the gradients saved
+        # for unit coefficients just need scaling by the upstream scalars (on the device, no sync)
+        ops.scale_(gl, g_cls)
+        ops.scale_(gd, g_reg)
+        return gl, gd, None, None, None
+
+
+class RetinaNetDensePath:
+    def __init__(self, num_classes=80, focal_loss_alpha=0.25, focal_loss_gamma=2.0, smooth_l1_loss_beta=0.1,
+                 score_threshold=0.05, topk_candidates=1000, nms_threshold=0.5, max_detections_per_image=100,
+                 iou_thresholds=(0.4, 0.5), iou_labels=(0, -1, 1), bbox_reg_weights=(1.0, 1.0, 1.0, 1.0)):
+        # retinanet.py:69-100
+        self.num_classes = num_classes
+        self.focal_loss_alpha = focal_loss_alpha
+        self.focal_loss_gamma = focal_loss_gamma
+        self.smooth_l1_loss_beta = smooth_l1_loss_beta
+        self.score_threshold = score_threshold
+        self.topk_candidates = topk_candidates
+        self.nms_threshold = nms_threshold
+        self.max_detections_per_image = max_detections_per_image
+        self.box2box_transform = Box2BoxTransform(weights=tuple(bbox_reg_weights))
+        self.matcher = Matcher(list(iou_thresholds), list(iou_labels), allow_low_quality_matches=True)
+        self.picky_matcher = Matcher([0.4, 0.9], list(iou_labels), allow_low_quality_matches=True)
+
+    @classmethod
+    def from_config(cfg_cls, cfg):
+        r = cfg.MODEL.RETINANET
+        return cfg_cls(r.NUM_CLASSES, r.FOCAL_LOSS_ALPHA, r.FOCAL_LOSS_GAMMA, r.SMOOTH_L1_LOSS_BETA,
+                       r.SCORE_THRESH_TEST, r.TOPK_CANDIDATES_TEST, r.NMS_THRESH_TEST,
+                       cfg.TEST.DETECTIONS_PER_IMAGE, r.IOU_THRESHOLDS, r.IOU_LABELS,
+                       cfg.MODEL.RPN.BBOX_REG_WEIGHTS)
+
+    # ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _anchor_tensor(anchors: List[List[Boxes]]):
+        """list[list[Boxes]] (per image, per level) -> (R,4) if every image carries the same anchors
+        (the reference deep-copies one set per image, anchor_generator.py:188), else (N,R,4)."""
+        per_image = [Boxes.cat(a).tensor for a in anchors]  # retinanet.py:339
+        first = per_image[0]
+        same = all(t.shape == first.shape and (t.data_ptr() == first.data_ptr() or torch.equal(t, first))
+                   for t in per_image[1:])
+        if same:
+            return first.contiguous()
+        return torch.stack(per_image).contiguous()
+
+    def _match(self, anchors, targets, want):
+        a = self._anchor_tensor(anchors)
+        dev = a.device
+        gt = ops.PackedGT.from_lists([t.gt_boxes.tensor for t in targets], [t.gt_classes for t in targets], dev)
+        return ops.match_anchors(a, gt, self.num_classes, self.matcher.thresholds[1:-1], self.matcher.labels,
+                                 self.picky_matcher.thresholds[1:-1], self.picky_matcher.labels,
+                                 self.box2box_transform.weights, want=want)
+
+    @torch.no_grad()
+    def get_ground_truth(self, anchors, targets):
+        """-> gt_classes (N,R) int64 in {-1, 0..K-1, K}, gt_anchors_deltas (N,R,4)."""
+        out = self._match(anchors, targets, ("gt_classes", "gt_deltas"))
+        return out["gt_classes"], out["gt_deltas"]
+
+    @torch.no_grad()
+    def get_picky_ground_truth(self, anchors, targets):
+        """-> mask (N,R) int64: 1 where the [0.4,0.9] matcher labels the anchor positive (IoU >= 0.9 or a
+        ground truth's best anchor), else 0; all K for an image without ground truth (retinanet.py:425)."""
+        return self._match(anchors, targets, ("mask",))["mask"]
+
+    def losses(self, gt_classes, gt_anchors_deltas, pred_class_logits, pred_anchor_deltas):
+        """-> {"loss_cls", "loss_box_reg"} (differentiable wrt the per-level head outputs)."""
+        x = levels_to_flat(list(pred_class_logits), self.num_classes)
+        d = levels_to_flat(list(pred_anchor_deltas), 4)
+        params = ops.make_loss_params(self.num_classes, self.focal_loss_alpha, self.focal_loss_gamma,
+                                      self.smooth_l1_loss_beta, 0.0, 1.0, "focal", _lib.NORM_NONE, 1.0, 1.0, 0.0,
+                                      self.box2box_transform.weights)
+        loss_cls, loss_box_reg = _RetinaLosses.apply(x, d, gt_classes.contiguous(),
+                                                     gt_anchors_deltas.to(torch.float32).contiguous(), params)
+        return {"loss_cls": loss_cls, "loss_box_reg": loss_box_reg}
+
+    # ---------------------------------------------------------------------------------------------
+    def _detect(self, logits_flat, deltas_flat, anchor_tensor, level_offsets, want_candidates=False):
+        return ops.detect(logits_flat, deltas_flat, anchor_tensor, level_offsets, self.score_threshold,
+                          self.topk_candidates, self.nms_threshold, self.max_detections_per_image,
+                          self.box2box_transform.weights, self.box2box_transform.scale_clamp, want_candidates)
+
+    @staticmethod
+    def _to_instances(res, n, image_size):
+        c = int(res["count"][n].item())
+        r = Instances(tuple(image_size))
+        r.pred_boxes = Boxes(res["boxes"][n, :c])
+        r.scores = res["scores"][n, :c]
+        r.pred_classes = res["classes"][n, :c]
+        return r
+
+    @torch.no_grad()
+    def inference(self, box_cls, box_delta, anchors, image_sizes):
+        """box_cls/box_delta: list over levels of (N, A*K|A*4, H, W); anchors: list[list[Boxes]];
+        image_sizes: list of (h, w).  All images go through one batched launch pair."""
+        assert len(anchors) == len(image_sizes)
+        x = ops.levels_to_flat([t.detach() for t in box_cls], self.num_classes)
+        d = ops.levels_to_flat([t.detach() for t in box_delta], 4)
+        offs = [0]
+        for a in anchors[0]:
+            offs.append(offs[-1] + len(a))
+        res = self._detect(x, d, self._anchor_tensor(anchors), offs)
+        return [self._to_instances(res, n, image_sizes[n]) for n in range(len(anchors))]
+
+    @torch.no_grad()
+    def inference_single_image(self, box_cls, box_delta, anchors, image_size):
+        """box_cls: list over levels of (HWA, K); box_delta: (HWA, 4); anchors: list[Boxes]."""
+        x = torch.cat([t.reshape(-1, self.num_classes) for t in box_cls]).to(torch.float32).contiguous()[None]
+        d = torch.cat([t.reshape(-1, 4) for t in box_delta]).to(torch.float32).contiguous()[None]
+        offs = [0]
+        for a in anchors:
+            offs.append(offs[-1] + len(a))
+        res = self._detect(x, d, Boxes.cat(list(anchors)).tensor.contiguous(), offs)
+        return self._to_instances(res, 0, image_size)

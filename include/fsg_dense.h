@@ -1,0 +1,237 @@
+/*
+ * fsg_dense.h -- C ABI of the B200-native (sm_100a) per-anchor dense-detection hot path.
+ *
+ * Drop-in boundary for the calls the reference makes on this path (paths relative to the
+ * reference tree):
+ *   detectron2/structures/boxes.py:243-275        pairwise_iou
+ *   detectron2/modeling/matcher.py:55-132         Matcher.__call__ / set_low_quality_matches_
+ *   detectron2/modeling/box_regression.py:34-107  Box2BoxTransform.get_deltas / apply_deltas
+ *   detectron2/modeling/meta_arch/retinanet.py:201-248,309-429,460-520
+ *                                                 RetinaNet.losses / get_ground_truth /
+ *                                                 get_picky_ground_truth / inference_single_image
+ *   ImbalanceDetection/imbalancedetection/gambler_heads.py:104-128,131-253,291-318,502-602
+ *                                                 calc_cls_loss / calc_gambler_loss / gambler_loss
+ *   detectron2/layers/nms.py:6,9-26               nms / batched_nms (torchvision semantics)
+ *
+ * The reference's own native FFI convention (detectron2/layers/csrc/vision.cpp:58-95: pybind11
+ * functions taking at::Tensor, CUDA stream from at::cuda::getCurrentCUDAStream(), errors through
+ * AT_ASSERTM) is replaced by this torch-free ABI: raw device pointers, explicit sizes, scalar
+ * hyper-parameters, a cudaStream_t, and an int status (0 = ok).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `h_` (host, read at call time);
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library never allocates,
+ *     never synchronises the device, never changes the current device, keeps no mutable global
+ *     state; every call only enqueues work on `stream`;
+ *   - all float data is fp32, boxes are XYXY, class ids / match indices are int64 at the boundary
+ *     (the reference's dtypes), match labels are int8;
+ *   - "anchor index" r runs over the reference's (N, sum_l H_l*W_l*A, K) flattening
+ *     (retinanet.py:24-54): r = level_offset + (h*W + w)*A + a.
+ */
+#ifndef FSG_DENSE_H_
+#define FSG_DENSE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FSG_API __attribute__((visibility("default")))
+#else
+#define FSG_API
+#endif
+
+typedef void* fsg_stream_t; /* cudaStream_t */
+
+enum fsg_status {
+  FSG_OK = 0,
+  FSG_ERR_INVALID_ARG = 1,  /* bad size / null pointer / unsupported combination      */
+  FSG_ERR_WORKSPACE = 2,    /* workspace too small (see the *_workspace_bytes queries) */
+  FSG_ERR_UNSUPPORTED = 3,  /* shape outside what the kernels cover                    */
+  FSG_ERR_CUDA = 1000       /* FSG_ERR_CUDA + cudaError_t of the failed launch         */
+};
+
+FSG_API int fsg_abi_version(void);
+/* static string for a status returned by any entry point */
+FSG_API const char* fsg_status_string(int status);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 -- IoU and matching
+ * ---------------------------------------------------------------------------------------- */
+
+/* boxes.py:243-275.  iou[i*n2 + j] = IoU(boxes1[i], boxes2[j]); exactly 0 where inter <= 0.
+ * Bit-exact with the reference's fp32 op sequence (no FMA contraction, IEEE division). */
+FSG_API int fsg_pairwise_iou(const float* boxes1, int64_t n1, const float* boxes2, int64_t n2, float* iou,
+                     fsg_stream_t stream);
+
+/* matcher.py:55-132 on a materialised (M, N) quality matrix (row-major).
+ * h_thresholds[num_thresholds] ascending, h_labels[num_thresholds + 1] in {-1,0,1}.
+ * M == 0: matches = 0, match_labels = h_labels[0] (matcher.py:70-80).
+ * ws_rowmax: workspace of M floats. */
+FSG_API int fsg_matcher(const float* mqm, int64_t M, int64_t N, const float* h_thresholds,
+                const int8_t* h_labels, int num_thresholds, int allow_low_quality_matches,
+                int64_t* matches, int8_t* match_labels, float* ws_rowmax, fsg_stream_t stream);
+
+/* Fused IoU + Matcher(s) + GT assignment for a batch of images, never materialising the
+ * (M, R) matrix.  Replaces, per image, retinanet.py:339-363 and :400-425:
+ *   pairwise_iou -> Matcher(thresholds) [-> picky Matcher(picky_thresholds)] ->
+ *   gt_classes relabel -> get_deltas -> picky mask.
+ *
+ * anchors            (R,4) shared by all images when anchor_image_stride == 0, else image n's
+ *                    anchors start at anchors + n*anchor_image_stride (in floats).
+ * gt_boxes           packed (sum_M, 4); image n owns rows gt_offsets[n] .. gt_offsets[n+1]-1
+ * gt_class_ids       packed (sum_M) int64; may be NULL when gt_classes_out == NULL
+ * gt_offsets         (N+1) int32, device
+ * allow_low_quality_matches applies to both matchers (RetinaNet: 1, retinanet.py:91-100)
+ * h_picky_thresholds NULL -> no second matcher (mask_out must be NULL)
+ * outputs (each may be NULL, shapes (N,R) unless noted):
+ *   matches int64, match_labels int8 (first matcher), picky_labels int8,
+ *   gt_classes_out int64 in {-1, 0..K-1, K}  (K = num_classes; image without GT -> all K),
+ *   mask_out int64 (1 iff picky label == 1; image without GT -> all K, retinanet.py:425),
+ *   gt_deltas (N,R,4) fp32 (zeros for an image without GT),
+ *   matched_idx32 (N,R) int32 copy of matches for the loss kernel.
+ * Optional fused loss pre-pass (bets != NULL): stats as defined by fsg_loss_prepass.
+ * workspace: fsg_match_workspace_bytes(N, R, sum_M) bytes, 16-byte aligned. */
+FSG_API size_t fsg_match_workspace_bytes(int N, int64_t R, int64_t sum_M);
+FSG_API int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor_image_stride,
+                      const float* gt_boxes, const int64_t* gt_class_ids, const int32_t* gt_offsets,
+                      int N, int64_t sum_M, int num_classes, const float* h_thresholds,
+                      const int8_t* h_labels, int num_thresholds, int allow_low_quality_matches,
+                      const float* h_picky_thresholds, const int8_t* h_picky_labels,
+                      int num_picky_thresholds, const float* h_box_weights /* 4 */, int64_t* matches, int8_t* match_labels,
+                      int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
+                      float* gt_deltas, int32_t* matched_idx32, const float* bets,
+                      float temperature, double* stats, void* workspace, size_t workspace_bytes,
+                      fsg_stream_t stream);
+
+/* box_regression.py:34-67 / :69-107.  h_weights = (wx, wy, ww, wh).
+ * apply_deltas: deltas (n, 4k) -> out (n, 4k), dw/dh clamped to scale_clamp (max only). */
+FSG_API int fsg_box2box_get_deltas(const float* src_boxes, const float* target_boxes, int64_t n,
+                           const float* h_weights, float* deltas, fsg_stream_t stream);
+FSG_API int fsg_box2box_apply_deltas(const float* deltas, const float* boxes, int64_t n, int k,
+                             const float* h_weights, float scale_clamp, float* out,
+                             fsg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Head-layout adapter (retinanet.py:24-54, gambler_heads.py:34-101)
+ * ---------------------------------------------------------------------------------------- */
+
+/* One FPN level: nchw (N, C, HW) with C = A*K  <->  flat[n*flat_image_stride + flat_offset + hw*C + c],
+ * i.e. rows (h*W+w)*A+a of the (N, sum HWA, K) layout when flat_offset = level_offset*K and
+ * flat_image_stride = R*K.  to_nchw == 0 reads nchw and writes flat; 1 is the inverse (gradients). */
+FSG_API int fsg_permute_level(float* nchw, float* flat, int N, int C, int64_t HW,
+                              int64_t flat_image_stride, int64_t flat_offset, int to_nchw,
+                              fsg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 -- fused gambler-weighted sigmoid-focal / smooth-L1 loss, forward + backward
+ * ---------------------------------------------------------------------------------------- */
+
+enum fsg_cls_mode { FSG_CLS_FOCAL = 0, FSG_CLS_SIGMOID = 1 };         /* GAMBLER_LOSS_MODE      */
+enum fsg_norm_mode { FSG_NORM_NONE = 0, FSG_NORM_IMAGE = 1, FSG_NORM_BATCH = 2 };
+/* NORMALIZE=False / L_BAHW (gambler_heads.py:311) / L_BAHW_extendtobatch (:308-309) */
+
+typedef struct fsg_loss_params {
+  int32_t num_classes;      /* K                                                          */
+  int32_t gambler_mode;     /* fsg_cls_mode for the gambler term (loss_cls is always focal) */
+  int32_t norm_mode;        /* fsg_norm_mode                                               */
+  int32_t reserved;
+  float focal_alpha;        /* < 0: no alpha weighting                                     */
+  float focal_gamma;        /* 2.0 takes the fast path                                     */
+  float smooth_l1_beta;     /* retinanet.py:241-246                                        */
+  float temperature;        /* GAMBLER_TEMPERATURE (added to bet*mask)                     */
+  float gambler_gamma;      /* GAMBLER_GAMMA: G = -sum w_hat^gamma * l                     */
+  float c_cls, c_reg, c_gam; /* the backward is that of c_cls*loss_cls + c_reg*loss_box_reg
+                                + c_gam*gambler_loss (train_net.py:1089-1098)              */
+  float box_weights[4];     /* Box2BoxTransform weights for the fused encode               */
+} fsg_loss_params;
+
+/* stats layout (double): [0] num_foreground  [1] S_batch = sum_n S[n]  [2+n] S[n] = sum_r (bet*mask+T)
+ * In a sharded (multi-GPU) run, all-reduce(SUM) stats[0..1] over ranks between the pre-pass and
+ * fsg_loss_main; S[n] stays local (per-image normaliser). */
+#define FSG_STATS_HEADER 2
+FSG_API size_t fsg_loss_prepass_workspace_bytes(int N, int64_t R);
+FSG_API int fsg_loss_prepass(const int64_t* gt_classes, const int64_t* mask, const float* bets, int N,
+                     int64_t R, int num_classes, float temperature, double* stats, void* workspace,
+                     size_t workspace_bytes, fsg_stream_t stream);
+
+/* scalars layout (double), written by fsg_loss_main:
+ *  [0] sum_valid focal          (loss_cls * max(1, nf))
+ *  [1] sum_fg smooth-L1         (loss_box_reg * max(1, nf))
+ *  [2] sum_n A[n]               (= -gambler_loss), A[n] = sum_r w_hat^gamma * l
+ *  [3] sum l                    (loss_before_weighting numerator)
+ *  [4] sum_n max_r l[n,r]       (get_loss_upper_bound, gambler_heads.py:17-31)
+ *  [5] loss_cls  [6] loss_box_reg  [7] gambler_loss   (local-rank values, normalised with stats[0])
+ *  [8] c_cls*[5] + c_reg*[6] + c_gam*[7]   [9] num_foreground used
+ *  [10+n] A[n]
+ * In a sharded run with FSG_NORM_BATCH, all-reduce(SUM) scalars[2] before fsg_loss_post. */
+#define FSG_SCALARS_HEADER 10
+FSG_API size_t fsg_loss_main_workspace_bytes(int N, int64_t R, int K);
+
+/* The main pass.  Reads logits (N,R,K) once and writes grad_logits once.
+ * Regression targets: either gt_deltas (N,R,4) explicit, or (gt_deltas == NULL) encoded on the fly
+ * from anchors + gt_boxes[gt_offsets[n] + matched_idx32[n,r]] (Box2BoxTransform.get_deltas fused).
+ * bets (N,R) may be NULL when c_gam == 0 and no gambler outputs are requested.
+ * Outputs (each may be NULL): grad_logits (N,R,K), grad_deltas (N,R,4), per_anchor_loss l (N,R)
+ * (the NAKHW_loss values, gambler_heads.py:218), weights_out w_hat (N,R). */
+FSG_API int fsg_loss_main(const float* logits, const float* pred_deltas, const float* gt_deltas,
+                  const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
+                  const int32_t* gt_offsets, const int32_t* matched_idx32,
+                  const int64_t* gt_classes, const int64_t* mask, const float* bets, int N,
+                  int64_t R, const fsg_loss_params* h_params, const double* stats,
+                  float* grad_logits, float* grad_deltas, float* per_anchor_loss,
+                  float* weights_out, double* scalars, void* workspace, size_t workspace_bytes,
+                  fsg_stream_t stream);
+
+/* d(c_gam * gambler_loss)/d bets  (SURVEY App. A item 12):
+ *   -(m/S) * gamma * (w_hat^(gamma-1) * l - A)     for FSG_NORM_IMAGE / _BATCH
+ *   -m * gamma * w^(gamma-1) * l                   for FSG_NORM_NONE */
+FSG_API int fsg_loss_post(const float* bets, const int64_t* mask, const float* per_anchor_loss, int N,
+                  int64_t R, const fsg_loss_params* h_params, const double* stats,
+                  const double* scalars, float* grad_bets, fsg_stream_t stream);
+
+/* in-place x *= *scale_dev or x *= scale_host (backward with a non-unit upstream gradient) */
+FSG_API int fsg_scale_inplace(float* x, int64_t n, const float* scale_dev, float scale_host,
+                      fsg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 -- decode + score threshold + top-k + batched NMS
+ * ---------------------------------------------------------------------------------------- */
+
+/* torchvision.ops.nms semantics (layers/nms.py:6): stable score-descending greedy NMS, suppress
+ * when IoU > iou_threshold (compared as the reference does, fp32 IoU against the double
+ * threshold).  class_ids == NULL: plain nms; else per-class (batched_nms, layers/nms.py:9-26,
+ * un-offset per-class algorithm).  keep (n) int64 receives the kept indices in score-descending
+ * order (ties: lower index first); *num_keep (device int32) their count.
+ * workspace: fsg_nms_workspace_bytes(n). */
+FSG_API size_t fsg_nms_workspace_bytes(int64_t n);
+FSG_API int fsg_nms(const float* boxes, const float* scores, const int64_t* class_ids, int64_t n,
+            double iou_threshold, int64_t* keep, int32_t* num_keep, void* workspace,
+            size_t workspace_bytes, fsg_stream_t stream);
+
+/* Batched RetinaNet.inference (retinanet.py:431-520) for N images at once.
+ * logits (N,R,K), deltas (N,R,4) in the flattened layout; anchors as in fsg_match_anchors;
+ * h_level_offsets[num_levels+1]: anchor ranges of the FPN levels (top-k is per level, :487).
+ * Outputs: out_boxes (N,max_det,4), out_scores (N,max_det), out_classes (N,max_det) int64,
+ * out_count (N) int32; rows >= out_count[n] are zero-filled.
+ * Optional pre-NMS candidates in the reference's concatenation order (level-major, score
+ * descending inside a level): cand_boxes (N,cap,4), cand_scores (N,cap), cand_classes (N,cap)
+ * int64, cand_count (N) int32, keep_idx (N,max_det) int64 with cap = num_levels*topk. */
+FSG_API size_t fsg_detect_workspace_bytes(int N, int64_t R, int K, int num_levels, int topk);
+FSG_API int fsg_detect(const float* logits, const float* deltas, const float* anchors,
+               int64_t anchor_image_stride, int N, int64_t R, int K,
+               const int64_t* h_level_offsets, int num_levels, float score_threshold, int topk,
+               double nms_threshold, int max_det, const float* h_box_weights, float scale_clamp,
+               float* out_boxes, float* out_scores, int64_t* out_classes, int32_t* out_count,
+               float* cand_boxes, float* cand_scores, int64_t* cand_classes, int32_t* cand_count,
+               int64_t* keep_idx, void* workspace, size_t workspace_bytes, fsg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSG_DENSE_H_ */

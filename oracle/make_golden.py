@@ -1,0 +1,256 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own source files (container only).
+
+    python -m oracle.make_golden          # writes tests/golden/, prints oracle-vs-reference deltas
+
+Each fixture stores seeded inputs *generation parameters* (regenerated deterministically by
+``full_scale_gambler_for_object_detection_b200.synthetic``) or small explicit inputs, together with the outputs the
+reference produced for them through ``oracle/ref_loader.py``.  ``tests/test_oracle_golden.py`` checks the
+oracle against these files on any machine; the GPU parity tests check the CUDA path against the same files.
+TEST INFRASTRUCTURE -- never imported by the product.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import dense_oracle as orc  # noqa: E402
+from oracle import ref_loader as rl  # noqa: E402
+from full_scale_gambler_for_object_detection_b200 import synthetic  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(d):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, torch.Tensor):
+            out[k] = v.detach().cpu().numpy()
+        elif isinstance(v, (list, tuple)) and v and isinstance(v[0], torch.Tensor):
+            for i, t in enumerate(v):
+                out["%s_%d" % (k, i)] = t.detach().cpu().numpy()
+        else:
+            out[k] = np.asarray(v)
+    return out
+
+
+def ref_targets(ref, inp, hw):
+    targets = []
+    for b, c in zip(inp["gt_boxes"], inp["gt_classes"]):
+        t = ref.Instances(hw)
+        t.gt_boxes = ref.Boxes(b)
+        t.gt_classes = c
+        targets.append(t)
+    return targets
+
+
+def ref_anchor_lists(ref, inp):
+    offs = inp["level_offsets"]
+    per_level = [ref.Boxes(inp["anchors"][offs[i]:offs[i + 1]].clone()) for i in range(len(offs) - 1)]
+    return [per_level for _ in range(inp["N"])]
+
+
+def flat_to_levels_nchw(flat, grids, A):
+    """(N,R,K) -> list[(N, A*K, H, W)], inverse of retinanet.py:24-33."""
+    N, R, K = flat.shape
+    out, off = [], 0
+    for H, W in grids:
+        n = H * W * A
+        t = flat[:, off:off + n].reshape(N, H, W, A, K).permute(0, 3, 4, 1, 2).reshape(N, A * K, H, W)
+        out.append(t.contiguous())
+        off += n
+    return out
+
+
+def run_reference_train(ref, inp, K, hw, coeffs=(1.0, 1.0, -1.0), detach_pred=False, **gcfg):
+    """The reference's own train-step path on flattened synthetic inputs: get_ground_truth,
+    get_picky_ground_truth, losses, gambler_loss, backward of the combination."""
+    cfg = rl.make_cfg(NUM_CLASSES=K, IN_LAYERS=[g[0] for g in inp["grids"]], **gcfg)
+    cfg.MODEL.RETINANET.NUM_CLASSES = K
+    rl.set_global_cfg(ref, cfg)
+    me = rl.retinanet_self(ref, num_classes=K)
+    anchors = ref_anchor_lists(ref, inp)
+    targets = ref_targets(ref, inp, hw)
+    gt_classes, gt_deltas = ref.RetinaNet.get_ground_truth(me, anchors, targets)
+    mask = ref.RetinaNet.get_picky_ground_truth(me, anchors, targets)
+    A = inp["A"]
+    cls_levels = [t.requires_grad_(True) for t in flat_to_levels_nchw(inp["logits"], inp["grids"], A)]
+    reg_levels = [t.requires_grad_(True) for t in flat_to_levels_nchw(inp["deltas"], inp["grids"], A)]
+    bet_levels = [t.reshape(t.shape[0], A, t.shape[2], t.shape[3]).requires_grad_(True)
+                  for t in flat_to_levels_nchw(inp["bets"][..., None], inp["grids"], A)]
+    losses = ref.RetinaNet.losses(me, gt_classes, gt_deltas, cls_levels, reg_levels)
+    g = rl.gambler_self(ref, cfg)
+    bets_in = list(bet_levels)
+    loss_dict, weights = g.gambler_loss(cls_levels, bets_in, gt_classes, mask, detach_pred=detach_pred)
+    total = coeffs[0] * losses["loss_cls"] + coeffs[1] * losses["loss_box_reg"] + coeffs[2] * loss_dict["gambler_loss"]
+    total.backward()
+
+    def flat_grad(levels, Kc):
+        gs = [t.grad if t.grad is not None else torch.zeros_like(t) for t in levels]
+        return orc.levels_to_flat(gs, Kc)
+
+    N = inp["N"]
+    ell = torch.cat([l.permute(0, 2, 3, 1).reshape(N, -1) for l in loss_dict["NAKHW_loss"]], dim=1)
+    return dict(
+        gt_classes=gt_classes, gt_deltas=gt_deltas, mask=mask,
+        loss_cls=losses["loss_cls"].detach(), loss_box_reg=losses["loss_box_reg"].detach(),
+        gambler_loss=loss_dict["gambler_loss"].detach(), total=total.detach(),
+        loss_before_weighting=loss_dict["loss_before_weighting"].detach(),
+        lower_bound=torch.as_tensor(ref.storage.scalars["loss_gambler/lower_bound"]).detach(),
+        per_anchor_loss=ell.detach(), weights=weights.reshape(N, -1),
+        grad_logits=flat_grad(cls_levels, K), grad_deltas=flat_grad(reg_levels, 4),
+        grad_bets=flat_grad(bet_levels, 1).reshape(N, -1),
+    )
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    d = (a - b).abs().max().item() if a.numel() else 0.0
+    s = b.abs().max().item() if b.numel() else 0.0
+    return d / s if s > 0 else d
+
+
+TRAIN_CASES = {
+    # name: (config_id, N, H, W, K, M, coeffs, detach_pred, gambler cfg overrides)
+    "train_config1": (1, 2, 512, 512, 80, 8, (1.0, 1.0, -1.0), False, {}),
+    "train_gphase": (2, 2, 256, 320, 80, 8, (0.0, 0.0, 1.0), True, {}),
+    "train_extendtobatch": (3, 3, 256, 256, 80, 5, (1.0, 0.5, -2.0), False, {"GAMBLER_OUTPUT": "L_BAHW_extendtobatch"}),
+    "train_sigmoid": (3, 3, 256, 256, 80, 5, (1.0, 0.5, -2.0), False, {"GAMBLER_LOSS_MODE": "sigmoid"}),
+    "train_nonorm": (3, 3, 256, 256, 80, 5, (1.0, 0.5, -2.0), False, {"NORMALIZE": False}),
+    "train_lvis_k1230": (4, 2, 192, 192, 1230, 6, (1.0, 1.0, -1.0), False, {}),
+}
+
+ORACLE_KW = {"GAMBLER_OUTPUT": "output", "GAMBLER_LOSS_MODE": "mode", "NORMALIZE": "normalize"}
+
+
+def make_train(ref):
+    for name, (cid, N, H, W, K, M, coeffs, detach, gcfg) in TRAIN_CASES.items():
+        inp = synthetic.train_inputs(cid, N, H, W, K, M=M)
+        want = run_reference_train(ref, inp, K, (H, W), coeffs, detach, **gcfg)
+        okw = {ORACLE_KW[k]: v for k, v in gcfg.items()}
+        got = orc.train_step(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], inp["logits"], inp["deltas"],
+                             inp["bets"], K, *coeffs, detach_pred=detach, **okw)
+        print("[%s] oracle vs reference:" % name)
+        for k in ("gt_classes", "mask"):
+            assert torch.equal(got[k], want[k]), k
+        for k in ("gt_deltas", "loss_cls", "loss_box_reg", "gambler_loss", "total", "loss_before_weighting",
+                  "lower_bound", "per_anchor_loss", "weights", "grad_logits", "grad_deltas", "grad_bets"):
+            print("    %-22s rel-to-max err %.3g" % (k, rel(got[k], want[k])))
+        keep = dict(want)
+        if K > 200:  # keep the LVIS fixture small: store a strided sample of the big tensors
+            keep["grad_logits"] = want["grad_logits"][:, ::37].contiguous()
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            params=np.asarray([cid, N, H, W, K, M], dtype=np.int64),
+                            coeffs=np.asarray(coeffs, dtype=np.float64), detach=np.asarray(int(detach)),
+                            gcfg=np.asarray(repr(gcfg)), **_np(keep))
+
+
+def make_matcher(ref):
+    """Matcher + pairwise_iou through the reference on the stress shape and on hand-made edge cases."""
+    inp = synthetic.matcher_stress_inputs(5, 2, 20000, 200)
+    inp["anchors"][0, 100] = inp["anchors"][0, 99]
+    inp["anchors"][1, :50] = inp["gt_boxes"][1][:50]
+    res = {}
+    for i in range(2):
+        q = ref.pairwise_iou(ref.Boxes(inp["gt_boxes"][i]), ref.Boxes(inp["anchors"][i]))
+        m = ref.Matcher([0.4, 0.5], [0, -1, 1], allow_low_quality_matches=True)
+        pm = ref.Matcher([0.4, 0.9], [0, -1, 1], allow_low_quality_matches=True)
+        nm = ref.Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=False)
+        res["matches_%d" % i], res["labels_%d" % i] = m(q)
+        _, res["picky_labels_%d" % i] = pm(q)
+        res["nolq_matches_%d" % i], res["nolq_labels_%d" % i] = nm(q)
+        res["iou_rowmax_%d" % i] = q.max(dim=1).values
+        res["iou_sample_%d" % i] = q[:, :512].contiguous()
+        oq = orc.pairwise_iou(inp["gt_boxes"][i], inp["anchors"][i])
+        assert torch.equal(oq, q), "oracle IoU differs from the reference"
+        om, ol = orc.matcher(oq, [0.4, 0.5], [0, -1, 1], True)
+        assert torch.equal(om, res["matches_%d" % i]) and torch.equal(ol, res["labels_%d" % i])
+    # quirks: zero-overlap GT, empty GT, tie rows
+    q = torch.tensor([[0.9, 0.3, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]])
+    res["quirk_matches"], res["quirk_labels"] = ref.Matcher([0.4, 0.5], [0, -1, 1], True)(q)
+    e = torch.zeros((0, 7))
+    res["empty_matches"], res["empty_labels"] = ref.Matcher([0.4, 0.5], [0, -1, 1], True)(e)
+    np.savez_compressed(os.path.join(OUT, "matcher_stress.npz"), params=np.asarray([5, 2, 20000, 200]), **_np(res))
+    print("[matcher_stress] oracle == reference (bit-exact)")
+
+
+def make_box2box(ref):
+    torch.manual_seed(3)
+    w = (5, 5, 10, 10)
+    src = torch.rand(10, 4) + torch.tensor([10, 10, 20, 20], dtype=torch.float)
+    dst = torch.rand(10, 4) + torch.tensor([10, 10, 20, 20], dtype=torch.float)
+    t = ref.Box2BoxTransform(weights=w)
+    deltas = t.get_deltas(src, dst)
+    big = torch.randn(64, 12) * 3
+    boxes = torch.rand(64, 4) * 50
+    boxes[:, 2:] += boxes[:, :2] + 1
+    applied = t.apply_deltas(big, boxes)
+    assert torch.allclose(orc.get_deltas(src, dst, w), deltas, rtol=1e-6, atol=0)
+    assert torch.allclose(orc.apply_deltas(big, boxes, w), applied, rtol=1e-6, atol=1e-6)
+    np.savez_compressed(os.path.join(OUT, "box2box.npz"), src=src.numpy(), dst=dst.numpy(), deltas=deltas.numpy(),
+                        big=big.numpy(), boxes=boxes.numpy(), applied=applied.numpy(), weights=np.asarray(w))
+    print("[box2box] ok")
+
+
+def make_nms(ref):
+    res = {}
+    for name, n, ncls, seed in (("a", 2000, 50, 2250), ("b", 5000, 80, 5280), ("c", 600, 3, 803)):
+        g = torch.Generator().manual_seed(seed)
+        boxes = torch.rand((n, 4), generator=g) * 100
+        boxes[:, 2:] += boxes[:, :2]
+        scores = torch.rand(n, generator=g)
+        scores[5] = scores[3]
+        boxes[7] = boxes[6]
+        boxes[9, 2:] = boxes[9, :2]
+        idxs = torch.randint(0, ncls, (n,), generator=g)
+        res["boxes_" + name], res["scores_" + name], res["idxs_" + name] = boxes, scores, idxs
+        for thr in (0.2, 0.5, 0.8):
+            tag = "%s_%02d" % (name, int(thr * 10))
+            # the reference's own entry points (detectron2/layers/nms.py) -> installed torchvision 0.26
+            res["nms_" + tag] = ref.nms(boxes, scores, thr)
+            res["batched_" + tag] = ref.batched_nms(boxes, scores, idxs, thr)
+            assert torch.equal(orc.nms(boxes, scores, thr), res["nms_" + tag]), "oracle nms != torchvision"
+            ob = orc.batched_nms(boxes, scores, idxs, thr)
+            same = torch.equal(ob, res["batched_" + tag])
+            print("[nms %s thr %.1f] oracle batched_nms == reference: %s (n=%d keep=%d)" % (name, thr, same, n, ob.numel()))
+            assert same
+    np.savez_compressed(os.path.join(OUT, "nms.npz"), **_np(res))
+
+
+def make_inference(ref):
+    K = 80
+    inp = synthetic.inference_inputs(41, 2, [3000, 800, 200, 60, 20], K)
+    me = rl.retinanet_self(ref, num_classes=K)
+    offs = inp["level_offsets"]
+    res = {}
+    for n in range(2):
+        cls = [inp["logits"][n, offs[i]:offs[i + 1]].clone() for i in range(5)]
+        reg = [inp["deltas"][n, offs[i]:offs[i + 1]] for i in range(5)]
+        anc = [ref.Boxes(inp["anchors"][offs[i]:offs[i + 1]]) for i in range(5)]
+        r = ref.RetinaNet.inference_single_image(me, cls, reg, anc, (800, 1344))
+        res["boxes_%d" % n], res["scores_%d" % n], res["classes_%d" % n] = r.pred_boxes.tensor, r.scores, r.pred_classes
+        cls2 = [inp["logits"][n, offs[i]:offs[i + 1]] for i in range(5)]
+        anc2 = [inp["anchors"][offs[i]:offs[i + 1]] for i in range(5)]
+        (ob, os_, oc), _, _ = orc.inference_single_image(cls2, reg, anc2, K)
+        assert torch.equal(oc, r.pred_classes) and torch.equal(os_, r.scores) and torch.equal(ob, r.pred_boxes.tensor), \
+            "oracle inference != reference"
+    np.savez_compressed(os.path.join(OUT, "inference.npz"), params=np.asarray([41, 2, 3000, 800, 200, 60, 20, K]), **_np(res))
+    print("[inference] oracle == reference (bit-exact on CPU)")
+
+
+def main():
+    assert rl.available(), "needs /root/reference"
+    os.makedirs(OUT, exist_ok=True)
+    ref = rl.load_reference()
+    make_matcher(ref)
+    make_box2box(ref)
+    make_nms(ref)
+    make_inference(ref)
+    make_train(ref)
+
+
+if __name__ == "__main__":
+    main()

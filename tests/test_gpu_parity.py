@@ -1,0 +1,431 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs."""
+import math
+
+import pytest
+import torch
+
+from oracle import dense_oracle as orc
+from tests.util import assert_close_scalar, assert_close_tensor, assert_equal_int
+
+pytestmark = pytest.mark.gpu
+
+
+def _fsg():
+    import full_scale_gambler_for_object_detection_b200 as fsg
+    return fsg
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def test_pairwise_iou_known_answer(cuda):
+    """The reference's own KAT, tests/test_boxes.py:36-59."""
+    fsg = _fsg()
+    b1 = torch.tensor([[0.0, 0.0, 1.0, 1.0], [0.0, 0.0, 1.0, 1.0]])
+    b2 = torch.tensor([[0.0, 0.0, 1.0, 1.0], [0.0, 0.0, 0.5, 1.0], [0.0, 0.0, 1.0, 0.5],
+                       [0.0, 0.0, 0.5, 0.5], [0.5, 0.5, 1.0, 1.0], [0.5, 0.5, 1.5, 1.5]])
+    expected = torch.tensor([[1.0, 0.5, 0.5, 0.25, 0.25, 0.25 / (2 - 0.25)]] * 2)
+    got = fsg.pairwise_iou(fsg.Boxes(b1.to(cuda)), fsg.Boxes(b2.to(cuda)))
+    assert torch.allclose(got.cpu(), expected)
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (7, 300), (33, 4097), (0, 5), (5, 0)])
+def test_pairwise_iou_bit_exact(cuda, n1, n2):
+    fsg = _fsg()
+    g = torch.Generator().manual_seed(n1 * 1000 + n2)
+    def boxes(n):
+        xy = torch.rand((n, 2), generator=g) * 100
+        wh = torch.rand((n, 2), generator=g) * 60
+        return torch.cat((xy, xy + wh), 1)
+    b1, b2 = boxes(n1), boxes(n2)
+    if n1 > 2:
+        b1[1] = b1[0]          # duplicates -> exact ties
+        b1[2, 2:] = b1[2, :2]  # zero-area box
+    want = orc.pairwise_iou(b1, b2)
+    got = fsg.pairwise_iou(fsg.Boxes(b1.to(cuda)), fsg.Boxes(b2.to(cuda)))
+    assert got.shape == want.shape
+    assert torch.equal(got.cpu(), want), "IoU must be bit-exact"
+
+
+@pytest.mark.parametrize("M,N,thr,lq", [(8, 1000, [0.4, 0.5], True), (3, 257, [0.3, 0.7], False),
+                                        (200, 5000, [0.4, 0.9], True), (0, 77, [0.4, 0.5], True),
+                                        (5, 64, [0.5], True)])
+def test_matcher_matrix(cuda, M, N, thr, lq):
+    fsg = _fsg()
+    g = torch.Generator().manual_seed(M * 7 + N)
+    q = torch.rand((M, N), generator=g)
+    q[q < 0.5] = 0.0                      # many zeros and zero columns
+    if M > 1:
+        q[1] = q[0]                       # tied rows -> argmax tie rule
+    labels = [0, -1, 1] if len(thr) == 2 else [0, 1]
+    want_m, want_l = orc.matcher(q, thr, labels, lq)
+    m = fsg.Matcher(list(thr), labels, allow_low_quality_matches=lq)
+    got_m, got_l = m(q.to(cuda))
+    assert_equal_int(got_m, want_m, "matches")
+    assert_equal_int(got_l, want_l, "match_labels")
+
+
+def test_matcher_zero_overlap_gt_quirk(cuda):
+    """A GT that overlaps nothing makes every zero-IoU anchor positive."""
+    fsg = _fsg()
+    q = torch.tensor([[0.9, 0.3, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]])
+    want = orc.matcher(q, [0.4, 0.5], [0, -1, 1], True)
+    got = fsg.Matcher([0.4, 0.5], [0, -1, 1], True)(q.to(cuda))
+    assert_equal_int(got[0], want[0], "matches")
+    assert_equal_int(got[1], want[1], "labels")
+    assert got[1].cpu().tolist() == [1, 1, 1, 1]
+
+
+def _train_inputs(cfg_id, N, H, W, K, M=8):
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    return synthetic.train_inputs(cfg_id, N, H, W, K, M=M)
+
+
+@pytest.mark.parametrize("N,H,W,M", [(2, 512, 512, 8), (3, 320, 480, 40), (1, 256, 256, 1)])
+def test_fused_match_vs_oracle(cuda, N, H, W, M):
+    fsg = _fsg()
+    inp = _train_inputs(1, N, H, W, 80, M)
+    want = orc.ground_truth(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], 80)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    got = fsg.ops.match_anchors(inp["anchors"].to(cuda), gt, 80,
+                                want=("matches", "match_labels", "picky_labels", "gt_classes", "mask", "gt_deltas"))
+    for k in ("matches", "match_labels", "picky_labels", "gt_classes", "mask"):
+        assert_equal_int(got[k], want[k], k)
+    assert_close_tensor(got["gt_deltas"], want["gt_deltas"], "gt_deltas")
+    assert int((want["match_labels"] == 1).sum()) > 0
+
+
+def test_fused_match_stress_slice(cuda):
+    """Config 5 shape at a size the oracle finishes in seconds: 200 GT x 50k free-form anchors, 2 images
+    with per-image anchors, > kGtChunk not needed; exercises ties through duplicated anchors."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    inp = synthetic.matcher_stress_inputs(5, 2, 50000, 200)
+    inp["anchors"][0, 100] = inp["anchors"][0, 99]
+    inp["anchors"][1, :50] = torch.cat((inp["gt_boxes"][1][:50, :2], inp["gt_boxes"][1][:50, 2:]), 1)  # IoU == 1
+    anchors_list = [inp["anchors"][i] for i in range(2)]
+    want = orc.ground_truth(anchors_list, inp["gt_boxes"], inp["gt_classes"], 80)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    got = fsg.ops.match_anchors(inp["anchors"].to(cuda), gt, 80,
+                                want=("matches", "match_labels", "gt_classes", "mask"))
+    for k in ("matches", "match_labels", "gt_classes", "mask"):
+        assert_equal_int(got[k], want[k], k)
+
+
+def test_fused_match_many_gt_chunks(cuda):
+    """More GT than one shared-memory chunk (1024)."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    inp = synthetic.matcher_stress_inputs(6, 1, 3000, 2500)
+    want = orc.ground_truth([inp["anchors"][0]], inp["gt_boxes"], inp["gt_classes"], 80)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    got = fsg.ops.match_anchors(inp["anchors"].to(cuda), gt, 80, want=("matches", "match_labels", "mask"))
+    for k in ("matches", "match_labels", "mask"):
+        assert_equal_int(got[k], want[k], k)
+
+
+def test_box2box_roundtrip_and_parity(cuda):
+    """tests/test_box2box_transform.py:16-30 (weights (5,5,10,10)) + parity with the oracle."""
+    fsg = _fsg()
+    torch.manual_seed(3)
+    w = (5, 5, 10, 10)
+    src = torch.rand(10, 4) * 1 + torch.tensor([10, 10, 20, 20], dtype=torch.float)
+    dst = torch.rand(10, 4) * 1 + torch.tensor([10, 10, 20, 20], dtype=torch.float)
+    t = fsg.Box2BoxTransform(weights=w)
+    d = t.get_deltas(src.to(cuda), dst.to(cuda))
+    rec = t.apply_deltas(d, src.to(cuda))
+    assert torch.allclose(dst, rec.cpu())
+    assert_close_tensor(d, orc.get_deltas(src, dst, w), "get_deltas")
+    big = torch.randn(64, 12) * 3
+    boxes = torch.rand(64, 4) * 50
+    boxes[:, 2:] += boxes[:, :2] + 1
+    assert_close_tensor(t.apply_deltas(big.to(cuda), boxes.to(cuda)), orc.apply_deltas(big, boxes, w), "apply_deltas")
+
+
+# ------------------------------------------------------------------------------------------------ K2
+def _check_step(cuda, inp, K, coeffs, cfg_kwargs=None, detach_pred=False):
+    fsg = _fsg()
+    cfg_kwargs = cfg_kwargs or {}
+    cfg = fsg.DenseLossConfig(num_classes=K, **cfg_kwargs)
+    want = orc.train_step(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], inp["logits"], inp["deltas"],
+                          inp["bets"], K, *coeffs, temperature=cfg.gambler_temperature, normalize=cfg.normalize,
+                          mode=cfg.gambler_loss_mode, alpha=cfg.focal_alpha, focal_gamma=cfg.focal_gamma,
+                          gambler_gamma=cfg.gambler_gamma, beta=cfg.smooth_l1_beta, output=cfg.gambler_output,
+                          detach_pred=detach_pred)
+    x = inp["logits"].to(cuda).requires_grad_(True)
+    d = inp["deltas"].to(cuda).requires_grad_(True)
+    b = inp["bets"].to(cuda).requires_grad_(True)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    res = fsg.dense_train_step(x, d, b, inp["anchors"].to(cuda), gt, cfg, coeffs, detach_pred=detach_pred,
+                               want_weights=True)
+    res.total.backward()
+    assert_equal_int(res.gt_classes, want["gt_classes"], "gt_classes")
+    assert_equal_int(res.mask, want["mask"], "mask")
+    assert int(res.num_foreground.item()) == int(want["num_foreground"])
+    assert_close_scalar(res.loss_cls.item(), want["loss_cls"], "loss_cls")
+    assert_close_scalar(res.loss_box_reg.item(), want["loss_box_reg"], "loss_box_reg")
+    assert_close_scalar(res.gambler_loss.item(), want["gambler_loss"], "gambler_loss")
+    assert_close_scalar(res.total.item(), want["total"], "total", rtol=2e-5)
+    assert_close_scalar(res.loss_before_weighting(cfg.gambler_loss_mode).item(), want["loss_before_weighting"],
+                        "loss_before_weighting")
+    assert_close_scalar(res.lower_bound(cfg.gambler_temperature, 1.0).item(), want["lower_bound"], "lower_bound")
+    assert_close_tensor(res.per_anchor_loss, want["per_anchor_loss"], "per_anchor_loss")
+    assert_close_tensor(res.weights, want["weights"], "weights")
+    if not detach_pred:
+        assert_close_tensor(x.grad, want["grad_logits"], "grad_logits")
+    else:
+        assert x.grad is None
+    if coeffs[1] != 0:
+        assert_close_tensor(d.grad, want["grad_deltas"], "grad_deltas")
+    assert_close_tensor(b.grad, want["grad_bets"], "grad_bets", rtol=2e-5)
+    return res
+
+
+def test_step_config1(cuda):
+    """BASELINE config 1: 2 x 512x512, K=80, one image without GT."""
+    inp = _train_inputs(1, 2, 512, 512, 80)
+    assert inp["R"] == 16368
+    _check_step(cuda, inp, 80, (1.0, 1.0, -1.0))
+
+
+def test_step_gambler_phase(cuda):
+    inp = _train_inputs(2, 2, 256, 320, 80)
+    _check_step(cuda, inp, 80, (0.0, 0.0, 1.0), detach_pred=True)
+
+
+@pytest.mark.parametrize("kw", [dict(gambler_output="L_BAHW_extendtobatch"), dict(normalize=False),
+                                dict(gambler_loss_mode="sigmoid"), dict(focal_gamma=1.5, focal_alpha=-1.0),
+                                dict(gambler_gamma=2.0), dict(smooth_l1_beta=0.0, gambler_temperature=0.03)])
+def test_step_variants(cuda, kw):
+    inp = _train_inputs(3, 3, 256, 256, 80, M=5)
+    _check_step(cuda, inp, 80, (1.0, 0.5, -2.0), kw)
+
+
+@pytest.mark.parametrize("K", [1230, 3, 20, 1])
+def test_step_other_class_counts(cuda, K):
+    """LVIS K=1230 (rows not 16-byte aligned -> float2 path), odd K (scalar path), small K."""
+    inp = _train_inputs(4, 2, 192, 192, K, M=6)
+    _check_step(cuda, inp, K, (1.0, 1.0, -1.0))
+
+
+def test_step_run_to_run_deterministic(cuda):
+    fsg = _fsg()
+    inp = _train_inputs(1, 2, 256, 256, 80)
+    cfg = fsg.DenseLossConfig()
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    outs = []
+    for _ in range(3):
+        x = inp["logits"].to(cuda).requires_grad_(True)
+        r = fsg.dense_train_step(x, inp["deltas"].to(cuda), inp["bets"].to(cuda), inp["anchors"].to(cuda), gt, cfg)
+        r.total.backward()
+        outs.append((r.scalars.clone(), x.grad.clone()))
+    for s, g in outs[1:]:
+        assert torch.equal(s, outs[0][0]) and torch.equal(g, outs[0][1])
+
+
+def test_upstream_gradient_scaling(cuda):
+    fsg = _fsg()
+    inp = _train_inputs(1, 1, 128, 128, 80, M=3)
+    cfg = fsg.DenseLossConfig()
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    grads = []
+    for scale in (1.0, 3.0):
+        x = inp["logits"].to(cuda).requires_grad_(True)
+        r = fsg.dense_train_step(x, inp["deltas"].to(cuda), inp["bets"].to(cuda), inp["anchors"].to(cuda), gt,
+                                 cfg, (1.0, 1.0, -1.0))
+        (r.total * scale).backward()
+        grads.append(x.grad.clone())
+    assert torch.allclose(grads[1], grads[0] * 3.0, rtol=1e-6, atol=0)
+
+
+# ---------------------------------------------------------------------------------- drop-in methods
+def _levels(inp, K, N, gen, scale=1.0, shift=0.0):
+    A = inp["A"]
+    return [torch.randn((N, A * K, h, w), generator=gen) * scale + shift for (h, w) in inp["grids"]]
+
+
+def test_dropin_retinanet_losses_and_gt(cuda):
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    N, K = 2, 80
+    inp = synthetic.train_inputs(7, N, 256, 384, K, logits=False)
+    gen = torch.Generator().manual_seed(11)
+    cls_l = _levels(inp, K, N, gen, 1.0, synthetic.PRIOR_LOGIT)
+    reg_l = _levels(inp, 4, N, gen, 0.1)
+    want_gt = orc.ground_truth(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], K)
+    xs = [t.clone().requires_grad_(True) for t in cls_l]
+    ds = [t.clone().requires_grad_(True) for t in reg_l]
+    lc, lr, _ = orc.retinanet_losses(want_gt["gt_classes"], want_gt["gt_deltas"], orc.levels_to_flat(xs, K),
+                                     orc.levels_to_flat(ds, 4), K)
+    (lc + 2 * lr).backward()
+
+    path = fsg.RetinaNetDensePath(num_classes=K)
+    offs = inp["level_offsets"]
+    anc_levels = [fsg.Boxes(inp["anchors"][offs[i]:offs[i + 1]].to(cuda)) for i in range(5)]
+    anchors = [anc_levels for _ in range(N)]
+    targets = []
+    for b, c in zip(inp["gt_boxes"], inp["gt_classes"]):
+        t = fsg.Instances((256, 384))
+        t.gt_boxes = fsg.Boxes(b.to(cuda))
+        t.gt_classes = c.to(cuda)
+        targets.append(t)
+    gt_classes, gt_deltas = path.get_ground_truth(anchors, targets)
+    mask = path.get_picky_ground_truth(anchors, targets)
+    assert_equal_int(gt_classes, want_gt["gt_classes"], "gt_classes")
+    assert_equal_int(mask, want_gt["mask"], "mask")
+    assert_close_tensor(gt_deltas, want_gt["gt_deltas"], "gt_deltas")
+    gx = [t.to(cuda).requires_grad_(True) for t in cls_l]
+    gd = [t.to(cuda).requires_grad_(True) for t in reg_l]
+    losses = path.losses(gt_classes, gt_deltas, gx, gd)
+    (losses["loss_cls"] + 2 * losses["loss_box_reg"]).backward()
+    assert_close_scalar(losses["loss_cls"].item(), lc, "loss_cls")
+    assert_close_scalar(losses["loss_box_reg"].item(), lr, "loss_box_reg")
+    for a, b in zip(gx, xs):
+        assert_close_tensor(a.grad, b.grad, "grad cls level")
+    for a, b in zip(gd, ds):
+        assert_close_tensor(a.grad, b.grad, "grad reg level")
+
+
+@pytest.mark.parametrize("detach", [False, True])
+def test_dropin_gambler_loss(cuda, detach):
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    N, K, A = 2, 80, 3
+    inp = synthetic.train_inputs(8, N, 256, 256, K, logits=False)
+    gen = torch.Generator().manual_seed(12)
+    cls_l = _levels(inp, K, N, gen, 1.0, synthetic.PRIOR_LOGIT)
+    bet_l = [torch.sigmoid(torch.randn((N, A, h, w), generator=gen) - 4.0) for (h, w) in inp["grids"]]
+    gtd = orc.ground_truth(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], K)
+    xs = [t.clone().requires_grad_(True) for t in cls_l]
+    bs = [t.clone().requires_grad_(True) for t in bet_l]
+    xf = orc.levels_to_flat(xs, K)
+    want = orc.gambler_loss(xf.detach() if detach else xf, orc.levels_to_flat(bs, 1).reshape(N, -1),
+                            gtd["gt_classes"], gtd["mask"], K)
+    want["gambler_loss"].backward()
+
+    head = fsg.GamblerLoss(num_classes=K)
+    gx = [t.to(cuda).requires_grad_(True) for t in cls_l]
+    gb = [t.to(cuda).requires_grad_(True) for t in bet_l]
+    bets_list = list(gb)
+    loss_dict, w = head.gambler_loss(gx, bets_list, gtd["gt_classes"].to(cuda), gtd["mask"].to(cuda), detach)
+    loss_dict["gambler_loss"].backward()
+    assert_close_scalar(loss_dict["gambler_loss"].item(), want["gambler_loss"], "gambler_loss")
+    assert_close_scalar(loss_dict["loss_before_weighting"].item(), want["loss_before_weighting"], "lbw")
+    assert_close_scalar(head.last_lower_bound.item(), want["lower_bound"], "lower_bound")
+    assert_close_tensor(w.reshape(N, -1), want["weights"], "weights")
+    nakhw_want = orc.flat_to_nahw(want["per_anchor_loss"], inp["grids"], A)
+    for a, b in zip(loss_dict["NAKHW_loss"], nakhw_want):
+        assert_close_tensor(a, b, "NAKHW_loss")
+    ub = fsg.get_loss_upper_bound(loss_dict["NAKHW_loss"], N, 0.1, 1.0)
+    assert_close_scalar(-ub.item(), want["lower_bound"], "get_loss_upper_bound")
+    for a, b in zip(gb, bs):
+        assert_close_tensor(a.grad, b.grad, "grad bets level", rtol=2e-5)
+    if detach:
+        assert all(t.grad is None for t in gx)
+    else:
+        for a, b in zip(gx, xs):
+            assert_close_tensor(a.grad, b.grad, "grad logits level")
+    # the reference's in-place masking of the caller's list (gambler_heads.py:568-569)
+    off = 0
+    for i, (h, w_) in enumerate(inp["grids"]):
+        n = h * w_ * A
+        m = gtd["mask"][:, off:off + n].reshape(N, h, w_, A).permute(0, 3, 1, 2)
+        assert torch.equal(bets_list[i].detach().cpu(), bet_l[i] * m)
+        off += n
+
+
+def test_layout_roundtrip(cuda):
+    fsg = _fsg()
+    gen = torch.Generator().manual_seed(5)
+    levels = [torch.randn((2, 3 * 7, h, w), generator=gen) for (h, w) in [(9, 13), (5, 6), (2, 2)]]
+    want = orc.levels_to_flat(levels, 7)
+    got = fsg.ops.levels_to_flat([t.to(cuda) for t in levels], 7)
+    assert torch.equal(got.cpu(), want)
+    back = fsg.ops.flat_to_levels(got, [tuple(t.shape[1:]) for t in levels])
+    for a, b in zip(back, levels):
+        assert torch.equal(a.cpu(), b)
+
+
+# ------------------------------------------------------------------------------------------------ K3
+def _nms_inputs(n, ncls, seed, dup=True):
+    g = torch.Generator().manual_seed(seed)
+    boxes = torch.rand((n, 4), generator=g) * 100
+    boxes[:, 2:] += boxes[:, :2]                       # tests/test_nms_rotated.py:35-43
+    scores = torch.rand(n, generator=g)
+    if dup and n > 10:
+        scores[5] = scores[3]                          # tied scores -> stable order
+        boxes[7] = boxes[6]                            # identical boxes -> IoU exactly 1
+        boxes[9, 2:] = boxes[9, :2]                    # zero-area box (0/0 -> NaN never suppresses)
+    idxs = torch.randint(0, ncls, (n,), generator=g)
+    return boxes, scores, idxs
+
+
+@pytest.mark.parametrize("n,thr", [(1, 0.5), (2, 0.5), (300, 0.2), (2000, 0.5), (5000, 0.8), (8192, 0.5), (0, 0.5)])
+def test_nms_bit_exact(cuda, n, thr):
+    fsg = _fsg()
+    boxes, scores, _ = _nms_inputs(n, 1, 100 + n)
+    want = orc.nms(boxes, scores, thr)
+    got = fsg.nms(boxes.to(cuda), scores.to(cuda), thr)
+    assert_equal_int(got, want, "nms keep")
+
+
+@pytest.mark.parametrize("n,ncls,thr", [(2000, 50, 0.5), (2000, 50, 0.2), (2000, 50, 0.8), (5000, 80, 0.5),
+                                        (4000, 1230, 0.5), (3000, 1, 0.5)])
+def test_batched_nms_bit_exact(cuda, n, ncls, thr):
+    """tests/test_nms_rotated.py:45-66 sizes (N=2000, 50 classes, IoU 0.2/0.5/0.8) and the RetinaNet sizes."""
+    fsg = _fsg()
+    boxes, scores, idxs = _nms_inputs(n, ncls, 200 + n + ncls)
+    want = orc.batched_nms(boxes, scores, idxs, thr)
+    got = fsg.batched_nms(boxes.to(cuda), scores.to(cuda), idxs.to(cuda), thr)
+    assert_equal_int(got, want, "batched_nms keep")
+
+
+def test_nms_threshold_compare_is_in_double(cuda):
+    """IoU float(1/3) against threshold 1/3 (double): float(1/3) > 1/3 -> suppressed."""
+    fsg = _fsg()
+    boxes = torch.tensor([[0.0, 0.0, 2.0, 1.0], [1.0, 0.0, 3.0, 1.0]])
+    scores = torch.tensor([0.9, 0.8])
+    want = orc.nms(boxes, scores, 1.0 / 3.0)
+    got = fsg.nms(boxes.to(cuda), scores.to(cuda), 1.0 / 3.0)
+    assert_equal_int(got, want, "keep")
+
+
+def _detect_case(cuda, N, counts, K, seed, topk=1000):
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    inp = synthetic.inference_inputs(seed, N, counts, K)
+    res = fsg.ops.detect(inp["logits"].to(cuda), inp["deltas"].to(cuda), inp["anchors"].to(cuda),
+                         inp["level_offsets"], topk=topk, want_candidates=True)
+    offs = inp["level_offsets"]
+    for n in range(N):
+        cls = [inp["logits"][n, offs[i]:offs[i + 1]] for i in range(len(counts))]
+        reg = [inp["deltas"][n, offs[i]:offs[i + 1]] for i in range(len(counts))]
+        anc = [inp["anchors"][offs[i]:offs[i + 1]] for i in range(len(counts))]
+        (wb, ws, wc), (cb, cs, cc), keep = orc.inference_single_image(cls, reg, anc, K, topk_candidates=topk)
+        cnt = int(res["cand_count"][n].item())
+        # candidate selection: same (anchor, class) set in the same order, scores/boxes within fp32 tolerance
+        assert cnt == cb.shape[0], "candidate count %d vs %d" % (cnt, cb.shape[0])
+        assert_equal_int(res["cand_classes"][n, :cnt], cc, "cand classes")
+        assert_close_tensor(res["cand_scores"][n, :cnt], cs, "cand scores")
+        assert_close_tensor(res["cand_boxes"][n, :cnt], cb, "cand boxes", atol_scale=1e-6)
+        # NMS on the GPU's own candidates must be bit-exact with the oracle NMS on the same candidates
+        gb, gs, gc = res["cand_boxes"][n, :cnt].cpu(), res["cand_scores"][n, :cnt].cpu(), res["cand_classes"][n, :cnt].cpu()
+        keep2 = orc.batched_nms(gb, gs, gc, 0.5)[:100]
+        d = int(res["count"][n].item())
+        assert d == keep2.shape[0]
+        assert_equal_int(res["keep_idx"][n, :d], keep2, "keep idx")
+        assert torch.equal(res["boxes"][n, :d].cpu(), gb[keep2])
+        assert torch.equal(res["scores"][n, :d].cpu(), gs[keep2])
+        assert torch.equal(res["classes"][n, :d].cpu(), gc[keep2])
+        assert float(res["scores"][n, d:].abs().sum()) == 0.0
+
+
+def test_detect_small(cuda):
+    _detect_case(cuda, 2, [3000, 800, 200, 60, 20], 80, 41)
+
+
+def test_detect_multi_part_levels(cuda):
+    """Levels large enough to be split over several CTAs (merge path) and to trigger in-loop pruning."""
+    _detect_case(cuda, 1, [24000, 6000, 1500], 80, 42)
+
+
+def test_detect_small_topk_and_lvis_classes(cuda):
+    _detect_case(cuda, 1, [900, 300], 1230, 43, topk=100)
