@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the per-anchor dense-detection hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-secondary]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A *step* is one pass of the fused match + gambler-loss forward/backward (K1 + K2: four kernel launches) over
+one batch of synthetic COCO-shaped input: BASELINE config 2 -- RetinaNet R50-FPN + gambler, 800x1333 images
+(padded to 800x1344), 16 images per GPU, K = 80 classes, A = 3 anchors/cell, R = 67 200 anchors/image,
+8 GT boxes/image with one GT-free image.  With N GPUs every rank owns 16 images (weak scaling); the only
+exchange is the all-reduce of [num_foreground, S_batch] between the matching and the loss kernels.
+
+Prints ONE JSON line (rank 0).  ``value`` = anchors/s with inputs resident in HBM, timed with CUDA events,
+max over ranks.  ``e2e`` = the same step through the public API from pinned HOST buffers (H2D of logits,
+deltas, bets, GT each step and a D2H read of the loss).  ``roofline`` = the dominant kernel (K2 main pass)
+against the measured HBM copy bandwidth.  ``cpu_baseline`` = the oracle port (the reference's algorithm in
+torch-CPU ops) timed on this box's host cores on a bounded sample.  ``--impl reference`` times only that.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "anchors/sec (match+gambler loss fwd/bwd)"
+UNIT = "anchors/s"
+IMG_H, IMG_W, K_CLASSES, IMGS_PER_GPU, GT_PER_IMG = 800, 1333, 80, 16, 8
+WORKLOAD = ("config2: RetinaNet R50-FPN + gambler, synthetic 800x1333 (padded 800x1344), %d img/GPU, K=%d, A=3, "
+            "R=67200 anchors/img, %d GT/img (one GT-free image), L_BAHW, focal(0.25,2), T=0.1"
+            % (IMGS_PER_GPU, K_CLASSES, GT_PER_IMG))
+CPU_SAMPLE_IMAGES = 2
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is busy (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(num_images):
+    """The reference's CPU implementation of the step (oracle port), on `num_images` images of config 2."""
+    from oracle import dense_oracle as orc
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    inp = synthetic.train_inputs(2, num_images, IMG_H, IMG_W, K_CLASSES, M=GT_PER_IMG, empty_image=False)
+
+    def step():
+        out = orc.train_step(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], inp["logits"], inp["deltas"],
+                             inp["bets"], K_CLASSES, 1.0, 1.0, -1.0)
+        return float(out["total"])
+
+    return step, num_images * inp["R"]
+
+
+def time_cpu(step, reps, warmup):
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path for this step, all host threads, bounded sample."""
+    if rank != 0:
+        return
+    step, anchors = cpu_reference_step_fn(CPU_SAMPLE_IMAGES)
+    ts = time_cpu(step, args.steps, max(1, min(args.warmup, 3)))
+    sec = sum(ts) / len(ts)
+    val = anchors / sec
+    cores = torch.get_num_threads()
+    sample = "%d of %d images of the config-2 batch per step (linear in images)" % (CPU_SAMPLE_IMAGES, IMGS_PER_GPU)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def secondary_metrics(dev, fsg):
+    """NMS images/s (config 4) and the matcher stress (config 5), short runs; reported beside the headline."""
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    out = {}
+    hbm, _ = measured_peaks()
+    # config 4: 32 images x 5 levels x 24 000 anchors, K=80, top-1000/level, NMS 0.5, 100 detections
+    N4 = 32
+    inp = synthetic.inference_inputs(4, 1, [24000] * 5, K_CLASSES)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    logits = (torch.randn((N4, inp["R"], K_CLASSES), generator=g) * 1.5 + synthetic.PRIOR_LOGIT).to(dev)
+    deltas = (torch.randn((N4, inp["R"], 4), generator=g) * 0.2).to(dev)
+    anchors = inp["anchors"].to(dev)
+    offs = inp["level_offsets"]
+    run = lambda: fsg.ops.detect(logits, deltas, anchors, offs)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    scan_bytes = 4.0 * K_CLASSES * inp["R"] * N4
+    out["detect_config4"] = {"images_per_s": N4 / (ms * 1e-3), "ms_per_batch": ms, "batch": N4,
+                             "scan_hbm_frac": scan_bytes / (ms * 1e-3) / (hbm * 1e9)}
+    del logits, deltas
+    # config 5: 200 GT x 1M anchors per image, 8 images, allow_low_quality_matches
+    inp5 = synthetic.matcher_stress_inputs(5, 8, 1000000, 200)
+    a5 = inp5["anchors"].to(dev)
+    gt5 = fsg.ops.PackedGT.from_lists(inp5["gt_boxes"], inp5["gt_classes"], dev)
+    run5 = lambda: fsg.ops.match_anchors(a5, gt5, 80, want=("matches", "match_labels"), picky_thresholds=None)
+    for _ in range(3):
+        run5()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        run5()
+    e1.record()
+    torch.cuda.synchronize()
+    ms5 = e0.elapsed_time(e1) / reps
+    out["match_config5"] = {"anchors_per_s": 8e6 / (ms5 * 1e-3), "ms_per_batch": ms5,
+                            "iou_pairs_per_s": 8e6 * 200 / (ms5 * 1e-3),
+                            "hbm_frac": 25.0 * 8e6 / (ms5 * 1e-3) / (hbm * 1e9)}
+    return out
+
+
+def run_ours(args, rank, local_rank, world):
+    import full_scale_gambler_for_object_detection_b200 as fsg
+    from full_scale_gambler_for_object_detection_b200 import _lib, synthetic
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: this path has no CPU implementation")
+    fsg.ops.lib()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    # ---- synthetic batch: identical generator on every rank, different seed offset per rank
+    inp = synthetic.train_inputs(2 + 1000 * rank, IMGS_PER_GPU, IMG_H, IMG_W, K_CLASSES, M=GT_PER_IMG)
+    N, R, K = inp["N"], inp["R"], K_CLASSES
+    host = {k: inp[k].pin_memory() for k in ("logits", "deltas", "bets")}
+    anchors = inp["anchors"].to(dev)
+    cfg = fsg.DenseLossConfig(num_classes=K)
+    coeffs = (1.0, 1.0, -1.0)
+
+    logits = host["logits"].to(dev).requires_grad_(True)
+    deltas = host["deltas"].to(dev).requires_grad_(True)
+    bets = host["bets"].to(dev).requires_grad_(True)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], dev)
+
+    main_events = []
+
+    def step(record=False):
+        if record:
+            orig = fsg.ops.loss_main
+
+            def timed(*a, **kw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = orig(*a, **kw)
+                e1.record()
+                main_events.append((e0, e1))
+                return r
+
+            fsg.ops.loss_main = timed
+            try:
+                return fsg.dense_train_step(logits, deltas, bets, anchors, gt, cfg, coeffs, group=group)
+            finally:
+                fsg.ops.loss_main = orig
+        return fsg.dense_train_step(logits, deltas, bets, anchors, gt, cfg, coeffs, group=group)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    for _ in range(args.warmup):
+        step()
+    # ---- timed region: exactly K steps, device-timed, barrier + synchronize on both sides
+    barrier()
+    launches0 = _lib.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        res = step(record=True)
+    ev1.record()
+    barrier()
+    launches = _lib.LAUNCHES - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    main_ms = sum(a.elapsed_time(b) for a, b in main_events) / max(1, len(main_events))
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * N * R / (ms_per_step * 1e-3)
+
+    # ---- end to end: host buffers in, loss out, through the public API
+    h2d = sum(host[k].numel() * 4 for k in host) + sum(b.numel() * 4 + c.numel() * 8 for b, c in
+                                                       zip(inp["gt_boxes"], inp["gt_classes"])) + 4 * (N + 1)
+    d2h = 4
+
+    def e2e_step():
+        x = host["logits"].to(dev, non_blocking=True).requires_grad_(True)
+        d = host["deltas"].to(dev, non_blocking=True).requires_grad_(True)
+        b = host["bets"].to(dev, non_blocking=True).requires_grad_(True)
+        g = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], dev)
+        r = fsg.dense_train_step(x, d, b, anchors, g, cfg, coeffs, group=group)
+        return r.total.item()
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(e2e_steps):
+        loss_val = e2e_step()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps
+    e2e_value = world * N * R / (e2e_ms * 1e-3)
+
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = secondary_metrics(dev, fsg)
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- CPU baseline on rank 0 at N=1 only (bounded sample)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        stepf, anchors_cpu = cpu_reference_step_fn(CPU_SAMPLE_IMAGES)
+        ts = time_cpu(stepf, 3, 1)
+        cpu_baseline = {"value": anchors_cpu / min(ts), "unit": UNIT, "cores": torch.get_num_threads(),
+                        "kind": "port", "host_cpus": os.cpu_count(),
+                        "sample": "%d of %d images of the config-2 batch, 1 warm-up + min of 3 (linear in images)"
+                                  % (CPU_SAMPLE_IMAGES, IMGS_PER_GPU)}
+
+    if rank == 0:
+        hbm, which = measured_peaks()
+        main_bytes = (8 * K + 72) * N * R                # K2 main pass, DESIGN.md section 4
+        step_bytes = (8 * K + 76) * N * R                # whole fused step, SURVEY.md section 8d
+        achieved = main_bytes / (main_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (344 MB logits + 344 MB grads per GPU)",
+                       "anchors_per_step_per_gpu": N * R, "parallelism": "image-sharded x%d" % world},
+            "roofline": {"bound": "hbm", "kernel": "loss_main_kernel (K2 main pass)", "achieved": achieved,
+                         "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": None, "bytes_per_anchor": 8 * K + 72, "kernel_ms": main_ms,
+                         "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps, "loss": loss_val},
+            "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "losses": {"loss_cls": float(res.loss_cls.item()), "loss_box_reg": float(res.loss_box_reg.item()),
+                       "gambler_loss": float(res.gambler_loss.item()),
+                       "num_foreground": float(res.num_foreground.item())},
+        }
+        if secondary is not None:
+            line["secondary"] = secondary
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-4 / config-5 side measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,7 @@ from typing import Optional, Sequence
 
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, sharded
 
 
 @dataclass
@@ -127,7 +127,7 @@ class _FusedStep(torch.autograd.Function):
         stats = m["stats"]
         if group is not None:
             # the path's only exchange step before the main pass: global foreground count (+ batch normaliser)
-            torch.distributed.all_reduce(stats[:_lib.STATS_HEADER], group=group)
+            sharded.all_reduce_stats(stats, group)
         need_gl = not detach_pred
         need_gd = c_reg != 0.0
         out = ops.loss_main(logits_c, m["gt_classes"], params, stats, pred_deltas=deltas_c, anchors=anchors, gt=gt,
@@ -135,7 +135,7 @@ class _FusedStep(torch.autograd.Function):
                             want_grad_logits=need_gl, want_grad_deltas=need_gd, want_weights=want_weights)
         scalars = out["scalars"]
         if group is not None and cfg.norm_mode == _lib.NORM_BATCH:
-            torch.distributed.all_reduce(scalars[2:3], group=group)
+            sharded.all_reduce_batch_weighted_sum(scalars, group)
         grad_bets = ops.loss_post(bets_c, m["mask"], out["per_anchor_loss"], params, stats, scalars)
         ctx.save_for_backward(out.get("grad_logits"), out.get("grad_deltas"), grad_bets)
         ctx.has_gl = need_gl

@@ -1,0 +1,57 @@
+"""Multi-GPU form of the path: shard the batch by image, one process per GPU.
+
+Matching, encode, per-anchor loss, d/d logits, decode and NMS are independent per image, so ranks own
+contiguous blocks of images (the reference's data-parallel split, detectron2/data/build.py:350-362) and the
+data path needs no collective.  The only exchange is a handful of scalars:
+
+  before the main pass   all-reduce(SUM) [num_foreground, S_batch]        (the gradient scale depends on it)
+  L_BAHW_extendtobatch   all-reduce(SUM) sum_n A[n]                       (before d/d bets)
+  for reporting          all-reduce(SUM) of the five loss sums
+
+Parity definition: the sharded result equals the reference run single-process on the whole batch (global
+``num_foreground``), which intentionally differs from the reference's own DDP behaviour (local normaliser,
+retinanet.py:226,238, gradients averaged by DDP).  These helpers are device-agnostic torch.distributed code
+(NCCL on the GPUs; the CPU tests drive them over gloo).
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def image_shard(num_images, world_size, rank):
+    """Contiguous block of images owned by ``rank`` (equal blocks; num_images must divide evenly, as
+    IMS_PER_BATCH // world_size does in the reference)."""
+    if num_images % world_size != 0:
+        raise ValueError("batch of %d images does not split evenly over %d ranks" % (num_images, world_size))
+    per = num_images // world_size
+    return slice(rank * per, (rank + 1) * per)
+
+
+def all_reduce_stats(stats, group=None):
+    """stats = [num_foreground, S_batch, S[n]...] (double).  Sums the two global entries over ranks in
+    place; the per-image normalisers S[n] stay local."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats[:_lib.STATS_HEADER], op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def all_reduce_batch_weighted_sum(scalars, group=None):
+    """L_BAHW_extendtobatch only: scalars[2] = sum_n A[n] must be global before the post pass."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(scalars[2:3], op=dist.ReduceOp.SUM, group=group)
+    return scalars
+
+
+def global_losses(scalars, stats, coeffs, group=None):
+    """Whole-batch loss values from the per-rank sums: returns a (4,) double tensor
+    [loss_cls, loss_box_reg, gambler_loss, total].  ``stats[0]`` must already be global."""
+    sums = scalars[:5].clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    nf = torch.clamp(stats[0], min=1.0)
+    loss_cls = sums[0] / nf
+    loss_reg = sums[1] / nf
+    gam = -sums[2]
+    total = coeffs[0] * loss_cls + coeffs[1] * loss_reg + coeffs[2] * gam
+    return torch.stack((loss_cls, loss_reg, gam, total))

@@ -106,6 +106,14 @@ def run_reference_train(ref, inp, K, hw, coeffs=(1.0, 1.0, -1.0), detach_pred=Fa
     )
 
 
+def sample_rows(gt_classes, K, stride=41):
+    """Flattened (n*R + r) anchor rows whose grad_logits go into the fixture."""
+    g = gt_classes.flatten()
+    special = (g != K).nonzero().flatten()           # foreground and ignored anchors
+    strided = torch.arange(0, g.numel(), stride)
+    return torch.unique(torch.cat((special, strided)))
+
+
 def rel(a, b):
     a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
     d = (a - b).abs().max().item() if a.numel() else 0.0
@@ -140,8 +148,10 @@ def make_train(ref):
                   "lower_bound", "per_anchor_loss", "weights", "grad_logits", "grad_deltas", "grad_bets"):
             print("    %-22s rel-to-max err %.3g" % (k, rel(got[k], want[k])))
         keep = dict(want)
-        if K > 200:  # keep the LVIS fixture small: store a strided sample of the big tensors
-            keep["grad_logits"] = want["grad_logits"][:, ::37].contiguous()
+        # keep fixtures small: grad_logits only for every foreground/ignored anchor plus a strided sample
+        rows = sample_rows(want["gt_classes"], K)
+        keep["grad_rows"] = rows
+        keep["grad_logits"] = want["grad_logits"].reshape(-1, K)[rows].contiguous()
         np.savez_compressed(os.path.join(OUT, name + ".npz"),
                             params=np.asarray([cid, N, H, W, K, M], dtype=np.int64),
                             coeffs=np.asarray(coeffs, dtype=np.float64), detach=np.asarray(int(detach)),

@@ -90,7 +90,8 @@ def test_fused_match_vs_oracle(cuda, N, H, W, M):
     for k in ("matches", "match_labels", "picky_labels", "gt_classes", "mask"):
         assert_equal_int(got[k], want[k], k)
     assert_close_tensor(got["gt_deltas"], want["gt_deltas"], "gt_deltas")
-    assert int((want["match_labels"] == 1).sum()) > 0
+    if N > 1:  # N == 1: the synthetic batch's only image is the GT-free one (all-background path)
+        assert int((want["match_labels"] == 1).sum()) > 0
 
 
 def test_fused_match_stress_slice(cuda):
@@ -141,7 +142,7 @@ def test_box2box_roundtrip_and_parity(cuda):
 
 
 # ------------------------------------------------------------------------------------------------ K2
-def _check_step(cuda, inp, K, coeffs, cfg_kwargs=None, detach_pred=False):
+def _check_step(cuda, inp, K, coeffs, cfg_kwargs=None, detach_pred=False, bets_floor=1e-6):
     fsg = _fsg()
     cfg_kwargs = cfg_kwargs or {}
     cfg = fsg.DenseLossConfig(num_classes=K, **cfg_kwargs)
@@ -175,7 +176,8 @@ def _check_step(cuda, inp, K, coeffs, cfg_kwargs=None, detach_pred=False):
         assert x.grad is None
     if coeffs[1] != 0:
         assert_close_tensor(d.grad, want["grad_deltas"], "grad_deltas")
-    assert_close_tensor(b.grad, want["grad_bets"], "grad_bets", rtol=2e-5)
+    # d/d bets = -(m/S)(l - A) cancels when l ~ A: absolute floor = fp32 rounding of l and A themselves
+    assert_close_tensor(b.grad, want["grad_bets"], "grad_bets", atol_scale=bets_floor)
     return res
 
 
@@ -196,7 +198,11 @@ def test_step_gambler_phase(cuda):
                                 dict(gambler_gamma=2.0), dict(smooth_l1_beta=0.0, gambler_temperature=0.03)])
 def test_step_variants(cuda, kw):
     inp = _train_inputs(3, 3, 256, 256, 80, M=5)
-    _check_step(cuda, inp, 80, (1.0, 0.5, -2.0), kw)
+    # "sigmoid" mode: torch computes BCE-with-logits as (1-t)*x - log_sigmoid(x), which cancels for the
+    # (typical) very negative logits, so the reference's own fp32 per-anchor loss is only good to ~5e-6 and its
+    # d/d bets to 4e-6 of the tensor's scale (measured against an fp64 evaluation of the same graph).
+    floor = 1e-5 if kw.get("gambler_loss_mode") == "sigmoid" else 1e-6
+    _check_step(cuda, inp, 80, (1.0, 0.5, -2.0), kw, bets_floor=floor)
 
 
 @pytest.mark.parametrize("K", [1230, 3, 20, 1])
@@ -317,7 +323,7 @@ def test_dropin_gambler_loss(cuda, detach):
     ub = fsg.get_loss_upper_bound(loss_dict["NAKHW_loss"], N, 0.1, 1.0)
     assert_close_scalar(-ub.item(), want["lower_bound"], "get_loss_upper_bound")
     for a, b in zip(gb, bs):
-        assert_close_tensor(a.grad, b.grad, "grad bets level", rtol=2e-5)
+        assert_close_tensor(a.grad, b.grad, "grad bets level", atol_scale=1e-6)
     if detach:
         assert all(t.grad is None for t in gx)
     else:

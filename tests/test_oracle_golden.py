@@ -1,0 +1,186 @@
+"""CPU: the oracle against the reference's outputs stored in tests/golden (and, when the reference tree is
+present -- the build container -- against the reference executed live)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dense_oracle as orc
+from oracle import ref_loader
+from tests import golden_util as gu
+from tests.util import assert_close_scalar, assert_close_tensor, assert_equal_int
+
+
+def test_pairwise_iou_reference_kat():
+    """tests/test_boxes.py:36-59 of the reference, replayed on the oracle."""
+    b1 = torch.tensor([[0.0, 0.0, 1.0, 1.0], [0.0, 0.0, 1.0, 1.0]])
+    b2 = torch.tensor([[0.0, 0.0, 1.0, 1.0], [0.0, 0.0, 0.5, 1.0], [0.0, 0.0, 1.0, 0.5],
+                       [0.0, 0.0, 0.5, 0.5], [0.5, 0.5, 1.0, 1.0], [0.5, 0.5, 1.5, 1.5]])
+    expected = torch.tensor([[1.0, 0.5, 0.5, 0.25, 0.25, 0.25 / (2 - 0.25)]] * 2)
+    assert torch.allclose(orc.pairwise_iou(b1, b2), expected)
+
+
+def test_anchor_generator_reference_kat():
+    """tests/test_anchor_generator.py:14-43 (sizes [32,64], ratios [.25,1,4], stride 4, 1x2 grid)."""
+    from full_scale_gambler_for_object_detection_b200.anchor_generator import grid_anchors
+
+    expected = torch.tensor([
+        [-32.0, -8.0, 32.0, 8.0], [-16.0, -16.0, 16.0, 16.0], [-8.0, -32.0, 8.0, 32.0],
+        [-64.0, -16.0, 64.0, 16.0], [-32.0, -32.0, 32.0, 32.0], [-16.0, -64.0, 16.0, 64.0],
+        [-28.0, -8.0, 36.0, 8.0], [-12.0, -16.0, 20.0, 16.0], [-4.0, -32.0, 12.0, 32.0],
+        [-60.0, -16.0, 68.0, 16.0], [-28.0, -32.0, 36.0, 32.0], [-12.0, -64.0, 20.0, 64.0]])
+    for fn in (grid_anchors, orc.grid_anchors):
+        got = fn([(1, 2)], [4], [[32, 64]], [[0.25, 1, 4]])[0]
+        assert torch.allclose(got, expected)
+
+
+def test_box2box_roundtrip_reference_test():
+    """tests/test_box2box_transform.py:16-30."""
+    torch.manual_seed(0)
+    w = (5, 5, 10, 10)
+    src = torch.rand(10, 4) + torch.tensor([10, 10, 20, 20], dtype=torch.float)
+    dst = torch.rand(10, 4) + torch.tensor([10, 10, 20, 20], dtype=torch.float)
+    assert torch.allclose(dst, orc.apply_deltas(orc.get_deltas(src, dst, w), src, w))
+
+
+def test_box2box_golden():
+    g = gu.load("box2box")
+    w = tuple(float(v) for v in g["weights"])
+    assert torch.allclose(orc.get_deltas(g["src"], g["dst"], w), g["deltas"], rtol=1e-6, atol=0)
+    assert torch.allclose(orc.apply_deltas(g["big"], g["boxes"], w), g["applied"], rtol=1e-6, atol=1e-6)
+
+
+def test_matcher_golden():
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    g = gu.load("matcher_stress")
+    cid, N, R, M = [int(v) for v in g["params"]]
+    inp = synthetic.matcher_stress_inputs(cid, N, R, M)
+    inp["anchors"][0, 100] = inp["anchors"][0, 99]
+    inp["anchors"][1, :50] = inp["gt_boxes"][1][:50]
+    for i in range(N):
+        q = orc.pairwise_iou(inp["gt_boxes"][i], inp["anchors"][i])
+        assert torch.equal(q[:, :512], g["iou_sample_%d" % i])
+        assert torch.equal(q.max(dim=1).values, g["iou_rowmax_%d" % i])
+        m, l = orc.matcher(q, [0.4, 0.5], [0, -1, 1], True)
+        assert_equal_int(m, g["matches_%d" % i], "matches")
+        assert_equal_int(l, g["labels_%d" % i], "labels")
+        _, pl = orc.matcher(q, [0.4, 0.9], [0, -1, 1], True)
+        assert_equal_int(pl, g["picky_labels_%d" % i], "picky labels")
+        m2, l2 = orc.matcher(q, [0.3, 0.7], [0, -1, 1], False)
+        assert_equal_int(m2, g["nolq_matches_%d" % i], "no-lq matches")
+        assert_equal_int(l2, g["nolq_labels_%d" % i], "no-lq labels")
+    q = torch.tensor([[0.9, 0.3, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]])
+    m, l = orc.matcher(q, [0.4, 0.5], [0, -1, 1], True)
+    assert_equal_int(m, g["quirk_matches"], "quirk matches")
+    assert_equal_int(l, g["quirk_labels"], "quirk labels")
+    m, l = orc.matcher(torch.zeros((0, 7)), [0.4, 0.5], [0, -1, 1], True)
+    assert_equal_int(m, g["empty_matches"], "empty matches")
+    assert_equal_int(l, g["empty_labels"], "empty labels")
+
+
+def test_nms_golden():
+    g = gu.load("nms")
+    for name in ("a", "b", "c"):
+        b, s, i = g["boxes_" + name], g["scores_" + name], g["idxs_" + name]
+        for thr in (0.2, 0.5, 0.8):
+            tag = "%s_%02d" % (name, int(thr * 10))
+            assert_equal_int(orc.nms(b, s, thr), g["nms_" + tag], "nms " + tag)
+            assert_equal_int(orc.batched_nms(b, s, i, thr), g["batched_" + tag], "batched " + tag)
+
+
+def test_nms_matches_reference_python_nms():
+    """The pure-Python greedy NMS the reference's tests use as their oracle (tests/test_nms_rotated.py:11-33):
+    sort descending, keep the head, drop everything with IoU > thr."""
+    g = torch.Generator().manual_seed(9)
+    boxes = torch.rand((300, 4), generator=g) * 100
+    boxes[:, 2:] += boxes[:, :2]
+    scores = torch.rand(300, generator=g)
+    for thr in (0.2, 0.5, 0.8):
+        picked = []
+        idx = scores.sort(descending=True, stable=True).indices
+        while len(idx) > 0:
+            cur = idx[0]
+            picked.append(int(cur))
+            if len(idx) == 1:
+                break
+            rest = idx[1:]
+            iou = orc.pairwise_iou(boxes[rest], boxes[cur][None]).squeeze(1)
+            idx = rest[iou <= thr]
+        assert orc.nms(boxes, scores, thr).tolist() == picked
+
+
+def test_inference_golden():
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    g = gu.load("inference")
+    p = [int(v) for v in g["params"]]
+    inp = synthetic.inference_inputs(p[0], p[1], p[2:7], p[7])
+    offs = inp["level_offsets"]
+    for n in range(p[1]):
+        cls = [inp["logits"][n, offs[i]:offs[i + 1]] for i in range(5)]
+        reg = [inp["deltas"][n, offs[i]:offs[i + 1]] for i in range(5)]
+        anc = [inp["anchors"][offs[i]:offs[i + 1]] for i in range(5)]
+        (b, s, c), _, _ = orc.inference_single_image(cls, reg, anc, p[7])
+        assert_equal_int(c, g["classes_%d" % n], "classes")
+        assert torch.equal(s, g["scores_%d" % n]) and torch.equal(b, g["boxes_%d" % n])
+
+
+@pytest.mark.parametrize("name", gu.TRAIN_CASES)
+def test_train_step_golden(name):
+    inp, g, coeffs, detach, gcfg, K = gu.train_case(name)
+    okw = {gu.ORACLE_KW[k]: v for k, v in gcfg.items()}
+    got = orc.train_step(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], inp["logits"], inp["deltas"],
+                         inp["bets"], K, *coeffs, detach_pred=detach, **okw)
+    assert_equal_int(got["gt_classes"], g["gt_classes"], "gt_classes")
+    assert_equal_int(got["mask"], g["mask"], "mask")
+    for k in ("loss_cls", "loss_box_reg", "gambler_loss", "total", "loss_before_weighting", "lower_bound"):
+        assert_close_scalar(got[k], g[k], k, rtol=2e-6)
+    for k in ("gt_deltas", "per_anchor_loss", "weights", "grad_deltas"):
+        assert_close_tensor(got[k], g[k], k, rtol=2e-6)
+    # d/d bets = -(m/S)(l - A) cancels when l ~ A: the absolute floor is fp32 rounding of l and A themselves
+    assert_close_tensor(got["grad_bets"], g["grad_bets"], "grad_bets", rtol=2e-6, atol_scale=1e-6)
+    assert_close_tensor(got["grad_logits"].reshape(-1, K)[g["grad_rows"]], g["grad_logits"], "grad_logits", rtol=2e-6)
+
+
+def test_gradient_formulas_match_autograd_fp64():
+    """the closed forms the CUDA kernels use, against autograd in fp64."""
+    torch.manual_seed(1)
+    N, R, K, T = 2, 50, 7, 0.1
+    x = torch.randn(N, R, K, dtype=torch.float64, requires_grad=True)
+    b = torch.rand(N, R, dtype=torch.float64, requires_grad=True)
+    gtc = torch.randint(-1, K + 1, (N, R))
+    m = torch.randint(0, 2, (N, R))
+    out = orc.gambler_loss(x, b, gtc, m, K, temperature=T)
+    out["gambler_loss"].backward()
+    t, _ = orc.one_hot_targets(gtc.flatten(), K, x.detach().reshape(-1, K))
+    t = t.reshape(N, R, K)
+    p = torch.sigmoid(x.detach())
+    pt = p * t + (1 - p) * (1 - t)
+    at = 0.25 * t + 0.75 * (1 - t)
+    fprime = at * (2 * t - 1) * (1 - pt) ** 2 * (2 * pt * torch.log(pt) - (1 - pt))
+    w = b.detach() * m + T
+    S = w.sum(1, keepdim=True)
+    w_hat = w / S
+    valid = (gtc >= 0).double()[..., None]
+    assert torch.allclose(x.grad, -w_hat[..., None] * fprime * valid, atol=1e-12)
+    ell = out["per_anchor_loss"]
+    A = (w_hat * ell).sum(1, keepdim=True)
+    assert torch.allclose(b.grad, -(m / S) * (ell - A), atol=1e-12)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_oracle_vs_live_reference():
+    """Build container only: run the reference's own files on a fresh seed and compare."""
+    from oracle import make_golden as mg
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    ref = ref_loader.load_reference()
+    inp = synthetic.train_inputs(77, 2, 192, 256, 80, M=4)
+    want = mg.run_reference_train(ref, inp, 80, (192, 256))
+    got = orc.train_step(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], inp["logits"], inp["deltas"],
+                         inp["bets"], 80, 1.0, 1.0, -1.0)
+    assert_equal_int(got["gt_classes"], want["gt_classes"], "gt_classes")
+    assert_equal_int(got["mask"], want["mask"], "mask")
+    for k in ("loss_cls", "loss_box_reg", "gambler_loss"):
+        assert_close_scalar(got[k], want[k], k, rtol=2e-6)
+    assert_close_tensor(got["grad_logits"], want["grad_logits"], "grad_logits", rtol=2e-6)
