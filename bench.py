@@ -38,6 +38,9 @@ WORKLOAD = ("config2: RetinaNet R50-FPN + gambler, synthetic 800x1333 (padded 80
             "R=67200 anchors/img, %d GT/img (one GT-free image), L_BAHW, focal(0.25,2), T=0.1"
             % (IMGS_PER_GPU, K_CLASSES, GT_PER_IMG))
 CPU_SAMPLE_IMAGES = 2
+# dram__bytes_read.sum + dram__bytes_write.sum of one loss_main_kernel launch on this workload, from the
+# committed `ncu --set full` capture (profiles/); None until a capture of the current kernel exists
+NCU_TRAFFIC_BYTES = None
 
 
 def measured_peaks():
@@ -225,26 +228,19 @@ def run_ours(args, rank, local_rank, world):
     bets = host["bets"].to(dev).requires_grad_(True)
     gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], dev)
 
-    main_events = []
+    plan = fsg.DenseStepPlan(N, R, K, cfg, dev, coeffs, group=group)
+    x_s, d_s, b_s = logits.detach(), deltas.detach(), bets.detach()
+    graphed = False
+    try:
+        plan.capture(x_s, d_s, b_s, anchors, gt)   # the whole step (4 kernels + 2 memset nodes) = one graph launch
+        graphed = True
+    except Exception as e:  # e.g. a collective that cannot be captured: fall back to direct launches
+        if rank == 0:
+            print("graph capture unavailable (%s); timing direct launches" % (type(e).__name__,), file=sys.stderr)
+        plan.graph = None
 
-    def step(record=False):
-        if record:
-            orig = fsg.ops.loss_main
-
-            def timed(*a, **kw):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                r = orig(*a, **kw)
-                e1.record()
-                main_events.append((e0, e1))
-                return r
-
-            fsg.ops.loss_main = timed
-            try:
-                return fsg.dense_train_step(logits, deltas, bets, anchors, gt, cfg, coeffs, group=group)
-            finally:
-                fsg.ops.loss_main = orig
-        return fsg.dense_train_step(logits, deltas, bets, anchors, gt, cfg, coeffs, group=group)
+    def step():
+        return plan.replay() if graphed else plan.run(x_s, d_s, b_s, anchors, gt)
 
     def barrier():
         if world > 1:
@@ -263,18 +259,37 @@ def run_ours(args, rank, local_rank, world):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        res = step(record=True)
+        res = step()
     ev1.record()
     barrier()
     launches = _lib.LAUNCHES - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
-    main_ms = sum(a.elapsed_time(b) for a, b in main_events) / max(1, len(main_events))
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = world * N * R / (ms_per_step * 1e-3)
+
+    # ---- per-kernel device time: each stage launched back to back K times between two CUDA events on the
+    #      launching stream (no host gaps: the queue stays ahead of the device); inputs exceed L2
+    def stage_ms(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    reps = max(10, min(args.steps, 100))
+    match_ms = stage_ms(lambda: plan.stage_match(b_s, anchors, gt), reps)
+    main_ms = stage_ms(lambda: plan.stage_main(x_s, d_s, b_s, anchors, gt), reps)
+    post_ms = stage_ms(lambda: plan.stage_post(b_s), reps)
+    barrier()
 
     # ---- end to end: host buffers in, loss out, through the public API
     h2d = sum(host[k].numel() * 4 for k in host) + sum(b.numel() * 4 + c.numel() * 8 for b, c in
@@ -286,9 +301,11 @@ def run_ours(args, rank, local_rank, world):
         d = host["deltas"].to(dev, non_blocking=True).requires_grad_(True)
         b = host["bets"].to(dev, non_blocking=True).requires_grad_(True)
         g = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], dev)
-        r = fsg.dense_train_step(x, d, b, anchors, g, cfg, coeffs, group=group)
+        r = fsg.dense_train_step(x, d, b, anchors, g, cfg, coeffs, group=group, plan=plan_e2e)
+        r.total.backward()          # grads are produced by the same fused kernels; this only hands them to autograd
         return r.total.item()
 
+    plan_e2e = fsg.DenseStepPlan(N, R, K, cfg, dev, coeffs, group=group)
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(3):
         e2e_step()
@@ -332,11 +349,14 @@ def run_ours(args, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (344 MB logits + 344 MB grads per GPU)",
-                       "anchors_per_step_per_gpu": N * R, "parallelism": "image-sharded x%d" % world},
+                       "anchors_per_step_per_gpu": N * R, "parallelism": "image-sharded x%d" % world,
+                       "launch": "CUDA graph replay" if graphed else "direct launches"},
             "roofline": {"bound": "hbm", "kernel": "loss_main_kernel (K2 main pass)", "achieved": achieved,
                          "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "bytes_per_anchor": 8 * K + 72, "kernel_ms": main_ms,
-                         "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm},
+                         "traffic": NCU_TRAFFIC_BYTES, "bytes_per_anchor": 8 * K + 72, "kernel_ms": main_ms,
+                         "timing": "%d back-to-back launches between two CUDA events" % reps,
+                         "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / hbm,
+                         "stage_ms": {"match_2_kernels": match_ms, "loss_main": main_ms, "loss_post": post_ms}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "loss": loss_val},
             "cpu_baseline": cpu_baseline,

@@ -91,17 +91,29 @@ __device__ __forceinline__ float log1p_unit(float e) {
   return p * e;
 }
 
+// MUFU.EX2 / MUFU.RCP without the libdevice range fix-ups (inputs are bounded: argument <= 0, 1+e in [1,2])
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // shared sub-expressions of sigmoid / BCE for one logit (t = 0 side):
 //   p = sigmoid(x), omp = 1 - p (computed as sigmoid(-x), no cancellation), ce0 = softplus(x)
 __device__ __forceinline__ void sigmoid_parts(float x, float& p, float& omp, float& ce0) {
-  const float e = exp2f(-fabsf(x) * 1.4426950408889634f);  // MUFU.EX2
-  const float r = __frcp_rn(1.f + e);
+  const float e = ex2_approx(fabsf(x) * -1.4426950408889634f);  // exp(-|x|) in (0,1]
+  const float r = rcp_approx(1.f + e);
   const float er = e * r;
   const float l1p = log1p_unit(e);
   const bool pos = x >= 0.f;
   p = pos ? r : er;
   omp = pos ? er : r;
-  ce0 = pos ? x + l1p : l1p;
+  ce0 = fmaxf(x, 0.f) + l1p;
 }
 
 // one element with target t = 0, gamma = 2:  loss/(1-alpha) and dloss/dx/(1-alpha)
@@ -219,8 +231,10 @@ __global__ void __launch_bounds__(256) loss_prepass_kernel(const int64_t* __rest
 // ------------------------------------------------------------------------------------------
 // main pass
 // ------------------------------------------------------------------------------------------
-template <int V, int BATCH, int VARIANT>
-__global__ void __launch_bounds__(kLossBlock) loss_main_kernel(const LossArgs A) {
+template <int V, int BATCH, int VARIANT, int GT>
+__global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 2)) loss_main_kernel(const LossArgs A) {
+  // GT > 0: "exact" instantiation, G == GT lanes per anchor and K == V*GT*BATCH (no predication in the
+  // element loop); GT == 0: G and K are run-time values.
   constexpr bool kWrite = (VARIANT != kFastNoWrite);
   constexpr bool kFast = (VARIANT != kGeneric);
   __shared__ float s_part[kLossBlock / 32][5];
@@ -228,10 +242,12 @@ __global__ void __launch_bounds__(kLossBlock) loss_main_kernel(const LossArgs A)
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = blockIdx.y;
-  const int G = A.G;
+  const int G = GT > 0 ? GT : A.G;
+  const int logG = GT > 0 ? (GT == 1 ? 0 : GT == 2 ? 1 : GT == 4 ? 2 : GT == 8 ? 3 : GT == 16 ? 4 : 5) : A.logG;
+  const int nvec = GT > 0 ? GT * BATCH : A.nvec;
   const int gl = tid & (G - 1);           // lane within the anchor group
-  const int grp = tid >> A.logG;          // group within the block
-  const int ngrp = kLossBlock >> A.logG;
+  const int grp = tid >> logG;            // group within the block
+  const int ngrp = kLossBlock >> logG;
   const int64_t tile_base = (int64_t)blockIdx.x * A.anchors_per_tile;
 
   __shared__ float s_inv[2];
@@ -256,8 +272,18 @@ __global__ void __launch_bounds__(kLossBlock) loss_main_kernel(const LossArgs A)
     const int64_t r = tile_base + (int64_t)it * ngrp + grp;
     const bool live = r < A.R;   // uniform within the group
     const int64_t o = (int64_t)n * A.R + (live ? r : 0);
+    const float* xrow = A.logits + o * A.K + gl * V;
+    float* grow = write_grad ? A.grad_logits + o * A.K + gl * V : nullptr;
 
-    // ---- per-anchor metadata (same address for the G lanes of a group: one broadcast request)
+    // ---- issue the row loads first, then the per-anchor metadata (same address for the G lanes of a
+    //      group: one broadcast request); the arithmetic below hides under both
+    Vec<V> x[BATCH];
+    if (GT > 0) {
+      if (live) {
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) x[b].load(xrow + b * (GT * V));
+      }
+    }
     int cls = -1;
     float w_hat = 0.f;
     if (live) {
@@ -283,8 +309,6 @@ __global__ void __launch_bounds__(kLossBlock) loss_main_kernel(const LossArgs A)
 
     float sum_f = 0.f, sum_b = 0.f;       // per-lane partial of sum_k focal / sum_k bce (unscaled for t=0)
     float pos_fix = 0.f;                  // (alpha_1 f_1 - alpha_0 f_0) of the positive element
-    const float* xrow = A.logits + o * A.K;
-    float* grow = write_grad ? A.grad_logits + o * A.K : nullptr;
 
     if (live && !valid) {
       // ignored anchor: zero loss, zero gradient (gambler_heads.py:554-555, retinanet.py:233)
@@ -292,54 +316,79 @@ __global__ void __launch_bounds__(kLossBlock) loss_main_kernel(const LossArgs A)
         Vec<V> z;
 #pragma unroll
         for (int k = 0; k < V; ++k) z.v[k] = 0.f;
-        for (int j = gl; j < A.nvec; j += G) z.store(grow + (int64_t)j * V);
+        for (int j = gl; j < nvec; j += G) z.store(grow + (int64_t)(j - gl) * V);
       }
     } else if (live) {
-      for (int j0 = gl; j0 < A.nvec; j0 += G * BATCH) {
-        Vec<V> x[BATCH];
+      if (GT > 0 && kFast) {
+        // exact fast path: every element treated as a negative, the one positive is patched afterwards
+        const float cf = coef_f * A.a0;
 #pragma unroll
         for (int b = 0; b < BATCH; ++b) {
-          const int j = j0 + b * G;
-          if (j < A.nvec) x[b].load(xrow + (int64_t)j * V);
+          Vec<V> g;
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            float l, d;
+            focal_neg_g2(x[b].v[k], l, d);
+            sum_f += l;
+            g.v[k] = d * cf;
+          }
+          if (write_grad) g.store(grow + b * (GT * V));
         }
+        if (fgc && (jpos & (GT - 1)) == gl) {   // rare: this lane owns the positive class
+          const float xv = A.logits[o * A.K + cls];
+          float l0, d0, f1, fg1, b1, bg1;
+          focal_neg_g2(xv, l0, d0);
+          cls_elem_general(xv, true, 2.f, f1, fg1, b1, bg1);
+          pos_fix = f1 * A.a1 - l0 * A.a0;
+          if (write_grad) A.grad_logits[o * A.K + cls] = fg1 * (coef_f * A.a1);
+        }
+      } else {
+        for (int j0 = gl; j0 < nvec; j0 += G * BATCH) {
+          Vec<V> y[BATCH];
 #pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-          const int j = j0 + b * G;
-          if (j < A.nvec) {
-            Vec<V> g;
-            if (kFast) {
+          for (int b = 0; b < BATCH; ++b) {
+            const int j = j0 + b * G;
+            if (j < nvec) y[b].load(xrow + (int64_t)(j - gl) * V);
+          }
 #pragma unroll
-              for (int k = 0; k < V; ++k) {
-                float l, d;
-                focal_neg_g2(x[b].v[k], l, d);
-                sum_f += l;
-                g.v[k] = d * (coef_f * A.a0);
-              }
-              if (j == jpos) {   // rare: patch the single positive element of this anchor
+          for (int b = 0; b < BATCH; ++b) {
+            const int j = j0 + b * G;
+            if (j < nvec) {
+              Vec<V> g;
+              if (kFast) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
-                  if (k == kpos) {
-                    float l0, d0, f1, fg1, b1, bg1;
-                    focal_neg_g2(x[b].v[k], l0, d0);
-                    cls_elem_general(x[b].v[k], true, 2.f, f1, fg1, b1, bg1);
-                    pos_fix = f1 * A.a1 - l0 * A.a0;
-                    g.v[k] = fg1 * (coef_f * A.a1);
+                  float l, d;
+                  focal_neg_g2(y[b].v[k], l, d);
+                  sum_f += l;
+                  g.v[k] = d * (coef_f * A.a0);
+                }
+                if (j == jpos) {   // rare: patch the single positive element of this anchor
+#pragma unroll
+                  for (int k = 0; k < V; ++k) {
+                    if (k == kpos) {
+                      float l0, d0, f1, fg1, b1, bg1;
+                      focal_neg_g2(y[b].v[k], l0, d0);
+                      cls_elem_general(y[b].v[k], true, 2.f, f1, fg1, b1, bg1);
+                      pos_fix = f1 * A.a1 - l0 * A.a0;
+                      g.v[k] = fg1 * (coef_f * A.a1);
+                    }
                   }
                 }
-              }
-            } else {
+              } else {
 #pragma unroll
-              for (int k = 0; k < V; ++k) {
-                const bool t = (j == jpos) && (k == kpos);
-                float f, fgd, bc, bgd;
-                cls_elem_general(x[b].v[k], t, A.gamma, f, fgd, bc, bgd);
-                const float at = t ? A.a1 : A.a0;
-                sum_f += f * at;
-                sum_b += bc;
-                g.v[k] = fmaf(fgd * at, coef_f, bgd * coef_b);
+                for (int k = 0; k < V; ++k) {
+                  const bool t = (j == jpos) && (k == kpos);
+                  float f, fgd, bc, bgd;
+                  cls_elem_general(y[b].v[k], t, A.gamma, f, fgd, bc, bgd);
+                  const float at = t ? A.a1 : A.a0;
+                  sum_f += f * at;
+                  sum_b += bc;
+                  g.v[k] = fmaf(fgd * at, coef_f, bgd * coef_b);
+                }
               }
+              if (write_grad) g.store(grow + (int64_t)(j - gl) * V);
             }
-            if (write_grad) g.store(grow + (int64_t)j * V);
           }
         }
       }
@@ -527,11 +576,11 @@ static LossWs loss_ws_layout(int N, const LossPlan& p) {
   return w;
 }
 
-template <int V, int BATCH>
+template <int V, int BATCH, int GT>
 static void launch_main(int variant, dim3 grid, cudaStream_t s, const LossArgs& a) {
-  if (variant == kFastWrite) loss_main_kernel<V, BATCH, kFastWrite><<<grid, kLossBlock, 0, s>>>(a);
-  else if (variant == kFastNoWrite) loss_main_kernel<V, BATCH, kFastNoWrite><<<grid, kLossBlock, 0, s>>>(a);
-  else loss_main_kernel<V, BATCH, kGeneric><<<grid, kLossBlock, 0, s>>>(a);
+  if (variant == kFastWrite) loss_main_kernel<V, BATCH, kFastWrite, GT><<<grid, kLossBlock, 0, s>>>(a);
+  else if (variant == kFastNoWrite) loss_main_kernel<V, BATCH, kFastNoWrite, GT><<<grid, kLossBlock, 0, s>>>(a);
+  else loss_main_kernel<V, BATCH, kGeneric, GT><<<grid, kLossBlock, 0, s>>>(a);
 }
 
 }  // namespace fsg
@@ -617,9 +666,11 @@ extern "C" int fsg_loss_main(const float* logits, const float* pred_deltas, cons
   const bool fast = (hp->focal_gamma == 2.f) && (hp->gambler_mode == FSG_CLS_FOCAL);
   const int variant = fast ? (grad_logits ? kFastWrite : kFastNoWrite) : kGeneric;
   dim3 grid((unsigned)p.tiles_per_image, (unsigned)N);
-  if (p.V == 4) { if (p.batch == 5) launch_main<4, 5>(variant, grid, s, a); else launch_main<4, 4>(variant, grid, s, a); }
-  else if (p.V == 2) { if (p.batch == 5) launch_main<2, 5>(variant, grid, s, a); else launch_main<2, 4>(variant, grid, s, a); }
-  else { if (p.batch == 5) launch_main<1, 5>(variant, grid, s, a); else launch_main<1, 4>(variant, grid, s, a); }
+  const bool exact = (p.nvec == p.G * p.batch);
+  if (p.V == 4 && p.G == 4 && p.batch == 5 && exact && variant != kGeneric) launch_main<4, 5, 4>(variant, grid, s, a);  // K = 80
+  else if (p.V == 4) { if (p.batch == 5) launch_main<4, 5, 0>(variant, grid, s, a); else launch_main<4, 4, 0>(variant, grid, s, a); }
+  else if (p.V == 2) { if (p.batch == 5) launch_main<2, 5, 0>(variant, grid, s, a); else launch_main<2, 4, 0>(variant, grid, s, a); }
+  else { if (p.batch == 5) launch_main<1, 5, 0>(variant, grid, s, a); else launch_main<1, 4, 0>(variant, grid, s, a); }
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

@@ -228,6 +228,8 @@ struct MatchOut {
   int32_t* matched_idx32;
 };
 
+constexpr int kPassBU = 4;  // anchors per thread in pass B
+
 __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
     const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
     const float4* __restrict__ gt_boxes, const int64_t* __restrict__ gt_class_ids,
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
     const int32_t* __restrict__ best_idx, const unsigned* __restrict__ gt_max, MatchOut out,
     const float* __restrict__ bets, float temperature, int* __restrict__ part_cnt,
     float* __restrict__ part_s, unsigned* __restrict__ done_counter, double* __restrict__ stats) {
+  constexpr int U = kPassBU;
   __shared__ __align__(16) float4 s_gt[kGtChunk];
   __shared__ float s_area[kGtChunk];
   __shared__ float s_max[kGtChunk];
@@ -249,17 +252,19 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
   const int m0 = gt_offsets[n];
   const int M = gt_offsets[n + 1] - m0;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t r = (int64_t)blockIdx.x * kMatchBlock + tid;
-  const bool live = r < R;
-  const int64_t o = (int64_t)n * R + r;
+  const int64_t base = (int64_t)blockIdx.x * (kMatchBlock * U);
+  const int64_t img = (int64_t)n * R;
+  const bool need_anchor = (out.gt_deltas != nullptr);
 
-  float val = 0.f;
-  int idx = 0;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (live) {
-    val = best_val[o];
-    idx = best_idx[o];
-    a = anchors[(int64_t)n * anchor_stride4 + r];
+  float val[U];
+  int idx[U];
+  bool live[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t r = base + u * kMatchBlock + tid;
+    live[u] = r < R;
+    val[u] = live[u] ? best_val[img + r] : -1.f;
+    idx[u] = live[u] ? best_idx[img + r] : 0;
   }
 
   // minimum over the image's per-GT maxima: an anchor can only equal some GT's maximum if its own
@@ -282,10 +287,23 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
   __syncthreads();
   const float min_gt_max = s_min;
 
-  bool lq = false;
-  const bool cand = allow_lq && live && M > 0 && val >= min_gt_max;
-  if (__syncthreads_or(cand)) {
-    const float aa = box_area(a);
+  bool lq[U], cand[U];
+  bool any_cand = false;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    lq[u] = false;
+    cand[u] = allow_lq && live[u] && M > 0 && val[u] >= min_gt_max;
+    any_cand |= cand[u];
+  }
+  if (__syncthreads_or(any_cand)) {
+    float4 a[U];
+    float aa[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      a[u] = cand[u] ? anchors[(int64_t)n * anchor_stride4 + base + u * kMatchBlock + tid]
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      aa[u] = box_area(a[u]);
+    }
     uint32_t phase = 0;
     for (int c = 0; c < M; c += kGtChunk) {
       const int cnt = min(kGtChunk, M - c);
@@ -301,12 +319,15 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
         s_max[g] = __uint_as_float(gt_max[m0 + c + g]);
       }
       __syncthreads();
-      if (__any_sync(kFull, cand)) {
+      if (__any_sync(kFull, any_cand)) {
         for (int g = 0; g < cnt; ++g) {
           const float gm = s_max[g];
-          if (cand && gm <= val) {
-            float v = iou_exact(s_gt[g], s_area[g], a, aa);
-            if (v == gm) lq = true;  // matcher.py:114-116 (ties included)
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (cand[u] && gm <= val[u]) {
+              float v = iou_exact(s_gt[g], s_area[g], a[u], aa[u]);
+              if (v == gm) lq[u] = true;  // matcher.py:114-116 (ties included)
+            }
           }
         }
       }
@@ -316,34 +337,40 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
 
   int fg = 0;
   float w_part = 0.f;
-  if (live) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!live[u]) continue;
+    const int64_t r = base + u * kMatchBlock + tid;
+    const int64_t o = img + r;
     int8_t l1, l2 = 0;
     int64_t cls, msk = 0;
+    int id = idx[u];
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     if (M > 0) {
-      l1 = lq ? (int8_t)1 : band_label(mb, val);
-      if (pmb.n) l2 = lq ? (int8_t)1 : band_label(pmb, val);
-      cls = gt_class_ids ? gt_class_ids[m0 + idx] : 0;
+      l1 = lq[u] ? (int8_t)1 : band_label(mb, val[u]);
+      if (pmb.n) l2 = lq[u] ? (int8_t)1 : band_label(pmb, val[u]);
+      cls = gt_class_ids ? gt_class_ids[m0 + id] : 0;
       if (l1 == 0) cls = num_classes;   // retinanet.py:356
       if (l1 == -1) cls = -1;           // :360
       msk = (l2 == 1) ? 1 : 0;          // :417-423
-      if (out.gt_deltas) d = encode_deltas(a, gt_boxes[m0 + idx], wx, wy, ww, wh);
+      if (need_anchor)
+        d = encode_deltas(anchors[(int64_t)n * anchor_stride4 + r], gt_boxes[m0 + id], wx, wy, ww, wh);
     } else {                            // matcher.py:70-80, retinanet.py:362-363, :425
       l1 = mb.lab[0];
       l2 = pmb.n ? pmb.lab[0] : 0;
       cls = num_classes;
       msk = num_classes;
-      idx = 0;
+      id = 0;
     }
-    if (out.matches) out.matches[o] = idx;
+    if (out.matches) out.matches[o] = id;
     if (out.match_labels) out.match_labels[o] = l1;
     if (out.picky_labels) out.picky_labels[o] = l2;
     if (out.gt_classes) out.gt_classes[o] = cls;
     if (out.mask) out.mask[o] = msk;
     if (out.gt_deltas) out.gt_deltas[o] = d;
-    if (out.matched_idx32) out.matched_idx32[o] = idx;
-    fg = (cls >= 0 && cls != num_classes) ? 1 : 0;
-    if (bets) w_part = __fadd_rn(__fmul_rn(bets[o], (float)msk), temperature);  // gambler_heads.py:569,304
+    if (out.matched_idx32) out.matched_idx32[o] = id;
+    fg += (cls >= 0 && cls != num_classes) ? 1 : 0;
+    if (bets) w_part += __fadd_rn(__fmul_rn(bets[o], (float)msk), temperature);  // gambler_heads.py:569,304
   }
 
   if (stats == nullptr) return;
@@ -491,7 +518,7 @@ struct MatchWs {
 };
 MatchWs match_ws_layout(int N, int64_t R, int64_t sum_M) {
   MatchWs w;
-  w.nb = (int)ceil_div(R > 0 ? R : 1, kMatchBlock);
+  w.nb = (int)ceil_div(R > 0 ? R : 1, kMatchBlock * kPassBU);
   size_t o = 0;
   w.off_counter = o; o += 16;
   w.off_gtmax = o;   o += align_up(sizeof(unsigned) * (size_t)(sum_M > 0 ? sum_M : 1), 16);
@@ -549,7 +576,7 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
   const float wx = h_box_weights ? h_box_weights[0] : 1.f, wy = h_box_weights ? h_box_weights[1] : 1.f;
   const float ww = h_box_weights ? h_box_weights[2] : 1.f, wh = h_box_weights ? h_box_weights[3] : 1.f;
 
-  constexpr int U = 2;
+  constexpr int U = 4;
   dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
   match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
                                                         (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);

@@ -107,10 +107,147 @@ class StepResult:
         return out
 
 
+class DenseStepPlan:
+    """Pre-allocated buffers, cached host-side arguments and (optionally) a CUDA graph for the fused step
+    at fixed shapes (N images, R anchors, K classes).  ``run`` enqueues the four kernels with no allocation
+    and ~4 ctypes calls; ``capture``/``replay`` turn that into one graph launch, which is how a B200 keeps up
+    with a step that is only ~200 us of device time.
+
+    Buffers returned by ``run`` are owned by the plan and overwritten by the next ``run``/``replay``.
+    """
+
+    def __init__(self, N, R, K, cfg, device, coeffs=(1.0, 1.0, -1.0), detach_pred=False, want_weights=False,
+                 max_total_gt=4096, group=None):
+        assert K == cfg.num_classes
+        self.N, self.R, self.K, self.cfg, self.device = N, R, K, cfg, torch.device(device)
+        self.coeffs = tuple(float(c) for c in coeffs)
+        self.detach_pred, self.group, self.max_total_gt = bool(detach_pred), group, int(max_total_gt)
+        self.params = cfg.loss_params(*self.coeffs)
+        L = self.L = ops.lib()
+        dev = self.device
+        f32, i64 = torch.float32, torch.int64
+        self.gt_classes = torch.empty((N, R), dtype=i64, device=dev)
+        self.mask = torch.empty((N, R), dtype=i64, device=dev)
+        self.matched = torch.empty((N, R), dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(_lib.STATS_HEADER + N, dtype=torch.float64, device=dev)
+        self.scalars = torch.zeros(_lib.SCALARS_HEADER + N, dtype=torch.float64, device=dev)
+        self.ell = torch.empty((N, R), dtype=f32, device=dev)
+        self.weights = torch.empty((N, R), dtype=f32, device=dev) if want_weights else None
+        self.need_gl = not self.detach_pred
+        self.need_gd = self.coeffs[1] != 0.0
+        self.grad_logits = torch.empty((N, R, K), dtype=f32, device=dev) if self.need_gl else None
+        self.grad_deltas = torch.empty((N, R, 4), dtype=f32, device=dev) if self.need_gd else None
+        self.grad_bets = torch.empty((N, R), dtype=f32, device=dev)
+        self.total = torch.zeros((), dtype=f32, device=dev)
+        self.ws_match = torch.empty(max(16, L.fsg_match_workspace_bytes(N, R, self.max_total_gt)), dtype=torch.uint8,
+                                    device=dev)
+        self.ws_loss = torch.empty(max(16, L.fsg_loss_main_workspace_bytes(N, R, K)), dtype=torch.uint8, device=dev)
+        self._thr = _lib.host_f32(cfg.iou_thresholds)
+        self._lab = _lib.host_i8(cfg.iou_labels)
+        self._pthr = _lib.host_f32(cfg.picky_thresholds)
+        self._bw = _lib.host_f32(cfg.bbox_reg_weights)
+        self.graph = None
+        self._static = None
+
+    def _check(self, logits, deltas, bets, anchors, gt):
+        N, R, K = self.N, self.R, self.K
+        for t, shape in ((logits, (N, R, K)), (deltas, (N, R, 4)), (bets, (N, R))):
+            if tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                raise RuntimeError("DenseStepPlan: expected contiguous CUDA fp32 tensor of shape %s" % (shape,))
+        if gt.num_images != N or gt.total > self.max_total_gt:
+            raise RuntimeError("DenseStepPlan: GT does not fit the plan (images %d, boxes %d > %d)"
+                               % (gt.num_images, gt.total, self.max_total_gt))
+        if anchors.dtype != torch.float32 or not anchors.is_contiguous() or anchors.shape[-2:] != (R, 4):
+            raise RuntimeError("DenseStepPlan: anchors must be contiguous fp32 (R,4) or (N,R,4)")
+
+    # ---- the three stages (K1 = two launches, K2 main, K2 post) ---------------------------------------
+    def stage_match(self, bets, anchors, gt):
+        L, N, R, cfg, P = self.L, self.N, self.R, self.cfg, _lib.ptr
+        a_stride = R * 4 if anchors.dim() == 3 else 0
+        _lib.check(L.fsg_match_anchors(
+            P(anchors), R, a_stride, P(gt.boxes), P(gt.classes), P(gt.offsets), N, gt.total, cfg.num_classes,
+            self._thr, self._lab, len(cfg.iou_thresholds), 1, self._pthr, self._lab, len(cfg.picky_thresholds),
+            self._bw, None, None, None, P(self.gt_classes), P(self.mask), None, P(self.matched), P(bets),
+            float(cfg.gambler_temperature), P(self.stats), P(self.ws_match), self.ws_match.numel(), _lib.stream()))
+        _lib.count_launches(2)
+
+    def stage_main(self, logits, deltas, bets, anchors, gt):
+        L, N, R, P = self.L, self.N, self.R, _lib.ptr
+        a_stride = R * 4 if anchors.dim() == 3 else 0
+        _lib.check(L.fsg_loss_main(
+            P(logits), P(deltas), None, P(anchors), a_stride, P(gt.boxes), P(gt.offsets), P(self.matched),
+            P(self.gt_classes), P(self.mask), P(bets), N, R, self.params, P(self.stats), P(self.grad_logits),
+            P(self.grad_deltas), P(self.ell), P(self.weights), P(self.scalars), P(self.ws_loss),
+            self.ws_loss.numel(), _lib.stream()))
+        _lib.count_launches(1)
+
+    def stage_post(self, bets):
+        P = _lib.ptr
+        _lib.check(self.L.fsg_loss_post(P(bets), P(self.mask), P(self.ell), self.N, self.R, self.params,
+                                        P(self.stats), P(self.scalars), P(self.grad_bets), _lib.stream()))
+        _lib.count_launches(1)
+
+    def run(self, logits, deltas, bets, anchors, gt):
+        """Enqueue the step on the current stream.  Inputs: detached contiguous CUDA fp32 tensors."""
+        self._check(logits, deltas, bets, anchors, gt)
+        self.stage_match(bets, anchors, gt)
+        if self.group is not None:
+            sharded.all_reduce_stats(self.stats, self.group)
+        self.stage_main(logits, deltas, bets, anchors, gt)
+        if self.group is not None and self.cfg.norm_mode == _lib.NORM_BATCH:
+            sharded.all_reduce_batch_weighted_sum(self.scalars, self.group)
+        self.stage_post(bets)
+        return self.result()
+
+    def result(self):
+        return StepResult(total=self.scalars[8], scalars=self.scalars, stats=self.stats, per_anchor_loss=self.ell,
+                          gt_classes=self.gt_classes, mask=self.mask, weights=self.weights,
+                          extras={"grad_logits": self.grad_logits, "grad_deltas": self.grad_deltas,
+                                  "grad_bets": self.grad_bets})
+
+    # ---- CUDA graph -----------------------------------------------------------------------------
+    def capture(self, logits, deltas, bets, anchors, gt, warmup=2):
+        """Capture the step reading from exactly these tensors (their storage must stay alive and is
+        refreshed in place by the caller between replays)."""
+        self._static = (logits, deltas, bets, anchors, gt)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.run(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(*self._static)
+        self.graph = g
+        return self
+
+    def replay(self):
+        """One graph launch = the whole step (4 kernels + 2 memset nodes)."""
+        self.graph.replay()
+        _lib.count_launches(4)
+        return self.result()
+
+
 class _FusedStep(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, pred_deltas, bets, anchors, gt, cfg, coeffs, detach_pred, group, want_weights):
+    def forward(ctx, logits, pred_deltas, bets, anchors, gt, cfg, coeffs, detach_pred, group, want_weights,
+                plan=None):
         c_cls, c_reg, c_gam = coeffs
+        if plan is not None:
+            x = logits.detach()
+            x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.to(torch.float32).contiguous()
+            r = plan.run(x, pred_deltas.detach().to(torch.float32).contiguous(),
+                         bets.detach().to(torch.float32).contiguous(), anchors, gt)
+            ctx.save_for_backward(plan.grad_logits, plan.grad_deltas, plan.grad_bets)
+            ctx.has_gl = plan.need_gl
+            total = r.scalars[8].to(torch.float32)
+            nd = [r.scalars, r.stats, r.per_anchor_loss, r.gt_classes, r.mask]
+            if r.weights is not None:
+                nd.append(r.weights)
+            ctx.mark_non_differentiable(*nd)
+            return (total,) + tuple(nd)
         params = cfg.loss_params(c_cls, c_reg, c_gam)
         logits_c = logits.detach()
         if logits_c.dtype != torch.float32 or not logits_c.is_contiguous():
@@ -158,11 +295,11 @@ class _FusedStep(torch.autograd.Function):
         if gd is not None:
             ops.scale_(gd, g_total)
         ops.scale_(gb, g_total)
-        return gl if ctx.has_gl else None, gd, gb, None, None, None, None, None, None, None
+        return gl if ctx.has_gl else None, gd, gb, None, None, None, None, None, None, None, None
 
 
 def dense_train_step(logits, pred_deltas, bets, anchors, gt, cfg, coeffs=(1.0, 1.0, -1.0), detach_pred=False,
-                     group=None, want_weights=False):
+                     group=None, want_weights=False, plan=None):
     """Fused match + loss step.
 
     logits (N,R,K), pred_deltas (N,R,4), bets (N,R): CUDA fp32, the flattened (N, sum HWA, .) layout;
@@ -171,11 +308,14 @@ def dense_train_step(logits, pred_deltas, bets, anchors, gt, cfg, coeffs=(1.0, 1
     ``c_cls*loss_cls + c_reg*loss_box_reg + c_gam*gambler_loss``; the detector phase of the reference is
     (1, lambda_reg, -lambda_out*kappa), the gambler phase (detach_pred=True) is (0, 0, kappa).
     group: a torch.distributed process group when the batch is sharded by image over ranks.
+    plan: a DenseStepPlan built for these shapes/coefficients: no allocation, outputs live in the plan.
     """
+    if plan is not None:
+        assert plan.coeffs == tuple(float(c) for c in coeffs) and plan.detach_pred == bool(detach_pred)
     if detach_pred:
         logits = logits.detach()
     res = _FusedStep.apply(logits, pred_deltas, bets, anchors, gt, cfg, tuple(float(c) for c in coeffs),
-                           bool(detach_pred), group, bool(want_weights))
+                           bool(detach_pred), group, bool(want_weights), plan)
     total, scalars, stats, ell, gtc, mask = res[:6]
     return StepResult(total=total, scalars=scalars, stats=stats, per_anchor_loss=ell, gt_classes=gtc, mask=mask,
                       weights=res[6] if len(res) > 6 else None)
