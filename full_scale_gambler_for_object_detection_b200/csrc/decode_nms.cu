@@ -194,21 +194,54 @@ struct SelectArgs {
   int* lvl_count;        // (N, L)
 };
 
-__device__ __forceinline__ void try_append(float x, uint32_t idx, float xb, float ts, uint64_t* buf, int* s_count) {
-  // warp-aggregated append; all 32 lanes call this together
-  bool p = x > xb;
-  float s = 0.f;
-  if (p) { s = sigmoid_score(x); p = s > ts; }
-  const unsigned m = __ballot_sync(kFull, p);
-  if (m == 0u) return;
+// Append the (up to four per lane) logits that pass the pre-filter.  The lanes that pass are first
+// compacted into a per-warp staging area so the sigmoid (expf + IEEE divide) and the exact score test
+// run on dense warps instead of once per element position with most lanes masked off.
+constexpr int kStagePerWarp = 128;
+__device__ __forceinline__ void staged_append4(const float* v, uint32_t idx0, float xb, float ts, float2* stage,
+                                               uint64_t* buf, int* s_count) {
   const int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == (__ffs(m) - 1)) base = atomicAdd(s_count, __popc(m));
-  base = __shfl_sync(kFull, base, __ffs(m) - 1);
-  if (p) buf[base + __popc(m & ((1u << lane) - 1u))] = make_key(s, idx);
+  unsigned flags = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) flags |= (v[j] > xb) ? (1u << j) : 0u;
+  const int c = __popc(flags);
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const int total = __shfl_sync(kFull, inc, 31);
+  if (total == 0) return;
+  int off = inc - c;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (flags & (1u << j)) stage[off++] = make_float2(v[j], __uint_as_float(idx0 + j));
+  __syncwarp();
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    bool p = i < total;
+    float sc = 0.f;
+    uint32_t id = 0u;
+    if (p) {
+      const float2 e = stage[i];
+      sc = sigmoid_score(e.x);
+      id = __float_as_uint(e.y);
+      p = sc > ts;
+    }
+    const unsigned m = __ballot_sync(kFull, p);
+    if (m != 0u) {
+      int base = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(s_count, __popc(m));
+      base = __shfl_sync(kFull, base, leader);
+      if (p) buf[base + __popc(m & ((1u << lane) - 1u))] = make_key(sc, id);
+    }
+  }
+  __syncwarp();
 }
 
-__global__ void __launch_bounds__(kSelThreads) detect_select_kernel(const SelectArgs A, const DetectLevels LV) {
+__global__ void __launch_bounds__(kSelThreads, 2) detect_select_kernel(const SelectArgs A, const DetectLevels LV) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);  // kSelCap
   __shared__ unsigned hist[256];
@@ -234,9 +267,9 @@ __global__ void __launch_bounds__(kSelThreads) detect_select_kernel(const Select
   __syncthreads();
 
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(slab) & 15) == 0);
-  for (int64_t base = e0; base < e1; base += kSelIter) {
-    const float xb = s_xb, ts = s_ts;
-    float v[8];
+  __shared__ float2 s_stage[kSelThreads / 32][kStagePerWarp];
+  float2* stage = s_stage[tid >> 5];
+  auto load8 = [&](int64_t base, float* v) {
     const int64_t p0 = base + (int64_t)tid * 4;
     const int64_t p1 = p0 + kSelThreads * 4;
     if (vec_ok && p0 + 4 <= e1) {
@@ -251,14 +284,21 @@ __global__ void __launch_bounds__(kSelThreads) detect_select_kernel(const Select
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[4 + j] = (p1 + j < e1) ? ldg_stream1(slab + p1 + j) : -INFINITY;
     }
+  };
+  float v[8], vn[8];
+  if (e0 < e1) load8(e0, v);
+  for (int64_t base = e0; base < e1; base += kSelIter) {
+    const float xb = s_xb, ts = s_ts;
+    const bool more = base + kSelIter < e1;
+    if (more) load8(base + kSelIter, vn);   // software prefetch: the next block's loads fly under this one
+    const int64_t p0 = base + (int64_t)tid * 4;
+    const int64_t p1 = p0 + kSelThreads * 4;
     bool any = false;
 #pragma unroll
     for (int j = 0; j < 8; ++j) any |= (v[j] > xb);
     if (__any_sync(kFull, any)) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) try_append(v[j], (uint32_t)(p0 + j), xb, ts, buf, &s_count);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) try_append(v[4 + j], (uint32_t)(p1 + j), xb, ts, buf, &s_count);
+      staged_append4(v, (uint32_t)p0, xb, ts, stage, buf, &s_count);
+      staged_append4(v + 4, (uint32_t)p1, xb, ts, stage, buf, &s_count);
     }
     __syncthreads();
     if (s_count > kSelTrigger) {   // uniform: read after the barrier
@@ -276,6 +316,10 @@ __global__ void __launch_bounds__(kSelThreads) detect_select_kernel(const Select
         }
       }
       __syncthreads();
+    }
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = vn[j];
     }
   }
   prune_topk<kSelThreads>(buf, &s_count, k, hist, s_tmp);
@@ -353,6 +397,11 @@ struct NmsArgs {
   int fixed_count;
   float thr;                // largest float <= the double threshold (strict > compare, see fsg_nms)
   int max_out;              // truncate to this many (DETECTIONS_PER_IMAGE); <= 0: all
+  int split;                // CTAs per image; CTA c owns the classes with class % split == c
+  int part_cap;             // survivors each CTA hands to the merge (max_out, or the candidate count)
+  uint64_t* part_keys;      // (N, split, part_cap) scratch
+  int* part_cnt;            // (N, split)
+  unsigned* done;           // (N)
   // outputs
   int64_t* keep;            // (N, keep_stride) candidate indices in concatenation order
   int64_t keep_stride;
@@ -384,6 +433,9 @@ __device__ void bitonic_asc(uint64_t* a, int m) {
   }
 }
 
+// Per-class NMS is independent across classes, so an image is split over `split` CTAs by class id; each
+// sorts and suppresses only its own candidates (4x fewer keys per bitonic network at split = 4) and hands
+// its best survivors to the last CTA of the image, which merges them by score.
 __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                      // kNmsCap * 8
@@ -392,10 +444,13 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
   unsigned char* dead = smem_raw + (size_t)kNmsCap * 26;                        // kNmsCap
   __shared__ int s_pref[kMaxLevels + 1];
   __shared__ int s_warp[kNmsThreads / 32];
-  __shared__ int s_nseg, s_next, s_nkeep;
+  __shared__ int s_nseg, s_next, s_nkeep, s_mine;
+  __shared__ bool s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int n = blockIdx.x;
+  const int part = blockIdx.x;
+  const int n = blockIdx.y;
+  const int S = A.split;
   if (tid == 0) {
     s_pref[0] = 0;
     if (A.lvl_count) {
@@ -403,7 +458,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
     } else {
       s_pref[1] = A.fixed_count;
     }
-    s_nseg = 0; s_next = 0; s_nkeep = 0;
+    s_nseg = 0; s_next = 0; s_nkeep = 0; s_mine = 0;
   }
   __syncthreads();
   const int L = A.lvl_count ? A.L : 1;
@@ -411,8 +466,6 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
   const float4* gbox = A.boxes + (int64_t)n * A.slots_per_image;
   const float* gscore = A.scores + (int64_t)n * A.slots_per_image;
   const int64_t* gcls = A.classes ? A.classes + (int64_t)n * A.slots_per_image : nullptr;
-  int m = 1;
-  while (m < nc) m <<= 1;
 
   // slot of concatenation index i
   auto slot_of = [&](int i) -> int {
@@ -421,39 +474,57 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
     return l * A.topk + (i - s_pref[l]);
   };
 
-  // ---- 1. composite keys: class (19 bits) | inverted score (32) | concat index (13)
+  // ---- 1. composite keys of this CTA's classes: class (19 bits) | inverted score (32) | concat index (13)
   //         ascending => class, score descending, index ascending
-  for (int i = tid; i < m; i += kNmsThreads) {
-    uint64_t key = ~0ull;
+  for (int i0 = 0; i0 < nc; i0 += kNmsThreads) {
+    const int i = i0 + tid;
+    bool mine = false;
+    uint64_t key = 0;
     if (i < nc) {
       const int s = slot_of(i);
-      const uint64_t c = gcls ? (uint64_t)(gcls[s] & 0x7ffff) : 0ull;
-      const uint32_t sb = __float_as_uint(gscore[s]);
-      // order-preserving map for any float (negative scores can reach the stand-alone nms)
-      const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
-      key = (c << 45) | ((uint64_t)(0xffffffffu - ord) << 13) | (uint64_t)i;
-      if (A.exp_boxes) {
+      const int64_t craw = gcls ? gcls[s] : 0;
+      const uint64_t c = (uint64_t)(craw & 0x7ffff);
+      mine = ((int)(c % (uint64_t)S) == part);
+      if (mine) {
+        const uint32_t sb = __float_as_uint(gscore[s]);
+        // order-preserving map for any float (negative scores can reach the stand-alone nms)
+        const uint32_t ord = (sb & 0x80000000u) ? ~sb : (sb | 0x80000000u);
+        key = (c << 45) | ((uint64_t)(0xffffffffu - ord) << 13) | (uint64_t)i;
+      }
+      if (A.exp_boxes && part == 0) {
         const int64_t eo = (int64_t)n * A.L * A.topk + i;
         A.exp_boxes[eo] = gbox[s];
         A.exp_scores[eo] = gscore[s];
-        A.exp_classes[eo] = gcls ? gcls[s] : 0;
+        A.exp_classes[eo] = craw;
       }
     }
-    keys[i] = key;
+    const unsigned bm = __ballot_sync(kFull, mine);
+    int base = 0;
+    if (bm != 0u) {
+      const int leader = __ffs(bm) - 1;
+      if (lane == leader) base = atomicAdd(&s_mine, __popc(bm));
+      base = __shfl_sync(kFull, base, leader);
+      if (mine) keys[base + __popc(bm & ((1u << lane) - 1u))] = key;
+    }
   }
-  if (tid == 0 && A.exp_count) A.exp_count[n] = nc;
+  if (tid == 0 && part == 0 && A.exp_count) A.exp_count[n] = nc;
+  __syncthreads();
+  const int mc = s_mine;
+  int m = 1;
+  while (m < mc) m <<= 1;
+  for (int i = mc + tid; i < m; i += kNmsThreads) keys[i] = ~0ull;
   __syncthreads();
   bitonic_asc<kNmsThreads>(keys, m);
 
   // ---- 2. boxes in sorted order, segment starts
-  for (int i = tid; i < nc; i += kNmsThreads) {
+  for (int i = tid; i < mc; i += kNmsThreads) {
     sbox[i] = gbox[slot_of((int)(keys[i] & 0x1fff))];
     dead[i] = 0;
   }
   __syncthreads();
-  for (int i0 = 0; i0 < nc; i0 += kNmsThreads) {
+  for (int i0 = 0; i0 < mc; i0 += kNmsThreads) {
     const int i = i0 + tid;
-    const bool start = (i < nc) && (i == 0 || (keys[i] >> 45) != (keys[i - 1] >> 45));
+    const bool start = (i < mc) && (i == 0 || (keys[i] >> 45) != (keys[i - 1] >> 45));
     const unsigned bm = __ballot_sync(kFull, start);
     if (lane == 0) s_warp[wid] = __popc(bm);
     __syncthreads();
@@ -476,7 +547,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
     s = __shfl_sync(kFull, s, 0);
     if (s >= nseg) break;
     const int b = seg[s];
-    const int e = (s + 1 < nseg) ? (int)seg[s + 1] : nc;
+    const int e = (s + 1 < nseg) ? (int)seg[s + 1] : mc;
     for (int i = b; i < e; ++i) {
       if (dead[i]) continue;   // warp-uniform (shared memory, synchronised below)
       const float4 bi = sbox[i];
@@ -496,29 +567,61 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
   }
   __syncthreads();
 
-  // ---- 4. survivors by score descending (ties: lower concat index first), truncate
+  // ---- 4. this CTA's survivors by score descending (ties: lower concat index first)
   uint64_t* k2 = reinterpret_cast<uint64_t*>(sbox);  // the sorted boxes are no longer needed
   for (int i = tid; i < m; i += kNmsThreads) {
     uint64_t key = ~0ull;
-    if (i < nc && !dead[i]) key = keys[i] & ((1ull << 45) - 1ull);  // drop the class field
+    if (i < mc && !dead[i]) key = keys[i] & ((1ull << 45) - 1ull);  // drop the class field
     k2[i] = key;
   }
   __syncthreads();
   {
     int c = 0;
-    for (int i = tid; i < nc; i += kNmsThreads) c += (k2[i] != ~0ull) ? 1 : 0;
+    for (int i = tid; i < mc; i += kNmsThreads) c += (k2[i] != ~0ull) ? 1 : 0;
     c = __reduce_add_sync(kFull, c);
     if (lane == 0 && c) atomicAdd(&s_nkeep, c);
   }
   __syncthreads();
   bitonic_asc<kNmsThreads>(k2, m);
-  int nk = s_nkeep;
+  int mine_keep = s_nkeep;
+  if (mine_keep > A.part_cap) mine_keep = A.part_cap;
+  uint64_t* pk = A.part_keys + ((int64_t)n * S + part) * A.part_cap;
+  for (int t = tid; t < mine_keep; t += kNmsThreads) pk[t] = k2[t];
+  __syncthreads();
+  if (tid == 0) {
+    A.part_cnt[n * S + part] = mine_keep;
+    __threadfence();
+    s_last = (atomicAdd(&A.done[n], 1u) == (unsigned)S - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // ---- 5. last CTA of the image: merge the parts' survivors by score and emit
+  if (tid == 0) { A.done[n] = 0u; s_mine = 0; }
+  __syncthreads();
+  for (int p = 0; p < S; ++p) {
+    const int c = __ldcg(&A.part_cnt[n * S + p]);
+    const uint64_t* src = A.part_keys + ((int64_t)n * S + p) * A.part_cap;
+    const int base = s_mine;
+    for (int t = tid; t < c; t += kNmsThreads) keys[base + t] = __ldcg(&src[t]);
+    __syncthreads();
+    if (tid == 0) s_mine = base + c;
+    __syncthreads();
+  }
+  const int tot = s_mine;
+  int m2 = 1;
+  while (m2 < tot) m2 <<= 1;
+  for (int i = tot + tid; i < m2; i += kNmsThreads) keys[i] = ~0ull;
+  __syncthreads();
+  if (S > 1) bitonic_asc<kNmsThreads>(keys, m2);
+  int nk = tot;
   if (A.max_out > 0 && nk > A.max_out) nk = A.max_out;
   if (tid == 0 && A.num_keep) A.num_keep[n] = nk;
   const int out_rows = (A.max_out > 0) ? A.max_out : nk;
   for (int t = tid; t < out_rows; t += kNmsThreads) {
     if (t < nk) {
-      const int ci = (int)(k2[t] & 0x1fff);
+      const int ci = (int)(keys[t] & 0x1fff);
       const int s = slot_of(ci);
       if (A.keep) A.keep[(int64_t)n * A.keep_stride + t] = ci;
       if (A.out_boxes) {
@@ -535,6 +638,24 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
       }
     }
   }
+}
+
+static int nms_split_for(int N) {
+  int s = 1;
+  while (s * 2 * N <= 148 && s < 8) s <<= 1;   // fill the 148 SMs: one CTA per SM, up to 8 per image
+  return s;
+}
+struct NmsWs {
+  size_t off_done, off_cnt, off_keys, total;
+};
+static NmsWs nms_ws_layout(int N, int split, int part_cap) {
+  NmsWs w;
+  size_t o = 0;
+  w.off_done = o; o += align_up(sizeof(unsigned) * (size_t)N, 16);
+  w.off_cnt = o;  o += align_up(sizeof(int) * (size_t)N * split, 16);
+  w.off_keys = o; o += align_up(sizeof(uint64_t) * (size_t)N * split * part_cap, 16);
+  w.total = o;
+  return w;
 }
 
 static float threshold_floor(double thr) {
@@ -577,9 +698,9 @@ static DetectLevels plan_levels(const int64_t* off, int num_levels, int K, int t
 }
 
 struct DetectWs {
-  size_t off_done, off_pcount, off_pkeys, off_lvl, off_cbox, off_cscore, off_ccls, total;
+  size_t off_done, off_pcount, off_pkeys, off_lvl, off_cbox, off_cscore, off_ccls, off_nms, total;
 };
-static DetectWs detect_ws_layout(int N, int num_levels, int topk, int max_parts) {
+static DetectWs detect_ws_layout(int N, int num_levels, int topk, int max_parts, int max_det = 0) {
   DetectWs w;
   size_t o = 0;
   const size_t slabs = (size_t)N * num_levels;
@@ -590,6 +711,7 @@ static DetectWs detect_ws_layout(int N, int num_levels, int topk, int max_parts)
   w.off_cbox = o;   o += align_up(sizeof(float4) * slabs * topk, 16);
   w.off_cscore = o; o += align_up(sizeof(float) * slabs * topk, 16);
   w.off_ccls = o;   o += align_up(sizeof(int64_t) * slabs * topk, 16);
+  w.off_nms = o;    o += nms_ws_layout(N, 8, max_det > 0 ? max_det : 1024).total;
   w.total = o;
   return w;
 }
@@ -598,12 +720,14 @@ static DetectWs detect_ws_layout(int N, int num_levels, int topk, int max_parts)
 
 using namespace fsg;
 
-extern "C" size_t fsg_nms_workspace_bytes(int64_t n) { return 16; }
+extern "C" size_t fsg_nms_workspace_bytes(int64_t n) {
+  if (n <= 0) return 16;
+  return nms_ws_layout(1, nms_split_for(1), (int)(n < kNmsCap ? n : kNmsCap)).total;
+}
 
 extern "C" int fsg_nms(const float* boxes, const float* scores, const int64_t* class_ids, int64_t n,
                        double iou_threshold, int64_t* keep, int32_t* num_keep, void* workspace,
                        size_t workspace_bytes, fsg_stream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   if (n < 0 || !num_keep) return FSG_ERR_INVALID_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (n == 0) {
@@ -612,13 +736,20 @@ extern "C" int fsg_nms(const float* boxes, const float* scores, const int64_t* c
   }
   if (!boxes || !scores || !keep) return FSG_ERR_INVALID_ARG;
   if (n > kNmsCap) return FSG_ERR_UNSUPPORTED;
+  const int split = class_ids ? nms_split_for(1) : 1;
+  const NmsWs w = nms_ws_layout(1, split, (int)n);
+  if (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  FSG_CUDA_TRY(cudaMemsetAsync(ws + w.off_done, 0, w.off_cnt - w.off_done, s));
   NmsArgs a = {};
   a.boxes = (const float4*)boxes; a.scores = scores; a.classes = class_ids;
   a.slots_per_image = n; a.lvl_count = nullptr; a.L = 1; a.topk = (int)n; a.fixed_count = (int)n;
   a.thr = threshold_floor(iou_threshold); a.max_out = 0;
+  a.split = split; a.part_cap = (int)n;
+  a.part_keys = (uint64_t*)(ws + w.off_keys); a.part_cnt = (int*)(ws + w.off_cnt); a.done = (unsigned*)(ws + w.off_done);
   a.keep = keep; a.keep_stride = n; a.num_keep = num_keep;
   FSG_CUDA_TRY(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmem));
-  nms_image_kernel<<<1, kNmsThreads, kNmsSmem, s>>>(a);
+  nms_image_kernel<<<dim3((unsigned)split, 1), kNmsThreads, kNmsSmem, s>>>(a);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }
@@ -644,6 +775,7 @@ extern "C" int fsg_detect(const float* logits, const float* deltas, const float*
   if (!logits || !deltas || !anchors || !out_boxes || !out_scores || !out_classes || !out_count || !h_box_weights)
     return FSG_ERR_INVALID_ARG;
   if (topk <= 0 || max_det <= 0) return FSG_ERR_INVALID_ARG;
+  if (max_det > 1024) return FSG_ERR_UNSUPPORTED;
   if (anchor_image_stride % 4 != 0) return FSG_ERR_INVALID_ARG;
   if (h_level_offsets[0] != 0 || h_level_offsets[num_levels] != R) return FSG_ERR_INVALID_ARG;
   if (topk > kSelTrigger || (int64_t)num_levels * topk > kNmsCap || K > 65535 || N > 65535)
@@ -692,12 +824,21 @@ extern "C" int fsg_detect(const float* logits, const float* deltas, const float*
   a.boxes = sa.cand_box; a.scores = sa.cand_score; a.classes = sa.cand_class;
   a.slots_per_image = (int64_t)num_levels * topk; a.lvl_count = sa.lvl_count; a.L = num_levels; a.topk = topk;
   a.fixed_count = 0; a.thr = threshold_floor(nms_threshold); a.max_out = max_det;
+  {
+    const int split = nms_split_for(N);
+    const NmsWs nw = nms_ws_layout(N, split, max_det);
+    char* nws = ws + w.off_nms;
+    FSG_CUDA_TRY(cudaMemsetAsync(nws + nw.off_done, 0, nw.off_cnt - nw.off_done, s));
+    a.split = split; a.part_cap = max_det;
+    a.part_keys = (uint64_t*)(nws + nw.off_keys); a.part_cnt = (int*)(nws + nw.off_cnt);
+    a.done = (unsigned*)(nws + nw.off_done);
+  }
   a.keep = keep_idx; a.keep_stride = max_det; a.num_keep = out_count;
   a.out_boxes = (float4*)out_boxes; a.out_scores = out_scores; a.out_classes = out_classes;
   a.exp_boxes = (float4*)cand_boxes; a.exp_scores = cand_scores; a.exp_classes = cand_classes;
   a.exp_count = cand_count;
   FSG_CUDA_TRY(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmem));
-  nms_image_kernel<<<(unsigned)N, kNmsThreads, kNmsSmem, s>>>(a);
+  nms_image_kernel<<<dim3((unsigned)a.split, (unsigned)N), kNmsThreads, kNmsSmem, s>>>(a);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

@@ -492,6 +492,18 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 2)) loss_main_kernel
 // ------------------------------------------------------------------------------------------
 // post pass: d(c_gam * G)/d bets
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float post_one(float b, float m, float l, float T, float ggamma, int nmode,
+                                          float inv_S, float Asum) {
+  const float w = __fadd_rn(__fmul_rn(b, m), T);
+  if (nmode == FSG_NORM_NONE) {
+    const float pw = (ggamma == 1.f) ? 1.f : powf(w, ggamma - 1.f);
+    return -m * ggamma * pw * l;
+  }
+  const float w_hat = w * inv_S;
+  const float pw = (ggamma == 1.f) ? 1.f : powf(w_hat, ggamma - 1.f);
+  return -(m * inv_S) * ggamma * (pw * l - Asum);
+}
+
 __global__ void __launch_bounds__(256) loss_post_kernel(const float* __restrict__ bets,
                                                         const int64_t* __restrict__ mask,
                                                         const float* __restrict__ ell, int N, int64_t R, float T,
@@ -499,26 +511,45 @@ __global__ void __launch_bounds__(256) loss_post_kernel(const float* __restrict_
                                                         const double* __restrict__ stats,
                                                         const double* __restrict__ scalars,
                                                         float* __restrict__ grad_bets) {
+  __shared__ float s_c[2];
   const int n = blockIdx.y;
-  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (r >= R) return;
-  const int64_t o = (int64_t)n * R + r;
-  const float m = mask ? (float)mask[o] : 1.f;
-  const float l = ell[o];
-  const float w = __fadd_rn(__fmul_rn(bets[o], m), T);
-  float g;
-  if (nmode == FSG_NORM_NONE) {
-    const float pw = (ggamma == 1.f) ? 1.f : powf(w, ggamma - 1.f);
-    g = -m * ggamma * pw * l;
-  } else {
-    const double S = (nmode == FSG_NORM_IMAGE) ? stats[FSG_STATS_HEADER + n] : stats[1];
-    const double Asum = (nmode == FSG_NORM_IMAGE) ? scalars[FSG_SCALARS_HEADER + n] : scalars[2];
-    const float inv_S = (float)(1.0 / S);
-    const float w_hat = w * inv_S;
-    const float pw = (ggamma == 1.f) ? 1.f : powf(w_hat, ggamma - 1.f);
-    g = -(m * inv_S) * ggamma * (pw * l - (float)Asum);
+  if (threadIdx.x == 0) {
+    float inv_S = 1.f, Asum = 0.f;
+    if (nmode != FSG_NORM_NONE) {
+      const double S = (nmode == FSG_NORM_IMAGE) ? stats[FSG_STATS_HEADER + n] : stats[1];
+      const double A = (nmode == FSG_NORM_IMAGE) ? scalars[FSG_SCALARS_HEADER + n] : scalars[2];
+      inv_S = (float)(1.0 / S);
+      Asum = (float)A;
+    }
+    s_c[0] = inv_S;
+    s_c[1] = Asum;
   }
-  grad_bets[o] = c_gam * g;
+  __syncthreads();
+  const float inv_S = s_c[0], Asum = s_c[1];
+  const int64_t r0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (r0 >= R) return;
+  const int64_t o = (int64_t)n * R + r0;
+  if (r0 + 4 <= R && (o & 3) == 0) {
+    const float4 b = *reinterpret_cast<const float4*>(bets + o);
+    const float4 l = *reinterpret_cast<const float4*>(ell + o);
+    float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
+    if (mask) {
+      const longlong2 ma = *reinterpret_cast<const longlong2*>(mask + o);
+      const longlong2 mb = *reinterpret_cast<const longlong2*>(mask + o + 2);
+      m0 = (float)ma.x; m1 = (float)ma.y; m2 = (float)mb.x; m3 = (float)mb.y;
+    }
+    float4 g;
+    g.x = c_gam * post_one(b.x, m0, l.x, T, ggamma, nmode, inv_S, Asum);
+    g.y = c_gam * post_one(b.y, m1, l.y, T, ggamma, nmode, inv_S, Asum);
+    g.z = c_gam * post_one(b.z, m2, l.z, T, ggamma, nmode, inv_S, Asum);
+    g.w = c_gam * post_one(b.w, m3, l.w, T, ggamma, nmode, inv_S, Asum);
+    *reinterpret_cast<float4*>(grad_bets + o) = g;
+  } else {
+    for (int k = 0; k < 4 && r0 + k < R; ++k) {
+      const float m = mask ? (float)mask[o + k] : 1.f;
+      grad_bets[o + k] = c_gam * post_one(bets[o + k], m, ell[o + k], T, ggamma, nmode, inv_S, Asum);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, int64_t n4, int64_t n,
@@ -681,7 +712,7 @@ extern "C" int fsg_loss_post(const float* bets, const int64_t* mask, const float
   if (!hp || N <= 0 || R <= 0 || !bets || !per_anchor_loss || !stats || !scalars || !grad_bets)
     return FSG_ERR_INVALID_ARG;
   if (N > 65535) return FSG_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)ceil_div(R, 256), (unsigned)N);
+  dim3 grid((unsigned)ceil_div(R, 1024), (unsigned)N);
   loss_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bets, mask, per_anchor_loss, N, R, hp->temperature,
                                                            hp->gambler_gamma, hp->norm_mode, hp->c_gam, stats,
                                                            scalars, grad_bets);

@@ -41,6 +41,41 @@ __device__ __forceinline__ float iou_exact(float4 a, float area_a, float4 b, flo
   return r;
 }
 
+// intersection area and the union denominator of boxes.py:261-272 (same op order as iou_exact)
+__device__ __forceinline__ float inter_area(float4 a, float4 b) {
+  float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+  float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+  return __fmul_rn(w, h);
+}
+// Conservative pre-test for "fl(inter/uni) >= bound": a correctly rounded quotient q satisfies
+// inter/uni >= q(1-2^-24), so q >= bound implies inter >= bound*uni*(1-2^-24); the factor 1-2^-21 below
+// leaves room for the two roundings of the product.  Never rejects a pair that could reach `bound`;
+// pairs it rejects are strictly below it, so skipping their IEEE division cannot change any max/argmax.
+__device__ __forceinline__ bool may_reach(float inter, float uni, float bound) {
+  return inter >= bound * uni * 0.99999952f;
+}
+
+// Pass A inner step for one (GT, anchor) pair.  Non-overlapping pairs (the vast majority) cost four
+// min/max, two subtractions and two compares; the clamp-to-zero of boxes.py:265 is implied by the
+// "both extents positive" test (a clamped extent of 0 gives inter == 0 -> IoU exactly 0, which can never
+// beat a running best that starts at 0 nor raise a per-GT maximum).
+__device__ __forceinline__ void pair_update(float4 G, float ga, float4 a, float aa, float known, int gidx,
+                                            float& bv, int& bi, float& m) {
+  const float w = __fsub_rn(fminf(G.z, a.z), fmaxf(G.x, a.x));
+  const float h = __fsub_rn(fminf(G.w, a.w), fmaxf(G.y, a.y));
+  if (w > 0.f && h > 0.f) {
+    const float inter = __fmul_rn(w, h);
+    if (inter > 0.f) {   // the product of two tiny positives can underflow to 0
+      const float uni = __fsub_rn(__fadd_rn(ga, aa), inter);
+      if (may_reach(inter, uni, fminf(bv, known))) {
+        const float v = __fdiv_rn(inter, uni);
+        if (v > bv) { bv = v; bi = gidx; }
+        m = fmaxf(m, v);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ int8_t band_label(const MatcherBands& mb, float v) {
   int8_t l = 1;  // matcher.py:88
 #pragma unroll
@@ -131,6 +166,8 @@ __global__ void __launch_bounds__(256) matrix_match_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------
 // Fused path, pass A: per-anchor max/argmax over the image's GT + per-GT max over anchors
 // ------------------------------------------------------------------------------------------
+constexpr int kSmallM = 32;  // images with at most this many GT skip the shared-memory staging entirely
+
 template <int U>
 __global__ void __launch_bounds__(kMatchBlock) match_pass_a_kernel(
     const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
@@ -157,52 +194,76 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_a_kernel(
     int64_t r = base + u * kMatchBlock + tid;
     a[u] = (r < R) ? a_img[r] : make_float4(0.f, 0.f, 0.f, 0.f);
     aa[u] = box_area(a[u]);
-    bv[u] = -1.f;  // first GT always wins the initial compare -> argmax of an all-zero column is 0
-    bi[u] = 0;
+    bv[u] = 0.f;   // running best starts at (IoU 0, GT 0): exactly torch's argmax of an all-zero column,
+    bi[u] = 0;     // and strict '>' keeps the lowest GT index among ties (matcher.py:86)
   }
 
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  uint32_t phase = 0;
-  for (int c = 0; c < M; c += kGtChunk) {
-    const int cnt = min(kGtChunk, M - c);
-    if (tid == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(&s_bar, (uint32_t)cnt * 16u);
-      tma_bulk_g2s(s_gt, gt_boxes + m0 + c, (uint32_t)cnt * 16u, &s_bar);
-    }
-    mbar_wait(&s_bar, phase);
-    phase ^= 1u;
-    for (int g = tid; g < cnt; g += kMatchBlock) {
-      s_area[g] = box_area(s_gt[g]);
-      s_max[g] = 0u;
-    }
+  if (M <= kSmallM) {
+    // ---- few GT (the detection-training case): GT boxes by broadcast loads straight from global/L1 (no
+    //      TMA round trip); per-GT maxima are still merged per CTA in shared memory first, because
+    //      same-address atomics serialise in L2 (~27 cycles each) and every overlapping warp would hit
+    //      the same M words
+    if (tid < kSmallM) s_max[tid] = 0u;
     __syncthreads();
-
-    for (int g = 0; g < cnt; ++g) {
-      const float4 G = s_gt[g];
-      const float ga = s_area[g];
+    for (int g = 0; g < M; ++g) {
+      const float4 G = gt_boxes[m0 + g];
+      const float ga = box_area(G);
+      const float known = __uint_as_float(gt_max[m0 + g]);  // may be stale: only makes the filter looser
       float m = 0.f;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float v = iou_exact(G, ga, a[u], aa[u]);
-        if (v > bv[u]) { bv[u] = v; bi[u] = c + g; }
-        m = fmaxf(m, v);
+      for (int u = 0; u < U; ++u) pair_update(G, ga, a[u], aa[u], known, g, bv[u], bi[u], m);
+      if (__any_sync(kFull, m > known)) {
+        const unsigned wm = __reduce_max_sync(kFull, __float_as_uint(m));
+        if (lane == 0) atomicMax(&s_max[g], wm);
       }
-      // padding lanes (r >= R) hold a zero box: inter == 0 -> v == 0, harmless for the max
-      unsigned wm = __reduce_max_sync(kFull, __float_as_uint(m));
-      if (lane == 0 && wm > 0u) atomicMax(&s_max[g], wm);
     }
     __syncthreads();
-    for (int g = tid; g < cnt; g += kMatchBlock) {
-      unsigned v = s_max[g];
-      if (v > 0u) atomicMax(&gt_max[m0 + c + g], v);
+    if (tid < M) {
+      const unsigned v = s_max[tid];
+      if (v > 0u) atomicMax(&gt_max[m0 + tid], v);
     }
-    __syncthreads();  // s_gt / s_max are rewritten by the next chunk
+  } else {
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int c = 0; c < M; c += kGtChunk) {
+      const int cnt = min(kGtChunk, M - c);
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar, (uint32_t)cnt * 16u);
+        tma_bulk_g2s(s_gt, gt_boxes + m0 + c, (uint32_t)cnt * 16u, &s_bar);
+      }
+      mbar_wait(&s_bar, phase);
+      phase ^= 1u;
+      for (int g = tid; g < cnt; g += kMatchBlock) {
+        s_area[g] = box_area(s_gt[g]);
+        s_max[g] = gt_max[m0 + c + g];   // what other CTAs found so far (stale is fine)
+      }
+      __syncthreads();
+
+      for (int g = 0; g < cnt; ++g) {
+        const float4 G = s_gt[g];
+        const float ga = s_area[g];
+        const float known = __uint_as_float(s_max[g]);
+        float m = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) pair_update(G, ga, a[u], aa[u], known, c + g, bv[u], bi[u], m);
+        // padding lanes (r >= R) hold a zero box: no overlap, harmless for the max
+        if (__any_sync(kFull, m > known)) {
+          const unsigned wm = __reduce_max_sync(kFull, __float_as_uint(m));
+          if (lane == 0) atomicMax(&s_max[g], wm);
+        }
+      }
+      __syncthreads();
+      for (int g = tid; g < cnt; g += kMatchBlock) {
+        const unsigned v = s_max[g];
+        if (v > 0u) atomicMax(&gt_max[m0 + c + g], v);
+      }
+      __syncthreads();  // s_gt / s_max are rewritten by the next chunk
+    }
   }
 
 #pragma unroll
@@ -229,8 +290,9 @@ struct MatchOut {
 };
 
 constexpr int kPassBU = 4;  // anchors per thread in pass B
+constexpr int kWarpsPerBlock = kMatchBlock / 32;
 
-__global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
+__global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
     const float4* __restrict__ gt_boxes, const int64_t* __restrict__ gt_class_ids,
     const int32_t* __restrict__ gt_offsets, int N, int num_classes, MatcherBands mb, MatcherBands pmb, int allow_lq,
@@ -242,11 +304,10 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
   __shared__ __align__(16) float4 s_gt[kGtChunk];
   __shared__ float s_area[kGtChunk];
   __shared__ float s_max[kGtChunk];
+  __shared__ __align__(8) uint64_t s_key[kGtChunk];   // (gt max bits << 32 | gt index), sorted ascending
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ float s_red[kMatchBlock / 32];
-  __shared__ int s_redi[kMatchBlock / 32];
+  __shared__ float s_red[kWarpsPerBlock];
   __shared__ float s_min;
-  __shared__ bool s_last;
 
   const int n = blockIdx.y;
   const int m0 = gt_offsets[n];
@@ -254,84 +315,143 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t base = (int64_t)blockIdx.x * (kMatchBlock * U);
   const int64_t img = (int64_t)n * R;
+  const float4* a_img = anchors + (int64_t)n * anchor_stride4;
   const bool need_anchor = (out.gt_deltas != nullptr);
 
   float val[U];
   int idx[U];
-  bool live[U];
+  bool live[U], lq[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int64_t r = base + u * kMatchBlock + tid;
     live[u] = r < R;
     val[u] = live[u] ? best_val[img + r] : -1.f;
     idx[u] = live[u] ? best_idx[img + r] : 0;
-  }
-
-  // minimum over the image's per-GT maxima: an anchor can only equal some GT's maximum if its own
-  // best IoU reaches that minimum (IoU(g,a) <= best(a)), which prunes almost every anchor.
-  float mn = __int_as_float(0x7f800000);
-  for (int g = tid; g < M; g += kMatchBlock) mn = fminf(mn, __uint_as_float(gt_max[m0 + g]));
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, s));
-  if (lane == 0) s_red[wid] = mn;
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    float v = s_red[0];
-    for (int w = 1; w < kMatchBlock / 32; ++w) v = fminf(v, s_red[w]);
-    s_min = v;
-  }
-  __syncthreads();
-  const float min_gt_max = s_min;
-
-  bool lq[U], cand[U];
-  bool any_cand = false;
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
     lq[u] = false;
-    cand[u] = allow_lq && live[u] && M > 0 && val[u] >= min_gt_max;
-    any_cand |= cand[u];
   }
-  if (__syncthreads_or(any_cand)) {
-    float4 a[U];
-    float aa[U];
+
+  // An anchor can equal some GT's maximum only if its own best IoU reaches the smallest per-GT maximum
+  // (IoU(g,a) <= best(a)); and it needs checking only against GTs whose maximum is <= its best IoU.
+  if (allow_lq && M > 0 && M <= kSmallM) {
+    // ---- few GT: everything from global/L1 with broadcast loads, warp-level control flow, no barriers
+    float mn = __int_as_float(0x7f800000);
+    for (int g = 0; g < M; ++g) mn = fminf(mn, __uint_as_float(gt_max[m0 + g]));
+    bool any_cand = false;
+    bool cand[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      a[u] = cand[u] ? anchors[(int64_t)n * anchor_stride4 + base + u * kMatchBlock + tid]
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
-      aa[u] = box_area(a[u]);
+      cand[u] = live[u] && val[u] >= mn;
+      any_cand |= cand[u];
     }
-    uint32_t phase = 0;
-    for (int c = 0; c < M; c += kGtChunk) {
-      const int cnt = min(kGtChunk, M - c);
-      if (tid == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(&s_bar, (uint32_t)cnt * 16u);
-        tma_bulk_g2s(s_gt, gt_boxes + m0 + c, (uint32_t)cnt * 16u, &s_bar);
-      }
-      mbar_wait(&s_bar, phase);
-      phase ^= 1u;
-      for (int g = tid; g < cnt; g += kMatchBlock) {
-        s_area[g] = box_area(s_gt[g]);
-        s_max[g] = __uint_as_float(gt_max[m0 + c + g]);
-      }
-      __syncthreads();
-      if (__any_sync(kFull, any_cand)) {
-        for (int g = 0; g < cnt; ++g) {
-          const float gm = s_max[g];
+    if (__any_sync(kFull, any_cand)) {
+      float4 a[U];
+      float aa[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (cand[u] && gm <= val[u]) {
-              float v = iou_exact(s_gt[g], s_area[g], a[u], aa[u]);
-              if (v == gm) lq[u] = true;  // matcher.py:114-116 (ties included)
-            }
+      for (int u = 0; u < U; ++u) {
+        a[u] = cand[u] ? a_img[base + u * kMatchBlock + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+        aa[u] = box_area(a[u]);
+      }
+      for (int g = 0; g < M; ++g) {
+        const float gm = __uint_as_float(gt_max[m0 + g]);
+        const float4 G = gt_boxes[m0 + g];
+        const float ga = box_area(G);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (cand[u] && gm <= val[u]) {
+            if (iou_exact(G, ga, a[u], aa[u]) == gm) lq[u] = true;  // matcher.py:114-116 (ties included)
           }
         }
       }
-      __syncthreads();
+    }
+  } else if (allow_lq && M > 0) {
+    float mn = __int_as_float(0x7f800000);
+    for (int g = tid; g < M; g += kMatchBlock) mn = fminf(mn, __uint_as_float(gt_max[m0 + g]));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, s));
+    if (lane == 0) s_red[wid] = mn;
+    if (tid == 0) {
+      mbar_init(&s_bar, 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float v = s_red[0];
+      for (int w = 1; w < kWarpsPerBlock; ++w) v = fminf(v, s_red[w]);
+      s_min = v;
+    }
+    __syncthreads();
+    const float min_gt_max = s_min;
+    bool cand[U];
+    bool any_cand = false;
+    float vmax = -1.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      cand[u] = live[u] && val[u] >= min_gt_max;
+      any_cand |= cand[u];
+      if (cand[u]) vmax = fmaxf(vmax, val[u]);
+    }
+    if (__syncthreads_or(any_cand)) {
+      float4 a[U];
+      float aa[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[u] = cand[u] ? a_img[base + u * kMatchBlock + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+        aa[u] = box_area(a[u]);
+      }
+      uint32_t phase = 0;
+      for (int c = 0; c < M; c += kGtChunk) {
+        const int cnt = min(kGtChunk, M - c);
+        if (tid == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(&s_bar, (uint32_t)cnt * 16u);
+          tma_bulk_g2s(s_gt, gt_boxes + m0 + c, (uint32_t)cnt * 16u, &s_bar);
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        int m2 = 1;
+        while (m2 < cnt) m2 <<= 1;
+        for (int g = tid; g < m2; g += kMatchBlock) {
+          if (g < cnt) {
+            const unsigned gmb = gt_max[m0 + c + g];
+            s_area[g] = box_area(s_gt[g]);
+            s_max[g] = __uint_as_float(gmb);
+            s_key[g] = ((uint64_t)gmb << 32) | (uint64_t)g;
+          } else {
+            s_key[g] = ~0ull;
+          }
+        }
+        __syncthreads();
+        // sort the chunk's GT by their maxima (ascending) so every anchor stops at the first GT whose
+        // maximum exceeds its own best IoU
+        for (int size = 2; size <= m2; size <<= 1) {
+          for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (m2 >> 1); t += kMatchBlock) {
+              const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+              const int hi = lo + stride;
+              const bool asc = ((lo & size) == 0);
+              const uint64_t x = s_key[lo], y = s_key[hi];
+              if (asc ? (x > y) : (x < y)) { s_key[lo] = y; s_key[hi] = x; }
+            }
+            __syncthreads();
+          }
+        }
+        if (__any_sync(kFull, any_cand)) {
+          const float wmax = warp_max(vmax);
+          for (int i = 0; i < cnt; ++i) {
+            const uint64_t key = s_key[i];
+            const float gm = __uint_as_float((unsigned)(key >> 32));
+            if (gm > wmax) break;   // warp-uniform: no anchor of this warp reaches the remaining GTs
+            const int g = (int)(key & 0xffffffffu);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (cand[u] && gm <= val[u]) {
+                if (iou_exact(s_gt[g], s_area[g], a[u], aa[u]) == gm) lq[u] = true;
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
     }
   }
 
@@ -353,8 +473,7 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
       if (l1 == 0) cls = num_classes;   // retinanet.py:356
       if (l1 == -1) cls = -1;           // :360
       msk = (l2 == 1) ? 1 : 0;          // :417-423
-      if (need_anchor)
-        d = encode_deltas(anchors[(int64_t)n * anchor_stride4 + r], gt_boxes[m0 + id], wx, wy, ww, wh);
+      if (need_anchor) d = encode_deltas(a_img[r], gt_boxes[m0 + id], wx, wy, ww, wh);
     } else {                            // matcher.py:70-80, retinanet.py:362-363, :425
       l1 = mb.lab[0];
       l2 = pmb.n ? pmb.lab[0] : 0;
@@ -374,48 +493,51 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_b_kernel(
   }
 
   if (stats == nullptr) return;
-  // ---- loss pre-pass: num_foreground and S[n] = sum_r (bet*mask + T), deterministic two-level sum
-  int fg_w = __reduce_add_sync(kFull, fg);
-  float s_w = warp_sum(w_part);
-  if (lane == 0) { s_redi[wid] = fg_w; s_red[wid] = s_w; }
+  // ---- loss pre-pass: num_foreground and S[n] = sum_r (bet*mask + T).  One partial per CTA in a fixed
+  //      slot, the last CTA to finish folds them in a fixed order => run-to-run deterministic.
+  __shared__ int s_redi[kWarpsPerBlock];
+  __shared__ float s_redf[kWarpsPerBlock];
+  __shared__ double s_tc[kWarpsPerBlock], s_ts[kWarpsPerBlock];
+  __shared__ bool s_last;
+  const int fg_w = __reduce_add_sync(kFull, fg);
+  const float s_w = warp_sum(w_part);
+  if (lane == 0) { s_redi[wid] = fg_w; s_redf[wid] = s_w; }
   __syncthreads();
   const int nb = gridDim.x;
   if (tid == 0) {
     int ci = 0;
     float cs = 0.f;
-    for (int w = 0; w < kMatchBlock / 32; ++w) { ci += s_redi[w]; cs += s_red[w]; }
+    for (int w = 0; w < kWarpsPerBlock; ++w) { ci += s_redi[w]; cs += s_redf[w]; }
     part_cnt[n * nb + blockIdx.x] = ci;
     part_s[n * nb + blockIdx.x] = cs;
     __threadfence();
-    unsigned prev = atomicAdd(done_counter, 1u);
-    s_last = (prev == (unsigned)(nb * N) - 1u);
+    s_last = (atomicAdd(done_counter, 1u) == (unsigned)(nb * N) - 1u);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double tot_cnt = 0.0, tot_s = 0.0;  // meaningful in warp 0 lane 0 after the loop below
-  for (int img = wid; img < N; img += kMatchBlock / 32) {
-    double c = 0.0, s = 0.0;
+  double tot_cnt = 0.0, tot_s = 0.0;
+  for (int im = wid; im < N; im += kWarpsPerBlock) {
+    double c = 0.0, sacc = 0.0;
     for (int b = lane; b < nb; b += 32) {
-      c += (double)__ldcg(&part_cnt[img * nb + b]);
-      s += (double)__ldcg(&part_s[img * nb + b]);
+      c += (double)__ldcg(&part_cnt[im * nb + b]);
+      sacc += (double)__ldcg(&part_s[im * nb + b]);
     }
     c = warp_sum_d(c);
-    s = warp_sum_d(s);
+    sacc = warp_sum_d(sacc);
     if (lane == 0) {
-      stats[FSG_STATS_HEADER + img] = s;
+      stats[FSG_STATS_HEADER + im] = sacc;
       tot_cnt += c;
-      tot_s += s;
+      tot_s += sacc;
     }
   }
-  __shared__ double s_tc[kMatchBlock / 32], s_ts[kMatchBlock / 32];
   if (lane == 0) { s_tc[wid] = tot_cnt; s_ts[wid] = tot_s; }
   __syncthreads();
   if (tid == 0) {
-    double c = 0.0, s = 0.0;
-    for (int w = 0; w < kMatchBlock / 32; ++w) { c += s_tc[w]; s += s_ts[w]; }
+    double c = 0.0, sacc = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) { c += s_tc[w]; sacc += s_ts[w]; }
     stats[0] = c;
-    stats[1] = s;
+    stats[1] = sacc;
     *done_counter = 0u;  // self-reset for the next call
   }
 }

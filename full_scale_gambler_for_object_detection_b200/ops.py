@@ -299,8 +299,10 @@ def nms_raw(boxes, scores, class_ids, iou_threshold):
     keep = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
     num = torch.zeros(1, dtype=torch.int32, device=b.device)
     c = class_ids.to(torch.int64).contiguous() if class_ids is not None else None
-    check(lib().fsg_nms(ptr(b) if n else None, ptr(s) if n else None, ptr(c), n, float(iou_threshold), ptr(keep),
-                        ptr(num), None, 0, stream()))
+    L = lib()
+    ws = _ws(L.fsg_nms_workspace_bytes(n), b.device)
+    check(L.fsg_nms(ptr(b) if n else None, ptr(s) if n else None, ptr(c), n, float(iou_threshold), ptr(keep),
+                    ptr(num), ptr(ws), ws.numel(), stream()))
     count_launches(1)
     return keep, num
 
