@@ -1,0 +1,79 @@
+"""CPU: the C-ABI library loads and exports exactly what include/fsg_dense.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fsg_dense.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"FSG_API\s+[\w\s\*]+?\b(fsg_\w+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from full_scale_gambler_for_object_detection_b200 import _lib
+
+    if not os.path.isfile(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.LIB_PATH
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    assert len(syms) == 19, syms
+    for s in ("fsg_pairwise_iou", "fsg_matcher", "fsg_match_anchors", "fsg_box2box_get_deltas",
+              "fsg_box2box_apply_deltas", "fsg_loss_main", "fsg_loss_post", "fsg_nms", "fsg_detect",
+              "fsg_permute_level"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (fsg_\w+)", out))
+    assert set(declared_symbols()) == exported
+
+
+def test_ctypes_prototypes_cover_the_header(lib_path):
+    from full_scale_gambler_for_object_detection_b200 import _lib
+
+    assert sorted(_lib.PROTOTYPES) == declared_symbols()
+    L = _lib.lib()
+    assert L.fsg_abi_version() == _lib.ABI_VERSION
+    assert L.fsg_status_string(0) == b"ok"
+    assert b"workspace" in L.fsg_status_string(2)
+    # pure host-side queries (no device work)
+    assert L.fsg_match_workspace_bytes(2, 1000, 16) > 2 * 1000 * 8
+    assert L.fsg_loss_main_workspace_bytes(2, 1000, 80) >= 16
+    assert L.fsg_detect_workspace_bytes(2, 1000, 80, 5, 1000) > 0
+    assert L.fsg_nms_workspace_bytes(100) > 0
+    assert ctypes.sizeof(_lib.LossParams) == 64
+
+
+def test_header_is_plain_c():
+    """The boundary compiles as C (no torch / C++ types in the signatures)."""
+    src = "#include \"fsg_dense.h\"\nint main(void){ fsg_loss_params p; (void)p; return FSG_ABI_VERSION - 1; }\n"
+    exe = "/tmp/fsg_header_check"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-x", "c", "-",
+                        "-o", exe], input=src, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are rejected loudly; nothing in the product imports the oracle."""
+    import torch
+    from full_scale_gambler_for_object_detection_b200 import _lib
+
+    with pytest.raises(RuntimeError):
+        _lib.ptr(torch.zeros(4))
+    pkg = os.path.join(ROOT, "full_scale_gambler_for_object_detection_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
