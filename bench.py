@@ -232,9 +232,11 @@ def run_ours(args, rank, local_rank, world):
     x_s, d_s, b_s = logits.detach(), deltas.detach(), bets.detach()
     graphed = False
     try:
-        plan.capture(x_s, d_s, b_s, anchors, gt)   # the whole step (4 kernels + 2 memset nodes) = one graph launch
+        # N = 1: the whole step (4 kernels + 2 memset nodes) is one graph launch; N > 1: two graphs with the
+        # eager NCCL all-reduce of [num_foreground, S_batch] between them (collectives stay outside graphs)
+        plan.capture(x_s, d_s, b_s, anchors, gt)
         graphed = True
-    except Exception as e:  # e.g. a collective that cannot be captured: fall back to direct launches
+    except Exception as e:  # fall back to direct launches
         if rank == 0:
             print("graph capture unavailable (%s); timing direct launches" % (type(e).__name__,), file=sys.stderr)
         plan.graph = None
@@ -270,6 +272,11 @@ def run_ours(args, rank, local_rank, world):
     elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = world * N * R / (ms_per_step * 1e-3)
+
+    from full_scale_gambler_for_object_detection_b200 import sharded as _sh
+    glob = _sh.global_losses(res.scalars, res.stats, coeffs, group).tolist()   # collective: every rank calls it
+    # (config 2 is L_BAHW: per-image normaliser, so scalars[2] is a per-rank sum here)
+    num_fg = float(res.num_foreground.item())
 
     # ---- per-kernel device time: each stage launched back to back K times between two CUDA events on the
     #      launching stream (no host gaps: the queue stays ahead of the device); inputs exceed L2
@@ -350,7 +357,8 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (344 MB logits + 344 MB grads per GPU)",
                        "anchors_per_step_per_gpu": N * R, "parallelism": "image-sharded x%d" % world,
-                       "launch": "CUDA graph replay" if graphed else "direct launches"},
+                       "launch": ("CUDA graph replay" if world == 1 else "2 CUDA graphs + eager NCCL all-reduce")
+                       if graphed else "direct launches"},
             "roofline": {"bound": "hbm", "kernel": "loss_main_kernel (K2 main pass)", "achieved": achieved,
                          "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": NCU_TRAFFIC_BYTES, "bytes_per_anchor": 8 * K + 72, "kernel_ms": main_ms,
@@ -362,15 +370,37 @@ def run_ours(args, rank, local_rank, world):
             "cpu_baseline": cpu_baseline,
             "gpu_launches": launches,
             "clocks": clocks,
-            "losses": {"loss_cls": float(res.loss_cls.item()), "loss_box_reg": float(res.loss_box_reg.item()),
-                       "gambler_loss": float(res.gambler_loss.item()),
-                       "num_foreground": float(res.num_foreground.item())},
+            "losses": {"loss_cls": float(glob[0]), "loss_box_reg": float(glob[1]), "gambler_loss": float(glob[2]),
+                       "num_foreground": num_fg, "scope": "whole batch over all ranks"},
         }
         if secondary is not None:
             line["secondary"] = secondary
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        shutdown_distributed(plan, plan_e2e)
+
+
+def shutdown_distributed(*plans):
+    """Leave the process group without ever hanging the box: drop the CUDA graphs, drain the device, meet the
+    other ranks, then destroy the group under a watchdog that hard-exits if teardown stalls."""
+    import torch.distributed as dist
+
+    for p in plans:
+        p.release_graphs()
+    torch.cuda.synchronize()
+    try:
+        dist.barrier()
+    except Exception:
+        pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    timer = threading.Timer(20.0, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    try:
+        dist.destroy_process_group()
+    finally:
+        timer.cancel()
 
 
 def main():

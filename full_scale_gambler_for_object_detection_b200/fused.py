@@ -208,7 +208,12 @@ class DenseStepPlan:
     # ---- CUDA graph -----------------------------------------------------------------------------
     def capture(self, logits, deltas, bets, anchors, gt, warmup=2):
         """Capture the step reading from exactly these tensors (their storage must stay alive and is
-        refreshed in place by the caller between replays)."""
+        refreshed in place by the caller between replays).
+
+        Single process: one graph (4 kernels + 2 memset nodes).  Sharded (``group`` set): the collectives stay
+        *outside* the graphs -- graph 1 = K1, eager all-reduce of the two scalars, graph 2 = K2 main (+ post);
+        for ``L_BAHW_extendtobatch`` the post pass is a third graph after the second all-reduce."""
+        self._check(logits, deltas, bets, anchors, gt)
         self._static = (logits, deltas, bets, anchors, gt)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -217,17 +222,43 @@ class DenseStepPlan:
                 self.run(*self._static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.run(*self._static)
-        self.graph = g
+
+        def cap(fn):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return g
+
+        if self.group is None:
+            self.graph = [cap(lambda: self.run(*self._static))]
+        else:
+            batch_norm = self.cfg.norm_mode == _lib.NORM_BATCH
+            g1 = cap(lambda: self.stage_match(bets, anchors, gt))
+            if batch_norm:
+                g2 = cap(lambda: self.stage_main(logits, deltas, bets, anchors, gt))
+                g3 = cap(lambda: self.stage_post(bets))
+                self.graph = [g1, g2, g3]
+            else:
+                g2 = cap(lambda: (self.stage_main(logits, deltas, bets, anchors, gt), self.stage_post(bets)))
+                self.graph = [g1, g2]
         return self
 
     def replay(self):
-        """One graph launch = the whole step (4 kernels + 2 memset nodes)."""
-        self.graph.replay()
+        """Graph launch(es) of the whole step; see ``capture``."""
+        g = self.graph
+        g[0].replay()
+        if self.group is not None:
+            sharded.all_reduce_stats(self.stats, self.group)
+            g[1].replay()
+            if len(g) == 3:
+                sharded.all_reduce_batch_weighted_sum(self.scalars, self.group)
+                g[2].replay()
         _lib.count_launches(4)
         return self.result()
+
+    def release_graphs(self):
+        self.graph = None
+        self._static = None
 
 
 class _FusedStep(torch.autograd.Function):

@@ -43,12 +43,17 @@ def all_reduce_batch_weighted_sum(scalars, group=None):
     return scalars
 
 
-def global_losses(scalars, stats, coeffs, group=None):
+def global_losses(scalars, stats, coeffs, group=None, batch_sum_is_global=False):
     """Whole-batch loss values from the per-rank sums: returns a (4,) double tensor
-    [loss_cls, loss_box_reg, gambler_loss, total].  ``stats[0]`` must already be global."""
+    [loss_cls, loss_box_reg, gambler_loss, total].  ``stats[0]`` must already be global.
+    ``batch_sum_is_global``: scalars[2] was already all-reduced (``all_reduce_batch_weighted_sum``, the
+    L_BAHW_extendtobatch exchange) and must not be summed over ranks a second time."""
     sums = scalars[:5].clone()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        keep = sums[2].clone()
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        if batch_sum_is_global:
+            sums[2] = keep
     nf = torch.clamp(stats[0], min=1.0)
     loss_cls = sums[0] / nf
     loss_reg = sums[1] / nf
