@@ -228,7 +228,16 @@ def run_ours(args, rank, local_rank, world):
     bets = host["bets"].to(dev).requires_grad_(True)
     gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], dev)
 
-    plan = fsg.DenseStepPlan(N, R, K, cfg, dev, coeffs, group=group)
+    peer = None
+    if world > 1 and not args.nccl_exchange:
+        from full_scale_gambler_for_object_detection_b200.sharded import PeerExchange
+        peer = PeerExchange.create(group, dev)
+        # all ranks must agree (a rank without P2P would otherwise wait for NCCL while the others spin)
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer = None
+    plan = fsg.DenseStepPlan(N, R, K, cfg, dev, coeffs, group=group, peer=peer)
     x_s, d_s, b_s = logits.detach(), deltas.detach(), bets.detach()
     graphed = False
     try:
@@ -312,7 +321,7 @@ def run_ours(args, rank, local_rank, world):
         r.total.backward()          # grads are produced by the same fused kernels; this only hands them to autograd
         return r.total.item()
 
-    plan_e2e = fsg.DenseStepPlan(N, R, K, cfg, dev, coeffs, group=group)
+    plan_e2e = fsg.DenseStepPlan(N, R, K, cfg, dev, coeffs, group=group, peer=peer)
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(3):
         e2e_step()
@@ -357,8 +366,11 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (344 MB logits + 344 MB grads per GPU)",
                        "anchors_per_step_per_gpu": N * R, "parallelism": "image-sharded x%d" % world,
-                       "launch": ("CUDA graph replay" if world == 1 else "2 CUDA graphs + eager NCCL all-reduce")
-                       if graphed else "direct launches"},
+                       "launch": ("CUDA graph replay" if (world == 1 or peer is not None)
+                                  else "2 CUDA graphs + eager NCCL all-reduce") if graphed else "direct launches",
+                       "exchange": ("none (1 GPU)" if world == 1 else
+                                    "in-kernel all-reduce of [num_fg, S_batch] over NVLink peer memory"
+                                    if peer is not None else "NCCL all-reduce of [num_fg, S_batch]")},
             "roofline": {"bound": "hbm", "kernel": "loss_main_kernel (K2 main pass)", "achieved": achieved,
                          "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": NCU_TRAFFIC_BYTES, "bytes_per_anchor": 8 * K + 72, "kernel_ms": main_ms,
@@ -411,6 +423,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the config-4 / config-5 side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="N > 1: use the NCCL all-reduce instead of the in-kernel peer-memory exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -40,6 +40,13 @@ class LossParams(ctypes.Structure):
     ]
 
 
+class PeerCtx(ctypes.Structure):
+    """``struct fsg_peer_ctx``."""
+
+    _fields_ = [("mailbox", ctypes.c_uint64 * 8), ("epoch", ctypes.c_uint64), ("error", ctypes.c_uint64),
+                ("rank", c_i32), ("world", c_i32)]
+
+
 CLS_MODES = {"focal": 0, "sigmoid": 1}
 NORM_NONE, NORM_IMAGE, NORM_BATCH = 0, 1, 2
 
@@ -53,7 +60,8 @@ PROTOTYPES = {
     "fsg_match_anchors": (
         c_i32,
         [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr,
-         c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_ptr, c_size, c_ptr],
+         c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr,
+         ctypes.POINTER(PeerCtx), c_ptr, c_size, c_ptr],
     ),
     "fsg_box2box_get_deltas": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "fsg_box2box_apply_deltas": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_f32, c_ptr, c_ptr]),

@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     float wx, float wy, float ww, float wh, const float* __restrict__ best_val,
     const int32_t* __restrict__ best_idx, const unsigned* __restrict__ gt_max, MatchOut out,
     const float* __restrict__ bets, float temperature, int* __restrict__ part_cnt,
-    float* __restrict__ part_s, unsigned* __restrict__ done_counter, double* __restrict__ stats) {
+    float* __restrict__ part_s, unsigned* __restrict__ done_counter, double* __restrict__ stats,
+    const fsg_peer_ctx peer) {
   constexpr int U = kPassBU;
   __shared__ __align__(16) float4 s_gt[kGtChunk];
   __shared__ float s_area[kGtChunk];
@@ -533,12 +534,55 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
   }
   if (lane == 0) { s_tc[wid] = tot_cnt; s_ts[wid] = tot_s; }
   __syncthreads();
+  __shared__ double s_loc[2];
   if (tid == 0) {
     double c = 0.0, sacc = 0.0;
     for (int w = 0; w < kWarpsPerBlock; ++w) { c += s_tc[w]; sacc += s_ts[w]; }
     stats[0] = c;
     stats[1] = sacc;
+    s_loc[0] = c;
+    s_loc[1] = sacc;
     *done_counter = 0u;  // self-reset for the next call
+  }
+  if (peer.world <= 1) return;
+
+  // ---- fused exchange over peer memory: all-reduce(SUM) of [num_foreground, S_batch] across the ranks.
+  //      Mailbox of a rank: 2 (epoch parity) x 8 (sender) slots of {double v0, double v1, u64 flag, pad}.
+  __shared__ double s_px[8], s_py[8];
+  __syncthreads();
+  unsigned long long* epoch_ptr = reinterpret_cast<unsigned long long*>(peer.epoch);
+  const unsigned long long ep = *epoch_ptr + 1ull;
+  if (tid < peer.world) {
+    const int slot_out = (int)(ep & 1ull) * 8 + peer.rank;
+    double* dst = reinterpret_cast<double*>(peer.mailbox[tid]) + slot_out * 4;
+    dst[0] = s_loc[0];
+    dst[1] = s_loc[1];
+    __threadfence_system();
+    unsigned long long* fl = reinterpret_cast<unsigned long long*>(dst + 2);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(ep) : "memory");
+    const int slot_in = (int)(ep & 1ull) * 8 + tid;
+    const double* src = reinterpret_cast<const double*>(peer.mailbox[peer.rank]) + slot_in * 4;
+    const unsigned long long* fin = reinterpret_cast<const unsigned long long*>(src + 2);
+    const long long t0 = clock64();
+    unsigned long long seen = 0ull;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fin) : "memory");
+      if (seen == ep) break;
+      if (clock64() - t0 > 6000000000ll) {   // ~3 s: a peer never arrived; fail loudly instead of hanging
+        *reinterpret_cast<int*>(peer.error) = 1;
+        break;
+      }
+    }
+    s_px[tid] = *reinterpret_cast<const volatile double*>(src);
+    s_py[tid] = *reinterpret_cast<const volatile double*>(src + 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double c = 0.0, sacc = 0.0;
+    for (int p = 0; p < peer.world; ++p) { c += s_px[p]; sacc += s_py[p]; }   // rank order: same sum everywhere
+    stats[0] = c;
+    stats[1] = sacc;
+    *epoch_ptr = ep;
   }
 }
 
@@ -667,7 +711,8 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
                                  const float* h_box_weights, int64_t* matches, int8_t* match_labels,
                                  int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
                                  float* gt_deltas, int32_t* matched_idx32, const float* bets, float temperature,
-                                 double* stats, void* workspace, size_t workspace_bytes, fsg_stream_t stream) {
+                                 double* stats, const fsg_peer_ctx* h_peer, void* workspace,
+                                 size_t workspace_bytes, fsg_stream_t stream) {
   if (N <= 0 || R < 0 || sum_M < 0 || !gt_offsets) return FSG_ERR_INVALID_ARG;
   if (R == 0) return FSG_OK;
   if (!anchors || (sum_M > 0 && !gt_boxes)) return FSG_ERR_INVALID_ARG;
@@ -685,6 +730,16 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
     pmb.n = 0;
   }
   if (bets && !stats) return FSG_ERR_INVALID_ARG;
+  fsg_peer_ctx peer = {};
+  peer.world = 1;
+  if (h_peer) {
+    if (!stats || h_peer->world < 1 || h_peer->world > 8 || h_peer->rank < 0 || h_peer->rank >= h_peer->world ||
+        !h_peer->epoch || !h_peer->error)
+      return FSG_ERR_INVALID_ARG;
+    for (int p = 0; p < h_peer->world; ++p)
+      if (!h_peer->mailbox[p]) return FSG_ERR_INVALID_ARG;
+    peer = *h_peer;
+  }
   const MatchWs w = match_ws_layout(N, R, sum_M);
   if (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
   char* ws = (char*)workspace;
@@ -708,7 +763,7 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
   match_pass_b_kernel<<<grid_b, kMatchBlock, 0, s>>>(
       (const float4*)anchors, R, anchor_image_stride / 4, (const float4*)gt_boxes, gt_class_ids, gt_offsets, N,
       num_classes, mb, pmb, allow_lq ? 1 : 0, wx, wy, ww, wh, bval, bidx, gtmax, out, bets, temperature,
-      (int*)(ws + w.off_pcnt), (float*)(ws + w.off_ps), counter, stats);
+      (int*)(ws + w.off_pcnt), (float*)(ws + w.off_ps), counter, stats, peer);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

@@ -117,11 +117,14 @@ class DenseStepPlan:
     """
 
     def __init__(self, N, R, K, cfg, device, coeffs=(1.0, 1.0, -1.0), detach_pred=False, want_weights=False,
-                 max_total_gt=4096, group=None):
+                 max_total_gt=4096, group=None, peer=None):
         assert K == cfg.num_classes
         self.N, self.R, self.K, self.cfg, self.device = N, R, K, cfg, torch.device(device)
         self.coeffs = tuple(float(c) for c in coeffs)
         self.detach_pred, self.group, self.max_total_gt = bool(detach_pred), group, int(max_total_gt)
+        # peer: sharded.PeerExchange -- the [num_foreground, S_batch] all-reduce then happens inside K1's
+        # second kernel over NVLink peer memory instead of an NCCL launch (and the step is one graph again)
+        self.peer = peer if (peer is not None and group is not None) else None
         self.params = cfg.loss_params(*self.coeffs)
         L = self.L = ops.lib()
         dev = self.device
@@ -168,7 +171,8 @@ class DenseStepPlan:
             P(anchors), R, a_stride, P(gt.boxes), P(gt.classes), P(gt.offsets), N, gt.total, cfg.num_classes,
             self._thr, self._lab, len(cfg.iou_thresholds), 1, self._pthr, self._lab, len(cfg.picky_thresholds),
             self._bw, None, None, None, P(self.gt_classes), P(self.mask), None, P(self.matched), P(bets),
-            float(cfg.gambler_temperature), P(self.stats), P(self.ws_match), self.ws_match.numel(), _lib.stream()))
+            float(cfg.gambler_temperature), P(self.stats), self.peer.ctx if self.peer is not None else None,
+            P(self.ws_match), self.ws_match.numel(), _lib.stream()))
         _lib.count_launches(2)
 
     def stage_main(self, logits, deltas, bets, anchors, gt):
@@ -191,7 +195,7 @@ class DenseStepPlan:
         """Enqueue the step on the current stream.  Inputs: detached contiguous CUDA fp32 tensors."""
         self._check(logits, deltas, bets, anchors, gt)
         self.stage_match(bets, anchors, gt)
-        if self.group is not None:
+        if self.group is not None and self.peer is None:
             sharded.all_reduce_stats(self.stats, self.group)
         self.stage_main(logits, deltas, bets, anchors, gt)
         if self.group is not None and self.cfg.norm_mode == _lib.NORM_BATCH:
@@ -229,7 +233,7 @@ class DenseStepPlan:
                 fn()
             return g
 
-        if self.group is None:
+        if self.group is None or (self.peer is not None and self.cfg.norm_mode != _lib.NORM_BATCH):
             self.graph = [cap(lambda: self.run(*self._static))]
         else:
             batch_norm = self.cfg.norm_mode == _lib.NORM_BATCH
@@ -247,8 +251,9 @@ class DenseStepPlan:
         """Graph launch(es) of the whole step; see ``capture``."""
         g = self.graph
         g[0].replay()
-        if self.group is not None:
-            sharded.all_reduce_stats(self.stats, self.group)
+        if len(g) > 1:
+            if self.peer is None:
+                sharded.all_reduce_stats(self.stats, self.group)
             g[1].replay()
             if len(g) == 3:
                 sharded.all_reduce_batch_weighted_sum(self.scalars, self.group)

@@ -132,7 +132,7 @@ def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1
             host_f32(box_weights), ptr(out.get("matches")), ptr(out.get("match_labels")),
             ptr(out.get("picky_labels")), ptr(out.get("gt_classes")), ptr(out.get("mask")),
             ptr(out.get("gt_deltas")), ptr(out.get("matched_idx32")), ptr(bets), float(temperature), ptr(stats),
-            ptr(ws), ws.numel(), stream()))
+            None, ptr(ws), ws.numel(), stream()))
         count_launches(2)
     if stats is not None:
         out["stats"] = stats

@@ -77,6 +77,21 @@ FSG_API int fsg_matcher(const float* mqm, int64_t M, int64_t N, const float* h_t
                 const int8_t* h_labels, int num_thresholds, int allow_low_quality_matches,
                 int64_t* matches, int8_t* match_labels, float* ws_rowmax, fsg_stream_t stream);
 
+/* Peer-memory exchange context for a batch sharded by image over the GPUs of one NVLink/NVSwitch box.
+ * mailbox[p] is rank p's mailbox (1 KiB of symmetric, zero-initialised device memory) as mapped in THIS
+ * process (its own mailbox included).  When a context is passed to fsg_match_anchors, the last CTA of its
+ * second kernel all-reduces stats[0..1] = [num_foreground, S_batch] itself: it stores its two partial sums
+ * and a release flag (a per-launch epoch) into every peer's mailbox with plain st.global over NVLink, spins
+ * (acquire loads, with a clock time-out that raises *error) until every peer's flag shows the same epoch,
+ * and sums the slots in rank order (identical result on every rank).  No NCCL launch, capturable in a CUDA
+ * graph; every rank must enqueue the same sequence of calls. */
+typedef struct fsg_peer_ctx {
+  uint64_t mailbox[8]; /* device pointers */
+  uint64_t epoch;      /* device pointer to a local uint64 counter, zero-initialised                */
+  uint64_t error;      /* device pointer to a local int32 flag, set to 1 if a peer never showed up  */
+  int32_t rank, world; /* world <= 8 */
+} fsg_peer_ctx;
+
 /* Fused IoU + Matcher(s) + GT assignment for a batch of images, never materialising the
  * (M, R) matrix.  Replaces, per image, retinanet.py:339-363 and :400-425:
  *   pairwise_iou -> Matcher(thresholds) [-> picky Matcher(picky_thresholds)] ->
@@ -106,8 +121,8 @@ FSG_API int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor_im
                       int num_picky_thresholds, const float* h_box_weights /* 4 */, int64_t* matches, int8_t* match_labels,
                       int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
                       float* gt_deltas, int32_t* matched_idx32, const float* bets,
-                      float temperature, double* stats, void* workspace, size_t workspace_bytes,
-                      fsg_stream_t stream);
+                      float temperature, double* stats, const fsg_peer_ctx* h_peer /* NULL: no exchange */,
+                      void* workspace, size_t workspace_bytes, fsg_stream_t stream);
 
 /* box_regression.py:34-67 / :69-107.  h_weights = (wx, wy, ww, wh).
  * apply_deltas: deltas (n, 4k) -> out (n, 4k), dw/dh clamped to scale_clamp (max only). */

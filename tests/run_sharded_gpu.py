@@ -38,7 +38,13 @@ def main():
     sl = sharded.image_shard(N, world, rank)
     coeffs = (1.0, 0.5, -2.0)
     anchors = inp["anchors"].to(dev)
-    for output in ("L_BAHW", "L_BAHW_extendtobatch"):
+    peer = sharded.PeerExchange.create(dist.group.WORLD, dev)
+    if rank == 0:
+        print("peer-memory exchange:", "available" if peer is not None else "unavailable (NCCL only)", flush=True)
+    for output, use_peer in (("L_BAHW", False), ("L_BAHW_extendtobatch", False), ("L_BAHW", True),
+                             ("L_BAHW_extendtobatch", True)):
+        if use_peer and peer is None:
+            continue
         cfg = fsg.DenseLossConfig(num_classes=K, gambler_output=output)
         # whole batch on this GPU, no group
         gt_all = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], dev)
@@ -49,7 +55,8 @@ def main():
         # my shard, with the exchange
         gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"][sl], inp["gt_classes"][sl], dev)
         x, d, b = (inp[k][sl].contiguous().to(dev) for k in ("logits", "deltas", "bets"))
-        plan = fsg.DenseStepPlan(per, R, K, cfg, dev, coeffs, group=dist.group.WORLD)
+        plan = fsg.DenseStepPlan(per, R, K, cfg, dev, coeffs, group=dist.group.WORLD,
+                                 peer=peer if use_peer else None)
         for mode in ("direct", "graph"):
             if mode == "graph":
                 plan.capture(x, d, b, anchors, gt)
@@ -60,11 +67,17 @@ def main():
             g = sharded.global_losses(r.scalars, r.stats, coeffs, dist.group.WORLD,
                                       batch_sum_is_global=(output == "L_BAHW_extendtobatch"))
             for i, j in enumerate((5, 6, 7, 8)):
-                assert abs(float(g[i]) - float(want["scal"][j])) <= 1e-6 * abs(float(want["scal"][j])), (output, mode, i)
+                assert abs(float(g[i]) - float(want["scal"][j])) <= 1e-6 * abs(float(want["scal"][j])), \
+                    (output, mode, use_peer, i)
             close(plan.grad_logits, want["gl"], 1e-6, "grad_logits")
             close(plan.grad_deltas, want["gd"], 1e-6, "grad_deltas")
             close(plan.grad_bets, want["gb"], 2e-6, "grad_bets")
         plan.release_graphs()
+        if use_peer:
+            for _ in range(5):      # repeated launches: epochs advance, mailboxes alternate
+                r = plan.run(x, d, b, anchors, gt)
+            assert float(r.stats[0]) == float(want["nf"])
+            peer.check()
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:

@@ -54,6 +54,7 @@ def test_ctypes_prototypes_cover_the_header(lib_path):
     assert L.fsg_detect_workspace_bytes(2, 1000, 80, 5, 1000) > 0
     assert L.fsg_nms_workspace_bytes(100) > 0
     assert ctypes.sizeof(_lib.LossParams) == 64
+    assert ctypes.sizeof(_lib.PeerCtx) == 88
 
 
 def test_header_is_plain_c():
