@@ -18,10 +18,13 @@
 
 namespace fsg {
 
-constexpr int kSelThreads = 512;
-constexpr int kSelCap = 8192;                       // candidate buffer entries (u64 keys)
+constexpr int kSelThreads = 256;
+constexpr int kSelCap = 4096;                       // candidate buffer entries (u64 keys): 32 KB -> 4 CTAs/SM
 constexpr int kSelIter = kSelThreads * 8;           // elements consumed per block iteration
-constexpr int kSelTrigger = kSelCap - kSelIter;     // prune when the buffer may overflow next iteration
+constexpr int kStagePerWarp = 32;                   // raw (logit, index) candidates a warp collects before it
+                                                    // evaluates their sigmoids as one dense batch
+// worst case a warp adds 8*32 new + one full stage per block iteration: prune while that still fits
+constexpr int kSelTrigger = kSelCap - (kSelThreads / 32) * (256 + kStagePerWarp);
 constexpr int kMaxLevels = 8;
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsCap = 8192;                       // candidates per image the NMS kernel holds
@@ -47,28 +50,40 @@ __device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
 __device__ __forceinline__ float key_score(uint64_t k) { return __uint_as_float((uint32_t)(k >> 32)); }
 __device__ __forceinline__ uint32_t key_index(uint64_t k) { return 0xffffffffu - (uint32_t)k; }
 
-// ---- block-wide exact k-th largest over 64-bit keys in shared memory (8-bit radix select) ----------
+// ---- block-wide exact k-th largest over 64-bit keys in shared memory (11-bit radix select) ---------
 // returns T such that exactly k keys are >= T (keys are distinct).  Requires count >= k >= 1.
+// Histogram increments are aggregated with match.any first: score keys share their exponent bits, so the
+// top digits put almost every key in one bin and un-aggregated shared atomics would serialise 32-fold.
+constexpr int kDigitBits = 10;
+constexpr int kBins = 1 << kDigitBits;
 template <int NT>
-__device__ uint64_t select_kth(const uint64_t* buf, int count, int k, unsigned* hist /*256*/, int* s_tmp /*4*/) {
+__device__ uint64_t select_kth(const uint64_t* buf, int count, int k, unsigned* hist /*kBins*/, int* s_tmp /*4*/) {
   const int tid = threadIdx.x, lane = tid & 31;
   uint64_t prefix = 0;
   int need = k;
-  for (int shift = 56; shift >= 0; shift -= 8) {
-    if (tid < 256) hist[tid] = 0u;
+  const int rounds = (count + NT - 1) / NT;
+  for (int top = 64; top > 0; top -= kDigitBits) {
+    const int width = top >= kDigitBits ? kDigitBits : top;   // 10,10,10,10,10,10,4
+    const int shift = top - width;
+    for (int b = tid; b < kBins; b += NT) hist[b] = 0u;
     __syncthreads();
-    for (int i = tid; i < count; i += NT) {
-      const uint64_t key = buf[i];
-      const bool match = (shift == 56) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
-      if (match) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int i = rd * NT + tid;
+      unsigned bin = 0x80000000u | (unsigned)lane;   // unique sentinel: lanes without a key match nobody
+      if (i < count) {
+        const uint64_t key = buf[i];
+        const bool match = (top == 64) || ((key >> top) == (prefix >> top));
+        if (match) bin = (unsigned)(key >> shift) & ((1u << width) - 1u);
+      }
+      const unsigned peers = __match_any_sync(kFull, bin);
+      if (!(bin & 0x80000000u) && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
     }
     __syncthreads();
     if (tid < 32) {
-      // lane L owns bins 255-8L .. 248-8L (descending)
-      unsigned loc[8];
+      // lane L owns the 64 bins kBins-1-64L .. kBins-64-64L (descending)
+      constexpr int PER = kBins / 32;
       unsigned sum = 0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) { loc[b] = hist[255 - 8 * lane - b]; sum += loc[b]; }
+      for (int b = 0; b < PER; ++b) sum += hist[kBins - 1 - PER * lane - b];
       unsigned inc = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -78,14 +93,14 @@ __device__ uint64_t select_kth(const uint64_t* buf, int count, int k, unsigned* 
       const unsigned before = inc - sum;
       if (before < (unsigned)need && inc >= (unsigned)need) {
         unsigned cum = before;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          if (cum < (unsigned)need && cum + loc[b] >= (unsigned)need) {
-            s_tmp[0] = 255 - 8 * lane - b;  // digit
-            s_tmp[1] = (int)cum;            // keys strictly above this digit (within prefix)
-            s_tmp[2] = (int)loc[b];         // keys in this digit's bin
+        for (int b = 0; b < PER; ++b) {
+          const unsigned h = hist[kBins - 1 - PER * lane - b];
+          if (cum < (unsigned)need && cum + h >= (unsigned)need) {
+            s_tmp[0] = kBins - 1 - PER * lane - b;  // digit
+            s_tmp[1] = (int)cum;                    // keys strictly above this digit (within prefix)
+            s_tmp[2] = (int)h;                      // keys in this digit's bin
           }
-          cum += loc[b];
+          cum += h;
         }
       }
     }
@@ -194,33 +209,13 @@ struct SelectArgs {
   int* lvl_count;        // (N, L)
 };
 
-// Append the (up to four per lane) logits that pass the pre-filter.  The lanes that pass are first
-// compacted into a per-warp staging area so the sigmoid (expf + IEEE divide) and the exact score test
-// run on dense warps instead of once per element position with most lanes masked off.
-constexpr int kStagePerWarp = 128;
-__device__ __forceinline__ void staged_append4(const float* v, uint32_t idx0, float xb, float ts, float2* stage,
-                                               uint64_t* buf, int* s_count) {
+// Evaluate the warp's staged raw candidates as dense batches: sigmoid (expf + IEEE divide), the exact
+// `score > ts` test and the append to the CTA's key buffer.  Called by all 32 lanes.
+__device__ __forceinline__ void flush_stage(const float2* stage, int n, float ts, uint64_t* buf, int* s_count) {
   const int lane = threadIdx.x & 31;
-  unsigned flags = 0u;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) flags |= (v[j] > xb) ? (1u << j) : 0u;
-  const int c = __popc(flags);
-  int inc = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(kFull, inc, o);
-    if (lane >= o) inc += t;
-  }
-  const int total = __shfl_sync(kFull, inc, 31);
-  if (total == 0) return;
-  int off = inc - c;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (flags & (1u << j)) stage[off++] = make_float2(v[j], __uint_as_float(idx0 + j));
-  __syncwarp();
-  for (int i0 = 0; i0 < total; i0 += 32) {
+  for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
-    bool p = i < total;
+    bool p = i < n;
     float sc = 0.f;
     uint32_t id = 0u;
     if (p) {
@@ -238,15 +233,64 @@ __device__ __forceinline__ void staged_append4(const float* v, uint32_t idx0, fl
       if (p) buf[base + __popc(m & ((1u << lane) - 1u))] = make_key(sc, id);
     }
   }
+}
+
+// Collect the lanes' logits that pass the (cheap, conservative) logit pre-filter into the warp's staging
+// queue; the expensive part runs later on full warps (flush_stage).  v[0..3] sit at idx0.., v[4..7] at idx1..
+__device__ __forceinline__ void stage_candidates(const float* v, uint32_t idx0, uint32_t idx1, float xb, float ts,
+                                                 float2* stage, int* s_scnt, uint64_t* buf, int* s_count) {
+  const int lane = threadIdx.x & 31;
+  unsigned flags = 0u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) flags |= (v[j] > xb) ? (1u << j) : 0u;
+  const int c = __popc(flags);
+  const int tot = __reduce_add_sync(kFull, c);
+  if (tot == 0) return;
+  int cur = *s_scnt;
+  if (cur + tot > kStagePerWarp) {
+    flush_stage(stage, cur, ts, buf, s_count);
+    __syncwarp();
+    if (lane == 0) *s_scnt = 0;
+    __syncwarp();
+    cur = 0;
+  }
+  if (tot > kStagePerWarp) {
+    // dense phase (pre-filter still loose): go through the stage in slices of one element position
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool p = (flags >> j) & 1u;
+      const unsigned m = __ballot_sync(kFull, p);
+      if (m == 0u) continue;
+      if (p) stage[__popc(m & ((1u << lane) - 1u))] = make_float2(v[j], __uint_as_float((j < 4 ? idx0 : idx1 - 4) + j));
+      __syncwarp();
+      flush_stage(stage, __popc(m), ts, buf, s_count);
+      __syncwarp();
+    }
+    return;
+  }
+  if (c == 1) {
+    // the common case late in the scan: one candidate in this lane -> pick it with a select tree
+    const int j = __ffs(flags) - 1;
+    const float lo = (j & 2) ? ((j & 1) ? v[3] : v[2]) : ((j & 1) ? v[1] : v[0]);
+    const float hi = (j & 2) ? ((j & 1) ? v[7] : v[6]) : ((j & 1) ? v[5] : v[4]);
+    const int off = atomicAdd(s_scnt, 1);
+    stage[off] = make_float2((j & 4) ? hi : lo, __uint_as_float(((j & 4) ? idx1 - 4 : idx0) + j));
+  } else if (c > 1) {
+    int off = atomicAdd(s_scnt, c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if ((flags >> j) & 1u) stage[off++] = make_float2(v[j], __uint_as_float((j < 4 ? idx0 : idx1 - 4) + j));
+  }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kSelThreads, 2) detect_select_kernel(const SelectArgs A, const DetectLevels LV) {
+__global__ void __launch_bounds__(kSelThreads, 4) detect_select_kernel(const SelectArgs A, const DetectLevels LV) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);  // kSelCap
-  __shared__ unsigned hist[256];
+  __shared__ unsigned hist[kBins];
   __shared__ int s_tmp[4];
   __shared__ int s_count;
+  __shared__ int s_scnt[kSelThreads / 32];
   __shared__ float s_xb, s_ts;
   __shared__ bool s_last;
   __shared__ uint64_t s_red64[kSelThreads / 32];
@@ -264,12 +308,14 @@ __global__ void __launch_bounds__(kSelThreads, 2) detect_select_kernel(const Sel
   const int64_t e1 = min(E, e0 + LV.part_len[l]);
 
   if (tid == 0) { s_count = 0; s_xb = A.xpre; s_ts = A.thr; }
+  if (tid < kSelThreads / 32) s_scnt[tid] = 0;
   __syncthreads();
 
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(slab) & 15) == 0);
   __shared__ float2 s_stage[kSelThreads / 32][kStagePerWarp];
   float2* stage = s_stage[tid >> 5];
-  auto load8 = [&](int64_t base, float* v) {
+  // checked loader for ragged ends / unaligned slabs
+  auto load8_checked = [&](int64_t base, float* v) {
     const int64_t p0 = base + (int64_t)tid * 4;
     const int64_t p1 = p0 + kSelThreads * 4;
     if (vec_ok && p0 + 4 <= e1) {
@@ -285,20 +331,13 @@ __global__ void __launch_bounds__(kSelThreads, 2) detect_select_kernel(const Sel
       for (int j = 0; j < 4; ++j) v[4 + j] = (p1 + j < e1) ? ldg_stream1(slab + p1 + j) : -INFINITY;
     }
   };
-  float v[8], vn[8];
-  if (e0 < e1) load8(e0, v);
-  for (int64_t base = e0; base < e1; base += kSelIter) {
+  // one block iteration: pre-filter, stage, barrier, prune when the key buffer may overflow
+  auto consume = [&](const float* v, int64_t base) {
     const float xb = s_xb, ts = s_ts;
-    const bool more = base + kSelIter < e1;
-    if (more) load8(base + kSelIter, vn);   // software prefetch: the next block's loads fly under this one
-    const int64_t p0 = base + (int64_t)tid * 4;
-    const int64_t p1 = p0 + kSelThreads * 4;
-    bool any = false;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) any |= (v[j] > xb);
-    if (__any_sync(kFull, any)) {
-      staged_append4(v, (uint32_t)p0, xb, ts, stage, buf, &s_count);
-      staged_append4(v + 4, (uint32_t)p1, xb, ts, stage, buf, &s_count);
+    const float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+    if (__any_sync(kFull, m > xb)) {
+      const uint32_t p0 = (uint32_t)(base + (int64_t)tid * 4);
+      stage_candidates(v, p0, p0 + kSelThreads * 4, xb, ts, stage, &s_scnt[tid >> 5], buf, &s_count);
     }
     __syncthreads();
     if (s_count > kSelTrigger) {   // uniform: read after the barrier
@@ -317,11 +356,34 @@ __global__ void __launch_bounds__(kSelThreads, 2) detect_select_kernel(const Sel
       }
       __syncthreads();
     }
-    if (more) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = vn[j];
+  };
+  // full iterations: unconditional 16-byte loads through a running pointer, two register sets in
+  // ping-pong so the next block's loads are in flight while this one is consumed
+  const int64_t n_full = vec_ok ? (e1 - e0) / kSelIter : 0;
+  {
+    const float* pa = slab + e0 + (int64_t)tid * 4;
+    float va[8], vb[8];
+    auto ld = [&](const float* p, float* v) {
+      const float4 t0 = ldg_stream4(p), t1 = ldg_stream4(p + kSelThreads * 4);
+      v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    };
+    if (n_full > 0) ld(pa, va);
+    for (int64_t it = 0; it < n_full; it += 2) {
+      if (it + 1 < n_full) ld(pa + (it + 1) * kSelIter, vb);
+      consume(va, e0 + it * kSelIter);
+      if (it + 1 < n_full) {
+        if (it + 2 < n_full) ld(pa + (it + 2) * kSelIter, va);
+        consume(vb, e0 + (it + 1) * kSelIter);
+      }
     }
   }
+  for (int64_t base = e0 + n_full * kSelIter; base < e1; base += kSelIter) {   // ragged end / unaligned slab
+    float v[8];
+    load8_checked(base, v);
+    consume(v, base);
+  }
+  flush_stage(stage, s_scnt[tid >> 5], s_ts, buf, &s_count);   // what is still waiting in the warp queues
+  __syncthreads();
   prune_topk<kSelThreads>(buf, &s_count, k, hist, s_tmp);
   __syncthreads();
 
@@ -668,7 +730,7 @@ static float threshold_floor(double thr) {
 constexpr size_t kNmsSmem = (size_t)kNmsCap * 27;
 constexpr size_t kSelSmem = (size_t)kSelCap * 8;
 
-static DetectLevels plan_levels(const int64_t* off, int num_levels, int K, int topk) {
+static DetectLevels plan_levels(const int64_t* off, int num_levels, int K, int topk, int N) {
   DetectLevels lv;
   lv.num_levels = num_levels;
   int base = 0, maxp = 1;
@@ -679,6 +741,11 @@ static DetectLevels plan_levels(const int64_t* off, int num_levels, int K, int t
     const int64_t E = hwa * K;
     lv.k[l] = (int)(hwa < topk ? hwa : topk);
     int parts = (int)ceil_div(E > 0 ? E : 1, (int64_t)64 * kSelIter);  // ~256K elements per CTA
+    // a longer stream per CTA tightens its running threshold (pass rate ~ k/n_seen) and needs fewer prunes:
+    // only split a slab as far as one wave of resident CTAs (4 per SM) can take
+    int want = (4 * 148) / (N * num_levels);   // 4 resident CTAs per SM: keep every stream in the first wave
+    if (want < 1) want = 1;
+    if (parts > want) parts = want;
     if (parts > 16) parts = 16;
     if (parts > cap_parts) parts = cap_parts;
     if (parts < 1) parts = 1;
@@ -786,7 +853,7 @@ extern "C" int fsg_detect(const float* logits, const float* deltas, const float*
   }
   if ((cand_boxes || cand_scores || cand_classes) && !(cand_boxes && cand_scores && cand_classes))
     return FSG_ERR_INVALID_ARG;
-  const DetectLevels lv = plan_levels(h_level_offsets, num_levels, K, topk);
+  const DetectLevels lv = plan_levels(h_level_offsets, num_levels, K, topk, N);
   int maxp = kSelCap / topk;
   if (maxp > 16) maxp = 16;
   if (maxp < 1) maxp = 1;
