@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) loss_prepass_kernel(const int64_t* __rest
 // main pass
 // ------------------------------------------------------------------------------------------
 template <int V, int BATCH, int VARIANT, int GT>
-__global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 2)) loss_main_kernel(const LossArgs A) {
+__global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 3)) loss_main_kernel(const LossArgs A) {
   // GT > 0: "exact" instantiation, G == GT lanes per anchor and K == V*GT*BATCH (no predication in the
   // element loop); GT == 0: G and K are run-time values.
   constexpr bool kWrite = (VARIANT != kFastNoWrite);
@@ -343,12 +343,18 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 2)) loss_main_kernel
           if (write_grad) A.grad_logits[o * A.K + cls] = fg1 * (coef_f * A.a1);
         }
       } else {
+        // double-buffered: the next batch of row pieces is in flight while this one is evaluated
+        Vec<V> y[BATCH], z[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int j = gl + b * G;
+          if (j < nvec) y[b].load(xrow + (int64_t)(j - gl) * V);
+        }
         for (int j0 = gl; j0 < nvec; j0 += G * BATCH) {
-          Vec<V> y[BATCH];
 #pragma unroll
           for (int b = 0; b < BATCH; ++b) {
-            const int j = j0 + b * G;
-            if (j < nvec) y[b].load(xrow + (int64_t)(j - gl) * V);
+            const int j = j0 + G * BATCH + b * G;
+            if (j < nvec) z[b].load(xrow + (int64_t)(j - gl) * V);
           }
 #pragma unroll
           for (int b = 0; b < BATCH; ++b) {
@@ -390,6 +396,8 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 2)) loss_main_kernel
               if (write_grad) g.store(grow + (int64_t)(j - gl) * V);
             }
           }
+#pragma unroll
+          for (int b = 0; b < BATCH; ++b) y[b] = z[b];
         }
       }
     }

@@ -1,0 +1,123 @@
+"""GPU: the CUDA path against the REFERENCE's own outputs committed under tests/golden/ (made by
+oracle/make_golden.py from the reference's source files) -- no oracle in between."""
+import pytest
+import torch
+
+from tests import golden_util as gu
+from tests.util import assert_close_scalar, assert_close_tensor, assert_equal_int
+
+pytestmark = pytest.mark.gpu
+
+
+def _fsg():
+    import full_scale_gambler_for_object_detection_b200 as fsg
+    return fsg
+
+
+@pytest.mark.parametrize("name", gu.TRAIN_CASES)
+def test_train_step_vs_reference(cuda, name):
+    fsg = _fsg()
+    inp, g, coeffs, detach, gcfg, K = gu.train_case(name)
+    cfg = fsg.DenseLossConfig(num_classes=K, **{gu.CFG_KW[k]: v for k, v in gcfg.items()})
+    x = inp["logits"].to(cuda).requires_grad_(True)
+    d = inp["deltas"].to(cuda).requires_grad_(True)
+    b = inp["bets"].to(cuda).requires_grad_(True)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    res = fsg.dense_train_step(x, d, b, inp["anchors"].to(cuda), gt, cfg, coeffs, detach_pred=detach, want_weights=True)
+    res.total.backward()
+    assert_equal_int(res.gt_classes, g["gt_classes"], "gt_classes")
+    assert_equal_int(res.mask, g["mask"], "mask")
+    assert_close_scalar(res.loss_cls.item(), g["loss_cls"], "loss_cls")
+    assert_close_scalar(res.loss_box_reg.item(), g["loss_box_reg"], "loss_box_reg")
+    assert_close_scalar(res.gambler_loss.item(), g["gambler_loss"], "gambler_loss")
+    assert_close_scalar(res.total.item(), g["total"], "total", rtol=2e-5)
+    assert_close_scalar(res.loss_before_weighting(cfg.gambler_loss_mode).item(), g["loss_before_weighting"], "lbw")
+    assert_close_scalar(res.lower_bound(cfg.gambler_temperature).item(), g["lower_bound"], "lower_bound")
+    assert_close_tensor(res.per_anchor_loss, g["per_anchor_loss"], "per_anchor_loss")
+    assert_close_tensor(res.weights, g["weights"], "weights")
+    if detach:
+        assert x.grad is None
+    else:
+        assert_close_tensor(x.grad.reshape(-1, K)[g["grad_rows"].to(cuda)], g["grad_logits"], "grad_logits")
+    if coeffs[1] != 0:
+        assert_close_tensor(d.grad, g["grad_deltas"], "grad_deltas")
+    floor = 1e-5 if gcfg.get("GAMBLER_LOSS_MODE") == "sigmoid" else 1e-6   # see test_step_variants
+    assert_close_tensor(b.grad, g["grad_bets"], "grad_bets", atol_scale=floor)
+
+
+def test_matcher_vs_reference(cuda):
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    g = gu.load("matcher_stress")
+    cid, N, R, M = [int(v) for v in g["params"]]
+    inp = synthetic.matcher_stress_inputs(cid, N, R, M)
+    inp["anchors"][0, 100] = inp["anchors"][0, 99]
+    inp["anchors"][1, :50] = inp["gt_boxes"][1][:50]
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    got = fsg.ops.match_anchors(inp["anchors"].to(cuda), gt, 80, want=("matches", "match_labels", "picky_labels"))
+    for i in range(N):
+        assert_equal_int(got["matches"][i], g["matches_%d" % i], "fused matches")
+        assert_equal_int(got["match_labels"][i], g["labels_%d" % i], "fused labels")
+        assert_equal_int(got["picky_labels"][i], g["picky_labels_%d" % i], "fused picky labels")
+        # drop-in forms: materialised IoU matrix + Matcher on it, with and without low-quality matches
+        q = fsg.pairwise_iou(fsg.Boxes(inp["gt_boxes"][i].to(cuda)), fsg.Boxes(inp["anchors"][i].to(cuda)))
+        assert torch.equal(q[:, :512].cpu(), g["iou_sample_%d" % i])
+        assert torch.equal(q.max(dim=1).values.cpu(), g["iou_rowmax_%d" % i])
+        m, l = fsg.Matcher([0.4, 0.5], [0, -1, 1], allow_low_quality_matches=True)(q)
+        assert_equal_int(m, g["matches_%d" % i], "matrix matches")
+        assert_equal_int(l, g["labels_%d" % i], "matrix labels")
+        m, l = fsg.Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=False)(q)
+        assert_equal_int(m, g["nolq_matches_%d" % i], "no-lq matches")
+        assert_equal_int(l, g["nolq_labels_%d" % i], "no-lq labels")
+        m, l = fsg.Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=False).match_boxes(
+            inp["gt_boxes"][i].to(cuda), inp["anchors"][i].to(cuda))
+        assert_equal_int(m, g["nolq_matches_%d" % i], "fused no-lq matches")
+        assert_equal_int(l, g["nolq_labels_%d" % i], "fused no-lq labels")
+    m, l = fsg.Matcher([0.4, 0.5], [0, -1, 1], True)(torch.tensor([[0.9, 0.3, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]]).to(cuda))
+    assert_equal_int(m, g["quirk_matches"], "quirk matches")
+    assert_equal_int(l, g["quirk_labels"], "quirk labels")
+    m, l = fsg.Matcher([0.4, 0.5], [0, -1, 1], True)(torch.zeros((0, 7), device=cuda))
+    assert_equal_int(m, g["empty_matches"], "empty matches")
+    assert_equal_int(l, g["empty_labels"], "empty labels")
+
+
+def test_box2box_vs_reference(cuda):
+    fsg = _fsg()
+    g = gu.load("box2box")
+    t = fsg.Box2BoxTransform(weights=tuple(float(v) for v in g["weights"]))
+    assert_close_tensor(t.get_deltas(g["src"].to(cuda), g["dst"].to(cuda)), g["deltas"], "get_deltas")
+    assert_close_tensor(t.apply_deltas(g["big"].to(cuda), g["boxes"].to(cuda)), g["applied"], "apply_deltas",
+                        atol_scale=1e-6)
+
+
+def test_nms_vs_reference(cuda):
+    """keep indices of the reference's nms / batched_nms (detectron2/layers/nms.py -> torchvision 0.26), bit-exact."""
+    fsg = _fsg()
+    g = gu.load("nms")
+    for name in ("a", "b", "c"):
+        b, s, i = g["boxes_" + name].to(cuda), g["scores_" + name].to(cuda), g["idxs_" + name].to(cuda)
+        for thr in (0.2, 0.5, 0.8):
+            tag = "%s_%02d" % (name, int(thr * 10))
+            assert_equal_int(fsg.nms(b, s, thr), g["nms_" + tag], "nms " + tag)
+            assert_equal_int(fsg.batched_nms(b, s, i, thr), g["batched_" + tag], "batched_nms " + tag)
+
+
+def test_inference_vs_reference(cuda):
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    g = gu.load("inference")
+    p = [int(v) for v in g["params"]]
+    inp = synthetic.inference_inputs(p[0], p[1], p[2:7], p[7])
+    path = fsg.RetinaNetDensePath(num_classes=p[7])
+    offs = inp["level_offsets"]
+    for n in range(p[1]):
+        cls = [inp["logits"][n, offs[i]:offs[i + 1]].to(cuda) for i in range(5)]
+        reg = [inp["deltas"][n, offs[i]:offs[i + 1]].to(cuda) for i in range(5)]
+        anc = [fsg.Boxes(inp["anchors"][offs[i]:offs[i + 1]].to(cuda)) for i in range(5)]
+        r = path.inference_single_image(cls, reg, anc, (800, 1344))
+        # same detections (class, order); scores/boxes within fp32 tolerance of the CPU sigmoid/exp
+        assert_equal_int(r.pred_classes, g["classes_%d" % n], "pred_classes")
+        assert_close_tensor(r.scores, g["scores_%d" % n], "scores")
+        assert_close_tensor(r.pred_boxes.tensor, g["boxes_%d" % n], "pred_boxes", atol_scale=1e-6)
