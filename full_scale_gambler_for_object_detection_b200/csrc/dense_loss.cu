@@ -519,21 +519,16 @@ __global__ void __launch_bounds__(256) loss_post_kernel(const float* __restrict_
                                                         const double* __restrict__ stats,
                                                         const double* __restrict__ scalars,
                                                         float* __restrict__ grad_bets) {
-  __shared__ float s_c[2];
   const int n = blockIdx.y;
-  if (threadIdx.x == 0) {
-    float inv_S = 1.f, Asum = 0.f;
-    if (nmode != FSG_NORM_NONE) {
-      const double S = (nmode == FSG_NORM_IMAGE) ? stats[FSG_STATS_HEADER + n] : stats[1];
-      const double A = (nmode == FSG_NORM_IMAGE) ? scalars[FSG_SCALARS_HEADER + n] : scalars[2];
-      inv_S = (float)(1.0 / S);
-      Asum = (float)A;
-    }
-    s_c[0] = inv_S;
-    s_c[1] = Asum;
+  // every thread derives the two per-image constants itself (broadcast loads, one fp32 reciprocal): a block
+  // barrier behind one thread's fp64 divide cost more than the whole rest of this kernel
+  float inv_S = 1.f, Asum = 0.f;
+  if (nmode != FSG_NORM_NONE) {
+    const double S = (nmode == FSG_NORM_IMAGE) ? stats[FSG_STATS_HEADER + n] : stats[1];
+    const double A = (nmode == FSG_NORM_IMAGE) ? scalars[FSG_SCALARS_HEADER + n] : scalars[2];
+    inv_S = __frcp_rn((float)S);
+    Asum = (float)A;
   }
-  __syncthreads();
-  const float inv_S = s_c[0], Asum = s_c[1];
   const int64_t r0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   if (r0 >= R) return;
   const int64_t o = (int64_t)n * R + r0;

@@ -84,6 +84,30 @@ __device__ __forceinline__ int8_t band_label(const MatcherBands& mb, float v) {
   return l;
 }
 
+// The same bands in registers: thresholds ascending, so the band index is the number of thresholds <= v and
+// the label comes out of a byte-packed word.  (For a NaN quality the reference keeps label 1, matcher.py:88;
+// IoU produced by this library is never NaN.)
+struct BandsReg {
+  float t[kMaxThr];          // thresholds; +inf beyond the last one
+  unsigned long long packed; // labels of bands 0..kMaxThr, one byte each
+};
+__host__ __device__ inline BandsReg make_bands_reg(const MatcherBands& mb) {
+  BandsReg b;
+  b.packed = 0ull;
+#pragma unroll
+  for (int i = 0; i < kMaxThr; ++i) b.t[i] = (i + 1 < mb.n) ? mb.hi[i] : __builtin_huge_valf();
+#pragma unroll
+  for (int i = 0; i <= kMaxThr; ++i)
+    b.packed |= (unsigned long long)(unsigned char)((i < mb.n) ? mb.lab[i] : (int8_t)1) << (8 * i);
+  return b;
+}
+__device__ __forceinline__ int8_t band_label_reg(const BandsReg& b, float v) {
+  int idx = 0;
+#pragma unroll
+  for (int i = 0; i < kMaxThr; ++i) idx += (v >= b.t[i]) ? 1 : 0;
+  return (int8_t)(unsigned char)(b.packed >> (8 * idx));
+}
+
 // box_regression.py:49-63 (mul-then-add order kept; 0.5*w is exact so the fused form is identical)
 __device__ __forceinline__ float4 encode_deltas(float4 s, float4 t, float wx, float wy, float ww, float wh) {
   float sw = __fsub_rn(s.z, s.x), sh = __fsub_rn(s.w, s.y);
@@ -299,8 +323,8 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     float wx, float wy, float ww, float wh, const float* __restrict__ best_val,
     const int32_t* __restrict__ best_idx, const unsigned* __restrict__ gt_max, MatchOut out,
     const float* __restrict__ bets, float temperature, int* __restrict__ part_cnt,
-    float* __restrict__ part_s, unsigned* __restrict__ done_counter, double* __restrict__ stats,
-    const fsg_peer_ctx peer) {
+    float* __restrict__ part_s, double* __restrict__ img_cnt, unsigned* __restrict__ done_counter,
+    double* __restrict__ stats, const fsg_peer_ctx peer, const BandsReg br, const BandsReg pbr) {
   constexpr int U = kPassBU;
   __shared__ __align__(16) float4 s_gt[kGtChunk];
   __shared__ float s_area[kGtChunk];
@@ -458,6 +482,11 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
 
   int fg = 0;
   float w_part = 0.f;
+  const bool has_picky = pmb.n != 0;
+  const bool o_matches = out.matches != nullptr, o_labels = out.match_labels != nullptr;
+  const bool o_picky = out.picky_labels != nullptr, o_cls = out.gt_classes != nullptr;
+  const bool o_mask = out.mask != nullptr, o_idx32 = out.matched_idx32 != nullptr;
+  const bool has_ids = gt_class_ids != nullptr, has_bets = bets != nullptr;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (!live[u]) continue;
@@ -468,9 +497,9 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     int id = idx[u];
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     if (M > 0) {
-      l1 = lq[u] ? (int8_t)1 : band_label(mb, val[u]);
-      if (pmb.n) l2 = lq[u] ? (int8_t)1 : band_label(pmb, val[u]);
-      cls = gt_class_ids ? gt_class_ids[m0 + id] : 0;
+      l1 = lq[u] ? (int8_t)1 : band_label_reg(br, val[u]);
+      if (has_picky) l2 = lq[u] ? (int8_t)1 : band_label_reg(pbr, val[u]);
+      cls = has_ids ? gt_class_ids[m0 + id] : 0;
       if (l1 == 0) cls = num_classes;   // retinanet.py:356
       if (l1 == -1) cls = -1;           // :360
       msk = (l2 == 1) ? 1 : 0;          // :417-423
@@ -482,15 +511,15 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
       msk = num_classes;
       id = 0;
     }
-    if (out.matches) out.matches[o] = id;
-    if (out.match_labels) out.match_labels[o] = l1;
-    if (out.picky_labels) out.picky_labels[o] = l2;
-    if (out.gt_classes) out.gt_classes[o] = cls;
-    if (out.mask) out.mask[o] = msk;
-    if (out.gt_deltas) out.gt_deltas[o] = d;
-    if (out.matched_idx32) out.matched_idx32[o] = id;
+    if (o_matches) out.matches[o] = id;
+    if (o_labels) out.match_labels[o] = l1;
+    if (o_picky) out.picky_labels[o] = l2;
+    if (o_cls) out.gt_classes[o] = cls;
+    if (o_mask) out.mask[o] = msk;
+    if (need_anchor) out.gt_deltas[o] = d;
+    if (o_idx32) out.matched_idx32[o] = id;
     fg += (cls >= 0 && cls != num_classes) ? 1 : 0;
-    if (bets) w_part += __fadd_rn(__fmul_rn(bets[o], (float)msk), temperature);  // gambler_heads.py:569,304
+    if (has_bets) w_part += __fadd_rn(__fmul_rn(bets[o], (float)msk), temperature);  // gambler_heads.py:569,304
   }
 
   if (stats == nullptr) return;
@@ -505,6 +534,9 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
   if (lane == 0) { s_redi[wid] = fg_w; s_redf[wid] = s_w; }
   __syncthreads();
   const int nb = gridDim.x;
+  // two-level completion counters (per image, then over images): 1000+ CTAs bumping ONE word and waiting for
+  // the returned value serialise in L2; with a counter per image the chains are N times shorter and the
+  // per-image folds run in parallel.  done_counter[0] = images finished, done_counter[1+n] = CTAs of image n.
   if (tid == 0) {
     int ci = 0;
     float cs = 0.f;
@@ -512,29 +544,49 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     part_cnt[n * nb + blockIdx.x] = ci;
     part_s[n * nb + blockIdx.x] = cs;
     __threadfence();
-    s_last = (atomicAdd(done_counter, 1u) == (unsigned)(nb * N) - 1u);
+    s_last = (atomicAdd(&done_counter[1 + n], 1u) == (unsigned)nb - 1u);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double tot_cnt = 0.0, tot_s = 0.0;
-  for (int im = wid; im < N; im += kWarpsPerBlock) {
+  // ---- last CTA of image n: fold the image's partials in a fixed order
+  {
     double c = 0.0, sacc = 0.0;
-    for (int b = lane; b < nb; b += 32) {
-      c += (double)__ldcg(&part_cnt[im * nb + b]);
-      sacc += (double)__ldcg(&part_s[im * nb + b]);
+    for (int b = tid; b < nb; b += kMatchBlock) {
+      c += (double)__ldcg(&part_cnt[n * nb + b]);
+      sacc += (double)__ldcg(&part_s[n * nb + b]);
     }
     c = warp_sum_d(c);
     sacc = warp_sum_d(sacc);
-    if (lane == 0) {
-      stats[FSG_STATS_HEADER + im] = sacc;
-      tot_cnt += c;
-      tot_s += sacc;
-    }
+    if (lane == 0) { s_tc[wid] = c; s_ts[wid] = sacc; }
   }
-  if (lane == 0) { s_tc[wid] = tot_cnt; s_ts[wid] = tot_s; }
   __syncthreads();
+  if (tid == 0) {
+    double c = 0.0, sacc = 0.0;
+    for (int w = 0; w < kWarpsPerBlock; ++w) { c += s_tc[w]; sacc += s_ts[w]; }
+    stats[FSG_STATS_HEADER + n] = sacc;
+    img_cnt[n] = c;
+    done_counter[1 + n] = 0u;   // self-reset for the next call
+    __threadfence();
+    s_last = (atomicAdd(&done_counter[0], 1u) == (unsigned)N - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last image: batch totals, in image order
   __shared__ double s_loc[2];
+  {
+    double c = 0.0, sacc = 0.0;
+    for (int im = tid; im < N; im += kMatchBlock) {
+      c += __ldcg(&img_cnt[im]);
+      sacc += __ldcg(&stats[FSG_STATS_HEADER + im]);
+    }
+    c = warp_sum_d(c);
+    sacc = warp_sum_d(sacc);
+    __syncthreads();   // s_tc / s_ts are reused
+    if (lane == 0) { s_tc[wid] = c; s_ts[wid] = sacc; }
+  }
+  __syncthreads();
   if (tid == 0) {
     double c = 0.0, sacc = 0.0;
     for (int w = 0; w < kWarpsPerBlock; ++w) { c += s_tc[w]; sacc += s_ts[w]; }
@@ -542,7 +594,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     stats[1] = sacc;
     s_loc[0] = c;
     s_loc[1] = sacc;
-    *done_counter = 0u;  // self-reset for the next call
+    done_counter[0] = 0u;
   }
   if (peer.world <= 1) return;
 
@@ -679,19 +731,20 @@ extern "C" int fsg_matcher(const float* mqm, int64_t M, int64_t N, const float* 
 
 namespace {
 struct MatchWs {
-  size_t off_counter, off_gtmax, off_val, off_idx, off_pcnt, off_ps, total;
+  size_t off_counter, off_gtmax, off_val, off_idx, off_pcnt, off_ps, off_icnt, total;
   int nb;
 };
 MatchWs match_ws_layout(int N, int64_t R, int64_t sum_M) {
   MatchWs w;
   w.nb = (int)ceil_div(R > 0 ? R : 1, kMatchBlock * kPassBU);
   size_t o = 0;
-  w.off_counter = o; o += 16;
+  w.off_counter = o; o += align_up(sizeof(unsigned) * (size_t)(N + 1), 16);
   w.off_gtmax = o;   o += align_up(sizeof(unsigned) * (size_t)(sum_M > 0 ? sum_M : 1), 16);
   w.off_val = o;     o += align_up(sizeof(float) * (size_t)N * (size_t)R, 16);
   w.off_idx = o;     o += align_up(sizeof(int32_t) * (size_t)N * (size_t)R, 16);
   w.off_pcnt = o;    o += align_up(sizeof(int) * (size_t)N * w.nb, 16);
   w.off_ps = o;      o += align_up(sizeof(float) * (size_t)N * w.nb, 16);
+  w.off_icnt = o;    o += align_up(sizeof(double) * (size_t)N, 16);
   w.total = o;
   return w;
 }
@@ -763,7 +816,9 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
   match_pass_b_kernel<<<grid_b, kMatchBlock, 0, s>>>(
       (const float4*)anchors, R, anchor_image_stride / 4, (const float4*)gt_boxes, gt_class_ids, gt_offsets, N,
       num_classes, mb, pmb, allow_lq ? 1 : 0, wx, wy, ww, wh, bval, bidx, gtmax, out, bets, temperature,
-      (int*)(ws + w.off_pcnt), (float*)(ws + w.off_ps), counter, stats, peer);
+      (int*)(ws + w.off_pcnt), (float*)(ws + w.off_ps), (double*)(ws + w.off_icnt), counter, stats, peer,
+      make_bands_reg(mb),
+      make_bands_reg(pmb));
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }
