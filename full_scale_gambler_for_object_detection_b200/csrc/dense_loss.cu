@@ -250,18 +250,14 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 3)) loss_main_kernel
   const int ngrp = kLossBlock >> logG;
   const int64_t tile_base = (int64_t)blockIdx.x * A.anchors_per_tile;
 
-  __shared__ float s_inv[2];
+  // normalisers: every thread derives them itself from two broadcast loads (no block barrier behind one
+  // thread's fp64 divide).  num_foreground is an integer < 2^24, so the fp32 reciprocal of max(1, nf) is the
+  // reference's own fp32 division; S[n] is rounded to fp32 like the reference's fp32 sum.
   const double nf_d = A.stats[0];
-  if (tid == 0) {
-    s_inv[0] = (float)(1.0 / (nf_d > 1.0 ? nf_d : 1.0));
-    float is = 1.f;
-    if (A.nmode == FSG_NORM_IMAGE) is = (float)(1.0 / A.stats[FSG_STATS_HEADER + n]);
-    else if (A.nmode == FSG_NORM_BATCH) is = (float)(1.0 / A.stats[1]);
-    s_inv[1] = is;
-  }
-  __syncthreads();
-  const float inv_nf = s_inv[0];
-  const float inv_S = s_inv[1];
+  const float inv_nf = __frcp_rn(fmaxf((float)nf_d, 1.f));
+  float inv_S = 1.f;
+  if (A.nmode == FSG_NORM_IMAGE) inv_S = __frcp_rn((float)A.stats[FSG_STATS_HEADER + n]);
+  else if (A.nmode == FSG_NORM_BATCH) inv_S = __frcp_rn((float)A.stats[1]);
   const int m0 = A.gt_offsets ? A.gt_offsets[n] : 0;
   const bool write_grad = kWrite && (A.grad_logits != nullptr);
 
