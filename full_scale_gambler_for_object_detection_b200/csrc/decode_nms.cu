@@ -15,6 +15,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "nms_large.cuh"
 
 namespace fsg {
 
@@ -789,6 +790,7 @@ using namespace fsg;
 
 extern "C" size_t fsg_nms_workspace_bytes(int64_t n) {
   if (n <= 0) return 16;
+  if (n > kNmsCap) return n > kNmsLargeMax ? 0 : nms_large_ws_layout(n).total;
   return nms_ws_layout(1, nms_split_for(1), (int)(n < kNmsCap ? n : kNmsCap)).total;
 }
 
@@ -802,7 +804,9 @@ extern "C" int fsg_nms(const float* boxes, const float* scores, const int64_t* c
     return FSG_OK;
   }
   if (!boxes || !scores || !keep) return FSG_ERR_INVALID_ARG;
-  if (n > kNmsCap) return FSG_ERR_UNSUPPORTED;
+  if (n > kNmsCap)   // more boxes than one CTA's shared memory holds: rank / bit-matrix / sweep kernels
+    return nms_large(boxes, scores, class_ids, n, threshold_floor(iou_threshold), keep, num_keep, workspace,
+                     workspace_bytes, s);
   const int split = class_ids ? nms_split_for(1) : 1;
   const NmsWs w = nms_ws_layout(1, split, (int)n);
   if (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;

@@ -287,7 +287,8 @@ def scale_(x, scale):
 # ------------------------------------------------------------------------------------------------
 # K3
 # ------------------------------------------------------------------------------------------------
-NMS_MAX_BOXES = 8192
+NMS_SMEM_BOXES = 8192      # up to here one CTA (or 8, split by class) does the whole call in shared memory
+NMS_MAX_BOXES = 262144     # beyond: rank / bit-matrix / sweep kernels (csrc/nms_large.cu), 8.6 GB mask at the cap
 
 
 def nms_raw(boxes, scores, class_ids, iou_threshold):
@@ -295,7 +296,7 @@ def nms_raw(boxes, scores, class_ids, iou_threshold):
     b, s = _f32c(boxes).reshape(-1, 4), _f32c(scores).reshape(-1)
     n = b.shape[0]
     if n > NMS_MAX_BOXES:
-        raise RuntimeError("fsg_nms holds at most %d boxes per call in shared memory; got %d" % (NMS_MAX_BOXES, n))
+        raise RuntimeError("fsg_nms takes at most %d boxes per call; got %d" % (NMS_MAX_BOXES, n))
     keep = torch.empty(max(n, 1), dtype=torch.int64, device=b.device)
     num = torch.zeros(1, dtype=torch.int32, device=b.device)
     c = class_ids.to(torch.int64).contiguous() if class_ids is not None else None
@@ -303,7 +304,7 @@ def nms_raw(boxes, scores, class_ids, iou_threshold):
     ws = _ws(L.fsg_nms_workspace_bytes(n), b.device)
     check(L.fsg_nms(ptr(b) if n else None, ptr(s) if n else None, ptr(c), n, float(iou_threshold), ptr(keep),
                     ptr(num), ptr(ws), ws.numel(), stream()))
-    count_launches(1)
+    count_launches(1 if n <= NMS_SMEM_BOXES else 3)
     return keep, num
 
 

@@ -384,6 +384,42 @@ def test_batched_nms_bit_exact(cuda, n, ncls, thr):
     assert_equal_int(got, want, "batched_nms keep")
 
 
+def _sparse_nms_inputs(n, ncls, seed, extent):
+    """Boxes spread over `extent` pixels so that a large share survives (long kept lists, every bit-matrix
+    column block in use); a few exact ties / duplicates as in _nms_inputs."""
+    g = torch.Generator().manual_seed(seed)
+    xy = torch.rand((n, 2), generator=g) * extent
+    wh = torch.rand((n, 2), generator=g) * 90 + 10
+    boxes = torch.cat([xy, xy + wh], dim=1)
+    scores = torch.rand(n, generator=g)
+    scores[n // 2] = scores[n // 3]
+    scores[n - 1] = scores[0]
+    boxes[n // 4] = boxes[n // 5]
+    idxs = torch.randint(0, ncls, (n,), generator=g)
+    return boxes, scores, idxs
+
+
+@pytest.mark.parametrize("n,thr,extent", [(8193, 0.5, 100.0), (8256, 0.5, 3000.0), (20000, 0.7, 2000.0),
+                                          (40000, 0.5, 800.0)])
+def test_nms_large_n_bit_exact(cuda, n, thr, extent):
+    """More boxes than the shared-memory kernel holds: rank / bit-matrix / sweep path (csrc/nms_large.cu)."""
+    fsg = _fsg()
+    boxes, scores, _ = _sparse_nms_inputs(n, 1, 300 + n, extent)
+    want = orc.nms(boxes, scores, thr)
+    got = fsg.nms(boxes.to(cuda), scores.to(cuda), thr)
+    assert_equal_int(got, want, "nms keep (large n)")
+
+
+@pytest.mark.parametrize("n,ncls,thr", [(12000, 5, 0.7), (30000, 80, 0.5)])
+def test_batched_nms_large_n_bit_exact(cuda, n, ncls, thr):
+    """RPN-sized call (5 levels x 2000+ proposals, rpn_outputs.py:137) and a large multi-class call."""
+    fsg = _fsg()
+    boxes, scores, idxs = _sparse_nms_inputs(n, ncls, 400 + n, 1200.0)
+    want = orc.batched_nms(boxes, scores, idxs, thr)
+    got = fsg.batched_nms(boxes.to(cuda), scores.to(cuda), idxs.to(cuda), thr)
+    assert_equal_int(got, want, "batched_nms keep (large n)")
+
+
 def test_nms_threshold_compare_is_in_double(cuda):
     """IoU float(1/3) against threshold 1/3 (double): float(1/3) > 1/3 -> suppressed."""
     fsg = _fsg()
