@@ -40,6 +40,13 @@ class LossParams(ctypes.Structure):
     ]
 
 
+class HeadLevel(ctypes.Structure):
+    """``struct fsg_head_level``."""
+
+    _fields_ = [("logits", c_ptr), ("grad_logits", c_ptr), ("pred_deltas", c_ptr), ("grad_deltas", c_ptr),
+                ("H", c_i32), ("W", c_i32)]
+
+
 class PeerCtx(ctypes.Structure):
     """``struct fsg_peer_ctx``."""
 
@@ -72,6 +79,12 @@ PROTOTYPES = {
         c_i32,
         [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64,
          ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
+    ),
+    "fsg_loss_main_levels_workspace_bytes": (c_size, [c_i32, ctypes.POINTER(HeadLevel), c_i32, c_i32]),
+    "fsg_loss_main_levels": (
+        c_i32,
+        [ctypes.POINTER(HeadLevel), c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+         c_i32, c_i64, ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
     ),
     "fsg_loss_post": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i64, ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr, c_ptr]),
     "fsg_scale_inplace": (c_i32, [c_ptr, c_i64, c_ptr, c_f32, c_ptr]),

@@ -16,12 +16,11 @@
 // S[n] up front (pre-pass over (N,R)-sized data, fused into K1's second pass), and d/d bets needs
 // A[n] = sum_r w_hat*l afterwards (post pass over (N,R)-sized data).
 #include "common.cuh"
+#include "loss_math.cuh"
 
 namespace fsg {
 
-constexpr int kLossBlock = 256;
 constexpr int kAnchorsPerGroup = 4;
-constexpr int kPartialStride = 8;  // floats per tile partial: cls, reg, wl, l, maxl
 
 enum LossVariant { kFastWrite = 0, kFastNoWrite = 1, kGeneric = 2 };
 
@@ -60,114 +59,6 @@ struct LossArgs {
   double* scalars;
 };
 
-// ---- vector load/store by width -------------------------------------------------------------
-template <int V> struct Vec;
-template <> struct Vec<4> {
-  float v[4];
-  __device__ __forceinline__ void load(const float* p) { float4 t = ldg_stream4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-  __device__ __forceinline__ void store(float* p) const { stg_stream4(p, make_float4(v[0], v[1], v[2], v[3])); }
-};
-template <> struct Vec<2> {
-  float v[2];
-  __device__ __forceinline__ void load(const float* p) { float2 t = ldg_stream2(p); v[0] = t.x; v[1] = t.y; }
-  __device__ __forceinline__ void store(float* p) const { stg_stream2(p, make_float2(v[0], v[1])); }
-};
-template <> struct Vec<1> {
-  float v[1];
-  __device__ __forceinline__ void load(const float* p) { v[0] = ldg_stream1(p); }
-  __device__ __forceinline__ void store(float* p) const { stg_stream1(p, v[0]); }
-};
-
-// log1p(e) for e in [0,1]: e * P7(e), max relative error 3.3e-7 (fit in DESIGN.md)
-__device__ __forceinline__ float log1p_unit(float e) {
-  float p = -8.539245470e-03f;
-  p = fmaf(p, e, 4.408976170e-02f);
-  p = fmaf(p, e, -1.076818928e-01f);
-  p = fmaf(p, e, 1.774525379e-01f);
-  p = fmaf(p, e, -2.449546718e-01f);
-  p = fmaf(p, e, 3.327548051e-01f);
-  p = fmaf(p, e, -4.999740544e-01f);
-  p = fmaf(p, e, 9.999998057e-01f);
-  return p * e;
-}
-
-// MUFU.EX2 / MUFU.RCP without the libdevice range fix-ups (inputs are bounded: argument <= 0, 1+e in [1,2])
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// shared sub-expressions of sigmoid / BCE for one logit (t = 0 side):
-//   p = sigmoid(x), omp = 1 - p (computed as sigmoid(-x), no cancellation), ce0 = softplus(x)
-__device__ __forceinline__ void sigmoid_parts(float x, float& p, float& omp, float& ce0) {
-  const float e = ex2_approx(fabsf(x) * -1.4426950408889634f);  // exp(-|x|) in (0,1]
-  const float r = rcp_approx(1.f + e);
-  const float er = e * r;
-  const float l1p = log1p_unit(e);
-  const bool pos = x >= 0.f;
-  p = pos ? r : er;
-  omp = pos ? er : r;
-  ce0 = fmaxf(x, 0.f) + l1p;
-}
-
-// one element with target t = 0, gamma = 2:  loss/(1-alpha) and dloss/dx/(1-alpha)
-__device__ __forceinline__ void focal_neg_g2(float x, float& loss, float& grad) {
-  float p, omp, ce;
-  sigmoid_parts(x, p, omp, ce);
-  const float p2 = p * p;
-  loss = p2 * ce;
-  grad = p2 * fmaf(2.f * omp, ce, p);
-}
-
-// general element (any t, any gamma, either mode); unscaled by alpha_t
-__device__ __forceinline__ void cls_elem_general(float x, bool t, float gamma, float& focal, float& fgrad,
-                                                 float& bce, float& bgrad) {
-  float p, omp, ce0;
-  sigmoid_parts(x, p, omp, ce0);
-  const float ce = t ? ce0 - x : ce0;   // BCE-with-logits
-  const float q = t ? omp : p;          // 1 - p_t
-  const float pt = t ? p : omp;
-  const float qg = (gamma == 2.f) ? q * q : ((gamma == 0.f) ? 1.f : powf(q, gamma));
-  focal = qg * ce;
-  const float inner = fmaf(gamma * pt, ce, q);
-  fgrad = t ? -qg * inner : qg * inner;
-  bce = ce;
-  bgrad = t ? -omp : p;
-}
-
-__device__ __forceinline__ float4 encode_deltas_loss(float4 s, float4 t, float wx, float wy, float ww, float wh) {
-  float sw = __fsub_rn(s.z, s.x), sh = __fsub_rn(s.w, s.y);
-  float sx = __fadd_rn(s.x, __fmul_rn(0.5f, sw)), sy = __fadd_rn(s.y, __fmul_rn(0.5f, sh));
-  float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
-  float tx = __fadd_rn(t.x, __fmul_rn(0.5f, tw)), ty = __fadd_rn(t.y, __fmul_rn(0.5f, th));
-  float4 d;
-  d.x = __fdiv_rn(__fmul_rn(wx, __fsub_rn(tx, sx)), sw);
-  d.y = __fdiv_rn(__fmul_rn(wy, __fsub_rn(ty, sy)), sh);
-  d.z = __fmul_rn(ww, logf(__fdiv_rn(tw, sw)));
-  d.w = __fmul_rn(wh, logf(__fdiv_rn(th, sh)));
-  return d;
-}
-
-__device__ __forceinline__ void smooth_l1_elem(float pd, float gd, float beta, float& loss, float& grad) {
-  const float d = pd - gd;
-  const float n = fabsf(d);
-  if (beta < 1e-5f) {
-    loss = n;
-    grad = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-  } else if (n < beta) {
-    loss = 0.5f * n * n / beta;
-    grad = d / beta;
-  } else {
-    loss = n - 0.5f * beta;
-    grad = (d > 0.f) ? 1.f : -1.f;
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // pre-pass (stand-alone form; K1's pass B carries the same reduction fused)
@@ -237,10 +128,7 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 3)) loss_main_kernel
   // element loop); GT == 0: G and K are run-time values.
   constexpr bool kWrite = (VARIANT != kFastNoWrite);
   constexpr bool kFast = (VARIANT != kGeneric);
-  __shared__ float s_part[kLossBlock / 32][5];
-  __shared__ bool s_last;
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x;
   const int n = blockIdx.y;
   const int G = GT > 0 ? GT : A.G;
   const int logG = GT > 0 ? (GT == 1 ? 0 : GT == 2 ? 1 : GT == 4 ? 2 : GT == 8 ? 3 : GT == 16 ? 4 : 5) : A.logG;
@@ -433,64 +321,11 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 3)) loss_main_kernel
     }
   }
 
-  // ---- tile partials (deterministic: one slot per tile, fixed reduction order)
+  // ---- tile partials -> scalars (deterministic: one slot per tile, fixed reduction order)
   acc_cls = warp_sum(acc_cls); acc_reg = warp_sum(acc_reg); acc_wl = warp_sum(acc_wl);
   acc_l = warp_sum(acc_l); max_l = warp_max(max_l);
-  if (lane == 0) {
-    s_part[wid][0] = acc_cls; s_part[wid][1] = acc_reg; s_part[wid][2] = acc_wl;
-    s_part[wid][3] = acc_l; s_part[wid][4] = max_l;
-  }
-  __syncthreads();
-  const int T = A.tiles_per_image;
-  if (tid == 0) {
-    float c = 0.f, g = 0.f, w = 0.f, l = 0.f, mx = 0.f;
-    for (int k = 0; k < kLossBlock / 32; ++k) {
-      c += s_part[k][0]; g += s_part[k][1]; w += s_part[k][2]; l += s_part[k][3];
-      mx = fmaxf(mx, s_part[k][4]);
-    }
-    float* P = A.partials + ((int64_t)n * T + blockIdx.x) * kPartialStride;
-    P[0] = c; P[1] = g; P[2] = w; P[3] = l; P[4] = mx;
-    __threadfence();
-    s_last = (atomicAdd(A.counter, 1u) == (unsigned)(T * A.N) - 1u);
-  }
-  __syncthreads();
-  if (!s_last) return;
-
-  // ---- last block: reduce all tile partials -> scalars (fixed order => run-to-run deterministic)
-  __threadfence();
-  __shared__ double s_tot[kLossBlock / 32][5];
-  double t_cls = 0.0, t_reg = 0.0, t_wl = 0.0, t_l = 0.0, t_mx = 0.0;
-  for (int img = wid; img < A.N; img += kLossBlock / 32) {
-    double c = 0.0, g = 0.0, w = 0.0, l = 0.0;
-    float mx = 0.f;
-    for (int b = lane; b < T; b += 32) {
-      const float* P = A.partials + ((int64_t)img * T + b) * kPartialStride;
-      c += (double)__ldcg(P + 0); g += (double)__ldcg(P + 1); w += (double)__ldcg(P + 2);
-      l += (double)__ldcg(P + 3); mx = fmaxf(mx, __ldcg(P + 4));
-    }
-    c = warp_sum_d(c); g = warp_sum_d(g); w = warp_sum_d(w); l = warp_sum_d(l); mx = warp_max(mx);
-    if (lane == 0) {
-      A.scalars[FSG_SCALARS_HEADER + img] = w;
-      t_cls += c; t_reg += g; t_wl += w; t_l += l; t_mx += (double)mx;
-    }
-  }
-  if (lane == 0) {
-    s_tot[wid][0] = t_cls; s_tot[wid][1] = t_reg; s_tot[wid][2] = t_wl; s_tot[wid][3] = t_l; s_tot[wid][4] = t_mx;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double v[5] = {0, 0, 0, 0, 0};
-    for (int k = 0; k < kLossBlock / 32; ++k)
-      for (int q = 0; q < 5; ++q) v[q] += s_tot[k][q];
-    const double nfc = nf_d > 1.0 ? nf_d : 1.0;
-    for (int q = 0; q < 5; ++q) A.scalars[q] = v[q];
-    A.scalars[5] = v[0] / nfc;
-    A.scalars[6] = v[1] / nfc;
-    A.scalars[7] = -v[2];
-    A.scalars[8] = (double)A.c_cls * A.scalars[5] + (double)A.c_reg * A.scalars[6] + (double)A.c_gam * A.scalars[7];
-    A.scalars[9] = nf_d;
-    *A.counter = 0u;
-  }
+  finish_tile(acc_cls, acc_reg, acc_wl, acc_l, max_l, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
+              A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam);
 }
 
 // ------------------------------------------------------------------------------------------

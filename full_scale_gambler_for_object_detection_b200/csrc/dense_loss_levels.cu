@@ -1,0 +1,295 @@
+// K2 on the head's native layout: the fused loss main pass reading the per-level conv outputs
+// (N, A*K, H, W) / (N, A*4, H, W) directly and writing the gradients in the same layout, so the
+// permute_to_N_HWA_K + cat copies (detectron2/modeling/meta_arch/retinanet.py:24-54,217-219 and again in
+// ImbalanceDetection/imbalancedetection/gambler_heads.py:34-101,538-540) and their inverses in the backward
+// disappear.  Same arithmetic, same scalars/partials as dense_loss.cu.
+//
+// Mapping: one thread per anchor (n, level, a, hw); consecutive lanes hold consecutive hw, so for every class
+// channel k a warp reads / writes one contiguous 128-byte piece of the (a*K + k) plane -- fully coalesced
+// without any shared-memory transpose, and the K-reduction of the per-anchor loss is a private register sum.
+// The (N,R)-sized side arrays (gt_classes, mask, bets, l, w_hat) keep the flattened anchor order
+// r = level_offset + hw*A + a of the rest of the library.
+#include "common.cuh"
+#include "loss_math.cuh"
+
+namespace fsg {
+
+constexpr int kLvMax = FSG_MAX_LEVELS;
+
+struct LevelTable {
+  const float* logits[kLvMax];
+  float* grad_logits[kLvMax];
+  const float* pred_deltas[kLvMax];
+  float* grad_deltas[kLvMax];
+  int64_t off[kLvMax + 1];   // first anchor index of the level
+  int HW[kLvMax];
+  int chunks[kLvMax];        // ceil(HW / kLossBlock)
+  int tile_base[kLvMax + 1]; // tiles of a level: A * chunks
+  int num_levels, A;
+};
+
+struct LevelLossArgs {
+  const float* gt_deltas;
+  const float4* anchors;
+  int64_t anchor_stride4;
+  const float4* gt_boxes;
+  const int32_t* gt_offsets;
+  const int32_t* matched;
+  const int64_t* gt_classes;
+  const int64_t* mask;
+  const float* bets;
+  int N;
+  int64_t R;
+  int K;
+  int tiles_per_image;
+  float a0, a1, gamma, beta, T, ggamma;
+  int gmode, nmode;
+  float c_cls, c_reg, c_gam;
+  float wx, wy, ww, wh;
+  const double* stats;
+  float* ell;
+  float* wout;
+  float* partials;
+  unsigned* counter;
+  double* scalars;
+};
+
+template <int BATCH, bool FAST>
+__global__ void __launch_bounds__(kLossBlock, 3) loss_main_levels_kernel(const LevelLossArgs A, const LevelTable LT) {
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y;
+  int l = 0;
+  while (l + 1 < LT.num_levels && (int)blockIdx.x >= LT.tile_base[l + 1]) ++l;
+  const int local = (int)blockIdx.x - LT.tile_base[l];
+  const int a = local / LT.chunks[l];
+  const int hw = (local - a * LT.chunks[l]) * kLossBlock + tid;
+  const int HW = LT.HW[l];
+  const bool live = hw < HW;
+  const int K = A.K;
+
+  const double nf_d = A.stats[0];
+  const float inv_nf = __frcp_rn(fmaxf((float)nf_d, 1.f));
+  float inv_S = 1.f;
+  if (A.nmode == FSG_NORM_IMAGE) inv_S = __frcp_rn((float)A.stats[FSG_STATS_HEADER + n]);
+  else if (A.nmode == FSG_NORM_BATCH) inv_S = __frcp_rn((float)A.stats[1]);
+
+  float acc_cls = 0.f, acc_reg = 0.f, acc_wl = 0.f, acc_l = 0.f, max_l = 0.f;
+
+  if (live) {
+    const int64_t r = LT.off[l] + (int64_t)hw * LT.A + a;
+    const int64_t o = (int64_t)n * A.R + r;
+    const int64_t plane0 = ((int64_t)n * LT.A + a) * K;          // first class plane of this anchor slot
+    const float* xcol = LT.logits[l] + plane0 * HW + hw;
+    float* gcol = LT.grad_logits[l] ? LT.grad_logits[l] + plane0 * HW + hw : nullptr;
+
+    // first batch of class planes in flight before the per-anchor metadata is touched
+    float x[BATCH];
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b)
+      if (b < K) x[b] = ldg_stream1(xcol + (int64_t)b * HW);
+
+    const int cls = (int)A.gt_classes[o];
+    float w_hat = 0.f;
+    if (A.bets) {
+      const float m = A.mask ? (float)A.mask[o] : 1.f;
+      const float w = __fadd_rn(__fmul_rn(A.bets[o], m), A.T);   // gambler_heads.py:569,304
+      w_hat = w * inv_S;                                        // :308-311
+    }
+    const bool valid = cls >= 0;
+    const bool fgc = valid && cls != K;
+    const float wg = (A.ggamma == 1.f) ? w_hat : powf(w_hat, A.ggamma);
+    float coef_f = 0.f, coef_b = 0.f;
+    if (valid) {
+      coef_f = A.c_cls * inv_nf;
+      if (A.gmode == FSG_CLS_FOCAL) coef_f = fmaf(-A.c_gam, wg, coef_f);
+      else coef_b = -A.c_gam * wg;
+    }
+
+    float sum_f = 0.f, sum_b = 0.f;
+    const float cf0 = coef_f * A.a0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += BATCH) {
+      float y[BATCH];
+      const int k1 = k0 + BATCH;
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b)
+        if (k1 + b < K) y[b] = ldg_stream1(xcol + (int64_t)(k1 + b) * HW);
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const int k = k0 + b;
+        if (k < K) {
+          float g;
+          if (FAST) {
+            float lo, d;
+            focal_neg_g2(x[b], lo, d);
+            sum_f += lo;
+            g = d * cf0;
+          } else {
+            const bool t = (k == cls);   // cls == K (background) or -1 (ignored) never matches
+            float f, fgd, bc, bgd;
+            cls_elem_general(x[b], t, A.gamma, f, fgd, bc, bgd);
+            const float at = t ? A.a1 : A.a0;
+            sum_f += f * at;
+            sum_b += bc;
+            g = fmaf(fgd * at, coef_f, bgd * coef_b);
+          }
+          if (gcol) stg_stream1(gcol + (int64_t)k * HW, valid ? g : 0.f);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) x[b] = y[b];
+    }
+    if (FAST) {
+      sum_f *= A.a0;
+      if (fgc) {   // patch the single positive class of a foreground anchor
+        const float xv = xcol[(int64_t)cls * HW];
+        float l0, d0, f1, fg1, b1, bg1;
+        focal_neg_g2(xv, l0, d0);
+        cls_elem_general(xv, true, 2.f, f1, fg1, b1, bg1);
+        sum_f += f1 * A.a1 - l0 * A.a0;
+        if (gcol) gcol[(int64_t)cls * HW] = fg1 * (coef_f * A.a1);
+      }
+    }
+    const float lf = valid ? sum_f : 0.f;                                   // gambler_heads.py:554-555
+    const float lg = (A.gmode == FSG_CLS_FOCAL) ? lf : (valid ? sum_b : 0.f);
+    if (A.ell) A.ell[o] = lg;
+    if (A.wout) A.wout[o] = w_hat;
+    acc_cls = lf;
+    acc_wl = wg * lg;
+    acc_l = lg;
+    max_l = lg;
+
+    // ---- regression planes (a*4 + j)
+    if (LT.pred_deltas[l]) {
+      const int64_t dplane = ((int64_t)n * LT.A + a) * 4;
+      const float* pcol = LT.pred_deltas[l] + dplane * HW + hw;
+      float g4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (fgc) {
+        float4 gd;
+        if (A.gt_deltas) gd = reinterpret_cast<const float4*>(A.gt_deltas)[o];
+        else gd = encode_deltas_loss(A.anchors[(int64_t)n * A.anchor_stride4 + r],
+                                     A.gt_boxes[A.gt_offsets[n] + A.matched[o]], A.wx, A.wy, A.ww, A.wh);
+        const float gdv[4] = {gd.x, gd.y, gd.z, gd.w};
+        const float sc = A.c_reg * inv_nf;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float lo, g;
+          smooth_l1_elem(ldg_stream1(pcol + (int64_t)j * HW), gdv[j], A.beta, lo, g);
+          acc_reg += lo;
+          g4[j] = g * sc;
+        }
+      }
+      if (LT.grad_deltas[l]) {
+        float* dcol = LT.grad_deltas[l] + dplane * HW + hw;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stg_stream1(dcol + (int64_t)j * HW, g4[j]);
+      }
+    }
+  }
+
+  acc_cls = warp_sum(acc_cls); acc_reg = warp_sum(acc_reg); acc_wl = warp_sum(acc_wl);
+  acc_l = warp_sum(acc_l); max_l = warp_max(max_l);
+  finish_tile(acc_cls, acc_reg, acc_wl, acc_l, max_l, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
+              A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam);
+}
+
+static int build_table(const fsg_head_level* h, int num_levels, int A, LevelTable* t, int64_t* R_out) {
+  if (!h || num_levels <= 0 || num_levels > kLvMax || A <= 0) return FSG_ERR_INVALID_ARG;
+  t->num_levels = num_levels;
+  t->A = A;
+  int64_t off = 0;
+  int tiles = 0;
+  for (int l = 0; l < kLvMax; ++l) {
+    if (l < num_levels) {
+      if (h[l].H <= 0 || h[l].W <= 0) return FSG_ERR_INVALID_ARG;
+      const int64_t hw = (int64_t)h[l].H * h[l].W;
+      if (hw > (1 << 30)) return FSG_ERR_UNSUPPORTED;
+      t->logits[l] = h[l].logits; t->grad_logits[l] = h[l].grad_logits;
+      t->pred_deltas[l] = h[l].pred_deltas; t->grad_deltas[l] = h[l].grad_deltas;
+      t->off[l] = off; t->HW[l] = (int)hw; t->chunks[l] = (int)ceil_div(hw, kLossBlock);
+      t->tile_base[l] = tiles;
+      off += hw * A;
+      tiles += A * t->chunks[l];
+    } else {
+      t->logits[l] = nullptr; t->grad_logits[l] = nullptr; t->pred_deltas[l] = nullptr; t->grad_deltas[l] = nullptr;
+      t->off[l] = off; t->HW[l] = 0; t->chunks[l] = 1; t->tile_base[l] = tiles;
+    }
+  }
+  t->off[kLvMax] = off;
+  t->tile_base[kLvMax] = tiles;
+  for (int l = num_levels; l < kLvMax; ++l) { t->off[l] = off; t->tile_base[l] = tiles; }
+  *R_out = off;
+  return FSG_OK;
+}
+
+}  // namespace fsg
+
+using namespace fsg;
+
+extern "C" size_t fsg_loss_main_levels_workspace_bytes(int N, const fsg_head_level* h_levels, int num_levels,
+                                                       int A) {
+  LevelTable t;
+  int64_t R;
+  if (N <= 0 || build_table(h_levels, num_levels, A, &t, &R) != FSG_OK) return 0;
+  return 16 + align_up(sizeof(float) * kPartialStride * (size_t)N * t.tile_base[kLvMax], 16);
+}
+
+extern "C" int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_levels, int A, const float* gt_deltas,
+                                    const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
+                                    const int32_t* gt_offsets, const int32_t* matched_idx32,
+                                    const int64_t* gt_classes, const int64_t* mask, const float* bets, int N,
+                                    int64_t R, const fsg_loss_params* hp, const double* stats,
+                                    float* per_anchor_loss, float* weights_out, double* scalars, void* workspace,
+                                    size_t workspace_bytes, fsg_stream_t stream) {
+  if (!hp || N <= 0 || R <= 0 || hp->num_classes <= 0) return FSG_ERR_INVALID_ARG;
+  if (!gt_classes || !stats || !scalars) return FSG_ERR_INVALID_ARG;
+  if (N > 65535) return FSG_ERR_UNSUPPORTED;
+  if (anchor_image_stride % 4 != 0) return FSG_ERR_INVALID_ARG;
+  LevelTable t;
+  int64_t Rt = 0;
+  const int st = build_table(h_levels, num_levels, A, &t, &Rt);
+  if (st != FSG_OK) return st;
+  if (Rt != R) return FSG_ERR_INVALID_ARG;
+  bool any_pred = false;
+  for (int l = 0; l < num_levels; ++l) {
+    if (!t.logits[l]) return FSG_ERR_INVALID_ARG;
+    if (t.grad_deltas[l] && !t.pred_deltas[l]) return FSG_ERR_INVALID_ARG;
+    any_pred = any_pred || t.pred_deltas[l];
+  }
+  if (any_pred && !gt_deltas && (!anchors || !gt_boxes || !gt_offsets || !matched_idx32)) return FSG_ERR_INVALID_ARG;
+  if (!bets && (hp->c_gam != 0.f || weights_out)) return FSG_ERR_INVALID_ARG;
+  if (hp->gambler_mode != FSG_CLS_FOCAL && hp->gambler_mode != FSG_CLS_SIGMOID) return FSG_ERR_INVALID_ARG;
+  if (hp->norm_mode < FSG_NORM_NONE || hp->norm_mode > FSG_NORM_BATCH) return FSG_ERR_INVALID_ARG;
+  const size_t need = 16 + align_up(sizeof(float) * kPartialStride * (size_t)N * t.tile_base[kLvMax], 16);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+
+  LevelLossArgs a;
+  a.gt_deltas = gt_deltas; a.anchors = (const float4*)anchors; a.anchor_stride4 = anchor_image_stride / 4;
+  a.gt_boxes = (const float4*)gt_boxes; a.gt_offsets = gt_offsets; a.matched = matched_idx32;
+  a.gt_classes = gt_classes; a.mask = mask; a.bets = bets;
+  a.N = N; a.R = R; a.K = hp->num_classes; a.tiles_per_image = t.tile_base[kLvMax];
+  a.a0 = hp->focal_alpha >= 0.f ? 1.f - hp->focal_alpha : 1.f;
+  a.a1 = hp->focal_alpha >= 0.f ? hp->focal_alpha : 1.f;
+  a.gamma = hp->focal_gamma; a.beta = hp->smooth_l1_beta; a.T = hp->temperature; a.ggamma = hp->gambler_gamma;
+  a.gmode = hp->gambler_mode; a.nmode = bets ? hp->norm_mode : FSG_NORM_NONE;
+  a.c_cls = hp->c_cls; a.c_reg = hp->c_reg; a.c_gam = hp->c_gam;
+  a.wx = hp->box_weights[0]; a.wy = hp->box_weights[1]; a.ww = hp->box_weights[2]; a.wh = hp->box_weights[3];
+  a.stats = stats; a.ell = per_anchor_loss; a.wout = weights_out;
+  a.partials = (float*)(ws + 16); a.counter = (unsigned*)ws; a.scalars = scalars;
+
+  FSG_CUDA_TRY(cudaMemsetAsync(a.counter, 0, 16, s));
+  const bool fast = (hp->focal_gamma == 2.f) && (hp->gambler_mode == FSG_CLS_FOCAL);
+  dim3 grid((unsigned)t.tile_base[kLvMax], (unsigned)N);
+  const bool b20 = (a.K % 20 == 0);
+  if (fast) {
+    if (b20) loss_main_levels_kernel<20, true><<<grid, kLossBlock, 0, s>>>(a, t);
+    else loss_main_levels_kernel<16, true><<<grid, kLossBlock, 0, s>>>(a, t);
+  } else {
+    if (b20) loss_main_levels_kernel<20, false><<<grid, kLossBlock, 0, s>>>(a, t);
+    else loss_main_levels_kernel<16, false><<<grid, kLossBlock, 0, s>>>(a, t);
+  }
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}

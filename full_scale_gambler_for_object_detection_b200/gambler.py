@@ -47,12 +47,42 @@ class _GamblerLossFn(torch.autograd.Function):
         return gl, gb, None, None, None
 
 
+class _GamblerLossLevelsFn(torch.autograd.Function):
+    """gambler_loss with the logits left in the head's native per-level layout (fsg_loss_main_levels); the
+    (N,R)-sized bets are flat.  Inputs: bets (N,R) then the L logit levels."""
+
+    @staticmethod
+    def forward(ctx, bets, gt_classes, params, need_logit_grad, *levels):
+        xs = [t.detach() for t in levels]
+        b = bets.detach().to(torch.float32).contiguous()
+        stats = ops.loss_prepass(gt_classes, None, b, params.num_classes, params.temperature)
+        out = ops.loss_main_levels(xs, gt_classes, params, stats, bets=b, want_grad_logits=need_logit_grad,
+                                   want_weights=True)
+        gb = ops.loss_post(b, None, out["per_anchor_loss"], params, stats, out["scalars"])
+        ctx.n_levels = len(xs) if need_logit_grad else 0
+        ctx.total_levels = len(xs)
+        ctx.save_for_backward(gb, *(out["grad_logits"] if need_logit_grad else []))
+        ctx.mark_non_differentiable(out["per_anchor_loss"], out["weights"], out["scalars"], stats)
+        return out["scalars"][7].to(torch.float32), out["per_anchor_loss"], out["weights"], out["scalars"], stats
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        saved = ctx.saved_tensors
+        gb, gls = saved[0], saved[1:]
+        for t in gls:
+            ops.scale_(t, g)
+        ops.scale_(gb, g)
+        gl_out = tuple(gls) if ctx.n_levels else (None,) * ctx.total_levels
+        return (gb, None, None, None) + gl_out
+
+
 class GamblerLoss:
     """Stand-in for the loss side of ``LayeredUnetGambler`` (the U-Net itself is out of scope)."""
 
     def __init__(self, num_classes=80, mode="focal", alpha=0.25, focal_gamma=2.0, normalize_w=True,
                  gambler_output="L_BAHW", gamma=1.0, temperature=0.1, kappa=1.0, num_scale=3,
-                 event_storage=None):
+                 event_storage=None, native_layout=True):
+        self.native_layout = native_layout   # read the (N, A*K, H, W) logits in place (no permute/cat copy)
         assert gambler_output in ("L_BAHW", "L_B1HW", "L_BAHW_extendtobatch"), "does not support other shapes!"
         if gambler_output == "L_B1HW":
             raise NotImplementedError("L_B1HW raises in the reference as well (mask broadcast, gambler_heads.py:568)")
@@ -82,7 +112,6 @@ class GamblerLoss:
         A = self.num_scale
         if detach_pred:
             pred_class_logits = [p.detach() for p in pred_class_logits]
-        x = levels_to_flat(list(pred_class_logits), self.num_classes)
         # mask -> per-level (N,A,H,W) and multiply into the caller's list (reference quirk kept)
         off = 0
         for i, (H, W) in enumerate(hw):
@@ -93,8 +122,14 @@ class GamblerLoss:
         b = levels_to_flat(list(weights), 1).reshape(N, -1)
         params = ops.make_loss_params(self.num_classes, self.alpha, self.focal_gamma, 0.1, self.temperature,
                                       self.gamma, self.mode, self._norm_mode(), 0.0, 0.0, 1.0)
-        G, ell, w_hat, scalars, stats = _GamblerLossFn.apply(x, b, gt_classes.contiguous(), params,
-                                                             not detach_pred)
+        if self.native_layout:
+            from .retinanet import _as_f32c
+            G, ell, w_hat, scalars, stats = _GamblerLossLevelsFn.apply(
+                b, gt_classes.contiguous(), params, not detach_pred, *[_as_f32c(p) for p in pred_class_logits])
+        else:
+            x = levels_to_flat(list(pred_class_logits), self.num_classes)
+            G, ell, w_hat, scalars, stats = _GamblerLossFn.apply(x, b, gt_classes.contiguous(), params,
+                                                                 not detach_pred)
         nakhw, off = [], 0
         for (H, W) in hw:
             n = H * W * A

@@ -262,6 +262,58 @@ def loss_main(logits, gt_classes, params, stats, pred_deltas=None, gt_deltas=Non
     return out
 
 
+def loss_main_levels(logit_levels, gt_classes, params, stats, delta_levels=None, gt_deltas=None, anchors=None,
+                     gt=None, matched_idx32=None, mask=None, bets=None, want_grad_logits=True,
+                     want_grad_deltas=True, want_weights=False):
+    """The fused main pass on the head's native layout: ``logit_levels`` list[(N, A*K, H, W)],
+    ``delta_levels`` list[(N, A*4, H, W)]; gradients come back as lists of the same shapes.  The
+    (N,R)-sized arguments are as in :func:`loss_main`.  No permute/cat copy of the logits is made."""
+    K = params.num_classes
+    N = logit_levels[0].shape[0]
+    A = logit_levels[0].shape[1] // K
+    dev = logit_levels[0].device
+    nl = len(logit_levels)
+    xs = [x if (x.dtype == torch.float32 and x.is_contiguous()) else _f32c(x) for x in logit_levels]
+    ds = None
+    if delta_levels is not None:
+        ds = [d if (d.dtype == torch.float32 and d.is_contiguous()) else _f32c(d) for d in delta_levels]
+    out = {}
+    if want_grad_logits:
+        out["grad_logits"] = [torch.empty_like(x) for x in xs]
+    if ds is not None and want_grad_deltas:
+        out["grad_deltas"] = [torch.empty_like(d) for d in ds]
+    R = sum(x.shape[2] * x.shape[3] * A for x in xs)
+    assert gt_classes.shape == (N, R), "gt_classes %s vs (N=%d, R=%d)" % (tuple(gt_classes.shape), N, R)
+    levels = (_lib.HeadLevel * nl)()
+    for i, x in enumerate(xs):
+        assert x.shape[0] == N and x.shape[1] == A * K
+        levels[i].logits = ptr(x)
+        levels[i].grad_logits = ptr(out["grad_logits"][i]) if want_grad_logits else None
+        levels[i].pred_deltas = ptr(ds[i]) if ds is not None else None
+        levels[i].grad_deltas = ptr(out["grad_deltas"][i]) if "grad_deltas" in out else None
+        levels[i].H, levels[i].W = x.shape[2], x.shape[3]
+        if ds is not None:
+            assert ds[i].shape == (N, A * 4, x.shape[2], x.shape[3])
+    out["per_anchor_loss"] = torch.empty((N, R), dtype=torch.float32, device=dev)
+    if want_weights:
+        out["weights"] = torch.empty((N, R), dtype=torch.float32, device=dev)
+    scalars = torch.empty(_lib.SCALARS_HEADER + N, dtype=torch.float64, device=dev)
+    out["scalars"] = scalars
+    a_ptr, a_stride = None, 0
+    if anchors is not None:
+        a_ptr = ptr(anchors)
+        a_stride = anchors.shape[1] * 4 if anchors.dim() == 3 else 0
+    L = lib()
+    ws = _ws(L.fsg_loss_main_levels_workspace_bytes(N, levels, nl, A), dev)
+    check(L.fsg_loss_main_levels(
+        levels, nl, A, ptr(gt_deltas), a_ptr, a_stride, ptr(gt.boxes) if gt is not None else None,
+        ptr(gt.offsets) if gt is not None else None, ptr(matched_idx32), ptr(gt_classes), ptr(mask), ptr(bets),
+        N, R, params, ptr(stats), ptr(out["per_anchor_loss"]), ptr(out.get("weights")), ptr(scalars), ptr(ws),
+        ws.numel(), stream()))
+    count_launches(1)
+    return out
+
+
 def loss_post(bets, mask, per_anchor_loss, params, stats, scalars):
     N, R = bets.shape
     g = torch.empty_like(bets)

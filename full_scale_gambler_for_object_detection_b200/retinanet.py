@@ -37,6 +37,10 @@ def levels_to_flat(levels, K):
     return _LevelsToFlat.apply(K, *levels)
 
 
+def _as_f32c(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
 class _RetinaLosses(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, deltas, gt_classes, gt_deltas, params):
@@ -58,11 +62,38 @@ class _RetinaLosses(torch.autograd.Function):
         return gl, gd, None, None, None
 
 
+class _RetinaLossesLevels(torch.autograd.Function):
+    """RetinaNet.losses on the head's native per-level layout: no permute/cat copy of the logits or deltas in
+    either direction (fsg_loss_main_levels).  Inputs: L logit levels then L delta levels."""
+
+    @staticmethod
+    def forward(ctx, gt_classes, gt_deltas, params, L, *levels):
+        xs = [t.detach() for t in levels[:L]]
+        ds = [t.detach() for t in levels[L:]]
+        stats = ops.loss_prepass(gt_classes, None, None, params.num_classes, 0.0)
+        out = ops.loss_main_levels(xs, gt_classes, params, stats, delta_levels=ds, gt_deltas=gt_deltas)
+        ctx.L = L
+        ctx.save_for_backward(*(out["grad_logits"] + out["grad_deltas"]))
+        s = out["scalars"]
+        return s[5].to(torch.float32), s[6].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g_cls, g_reg):
+        saved = ctx.saved_tensors
+        for t in saved[:ctx.L]:
+            ops.scale_(t, g_cls)
+        for t in saved[ctx.L:]:
+            ops.scale_(t, g_reg)
+        return (None, None, None, None) + tuple(saved)
+
+
 class RetinaNetDensePath:
     def __init__(self, num_classes=80, focal_loss_alpha=0.25, focal_loss_gamma=2.0, smooth_l1_loss_beta=0.1,
                  score_threshold=0.05, topk_candidates=1000, nms_threshold=0.5, max_detections_per_image=100,
-                 iou_thresholds=(0.4, 0.5), iou_labels=(0, -1, 1), bbox_reg_weights=(1.0, 1.0, 1.0, 1.0)):
+                 iou_thresholds=(0.4, 0.5), iou_labels=(0, -1, 1), bbox_reg_weights=(1.0, 1.0, 1.0, 1.0),
+                 native_layout=True):
         # retinanet.py:69-100
+        self.native_layout = native_layout   # losses() reads the (N, A*K, H, W) head outputs in place
         self.num_classes = num_classes
         self.focal_loss_alpha = focal_loss_alpha
         self.focal_loss_gamma = focal_loss_gamma
@@ -118,13 +149,19 @@ class RetinaNetDensePath:
 
     def losses(self, gt_classes, gt_anchors_deltas, pred_class_logits, pred_anchor_deltas):
         """-> {"loss_cls", "loss_box_reg"} (differentiable wrt the per-level head outputs)."""
-        x = levels_to_flat(list(pred_class_logits), self.num_classes)
-        d = levels_to_flat(list(pred_anchor_deltas), 4)
         params = ops.make_loss_params(self.num_classes, self.focal_loss_alpha, self.focal_loss_gamma,
                                       self.smooth_l1_loss_beta, 0.0, 1.0, "focal", _lib.NORM_NONE, 1.0, 1.0, 0.0,
                                       self.box2box_transform.weights)
-        loss_cls, loss_box_reg = _RetinaLosses.apply(x, d, gt_classes.contiguous(),
-                                                     gt_anchors_deltas.to(torch.float32).contiguous(), params)
+        gt_classes = gt_classes.contiguous()
+        gt_anchors_deltas = gt_anchors_deltas.to(torch.float32).contiguous()
+        if self.native_layout:
+            levels = [_as_f32c(t) for t in list(pred_class_logits) + list(pred_anchor_deltas)]
+            loss_cls, loss_box_reg = _RetinaLossesLevels.apply(gt_classes, gt_anchors_deltas, params,
+                                                               len(pred_class_logits), *levels)
+        else:   # the reference's own data flow: permute + cat, then the (N, R, K) kernel
+            x = levels_to_flat(list(pred_class_logits), self.num_classes)
+            d = levels_to_flat(list(pred_anchor_deltas), 4)
+            loss_cls, loss_box_reg = _RetinaLosses.apply(x, d, gt_classes, gt_anchors_deltas, params)
         return {"loss_cls": loss_cls, "loss_box_reg": loss_box_reg}
 
     # ---------------------------------------------------------------------------------------------

@@ -203,6 +203,31 @@ FSG_API int fsg_loss_main(const float* logits, const float* pred_deltas, const f
                   float* weights_out, double* scalars, void* workspace, size_t workspace_bytes,
                   fsg_stream_t stream);
 
+/* The main pass on the head's NATIVE layout: per-level conv outputs are read in place
+ * and the gradients are written in the same layout, so permute_to_N_HWA_K + cat (retinanet.py:24-54,217-219;
+ * gambler_heads.py:34-101,538-540) and their inverses in the backward are never materialised.
+ * Level l: logits (N, A*K, H_l, W_l), pred_deltas (N, A*4, H_l, W_l) (channel a*K+k / a*4+j, retinanet.py:40-43),
+ * grad_* of the same shapes (each may be NULL).  Levels are concatenated in the order given; R must equal
+ * sum_l H_l*W_l*A.  Everything (N,R)-sized keeps the flattened anchor order r = level_offset + (h*W+w)*A + a:
+ * gt_classes, mask, bets, matched_idx32, gt_deltas (N,R,4), per_anchor_loss, weights_out.
+ * All other arguments, stats and scalars exactly as fsg_loss_main. */
+#define FSG_MAX_LEVELS 8
+typedef struct fsg_head_level {
+  const float* logits;
+  float* grad_logits;
+  const float* pred_deltas;
+  float* grad_deltas;
+  int32_t H, W;
+} fsg_head_level;
+FSG_API size_t fsg_loss_main_levels_workspace_bytes(int N, const fsg_head_level* h_levels, int num_levels, int A);
+FSG_API int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_levels, int A, const float* gt_deltas,
+                         const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
+                         const int32_t* gt_offsets, const int32_t* matched_idx32, const int64_t* gt_classes,
+                         const int64_t* mask, const float* bets, int N, int64_t R,
+                         const fsg_loss_params* h_params, const double* stats, float* per_anchor_loss,
+                         float* weights_out, double* scalars, void* workspace, size_t workspace_bytes,
+                         fsg_stream_t stream);
+
 /* d(c_gam * gambler_loss)/d bets  (SURVEY App. A item 12):
  *   -(m/S) * gamma * (w_hat^(gamma-1) * l - A)     for FSG_NORM_IMAGE / _BATCH
  *   -m * gamma * w^(gamma-1) * l                   for FSG_NORM_NONE */

@@ -248,7 +248,63 @@ def _levels(inp, K, N, gen, scale=1.0, shift=0.0):
     return [torch.randn((N, A * K, h, w), generator=gen) * scale + shift for (h, w) in inp["grids"]]
 
 
-def test_dropin_retinanet_losses_and_gt(cuda):
+@pytest.mark.parametrize("kw,K,coeffs", [
+    (dict(), 80, (1.0, 1.0, -1.0)),
+    (dict(gambler_output="L_BAHW_extendtobatch"), 80, (1.0, 0.5, -2.0)),
+    (dict(gambler_loss_mode="sigmoid"), 80, (1.0, 0.5, -2.0)),
+    (dict(focal_gamma=1.5, focal_alpha=-1.0, gambler_gamma=2.0), 20, (1.0, 1.0, -1.0)),
+    (dict(normalize=False, smooth_l1_beta=0.0), 7, (1.0, 1.0, -1.0)),
+    (dict(), 1230, (1.0, 1.0, -1.0)),
+])
+def test_loss_main_on_native_head_layout(cuda, kw, K, coeffs):
+    """fsg_loss_main_levels: the fused main pass reading (N, A*K, H, W) / (N, A*4, H, W) in place and writing the
+    gradients in that layout, against the oracle's permute+cat data flow."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import _lib, synthetic
+    N = 3
+    inp = synthetic.train_inputs(21, N, 200, 264, K, M=5, logits=False)
+    A, grids = inp["A"], inp["grids"]
+    gen = torch.Generator().manual_seed(22)
+    cls_l = _levels(inp, K, N, gen, 1.0, synthetic.PRIOR_LOGIT)
+    reg_l = _levels(inp, 4, N, gen, 0.1)
+    bets = torch.sigmoid(torch.randn((N, inp["R"]), generator=gen) - 4.0)
+    cfg = fsg.DenseLossConfig(num_classes=K, **kw)
+    want = orc.train_step(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], orc.levels_to_flat(cls_l, K),
+                          orc.levels_to_flat(reg_l, 4), bets, K, *coeffs, temperature=cfg.gambler_temperature,
+                          normalize=cfg.normalize, mode=cfg.gambler_loss_mode, alpha=cfg.focal_alpha,
+                          focal_gamma=cfg.focal_gamma, gambler_gamma=cfg.gambler_gamma, beta=cfg.smooth_l1_beta,
+                          output=cfg.gambler_output)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    anchors = inp["anchors"].to(cuda)
+    b = bets.to(cuda)
+    m = fsg.ops.match_anchors(anchors, gt, K, bets=b, temperature=cfg.gambler_temperature)
+    params = cfg.loss_params(*coeffs)
+    out = fsg.ops.loss_main_levels([t.to(cuda) for t in cls_l], m["gt_classes"], params, m["stats"],
+                                   delta_levels=[t.to(cuda) for t in reg_l], anchors=anchors, gt=gt,
+                                   matched_idx32=m["matched_idx32"], mask=m["mask"], bets=b, want_weights=True)
+    gb = fsg.ops.loss_post(b, m["mask"], out["per_anchor_loss"], params, m["stats"], out["scalars"])
+    sc = out["scalars"].cpu()
+    assert_close_scalar(sc[5], want["loss_cls"], "loss_cls")
+    assert_close_scalar(sc[6], want["loss_box_reg"], "loss_box_reg")
+    assert_close_scalar(sc[7], want["gambler_loss"], "gambler_loss")
+    assert_close_tensor(out["per_anchor_loss"], want["per_anchor_loss"], "per_anchor_loss")
+    assert_close_tensor(out["weights"], want["weights"], "weights")
+    assert_close_tensor(orc.levels_to_flat([g.cpu() for g in out["grad_logits"]], K), want["grad_logits"], "grad_logits")
+    assert_close_tensor(orc.levels_to_flat([g.cpu() for g in out["grad_deltas"]], 4), want["grad_deltas"], "grad_deltas")
+    floor = 1e-5 if kw.get("gambler_loss_mode") == "sigmoid" else 1e-6
+    assert_close_tensor(gb, want["grad_bets"], "grad_bets", atol_scale=floor)
+    # and against the (N, R, K) kernel on the permuted copy: same element arithmetic, so the per-element
+    # gradients agree to the last bit; sums differ only by the order of the K-reduction
+    flat = fsg.ops.loss_main(fsg.ops.levels_to_flat([t.to(cuda) for t in cls_l], K), m["gt_classes"], params,
+                             m["stats"], pred_deltas=fsg.ops.levels_to_flat([t.to(cuda) for t in reg_l], 4),
+                             anchors=anchors, gt=gt, matched_idx32=m["matched_idx32"], mask=m["mask"], bets=b)
+    lv = fsg.ops.levels_to_flat(out["grad_logits"], K)
+    assert torch.equal(lv, flat["grad_logits"])
+    assert torch.equal(fsg.ops.levels_to_flat(out["grad_deltas"], 4), flat["grad_deltas"])
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_dropin_retinanet_losses_and_gt(cuda, native):
     fsg = _fsg()
     from full_scale_gambler_for_object_detection_b200 import synthetic
     N, K = 2, 80
@@ -263,7 +319,7 @@ def test_dropin_retinanet_losses_and_gt(cuda):
                                      orc.levels_to_flat(ds, 4), K)
     (lc + 2 * lr).backward()
 
-    path = fsg.RetinaNetDensePath(num_classes=K)
+    path = fsg.RetinaNetDensePath(num_classes=K, native_layout=native)
     offs = inp["level_offsets"]
     anc_levels = [fsg.Boxes(inp["anchors"][offs[i]:offs[i + 1]].to(cuda)) for i in range(5)]
     anchors = [anc_levels for _ in range(N)]
@@ -290,8 +346,8 @@ def test_dropin_retinanet_losses_and_gt(cuda):
         assert_close_tensor(a.grad, b.grad, "grad reg level")
 
 
-@pytest.mark.parametrize("detach", [False, True])
-def test_dropin_gambler_loss(cuda, detach):
+@pytest.mark.parametrize("detach,native", [(False, True), (True, True), (False, False), (True, False)])
+def test_dropin_gambler_loss(cuda, detach, native):
     fsg = _fsg()
     from full_scale_gambler_for_object_detection_b200 import synthetic
     N, K, A = 2, 80, 3
@@ -307,7 +363,7 @@ def test_dropin_gambler_loss(cuda, detach):
                             gtd["gt_classes"], gtd["mask"], K)
     want["gambler_loss"].backward()
 
-    head = fsg.GamblerLoss(num_classes=K)
+    head = fsg.GamblerLoss(num_classes=K, native_layout=native)
     gx = [t.to(cuda).requires_grad_(True) for t in cls_l]
     gb = [t.to(cuda).requires_grad_(True) for t in bet_l]
     bets_list = list(gb)
