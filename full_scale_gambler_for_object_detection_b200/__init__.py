@@ -8,22 +8,26 @@ library is not built or a tensor is not on a CUDA device.
     matcher        Matcher                                 (detectron2/modeling/matcher.py)
     box_regression Box2BoxTransform                        (detectron2/modeling/box_regression.py)
     nms            nms, batched_nms                        (detectron2/layers/nms.py)
+    anchor_generator DefaultAnchorGenerator                (detectron2/modeling/anchor_generator.py)
+    postprocessing detector_postprocess                    (detectron2/modeling/postprocessing.py)
     retinanet      RetinaNetDensePath                      (meta_arch/retinanet.py: GT, losses, inference)
     gambler        GamblerLoss, get_loss_upper_bound       (imbalancedetection/gambler_heads.py)
     fused          dense_train_step, DenseLossConfig       (the fused K1+K2 step)
     ops            one function per C-ABI entry point
 """
 from . import _lib, ops  # noqa: F401
+from .anchor_generator import DefaultAnchorGenerator  # noqa: F401
 from .box_regression import Box2BoxTransform  # noqa: F401
 from .fused import DenseLossConfig, DenseStepPlan, StepResult, dense_train_step  # noqa: F401
 from .gambler import GamblerLoss, get_loss_upper_bound  # noqa: F401
 from .matcher import Matcher  # noqa: F401
 from .nms import batched_nms, nms  # noqa: F401
+from .postprocessing import detector_postprocess  # noqa: F401
 from .retinanet import RetinaNetDensePath  # noqa: F401
 from .structures import Boxes, Instances, pairwise_iou  # noqa: F401
 
 __all__ = [
     "Boxes", "Instances", "pairwise_iou", "Matcher", "Box2BoxTransform", "nms", "batched_nms",
     "RetinaNetDensePath", "GamblerLoss", "get_loss_upper_bound", "dense_train_step", "DenseLossConfig",
-    "StepResult", "DenseStepPlan", "ops",
+    "StepResult", "DenseStepPlan", "ops", "DefaultAnchorGenerator", "detector_postprocess",
 ]

@@ -11,8 +11,8 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfsg_dense.so")
-ABI_VERSION = 1
+LIB_PATH = os.environ.get("FSG_DENSE_LIB") or os.path.join(_HERE, "libfsg_dense.so")  # override: kernel experiments
+ABI_VERSION = 2
 STATS_HEADER = 2
 SCALARS_HEADER = 10
 
@@ -45,6 +45,12 @@ class HeadLevel(ctypes.Structure):
 
     _fields_ = [("logits", c_ptr), ("grad_logits", c_ptr), ("pred_deltas", c_ptr), ("grad_deltas", c_ptr),
                 ("H", c_i32), ("W", c_i32)]
+
+
+class AnchorLevel(ctypes.Structure):
+    """``struct fsg_anchor_level``."""
+
+    _fields_ = [("H", c_i32), ("W", c_i32), ("stride", c_i32), ("A", c_i32), ("cell", (c_f32 * 4) * 16)]
 
 
 class PeerCtx(ctypes.Structure):
@@ -94,8 +100,10 @@ PROTOTYPES = {
     "fsg_detect": (
         c_i32,
         [c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i64, c_i32, c_ptr, c_i32, c_f32, c_i32, c_f64, c_i32, c_ptr, c_f32,
-         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
+         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
     ),
+    "fsg_postprocess_boxes": (c_i32, [c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
+    "fsg_grid_anchors": (c_i32, [ctypes.POINTER(AnchorLevel), c_i32, c_ptr, c_i64, c_ptr]),
     "fsg_permute_level": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i64, c_i64, c_i64, c_i32, c_ptr]),
 }
 

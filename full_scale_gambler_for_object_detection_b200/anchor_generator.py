@@ -1,8 +1,10 @@
 """Anchor grids with ``DefaultAnchorGenerator`` semantics (detectron2/modeling/anchor_generator.py:121-168).
 
-Host-side closed form (torch ops on whatever device is asked for): cell anchors per level from
-(sizes, aspect_ratios), shifted over the (H, W) grid with the level stride; order (h, w, a), XYXY fp32.
-Generating them inside K1/K3 is the "next" row (f1) of SURVEY.md section 8.
+``DefaultAnchorGenerator`` produces the grid on the device with one kernel launch (``fsg_grid_anchors``) and
+caches it per grid shape; every image of a batch shares that one (R,4) tensor (1 MB at 800x1333: it stays
+L2-resident across the images of a batch, which is why the matching / loss / decode kernels read it instead of
+re-deriving (level, y, x, a) per anchor with integer divisions).  ``grid_anchors`` below is the host-side closed
+form used to build synthetic inputs on the CPU.  Order (h, w, a), XYXY fp32.
 """
 import math
 
@@ -59,3 +61,53 @@ def retinanet_anchors(height, width, device="cpu", sizes=RETINANET_SIZES, aspect
     for a in per_level:
         offs.append(offs[-1] + a.shape[0])
     return torch.cat(per_level).contiguous(), offs, grids
+
+
+class DefaultAnchorGenerator:
+    """anchor_generator.py:53-191 with the reference's call shape: ``gen(features) -> list[list[Boxes]]``
+    (#images x #levels).  ``sizes`` / ``aspect_ratios`` broadcast over levels like the reference (:83-90).
+    The per-image deep copies of the reference (:188) are replaced by references to one cached set of
+    ``Boxes`` (nothing on this path mutates anchors); ``flat(features)`` gives the (R,4) tensor + level offsets
+    the fused entry points take."""
+
+    def __init__(self, sizes, aspect_ratios, strides, device="cuda"):
+        self.strides = [int(s) for s in strides]
+        n = len(self.strides)
+        sizes = [list(s) for s in sizes] * (n if len(sizes) == 1 else 1)
+        aspect_ratios = [list(a) for a in aspect_ratios] * (n if len(aspect_ratios) == 1 else 1)
+        assert n == len(sizes) and n == len(aspect_ratios)
+        self.cell_anchors = [generate_cell_anchors(s, a) for s, a in zip(sizes, aspect_ratios)]
+        self.device = device
+        self._cache = {}
+
+    @classmethod
+    def from_config(cls, cfg, input_shape, device="cuda"):
+        return cls(cfg.MODEL.ANCHOR_GENERATOR.SIZES, cfg.MODEL.ANCHOR_GENERATOR.ASPECT_RATIOS,
+                   [x.stride for x in input_shape], device)
+
+    @property
+    def num_cell_anchors(self):
+        return [len(c) for c in self.cell_anchors]
+
+    @property
+    def box_dim(self):
+        return 4
+
+    def flat_for_grids(self, grid_sizes):
+        from . import ops
+        key = tuple((int(h), int(w)) for h, w in grid_sizes)
+        if key not in self._cache:
+            self._cache[key] = ops.grid_anchors(key, self.strides, self.cell_anchors, self.device)
+        return self._cache[key]
+
+    def flat(self, features):
+        return self.flat_for_grids([f.shape[-2:] for f in features])
+
+    def grid_anchors(self, grid_sizes):
+        flat, offs = self.flat_for_grids(grid_sizes)
+        return [flat[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+
+    def __call__(self, features):
+        from .structures import Boxes
+        per_level = [Boxes(t) for t in self.grid_anchors([f.shape[-2:] for f in features])]
+        return [per_level for _ in range(len(features[0]))]

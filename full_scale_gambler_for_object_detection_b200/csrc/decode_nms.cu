@@ -472,12 +472,23 @@ struct NmsArgs {
   float4* out_boxes;        // (N, max_out) or NULL
   float* out_scores;
   int64_t* out_classes;
+  const float4* post;       // (N) [scale_x, scale_y, clip_w, clip_h] or NULL: detector_postprocess fused in
   // optional compact export of the candidates
   float4* exp_boxes;        // (N, L*topk)
   float* exp_scores;
   int64_t* exp_classes;
   int32_t* exp_count;
 };
+
+// Boxes.scale (boxes.py:205-210: fp32 * fp32(scale)) then Boxes.clip (boxes.py:122-136: clamp(min=0, max=size));
+// pp = [scale_x, scale_y, clip_w, clip_h]
+__device__ __forceinline__ float4 postprocess_box(float4 b, float4 pp) {
+  b.x = fminf(fmaxf(__fmul_rn(b.x, pp.x), 0.f), pp.z);
+  b.y = fminf(fmaxf(__fmul_rn(b.y, pp.y), 0.f), pp.w);
+  b.z = fminf(fmaxf(__fmul_rn(b.z, pp.x), 0.f), pp.z);
+  b.w = fminf(fmaxf(__fmul_rn(b.w, pp.y), 0.f), pp.w);
+  return b;
+}
 
 // ascending bitonic sort
 template <int NT>
@@ -680,6 +691,50 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
   if (S > 1) bitonic_asc<kNmsThreads>(keys, m2);
   int nk = tot;
   if (A.max_out > 0 && nk > A.max_out) nk = A.max_out;
+  if (A.post && A.out_boxes) {
+    // detector_postprocess (modeling/postprocessing.py:8-52) on the final detections: Boxes.scale, Boxes.clip,
+    // drop boxes that became empty (Boxes.nonempty), stable compaction.  max_out <= kNmsThreads: one row per thread.
+    const float4 pp = A.post[n];
+    const int t = tid;
+    bool ok = false;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = 0.f;
+    int64_t cl = 0;
+    int ci = -1;
+    if (t < nk) {
+      ci = (int)(keys[t] & 0x1fff);
+      const int s = slot_of(ci);
+      b = postprocess_box(gbox[s], pp);
+      sc = gscore[s];
+      cl = gcls ? gcls[s] : 0;
+      ok = (__fsub_rn(b.z, b.x) > 0.f) && (__fsub_rn(b.w, b.y) > 0.f);
+    }
+    const unsigned bm = __ballot_sync(kFull, ok);
+    if (lane == 0) s_warp[wid] = __popc(bm);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kNmsThreads / 32; ++w) {
+      const int c = s_warp[w];
+      if (w < wid) before += c;
+      total += c;
+    }
+    const int pos = before + __popc(bm & ((1u << lane) - 1u));
+    const int64_t ob = (int64_t)n * A.max_out;
+    if (ok) {
+      A.out_boxes[ob + pos] = b;
+      A.out_scores[ob + pos] = sc;
+      A.out_classes[ob + pos] = cl;
+      if (A.keep) A.keep[(int64_t)n * A.keep_stride + pos] = ci;
+    }
+    if (t >= total && t < A.max_out) {
+      A.out_boxes[ob + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      A.out_scores[ob + t] = 0.f;
+      A.out_classes[ob + t] = 0;
+      if (A.keep && t < A.keep_stride) A.keep[(int64_t)n * A.keep_stride + t] = -1;
+    }
+    if (tid == 0 && A.num_keep) A.num_keep[n] = total;
+    return;
+  }
   if (tid == 0 && A.num_keep) A.num_keep[n] = nk;
   const int out_rows = (A.max_out > 0) ? A.max_out : nk;
   for (int t = tid; t < out_rows; t += kNmsThreads) {
@@ -701,6 +756,16 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
       }
     }
   }
+}
+
+// stand-alone detector_postprocess on any (n,4) box list: scaled + clipped boxes and a keep flag per box
+__global__ void __launch_bounds__(256) postprocess_boxes_kernel(const float4* __restrict__ boxes, int64_t n, float4 pp,
+                                                                float4* __restrict__ out, uint8_t* __restrict__ keep) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float4 b = postprocess_box(boxes[i], pp);
+  out[i] = b;
+  keep[i] = ((__fsub_rn(b.z, b.x) > 0.f) && (__fsub_rn(b.w, b.y) > 0.f)) ? 1 : 0;
 }
 
 static int nms_split_for(int N) {
@@ -839,8 +904,9 @@ extern "C" int fsg_detect(const float* logits, const float* deltas, const float*
                           int num_levels, float score_threshold, int topk, double nms_threshold, int max_det,
                           const float* h_box_weights, float scale_clamp, float* out_boxes, float* out_scores,
                           int64_t* out_classes, int32_t* out_count, float* cand_boxes, float* cand_scores,
-                          int64_t* cand_classes, int32_t* cand_count, int64_t* keep_idx, void* workspace,
-                          size_t workspace_bytes, fsg_stream_t stream) {
+                          int64_t* cand_classes, int32_t* cand_count, int64_t* keep_idx, const float* postprocess,
+                          void* workspace, size_t workspace_bytes, fsg_stream_t stream) {
+  if (postprocess && ((uintptr_t)postprocess & 15)) return FSG_ERR_INVALID_ARG;
   if (N <= 0 || R <= 0 || K <= 0 || !h_level_offsets || num_levels <= 0 || num_levels > kMaxLevels)
     return FSG_ERR_INVALID_ARG;
   if (!logits || !deltas || !anchors || !out_boxes || !out_scores || !out_classes || !out_count || !h_box_weights)
@@ -906,10 +972,23 @@ extern "C" int fsg_detect(const float* logits, const float* deltas, const float*
   }
   a.keep = keep_idx; a.keep_stride = max_det; a.num_keep = out_count;
   a.out_boxes = (float4*)out_boxes; a.out_scores = out_scores; a.out_classes = out_classes;
+  a.post = (const float4*)postprocess;
   a.exp_boxes = (float4*)cand_boxes; a.exp_scores = cand_scores; a.exp_classes = cand_classes;
   a.exp_count = cand_count;
   FSG_CUDA_TRY(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmem));
   nms_image_kernel<<<dim3((unsigned)a.split, (unsigned)N), kNmsThreads, kNmsSmem, s>>>(a);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" int fsg_postprocess_boxes(const float* boxes, int64_t n, float scale_x, float scale_y, float clip_w,
+                                     float clip_h, float* out_boxes, uint8_t* keep, fsg_stream_t stream) {
+  if (n < 0) return FSG_ERR_INVALID_ARG;
+  if (n == 0) return FSG_OK;
+  if (!boxes || !out_boxes || !keep) return FSG_ERR_INVALID_ARG;
+  if (((uintptr_t)boxes | (uintptr_t)out_boxes) & 15) return FSG_ERR_INVALID_ARG;
+  postprocess_boxes_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)boxes, n, make_float4(scale_x, scale_y, clip_w, clip_h), (float4*)out_boxes, keep);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

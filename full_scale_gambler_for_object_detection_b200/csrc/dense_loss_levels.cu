@@ -16,6 +16,17 @@ namespace fsg {
 
 constexpr int kLvMax = FSG_MAX_LEVELS;
 
+#ifndef LV_MINB
+#define LV_MINB 4
+#endif
+#ifndef LV_VEC4
+#define LV_VEC4 0
+#endif
+#ifndef LV_BLOCK
+#define LV_BLOCK 256
+#endif
+constexpr int kLvBlock = LV_BLOCK;   // threads per CTA; a CTA covers kLvBlock * vec consecutive hw of one anchor slot
+
 struct LevelTable {
   const float* logits[kLvMax];
   float* grad_logits[kLvMax];
@@ -23,7 +34,8 @@ struct LevelTable {
   float* grad_deltas[kLvMax];
   int64_t off[kLvMax + 1];   // first anchor index of the level
   int HW[kLvMax];
-  int chunks[kLvMax];        // ceil(HW / kLossBlock)
+  int vec[kLvMax];           // hw positions per thread (2 when every plane of the level is 8-byte aligned)
+  int chunks[kLvMax];        // ceil(HW / (kLvBlock * vec))
   int tile_base[kLvMax + 1]; // tiles of a level: A * chunks
   int num_levels, A;
 };
@@ -54,18 +66,169 @@ struct LevelLossArgs {
   double* scalars;
 };
 
-template <int BATCH, bool FAST>
-__global__ void __launch_bounds__(kLossBlock, 3) loss_main_levels_kernel(const LevelLossArgs A, const LevelTable LT) {
+struct TileSums {
+  float cls, reg, wl, l, mx;
+};
+
+// One thread: VEC consecutive hw positions of anchor slot `a` (VEC anchors), all K class planes.
+// BATCH planes are in flight while the previous BATCH are evaluated; EXACT: K % BATCH == 0 (no predication in
+// the element loop); FAST: focal gamma == 2 in focal gambler mode; WRITE: gradient planes are written.
+template <int VEC, int BATCH, bool EXACT, bool FAST, bool WRITE>
+__device__ __forceinline__ void level_body(const LevelLossArgs& A, const LevelTable& LT, int l, int a, int hw0, int n,
+                                           float inv_nf, float inv_S, TileSums& S) {
+  const int HW = LT.HW[l];
+  const int K = A.K;
+  const int64_t r0 = LT.off[l] + (int64_t)hw0 * LT.A + a;
+  const int64_t o0 = (int64_t)n * A.R + r0;
+  const int64_t plane0 = ((int64_t)n * LT.A + a) * K;
+  const float* xcol = LT.logits[l] + plane0 * HW + hw0;
+  float* gcol = WRITE ? LT.grad_logits[l] + plane0 * HW + hw0 : nullptr;
+
+  Vec<VEC> x[BATCH];
+#pragma unroll
+  for (int b = 0; b < BATCH; ++b)
+    if (EXACT || b < K) x[b].load(xcol + (int64_t)b * HW);
+
+  int cls[VEC];
+  float wg[VEC], w_hat[VEC], cf[VEC], cfr[VEC], cb[VEC], sum_f[VEC], sum_b[VEC];
+  bool valid[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const bool in = (VEC == 1) || (hw0 + v < HW);   // HW % VEC == 0 whenever VEC > 1, kept for clarity
+    const int64_t o = o0 + (int64_t)v * LT.A;
+    cls[v] = in ? (int)A.gt_classes[o] : -1;
+    w_hat[v] = 0.f;
+    if (A.bets && in) {
+      const float m = A.mask ? (float)A.mask[o] : 1.f;
+      const float w = __fadd_rn(__fmul_rn(A.bets[o], m), A.T);   // gambler_heads.py:569,304
+      w_hat[v] = w * inv_S;                                      // :308-311
+    }
+    valid[v] = cls[v] >= 0;
+    wg[v] = (A.ggamma == 1.f) ? w_hat[v] : powf(w_hat[v], A.ggamma);
+    float coef_f = 0.f, coef_b = 0.f;
+    if (valid[v]) {
+      coef_f = A.c_cls * inv_nf;
+      if (A.gmode == FSG_CLS_FOCAL) coef_f = fmaf(-A.c_gam, wg[v], coef_f);
+      else coef_b = -A.c_gam * wg[v];
+    }
+    cf[v] = FAST ? coef_f * A.a0 : coef_f;   // ignored anchors: zero coefficient -> zero gradient
+    cfr[v] = coef_f;
+    cb[v] = coef_b;
+    sum_f[v] = 0.f;
+    sum_b[v] = 0.f;
+  }
+
+#pragma unroll 1
+  for (int k0 = 0; k0 < K; k0 += BATCH) {
+    Vec<VEC> y[BATCH];
+    const int k1 = k0 + BATCH;
+    if (k1 < K) {
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b)
+        if (EXACT || k1 + b < K) y[b].load(xcol + (int64_t)(k1 + b) * HW);
+    }
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) {
+      const int k = k0 + b;
+      if (EXACT || k < K) {
+        Vec<VEC> g;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          if (FAST) {
+            float lo, d;
+            focal_neg_g2(x[b].v[v], lo, d);
+            sum_f[v] += lo;
+            g.v[v] = d * cf[v];
+          } else {
+            const bool t = (k == cls[v]);   // cls == K (background) or -1 (ignored) never matches
+            float f, fgd, bc, bgd;
+            cls_elem_general(x[b].v[v], t, A.gamma, f, fgd, bc, bgd);
+            const float at = t ? A.a1 : A.a0;
+            sum_f[v] += f * at;
+            sum_b[v] += bc;
+            g.v[v] = fmaf(fgd * at, cf[v], bgd * cb[v]);
+          }
+        }
+        if (WRITE) g.store(gcol + (int64_t)k * HW);
+      }
+    }
+    if (k1 < K) {
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) x[b] = y[b];
+    }
+  }
+
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int64_t o = o0 + (int64_t)v * LT.A;
+    const bool fgc = valid[v] && cls[v] != K;
+    if (FAST) {
+      sum_f[v] *= A.a0;
+      if (fgc) {   // patch the single positive class of a foreground anchor
+        const float xv = xcol[(int64_t)cls[v] * HW + v];
+        float l0, d0, f1, fg1, b1, bg1;
+        focal_neg_g2(xv, l0, d0);
+        cls_elem_general(xv, true, 2.f, f1, fg1, b1, bg1);
+        sum_f[v] += f1 * A.a1 - l0 * A.a0;
+        if (WRITE) gcol[(int64_t)cls[v] * HW + v] = fg1 * (cfr[v] * A.a1);
+      }
+    }
+    const float lf = valid[v] ? sum_f[v] : 0.f;                                   // gambler_heads.py:554-555
+    const float lg = (A.gmode == FSG_CLS_FOCAL) ? lf : (valid[v] ? sum_b[v] : 0.f);
+    if (A.ell) A.ell[o] = lg;
+    if (A.wout) A.wout[o] = w_hat[v];
+    S.cls += lf;
+    S.wl = fmaf(wg[v], lg, S.wl);
+    S.l += lg;
+    S.mx = fmaxf(S.mx, lg);
+  }
+
+  // ---- regression planes (a*4 + j)
+  if (LT.pred_deltas[l]) {
+    const int64_t dplane = ((int64_t)n * LT.A + a) * 4;
+    const float* pcol = LT.pred_deltas[l] + dplane * HW + hw0;
+    Vec<VEC> g4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) g4[j].v[v] = 0.f;
+    const float sc = A.c_reg * inv_nf;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      if (valid[v] && cls[v] != K) {
+        const int64_t o = o0 + (int64_t)v * LT.A;
+        float4 gd;
+        if (A.gt_deltas) gd = reinterpret_cast<const float4*>(A.gt_deltas)[o];
+        else gd = encode_deltas_loss(A.anchors[(int64_t)n * A.anchor_stride4 + r0 + (int64_t)v * LT.A],
+                                     A.gt_boxes[A.gt_offsets[n] + A.matched[o]], A.wx, A.wy, A.ww, A.wh);
+        const float gdv[4] = {gd.x, gd.y, gd.z, gd.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float lo, g;
+          smooth_l1_elem(pcol[(int64_t)j * HW + v], gdv[j], A.beta, lo, g);
+          S.reg += lo;
+          g4[j].v[v] = g * sc;
+        }
+      }
+    }
+    if (LT.grad_deltas[l]) {
+      float* dcol = LT.grad_deltas[l] + dplane * HW + hw0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g4[j].store(dcol + (int64_t)j * HW);
+    }
+  }
+}
+
+template <int BATCH, bool EXACT, bool FAST, bool WRITE>
+__global__ void __launch_bounds__(kLvBlock, LV_MINB) loss_main_levels_kernel(const LevelLossArgs A, const LevelTable LT) {
   const int tid = threadIdx.x;
   const int n = blockIdx.y;
   int l = 0;
   while (l + 1 < LT.num_levels && (int)blockIdx.x >= LT.tile_base[l + 1]) ++l;
   const int local = (int)blockIdx.x - LT.tile_base[l];
   const int a = local / LT.chunks[l];
-  const int hw = (local - a * LT.chunks[l]) * kLossBlock + tid;
-  const int HW = LT.HW[l];
-  const bool live = hw < HW;
-  const int K = A.K;
+  const int vec = LT.vec[l];
+  const int hw0 = ((local - a * LT.chunks[l]) * kLvBlock + tid) * vec;
 
   const double nf_d = A.stats[0];
   const float inv_nf = __frcp_rn(fmaxf((float)nf_d, 1.f));
@@ -73,124 +236,19 @@ __global__ void __launch_bounds__(kLossBlock, 3) loss_main_levels_kernel(const L
   if (A.nmode == FSG_NORM_IMAGE) inv_S = __frcp_rn((float)A.stats[FSG_STATS_HEADER + n]);
   else if (A.nmode == FSG_NORM_BATCH) inv_S = __frcp_rn((float)A.stats[1]);
 
-  float acc_cls = 0.f, acc_reg = 0.f, acc_wl = 0.f, acc_l = 0.f, max_l = 0.f;
-
-  if (live) {
-    const int64_t r = LT.off[l] + (int64_t)hw * LT.A + a;
-    const int64_t o = (int64_t)n * A.R + r;
-    const int64_t plane0 = ((int64_t)n * LT.A + a) * K;          // first class plane of this anchor slot
-    const float* xcol = LT.logits[l] + plane0 * HW + hw;
-    float* gcol = LT.grad_logits[l] ? LT.grad_logits[l] + plane0 * HW + hw : nullptr;
-
-    // first batch of class planes in flight before the per-anchor metadata is touched
-    float x[BATCH];
-#pragma unroll
-    for (int b = 0; b < BATCH; ++b)
-      if (b < K) x[b] = ldg_stream1(xcol + (int64_t)b * HW);
-
-    const int cls = (int)A.gt_classes[o];
-    float w_hat = 0.f;
-    if (A.bets) {
-      const float m = A.mask ? (float)A.mask[o] : 1.f;
-      const float w = __fadd_rn(__fmul_rn(A.bets[o], m), A.T);   // gambler_heads.py:569,304
-      w_hat = w * inv_S;                                        // :308-311
-    }
-    const bool valid = cls >= 0;
-    const bool fgc = valid && cls != K;
-    const float wg = (A.ggamma == 1.f) ? w_hat : powf(w_hat, A.ggamma);
-    float coef_f = 0.f, coef_b = 0.f;
-    if (valid) {
-      coef_f = A.c_cls * inv_nf;
-      if (A.gmode == FSG_CLS_FOCAL) coef_f = fmaf(-A.c_gam, wg, coef_f);
-      else coef_b = -A.c_gam * wg;
-    }
-
-    float sum_f = 0.f, sum_b = 0.f;
-    const float cf0 = coef_f * A.a0;
-#pragma unroll 1
-    for (int k0 = 0; k0 < K; k0 += BATCH) {
-      float y[BATCH];
-      const int k1 = k0 + BATCH;
-#pragma unroll
-      for (int b = 0; b < BATCH; ++b)
-        if (k1 + b < K) y[b] = ldg_stream1(xcol + (int64_t)(k1 + b) * HW);
-#pragma unroll
-      for (int b = 0; b < BATCH; ++b) {
-        const int k = k0 + b;
-        if (k < K) {
-          float g;
-          if (FAST) {
-            float lo, d;
-            focal_neg_g2(x[b], lo, d);
-            sum_f += lo;
-            g = d * cf0;
-          } else {
-            const bool t = (k == cls);   // cls == K (background) or -1 (ignored) never matches
-            float f, fgd, bc, bgd;
-            cls_elem_general(x[b], t, A.gamma, f, fgd, bc, bgd);
-            const float at = t ? A.a1 : A.a0;
-            sum_f += f * at;
-            sum_b += bc;
-            g = fmaf(fgd * at, coef_f, bgd * coef_b);
-          }
-          if (gcol) stg_stream1(gcol + (int64_t)k * HW, valid ? g : 0.f);
-        }
-      }
-#pragma unroll
-      for (int b = 0; b < BATCH; ++b) x[b] = y[b];
-    }
-    if (FAST) {
-      sum_f *= A.a0;
-      if (fgc) {   // patch the single positive class of a foreground anchor
-        const float xv = xcol[(int64_t)cls * HW];
-        float l0, d0, f1, fg1, b1, bg1;
-        focal_neg_g2(xv, l0, d0);
-        cls_elem_general(xv, true, 2.f, f1, fg1, b1, bg1);
-        sum_f += f1 * A.a1 - l0 * A.a0;
-        if (gcol) gcol[(int64_t)cls * HW] = fg1 * (coef_f * A.a1);
-      }
-    }
-    const float lf = valid ? sum_f : 0.f;                                   // gambler_heads.py:554-555
-    const float lg = (A.gmode == FSG_CLS_FOCAL) ? lf : (valid ? sum_b : 0.f);
-    if (A.ell) A.ell[o] = lg;
-    if (A.wout) A.wout[o] = w_hat;
-    acc_cls = lf;
-    acc_wl = wg * lg;
-    acc_l = lg;
-    max_l = lg;
-
-    // ---- regression planes (a*4 + j)
-    if (LT.pred_deltas[l]) {
-      const int64_t dplane = ((int64_t)n * LT.A + a) * 4;
-      const float* pcol = LT.pred_deltas[l] + dplane * HW + hw;
-      float g4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (fgc) {
-        float4 gd;
-        if (A.gt_deltas) gd = reinterpret_cast<const float4*>(A.gt_deltas)[o];
-        else gd = encode_deltas_loss(A.anchors[(int64_t)n * A.anchor_stride4 + r],
-                                     A.gt_boxes[A.gt_offsets[n] + A.matched[o]], A.wx, A.wy, A.ww, A.wh);
-        const float gdv[4] = {gd.x, gd.y, gd.z, gd.w};
-        const float sc = A.c_reg * inv_nf;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float lo, g;
-          smooth_l1_elem(ldg_stream1(pcol + (int64_t)j * HW), gdv[j], A.beta, lo, g);
-          acc_reg += lo;
-          g4[j] = g * sc;
-        }
-      }
-      if (LT.grad_deltas[l]) {
-        float* dcol = LT.grad_deltas[l] + dplane * HW + hw;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) stg_stream1(dcol + (int64_t)j * HW, g4[j]);
-      }
-    }
+  TileSums S = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (hw0 < LT.HW[l]) {
+#if LV_VEC4
+    if (vec == 4) level_body<4, BATCH / 2, EXACT, FAST, WRITE>(A, LT, l, a, hw0, n, inv_nf, inv_S, S);
+    else
+#endif
+    if (vec == 2) level_body<2, BATCH, EXACT, FAST, WRITE>(A, LT, l, a, hw0, n, inv_nf, inv_S, S);
+    else level_body<1, BATCH, EXACT, FAST, WRITE>(A, LT, l, a, hw0, n, inv_nf, inv_S, S);
   }
-
-  acc_cls = warp_sum(acc_cls); acc_reg = warp_sum(acc_reg); acc_wl = warp_sum(acc_wl);
-  acc_l = warp_sum(acc_l); max_l = warp_max(max_l);
-  finish_tile(acc_cls, acc_reg, acc_wl, acc_l, max_l, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
-              A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam);
+  S.cls = warp_sum(S.cls); S.reg = warp_sum(S.reg); S.wl = warp_sum(S.wl);
+  S.l = warp_sum(S.l); S.mx = warp_max(S.mx);
+  finish_tile<kLvBlock>(S.cls, S.reg, S.wl, S.l, S.mx, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
+                        A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam);
 }
 
 static int build_table(const fsg_head_level* h, int num_levels, int A, LevelTable* t, int64_t* R_out) {
@@ -206,13 +264,19 @@ static int build_table(const fsg_head_level* h, int num_levels, int A, LevelTabl
       if (hw > (1 << 30)) return FSG_ERR_UNSUPPORTED;
       t->logits[l] = h[l].logits; t->grad_logits[l] = h[l].grad_logits;
       t->pred_deltas[l] = h[l].pred_deltas; t->grad_deltas[l] = h[l].grad_deltas;
-      t->off[l] = off; t->HW[l] = (int)hw; t->chunks[l] = (int)ceil_div(hw, kLossBlock);
+      // two hw per thread when every (channel) plane of the level starts 8-byte aligned
+      const bool al8 = (hw % 2 == 0) && !(((uintptr_t)h[l].logits | (uintptr_t)h[l].grad_logits |
+                                           (uintptr_t)h[l].pred_deltas | (uintptr_t)h[l].grad_deltas) & 7);
+      const bool al16 = LV_VEC4 && (hw % 4 == 0) && !(((uintptr_t)h[l].logits | (uintptr_t)h[l].grad_logits |
+                                                         (uintptr_t)h[l].pred_deltas | (uintptr_t)h[l].grad_deltas) & 15);
+      t->vec[l] = al16 ? 4 : (al8 ? 2 : 1);
+      t->off[l] = off; t->HW[l] = (int)hw; t->chunks[l] = (int)ceil_div(hw, (int64_t)kLvBlock * t->vec[l]);
       t->tile_base[l] = tiles;
       off += hw * A;
       tiles += A * t->chunks[l];
     } else {
       t->logits[l] = nullptr; t->grad_logits[l] = nullptr; t->pred_deltas[l] = nullptr; t->grad_deltas[l] = nullptr;
-      t->off[l] = off; t->HW[l] = 0; t->chunks[l] = 1; t->tile_base[l] = tiles;
+      t->off[l] = off; t->HW[l] = 0; t->vec[l] = 1; t->chunks[l] = 1; t->tile_base[l] = tiles;
     }
   }
   t->off[kLvMax] = off;
@@ -220,6 +284,24 @@ static int build_table(const fsg_head_level* h, int num_levels, int A, LevelTabl
   for (int l = num_levels; l < kLvMax; ++l) { t->off[l] = off; t->tile_base[l] = tiles; }
   *R_out = off;
   return FSG_OK;
+}
+
+template <int BATCH, bool EXACT>
+static void launch_levels2(bool fast, bool write, dim3 grid, cudaStream_t s, const LevelLossArgs& a,
+                           const LevelTable& t) {
+  if (fast) {
+    if (write) loss_main_levels_kernel<BATCH, EXACT, true, true><<<grid, kLvBlock, 0, s>>>(a, t);
+    else loss_main_levels_kernel<BATCH, EXACT, true, false><<<grid, kLvBlock, 0, s>>>(a, t);
+  } else {
+    if (write) loss_main_levels_kernel<BATCH, EXACT, false, true><<<grid, kLvBlock, 0, s>>>(a, t);
+    else loss_main_levels_kernel<BATCH, EXACT, false, false><<<grid, kLvBlock, 0, s>>>(a, t);
+  }
+}
+static void launch_levels(int K, bool fast, bool write, dim3 grid, cudaStream_t s, const LevelLossArgs& a,
+                          const LevelTable& t) {
+  if (K % 10 == 0) launch_levels2<10, true>(fast, write, grid, s, a, t);
+  else if (K % 8 == 0) launch_levels2<8, true>(fast, write, grid, s, a, t);
+  else launch_levels2<8, false>(fast, write, grid, s, a, t);
 }
 
 }  // namespace fsg
@@ -282,14 +364,11 @@ extern "C" int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_leve
   FSG_CUDA_TRY(cudaMemsetAsync(a.counter, 0, 16, s));
   const bool fast = (hp->focal_gamma == 2.f) && (hp->gambler_mode == FSG_CLS_FOCAL);
   dim3 grid((unsigned)t.tile_base[kLvMax], (unsigned)N);
-  const bool b20 = (a.K % 20 == 0);
-  if (fast) {
-    if (b20) loss_main_levels_kernel<20, true><<<grid, kLossBlock, 0, s>>>(a, t);
-    else loss_main_levels_kernel<16, true><<<grid, kLossBlock, 0, s>>>(a, t);
-  } else {
-    if (b20) loss_main_levels_kernel<20, false><<<grid, kLossBlock, 0, s>>>(a, t);
-    else loss_main_levels_kernel<16, false><<<grid, kLossBlock, 0, s>>>(a, t);
-  }
+  bool write = false;
+  for (int l = 0; l < num_levels; ++l) write = write || t.grad_logits[l];
+  for (int l = 0; l < num_levels; ++l)
+    if (write && !t.grad_logits[l]) return FSG_ERR_INVALID_ARG;   // gradients for all levels or for none
+  launch_levels(a.K, fast, write, grid, s, a, t);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

@@ -55,9 +55,61 @@ __global__ void __launch_bounds__(256) permute_level_kernel(float* __restrict__ 
   }
 }
 
+// DefaultAnchorGenerator.grid_anchors (detectron2/modeling/anchor_generator.py:41-50,121-129): anchor
+// (level, y, x, a) = (x*stride, y*stride, x*stride, y*stride) + cell_anchor[a] in fp32, flattened in the order
+// (level, y, x, a) = the r index every other kernel uses.  x*stride is an exact fp32 integer (arange with an integer
+// step), so one rounded addition reproduces the reference bit for bit.
+struct AnchorGrid {
+  int64_t off[FSG_MAX_LEVELS + 1];
+  int W[FSG_MAX_LEVELS], stride[FSG_MAX_LEVELS], A[FSG_MAX_LEVELS];
+  float cell[FSG_MAX_LEVELS][FSG_MAX_CELL_ANCHORS][4];
+  int num_levels;
+};
+
+__global__ void __launch_bounds__(256) grid_anchors_kernel(const AnchorGrid G, float4* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= G.off[G.num_levels]) return;
+  int l = 0;
+  while (l + 1 < G.num_levels && r >= G.off[l + 1]) ++l;
+  const int64_t local = r - G.off[l];
+  const int A = G.A[l];
+  const int64_t cellidx = local / A;
+  const int a = (int)(local - cellidx * A);
+  const int y = (int)(cellidx / G.W[l]);
+  const int x = (int)(cellidx - (int64_t)y * G.W[l]);
+  const float sx = (float)(x * G.stride[l]), sy = (float)(y * G.stride[l]);
+  const float* c = G.cell[l][a];
+  out[r] = make_float4(__fadd_rn(sx, c[0]), __fadd_rn(sy, c[1]), __fadd_rn(sx, c[2]), __fadd_rn(sy, c[3]));
+}
+
 }  // namespace fsg
 
 using namespace fsg;
+
+extern "C" int fsg_grid_anchors(const fsg_anchor_level* h_levels, int num_levels, float* anchors, int64_t R,
+                                fsg_stream_t stream) {
+  if (!h_levels || num_levels <= 0 || num_levels > FSG_MAX_LEVELS || R < 0) return FSG_ERR_INVALID_ARG;
+  AnchorGrid g;
+  int64_t off = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const fsg_anchor_level& L = h_levels[l];
+    if (L.H < 0 || L.W < 0 || L.stride <= 0 || L.A <= 0 || L.A > FSG_MAX_CELL_ANCHORS) return FSG_ERR_INVALID_ARG;
+    if ((int64_t)(L.H > L.W ? L.H : L.W) * L.stride >= (1 << 24)) return FSG_ERR_UNSUPPORTED;  // exact in fp32
+    g.off[l] = off; g.W[l] = L.W > 0 ? L.W : 1; g.stride[l] = L.stride; g.A[l] = L.A;
+    for (int a = 0; a < FSG_MAX_CELL_ANCHORS; ++a)
+      for (int j = 0; j < 4; ++j) g.cell[l][a][j] = a < L.A ? L.cell[a][j] : 0.f;
+    off += (int64_t)L.H * L.W * L.A;
+  }
+  for (int l = num_levels; l <= FSG_MAX_LEVELS; ++l) g.off[l] = off;
+  g.num_levels = num_levels;
+  if (off != R) return FSG_ERR_INVALID_ARG;
+  if (R == 0) return FSG_OK;
+  if (!anchors || ((uintptr_t)anchors & 15)) return FSG_ERR_INVALID_ARG;
+  grid_anchors_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, (cudaStream_t)stream>>>(g, (float4*)anchors);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
 
 extern "C" int fsg_permute_level(float* nchw, float* flat, int N, int C, int64_t HW, int64_t flat_image_stride,
                                  int64_t flat_offset, int to_nchw, fsg_stream_t stream) {

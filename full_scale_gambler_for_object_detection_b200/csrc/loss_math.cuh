@@ -118,14 +118,15 @@ __device__ __forceinline__ void smooth_l1_elem(float pd, float gd, float beta, f
 }
 
 // ---- per-tile partials -> scalars --------------------------------------------------------------
-// Called by every thread of a kLossBlock-thread CTA after it has reduced its own five sums into registers of
+// Called by every thread of an NT-thread CTA after it has reduced its own five sums into registers of
 // warp lane 0 (acc_* already warp-reduced).  Writes the tile's slot, elects the last CTA of the grid and lets it
 // fold all slots in a fixed order (run-to-run deterministic), producing the scalars of include/fsg_dense.h.
+template <int NT = kLossBlock>
 __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float acc_wl, float acc_l, float max_l,
                                             int n, int tile, int T, int N, float* partials, unsigned* counter,
                                             double* scalars, double nf_d, float c_cls, float c_reg, float c_gam) {
-  __shared__ float s_part[kLossBlock / 32][5];
-  __shared__ double s_tot[kLossBlock / 32][5];
+  __shared__ float s_part[NT / 32][5];
+  __shared__ double s_tot[NT / 32][5];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (lane == 0) {
@@ -135,7 +136,7 @@ __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float 
   __syncthreads();
   if (tid == 0) {
     float c = 0.f, g = 0.f, w = 0.f, l = 0.f, mx = 0.f;
-    for (int k = 0; k < kLossBlock / 32; ++k) {
+    for (int k = 0; k < NT / 32; ++k) {
       c += s_part[k][0]; g += s_part[k][1]; w += s_part[k][2]; l += s_part[k][3];
       mx = fmaxf(mx, s_part[k][4]);
     }
@@ -149,7 +150,7 @@ __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float 
 
   __threadfence();
   double t_cls = 0.0, t_reg = 0.0, t_wl = 0.0, t_l = 0.0, t_mx = 0.0;
-  for (int img = wid; img < N; img += kLossBlock / 32) {
+  for (int img = wid; img < N; img += NT / 32) {
     double c = 0.0, g = 0.0, w = 0.0, l = 0.0;
     float mx = 0.f;
     for (int b = lane; b < T; b += 32) {
@@ -169,7 +170,7 @@ __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float 
   __syncthreads();
   if (tid == 0) {
     double v[5] = {0, 0, 0, 0, 0};
-    for (int k = 0; k < kLossBlock / 32; ++k)
+    for (int k = 0; k < NT / 32; ++k)
       for (int q = 0; q < 5; ++q) v[q] += s_tot[k][q];
     const double nfc = nf_d > 1.0 ? nf_d : 1.0;
     for (int q = 0; q < 5; ++q) scalars[q] = v[q];

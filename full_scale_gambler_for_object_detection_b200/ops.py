@@ -361,12 +361,16 @@ def nms_raw(boxes, scores, class_ids, iou_threshold):
 
 
 def detect(logits, deltas, anchors, level_offsets, score_threshold=0.05, topk=1000, nms_threshold=0.5,
-           max_det=100, box_weights=(1.0, 1.0, 1.0, 1.0), scale_clamp=SCALE_CLAMP, want_candidates=False):
+           max_det=100, box_weights=(1.0, 1.0, 1.0, 1.0), scale_clamp=SCALE_CLAMP, want_candidates=False,
+           postprocess=None):
     """Batched RetinaNet.inference (retinanet.py:431-520) on flattened predictions.
 
     logits (N,R,K), deltas (N,R,4), anchors (R,4) or (N,R,4); level_offsets: list of L+1 anchor offsets.
     Returns dict(boxes (N,max_det,4), scores (N,max_det), classes (N,max_det) int64, count (N) int32
-    [, cand_boxes, cand_scores, cand_classes, cand_count, keep_idx])."""
+    [, cand_boxes, cand_scores, cand_classes, cand_count, keep_idx]).
+
+    postprocess: optional (N,4) CUDA fp32 rows [scale_x, scale_y, clip_w, clip_h] -- detector_postprocess
+    (modeling/postprocessing.py:8-52) fused into the NMS epilogue (see :func:`postprocess_rows`)."""
     x, d, a = logits, _f32c(deltas), _f32c(anchors)
     assert x.dtype == torch.float32 and x.is_contiguous()
     N, R, K = x.shape
@@ -392,6 +396,54 @@ def detect(logits, deltas, anchors, level_offsets, score_threshold=0.05, topk=10
         float(score_threshold), int(topk), float(nms_threshold), int(max_det), host_f32(box_weights),
         float(scale_clamp), ptr(out["boxes"]), ptr(out["scores"]), ptr(out["classes"]), ptr(out["count"]),
         ptr(out.get("cand_boxes")), ptr(out.get("cand_scores")), ptr(out.get("cand_classes")),
-        ptr(out.get("cand_count")), ptr(out.get("keep_idx")), ptr(ws), ws.numel(), stream()))
+        ptr(out.get("cand_count")), ptr(out.get("keep_idx")), ptr(postprocess), ptr(ws), ws.numel(), stream()))
     count_launches(2)
     return out
+
+
+def postprocess_rows(image_sizes, output_sizes, device):
+    """[(h, w)] network-input sizes and [(out_h, out_w)] requested sizes -> the (N,4) fp32 device table
+    [scale_x, scale_y, clip_w, clip_h] that :func:`detect` takes (postprocessing.py:27: scales are Python
+    doubles, applied to fp32 boxes as fp32 factors)."""
+    rows = []
+    for (h, w), (oh, ow) in zip(image_sizes, output_sizes):
+        rows.append([ow / w, oh / h, float(ow), float(oh)])
+    return torch.tensor(rows, dtype=torch.float32).to(device)
+
+
+def postprocess_boxes(boxes, image_size, output_height, output_width):
+    """Boxes.scale + Boxes.clip + Boxes.nonempty of detector_postprocess for one image.
+    -> (boxes (n,4) at the output resolution, keep (n) bool)."""
+    b = _f32c(boxes).reshape(-1, 4)
+    n = b.shape[0]
+    out = torch.empty_like(b)
+    keep = torch.empty(n, dtype=torch.uint8, device=b.device)
+    if n:
+        sx, sy = output_width / image_size[1], output_height / image_size[0]
+        check(lib().fsg_postprocess_boxes(ptr(b), n, sx, sy, float(output_width), float(output_height), ptr(out),
+                                          ptr(keep), stream()))
+        count_launches(1)
+    return out, keep.to(torch.bool)
+
+
+def grid_anchors(grid_sizes, strides, cell_anchors, device):
+    """DefaultAnchorGenerator.grid_anchors (anchor_generator.py:121-129) in one launch.
+    grid_sizes [(H, W)], strides [int], cell_anchors [tensor (A_l, 4) fp32 on the host] per level.
+    -> (anchors (R,4) on ``device``, level_offsets [L+1])."""
+    nl = len(grid_sizes)
+    levels = (_lib.AnchorLevel * nl)()
+    offs = [0]
+    for i, ((H, W), st, cell) in enumerate(zip(grid_sizes, strides, cell_anchors)):
+        cell = torch.as_tensor(cell, dtype=torch.float32).cpu()
+        A = cell.shape[0]
+        if A > 16:
+            raise RuntimeError("fsg_grid_anchors holds at most 16 cell anchors per level; got %d" % A)
+        levels[i].H, levels[i].W, levels[i].stride, levels[i].A = int(H), int(W), int(st), A
+        for a in range(A):
+            for j in range(4):
+                levels[i].cell[a][j] = float(cell[a, j])
+        offs.append(offs[-1] + int(H) * int(W) * A)
+    out = torch.empty((offs[-1], 4), dtype=torch.float32, device=device)
+    check(lib().fsg_grid_anchors(levels, nl, ptr(out) if offs[-1] else None, offs[-1], stream()))
+    count_launches(1)
+    return out, offs

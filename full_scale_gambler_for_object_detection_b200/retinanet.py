@@ -165,10 +165,12 @@ class RetinaNetDensePath:
         return {"loss_cls": loss_cls, "loss_box_reg": loss_box_reg}
 
     # ---------------------------------------------------------------------------------------------
-    def _detect(self, logits_flat, deltas_flat, anchor_tensor, level_offsets, want_candidates=False):
+    def _detect(self, logits_flat, deltas_flat, anchor_tensor, level_offsets, want_candidates=False,
+                postprocess=None):
         return ops.detect(logits_flat, deltas_flat, anchor_tensor, level_offsets, self.score_threshold,
                           self.topk_candidates, self.nms_threshold, self.max_detections_per_image,
-                          self.box2box_transform.weights, self.box2box_transform.scale_clamp, want_candidates)
+                          self.box2box_transform.weights, self.box2box_transform.scale_clamp, want_candidates,
+                          postprocess)
 
     @staticmethod
     def _to_instances(res, n, image_size):
@@ -180,16 +182,24 @@ class RetinaNetDensePath:
         return r
 
     @torch.no_grad()
-    def inference(self, box_cls, box_delta, anchors, image_sizes):
+    def inference(self, box_cls, box_delta, anchors, image_sizes, output_sizes=None):
         """box_cls/box_delta: list over levels of (N, A*K|A*4, H, W); anchors: list[list[Boxes]];
-        image_sizes: list of (h, w).  All images go through one batched launch pair."""
+        image_sizes: list of (h, w).  All images go through one batched launch pair.
+        output_sizes: optional list of (height, width) -- ``detector_postprocess`` (postprocessing.py:8-52,
+        what RetinaNet.forward applies to every result, retinanet.py:150-157) is then fused into the NMS
+        epilogue and the returned Instances are at the output resolution."""
         assert len(anchors) == len(image_sizes)
         x = ops.levels_to_flat([t.detach() for t in box_cls], self.num_classes)
         d = ops.levels_to_flat([t.detach() for t in box_delta], 4)
         offs = [0]
         for a in anchors[0]:
             offs.append(offs[-1] + len(a))
-        res = self._detect(x, d, self._anchor_tensor(anchors), offs)
+        post = None
+        if output_sizes is not None:
+            assert len(output_sizes) == len(image_sizes)
+            post = ops.postprocess_rows(image_sizes, output_sizes, x.device)
+            image_sizes = [tuple(s) for s in output_sizes]
+        res = self._detect(x, d, self._anchor_tensor(anchors), offs, postprocess=post)
         return [self._to_instances(res, n, image_sizes[n]) for n in range(len(anchors))]
 
     @torch.no_grad()

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FSG_ABI_VERSION 1
+#define FSG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FSG_API __attribute__((visibility("default")))
@@ -132,6 +132,19 @@ FSG_API int fsg_box2box_apply_deltas(const float* deltas, const float* boxes, in
                              const float* h_weights, float scale_clamp, float* out,
                              fsg_stream_t stream);
 
+/* DefaultAnchorGenerator.grid_anchors (anchor_generator.py:41-50,121-129) on the device, one launch for all
+ * levels: anchors[r] for r = level_offset + (y*W + x)*A + a is (x*stride, y*stride, x*stride, y*stride) +
+ * cell[a] in fp32 (bit-exact with the reference).  cell = generate_cell_anchors(sizes, aspect_ratios)
+ * (:131-168, host arithmetic in double, rounded to fp32).  R must equal sum_l H*W*A. */
+#define FSG_MAX_LEVELS 8
+#define FSG_MAX_CELL_ANCHORS 16
+typedef struct fsg_anchor_level {
+  int32_t H, W, stride, A;
+  float cell[FSG_MAX_CELL_ANCHORS][4];
+} fsg_anchor_level;
+FSG_API int fsg_grid_anchors(const fsg_anchor_level* h_levels, int num_levels, float* anchors, int64_t R,
+                     fsg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Head-layout adapter (retinanet.py:24-54, gambler_heads.py:34-101)
  * ---------------------------------------------------------------------------------------- */
@@ -211,7 +224,6 @@ FSG_API int fsg_loss_main(const float* logits, const float* pred_deltas, const f
  * sum_l H_l*W_l*A.  Everything (N,R)-sized keeps the flattened anchor order r = level_offset + (h*W+w)*A + a:
  * gt_classes, mask, bets, matched_idx32, gt_deltas (N,R,4), per_anchor_loss, weights_out.
  * All other arguments, stats and scalars exactly as fsg_loss_main. */
-#define FSG_MAX_LEVELS 8
 typedef struct fsg_head_level {
   const float* logits;
   float* grad_logits;
@@ -261,7 +273,11 @@ FSG_API int fsg_nms(const float* boxes, const float* scores, const int64_t* clas
  * out_count (N) int32; rows >= out_count[n] are zero-filled.
  * Optional pre-NMS candidates in the reference's concatenation order (level-major, score
  * descending inside a level): cand_boxes (N,cap,4), cand_scores (N,cap), cand_classes (N,cap)
- * int64, cand_count (N) int32, keep_idx (N,max_det) int64 with cap = num_levels*topk. */
+ * int64, cand_count (N) int32, keep_idx (N,max_det) int64 with cap = num_levels*topk.
+ * postprocess (device, (N,4) fp32 rows [scale_x, scale_y, clip_w, clip_h], 16-byte aligned, or NULL):
+ * detector_postprocess (modeling/postprocessing.py:8-52) fused into the NMS epilogue -- the max_det survivors
+ * are scaled (Boxes.scale), clipped to the output size (Boxes.clip) and the ones that became empty
+ * (Boxes.nonempty) are dropped, stable; out_count / keep_idx then describe the filtered list. */
 FSG_API size_t fsg_detect_workspace_bytes(int N, int64_t R, int K, int num_levels, int topk);
 FSG_API int fsg_detect(const float* logits, const float* deltas, const float* anchors,
                int64_t anchor_image_stride, int N, int64_t R, int K,
@@ -269,7 +285,13 @@ FSG_API int fsg_detect(const float* logits, const float* deltas, const float* an
                double nms_threshold, int max_det, const float* h_box_weights, float scale_clamp,
                float* out_boxes, float* out_scores, int64_t* out_classes, int32_t* out_count,
                float* cand_boxes, float* cand_scores, int64_t* cand_classes, int32_t* cand_count,
-               int64_t* keep_idx, void* workspace, size_t workspace_bytes, fsg_stream_t stream);
+               int64_t* keep_idx, const float* postprocess, void* workspace, size_t workspace_bytes,
+               fsg_stream_t stream);
+
+/* detector_postprocess on an arbitrary box list (e.g. an Instances of another detector head):
+ * out_boxes[i] = clip(scale(boxes[i])), keep[i] = 1 iff the result is non-empty (width > 0 and height > 0). */
+FSG_API int fsg_postprocess_boxes(const float* boxes, int64_t n, float scale_x, float scale_y, float clip_w,
+                          float clip_h, float* out_boxes, uint8_t* keep, fsg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -331,6 +331,25 @@ def grid_anchors(grid_sizes, strides, sizes, aspect_ratios):
 
 
 # ----------------------------------------------------------------------------------------
+# detector_postprocess (modeling/postprocessing.py:8-52 with Boxes.scale/clip/nonempty,
+# structures/boxes.py:122-151,205-210) for an Instances carrying pred_boxes/scores/pred_classes
+# ----------------------------------------------------------------------------------------
+def detector_postprocess(boxes, scores, classes, image_size, output_height, output_width):
+    """-> (boxes, scores, classes) at the output resolution; empty boxes dropped (stable)."""
+    scale_x, scale_y = (output_width / image_size[1], output_height / image_size[0])
+    b = boxes.clone().to(torch.float32)
+    b[:, 0::2] *= scale_x
+    b[:, 1::2] *= scale_y
+    h, w = output_height, output_width
+    b[:, 0].clamp_(min=0, max=w)
+    b[:, 1].clamp_(min=0, max=h)
+    b[:, 2].clamp_(min=0, max=w)
+    b[:, 3].clamp_(min=0, max=h)
+    keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+    return b[keep], scores[keep], classes[keep]
+
+
+# ----------------------------------------------------------------------------------------
 # inference: decode + top-k + NMS
 # ----------------------------------------------------------------------------------------
 def nms(boxes, scores, iou_threshold):

@@ -251,10 +251,71 @@ def make_inference(ref):
     print("[inference] oracle == reference (bit-exact on CPU)")
 
 
+def make_postprocess(ref):
+    """detector_postprocess on the reference's own Instances: down- and up-scaling, boxes leaving the image."""
+    g = torch.Generator().manual_seed(77)
+    res = {}
+    for idx, (img, out) in enumerate([((800, 1344), (480, 640)), ((512, 512), (1024, 768)), ((800, 1216), (427, 640))]):
+        n = 300
+        xy = torch.rand((n, 2), generator=g) * torch.tensor([img[1] * 1.2, img[0] * 1.2]) - 60.0
+        wh = torch.rand((n, 2), generator=g) * 200
+        wh[::17] = 0.0                       # zero-area boxes
+        boxes = torch.cat([xy, xy + wh], dim=1)
+        boxes[5] = torch.tensor([img[1] + 3.0, 10.0, img[1] + 50.0, 60.0])   # entirely right of the image
+        boxes[6] = torch.tensor([-80.0, -40.0, -1.0, -2.0])                  # entirely outside (top-left)
+        scores = torch.rand(n, generator=g)
+        classes = torch.randint(0, 80, (n,), generator=g)
+        inst = ref.Instances(img)
+        inst.pred_boxes = ref.Boxes(boxes.clone())
+        inst.scores = scores.clone()
+        inst.pred_classes = classes.clone()
+        r = ref.detector_postprocess(inst, out[0], out[1])
+        ob, os_, oc = orc.detector_postprocess(boxes, scores, classes, img, out[0], out[1])
+        assert torch.equal(ob, r.pred_boxes.tensor) and torch.equal(os_, r.scores) and torch.equal(oc, r.pred_classes), \
+            "oracle detector_postprocess != reference"
+        assert tuple(r.image_size) == out
+        res.update({"in_boxes_%d" % idx: boxes, "in_scores_%d" % idx: scores, "in_classes_%d" % idx: classes,
+                    "sizes_%d" % idx: torch.tensor([img[0], img[1], out[0], out[1]]),
+                    "boxes_%d" % idx: r.pred_boxes.tensor, "scores_%d" % idx: r.scores, "classes_%d" % idx: r.pred_classes})
+    np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **_np(res))
+    print("[postprocess] oracle == reference (bit-exact on CPU)")
+
+
+def make_anchors(ref):
+    """DefaultAnchorGenerator of the reference on the RetinaNet+gambler config (A = 3) and on upstream RetinaNet
+    (3 scales x 3 ratios, A = 9): oracle grid_anchors must be bit-identical; a strided sample is stored."""
+    import types as _t
+    from full_scale_gambler_for_object_detection_b200 import anchor_generator as ag
+    res = {}
+    cases = {"a3": (ag.RETINANET_SIZES, ((1.0,),) * 5),
+             "a9": (ag.RETINANET_SIZES, ((0.5, 1.0, 2.0),) * 5)}
+    for name, (sizes, ratios) in cases.items():
+        cfg = rl._AttrDict(MODEL=rl._AttrDict(ANCHOR_GENERATOR=rl._AttrDict(
+            SIZES=[list(s) for s in sizes], ASPECT_RATIOS=[list(r) for r in ratios])))
+        shapes = [_t.SimpleNamespace(stride=s) for s in ag.RETINANET_STRIDES]
+        gen = ref.anchor_generator.DefaultAnchorGenerator(cfg, shapes)
+        grids = ag.retinanet_grid_sizes(800, 1333)
+        want = gen.grid_anchors(grids)
+        got = orc.grid_anchors(grids, ag.RETINANET_STRIDES, sizes, ratios)
+        for w, g_ in zip(want, got):
+            assert torch.equal(w, g_), "oracle grid_anchors != reference"
+        flat = torch.cat(want)
+        res["grids_" + name] = torch.tensor(grids)
+        res["count_" + name] = torch.tensor([flat.shape[0]])
+        res["sample_" + name] = flat[::97].clone()
+        res["checksum_" + name] = flat.double().sum(dim=0)
+    np.savez_compressed(os.path.join(OUT, "anchors.npz"), **_np(res))
+    print("[anchors] oracle == reference (bit-exact on CPU)")
+
+
 def main():
     assert rl.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     ref = rl.load_reference()
+    make_postprocess(ref)
+    make_anchors(ref)
+    if "--only-new" in sys.argv:
+        return
     make_matcher(ref)
     make_box2box(ref)
     make_nms(ref)

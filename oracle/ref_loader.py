@@ -244,7 +244,14 @@ def load_reference():
     )
     gh_mod = _load("imbalancedetection.gambler_heads", "ImbalanceDetection/imbalancedetection/gambler_heads.py")
 
+    # the real post-processing and anchor-generator modules (their stand-ins above only satisfy
+    # retinanet.py's imports), loaded under private names
+    post_mod = _load("detectron2.modeling._postprocessing_real", "detectron2/modeling/postprocessing.py")
+    ag_mod = _load("detectron2.modeling._anchor_generator_real", "detectron2/modeling/anchor_generator.py")
+
     ns = types.SimpleNamespace(
+        detector_postprocess=post_mod.detector_postprocess,
+        anchor_generator=ag_mod,
         Boxes=boxes_mod.Boxes,
         pairwise_iou=boxes_mod.pairwise_iou,
         Instances=inst_mod.Instances,

@@ -18,11 +18,19 @@ m = fsg.ops.match_anchors(anchors, gt, K, bets=bets, temperature=0.1)
 def run():
     return fsg.ops.loss_main_levels(cls_l, m["gt_classes"], params, m["stats"], delta_levels=reg_l, anchors=anchors, gt=gt,
                                     matched_idx32=m["matched_idx32"], mask=m["mask"], bets=bets)
-for _ in range(3): run()
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(3): run()
+torch.cuda.current_stream().wait_stream(side)
 torch.cuda.synchronize()
+gr = torch.cuda.CUDAGraph()
+with torch.cuda.graph(gr):
+    for _ in range(10): keep = run()
+gr.replay(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(20): run()
+for _ in range(5): gr.replay()
 e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1)/20
+ms = e0.elapsed_time(e1)/50
 print("levels main: %.1f us  %.0f GB/s (%.1f%% of 6461)" % (ms*1e3, (8*K+72)*N*R/ms/1e6, (8*K+72)*N*R/ms/1e6/64.612))

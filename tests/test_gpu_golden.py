@@ -121,3 +121,42 @@ def test_inference_vs_reference(cuda):
         assert_equal_int(r.pred_classes, g["classes_%d" % n], "pred_classes")
         assert_close_tensor(r.scores, g["scores_%d" % n], "scores")
         assert_close_tensor(r.pred_boxes.tensor, g["boxes_%d" % n], "pred_boxes", atol_scale=1e-6)
+
+
+def test_gpu_detector_postprocess_vs_reference(cuda):
+    """fsg_postprocess_boxes / fsg.detector_postprocess against the reference's stored outputs (bit-exact)."""
+    import full_scale_gambler_for_object_detection_b200 as fsg
+
+    g = gu.load("postprocess")
+    for i in range(3):
+        ih, iw, oh, ow = [int(v) for v in g["sizes_%d" % i]]
+        inst = fsg.Instances((ih, iw))
+        inst.pred_boxes = fsg.Boxes(g["in_boxes_%d" % i].to(cuda))
+        inst.scores = g["in_scores_%d" % i].to(cuda)
+        inst.pred_classes = g["in_classes_%d" % i].to(cuda)
+        r = fsg.detector_postprocess(inst, oh, ow)
+        assert tuple(r.image_size) == (oh, ow)
+        assert torch.equal(r.pred_boxes.tensor.cpu(), g["boxes_%d" % i])
+        assert torch.equal(r.scores.cpu(), g["scores_%d" % i])
+        assert_equal_int(r.pred_classes, g["classes_%d" % i], "classes")
+
+
+def test_gpu_grid_anchors_vs_reference(cuda):
+    """fsg_grid_anchors (device-side DefaultAnchorGenerator) against the reference's stored anchors."""
+    import full_scale_gambler_for_object_detection_b200 as fsg
+    from full_scale_gambler_for_object_detection_b200 import anchor_generator as ag
+
+    g = gu.load("anchors")
+    for name, ratios in (("a3", [[1.0]]), ("a9", [[0.5, 1.0, 2.0]])):
+        grids = [tuple(int(v) for v in r) for r in g["grids_" + name]]
+        gen = fsg.DefaultAnchorGenerator([list(s) for s in ag.RETINANET_SIZES], ratios, ag.RETINANET_STRIDES, cuda)
+        flat, offs = gen.flat_for_grids(grids)
+        assert flat.shape[0] == int(g["count_" + name][0]) == offs[-1]
+        assert torch.equal(flat[::97].cpu(), g["sample_" + name])
+        assert torch.equal(flat.cpu().double().sum(dim=0), g["checksum_" + name])
+        want = torch.cat(ag.grid_anchors(grids, ag.RETINANET_STRIDES, ag.RETINANET_SIZES,
+                                         [r for r in ratios] * 5))
+        assert torch.equal(flat.cpu(), want)
+        feats = [torch.empty((2, 1, h, w), device=cuda) for h, w in grids]
+        per_image = gen(feats)
+        assert len(per_image) == 2 and len(per_image[0]) == 5 and len(per_image[0][0]) == offs[1]

@@ -527,3 +527,44 @@ def test_detect_multi_part_levels(cuda):
 
 def test_detect_small_topk_and_lvis_classes(cuda):
     _detect_case(cuda, 1, [900, 300], 1230, 43, topk=100)
+
+
+def test_inference_with_fused_detector_postprocess(cuda):
+    """RetinaNet.forward's inference tail (retinanet.py:150-157): inference -> detector_postprocess per image, with
+    the post-processing fused into the NMS epilogue; against oracle inference + oracle detector_postprocess."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    N, K, A = 3, 80, 3
+    inp = synthetic.train_inputs(31, N, 256, 320, K, logits=False)
+    gen = torch.Generator().manual_seed(32)
+    cls_l = _levels(inp, K, N, gen, 1.5, synthetic.PRIOR_LOGIT + 1.0)
+    reg_l = _levels(inp, 4, N, gen, 0.5)
+    # push some boxes out of the image so that clipping empties them
+    reg_l[0][:, 0::4] += 3.0
+    offs = inp["level_offsets"]
+    anc_levels = [fsg.Boxes(inp["anchors"][offs[i]:offs[i + 1]].to(cuda)) for i in range(5)]
+    path = fsg.RetinaNetDensePath(num_classes=K)
+    image_sizes = [(256, 320), (250, 300), (256, 310)]
+    output_sizes = [(480, 640), (125, 150), (1000, 333)]
+    got = path.inference([t.to(cuda) for t in cls_l], [t.to(cuda) for t in reg_l], [anc_levels] * N, image_sizes,
+                         output_sizes=output_sizes)
+    plain = path.inference([t.to(cuda) for t in cls_l], [t.to(cuda) for t in reg_l], [anc_levels] * N, image_sizes)
+    dropped = 0
+    for n in range(N):
+        cls = [orc.nchw_to_n_hwa_k(t, K)[n] for t in cls_l]
+        reg = [orc.nchw_to_n_hwa_k(t, 4)[n] for t in reg_l]
+        anc = [inp["anchors"][offs[i]:offs[i + 1]] for i in range(5)]
+        (wb, ws, wc), _, _ = orc.inference_single_image(cls, reg, anc, K)
+        # the GPU's own pre-postprocess detections must match the oracle's inference (scores within tolerance)
+        assert_equal_int(plain[n].pred_classes, wc, "classes before postprocess")
+        pb, ps, pc = orc.detector_postprocess(plain[n].pred_boxes.tensor.cpu(), plain[n].scores.cpu(),
+                                              plain[n].pred_classes.cpu(), image_sizes[n], *output_sizes[n])
+        assert tuple(got[n].image_size) == output_sizes[n]
+        assert torch.equal(got[n].pred_boxes.tensor.cpu(), pb)
+        assert torch.equal(got[n].scores.cpu(), ps)
+        assert_equal_int(got[n].pred_classes, pc, "classes after postprocess")
+        # and the stand-alone drop-in on the un-postprocessed Instances gives the same thing
+        alone = fsg.detector_postprocess(plain[n], *output_sizes[n])
+        assert torch.equal(alone.pred_boxes.tensor, got[n].pred_boxes.tensor)
+        dropped += len(plain[n]) - len(got[n])
+    assert dropped > 0, "test inputs should make at least one detection empty after clipping"

@@ -184,3 +184,29 @@ def test_oracle_vs_live_reference():
     for k in ("loss_cls", "loss_box_reg", "gambler_loss"):
         assert_close_scalar(got[k], want[k], k, rtol=2e-6)
     assert_close_tensor(got["grad_logits"], want["grad_logits"], "grad_logits", rtol=2e-6)
+
+
+def test_detector_postprocess_golden():
+    """oracle detector_postprocess == the reference's (postprocessing.py:8-52) stored outputs."""
+    g = gu.load("postprocess")
+    for i in range(3):
+        ih, iw, oh, ow = [int(v) for v in g["sizes_%d" % i]]
+        b, s, c = orc.detector_postprocess(g["in_boxes_%d" % i], g["in_scores_%d" % i], g["in_classes_%d" % i],
+                                           (ih, iw), oh, ow)
+        assert torch.equal(b, g["boxes_%d" % i]) and torch.equal(s, g["scores_%d" % i])
+        assert_equal_int(c, g["classes_%d" % i], "classes")
+        assert 0 < b.shape[0] < g["in_boxes_%d" % i].shape[0]   # some boxes really were dropped
+
+
+def test_grid_anchors_golden():
+    """oracle grid_anchors == the reference's DefaultAnchorGenerator (A = 3 gambler config and A = 9 upstream)."""
+    from full_scale_gambler_for_object_detection_b200 import anchor_generator as ag
+
+    g = gu.load("anchors")
+    for name, ratios in (("a3", ((1.0,),) * 5), ("a9", ((0.5, 1.0, 2.0),) * 5)):
+        grids = [tuple(int(v) for v in r) for r in g["grids_" + name]]
+        for fn in (orc.grid_anchors, ag.grid_anchors):
+            flat = torch.cat(fn(grids, ag.RETINANET_STRIDES, ag.RETINANET_SIZES, ratios))
+            assert flat.shape[0] == int(g["count_" + name][0])
+            assert torch.equal(flat[::97], g["sample_" + name])
+            assert torch.equal(flat.double().sum(dim=0), g["checksum_" + name])
