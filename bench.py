@@ -181,6 +181,7 @@ def secondary_metrics(dev, fsg):
     out["detect_config4"] = {"images_per_s": N4 / (ms * 1e-3), "ms_per_batch": ms, "batch": N4,
                              "scan_hbm_frac": scan_bytes / (ms * 1e-3) / (hbm * 1e9)}
     del logits, deltas
+    out["native_layout_step_config2"] = native_layout_step(dev, fsg)
     # config 5: 200 GT x 1M anchors per image, 8 images, allow_low_quality_matches
     inp5 = synthetic.matcher_stress_inputs(5, 8, 1000000, 200)
     a5 = inp5["anchors"].to(dev)
@@ -199,6 +200,78 @@ def secondary_metrics(dev, fsg):
                             "iou_pairs_per_s": 8e6 * 200 / (ms5 * 1e-3),
                             "hbm_frac": 25.0 * 8e6 / (ms5 * 1e-3) / (hbm * 1e9)}
     return out
+
+
+def native_layout_step(dev, fsg):
+    """Config 2 again, but from what the head really produces: per-level (N, A*K, H, W) logits, (N, A*4, H, W)
+    deltas and (N, A, H, W) betting maps, gradients delivered in the same layout (dense_train_step_levels:
+    K2 reads the conv outputs in place).  Beside it: the reference's data flow on our kernels (permute + cat to
+    (N, R, K), the flat fused step, inverse permutes of the gradients)."""
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    N, K = IMGS_PER_GPU, K_CLASSES
+    inp = synthetic.train_inputs(2, N, IMG_H, IMG_W, K, M=GT_PER_IMG, logits=False)
+    A, grids, R = inp["A"], inp["grids"], inp["R"]
+    g = torch.Generator(device=dev).manual_seed(7)
+    xs = [torch.randn((N, A * K, h, w), device=dev, generator=g) + synthetic.PRIOR_LOGIT for h, w in grids]
+    ds = [torch.randn((N, A * 4, h, w), device=dev, generator=g) * 0.1 for h, w in grids]
+    bs = [torch.sigmoid(torch.randn((N, A, h, w), device=dev, generator=g) + synthetic.PRIOR_LOGIT) for h, w in grids]
+    anchors = inp["anchors"].to(dev)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], dev)
+    cfg = fsg.DenseLossConfig(num_classes=K)
+    params = cfg.loss_params(1.0, 1.0, -1.0)
+    ops = fsg.ops
+    shapes = [tuple(b.shape[1:]) for b in bs]
+
+    def native():
+        bets = ops.anchor_maps_to_flat([bs])[0]
+        m = ops.match_anchors(anchors, gt, K, bets=bets, temperature=cfg.gambler_temperature)
+        o = ops.loss_main_levels(xs, m["gt_classes"], params, m["stats"], delta_levels=ds, anchors=anchors, gt=gt,
+                                 matched_idx32=m["matched_idx32"], mask=m["mask"], bets=bets)
+        gb = ops.loss_post(bets, m["mask"], o["per_anchor_loss"], params, m["stats"], o["scalars"])
+        return o, ops.anchor_maps_to_levels([gb, o["per_anchor_loss"]], shapes)
+
+    def permuted():
+        x, d = ops.levels_to_flat(xs, K), ops.levels_to_flat(ds, 4)
+        bets = ops.anchor_maps_to_flat([bs])[0]
+        m = ops.match_anchors(anchors, gt, K, bets=bets, temperature=cfg.gambler_temperature)
+        o = ops.loss_main(x, m["gt_classes"], params, m["stats"], pred_deltas=d, anchors=anchors, gt=gt,
+                          matched_idx32=m["matched_idx32"], mask=m["mask"], bets=bets)
+        gb = ops.loss_post(bets, m["mask"], o["per_anchor_loss"], params, m["stats"], o["scalars"])
+        gl = ops.flat_to_levels(o["grad_logits"], [tuple(t.shape[1:]) for t in xs])
+        gd = ops.flat_to_levels(o["grad_deltas"], [tuple(t.shape[1:]) for t in ds])
+        return o, gl, gd, ops.anchor_maps_to_levels([gb, o["per_anchor_loss"]], shapes)
+
+    def graph_ms(fn, reps=20):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            keep = fn()
+        gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        del keep
+        return e0.elapsed_time(e1) / reps
+
+    hbm, _ = measured_peaks()
+    ms_n = graph_ms(native)
+    ms_p = graph_ms(permuted)
+    step_bytes = (8 * K + 76) * N * R
+    return {"anchors_per_s": N * R / (ms_n * 1e-3), "ms_per_step": ms_n,
+            "step_hbm_frac": step_bytes / (ms_n * 1e-3) / 1e9 / hbm,
+            "launches": "bets gather, K1 x2, K2 native, K2 post, scatter (CUDA graph)",
+            "permute_cat_flow_ms_per_step": ms_p, "speedup_vs_permute_cat_flow": ms_p / ms_n}
 
 
 def run_ours(args, rank, local_rank, world):

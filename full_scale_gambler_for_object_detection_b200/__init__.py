@@ -18,7 +18,8 @@ library is not built or a tensor is not on a CUDA device.
 from . import _lib, ops  # noqa: F401
 from .anchor_generator import DefaultAnchorGenerator  # noqa: F401
 from .box_regression import Box2BoxTransform  # noqa: F401
-from .fused import DenseLossConfig, DenseStepPlan, StepResult, dense_train_step  # noqa: F401
+from .fused import (DenseLossConfig, DenseStepPlan, StepResult, dense_train_step,  # noqa: F401
+                    dense_train_step_levels)
 from .gambler import GamblerLoss, get_loss_upper_bound  # noqa: F401
 from .matcher import Matcher  # noqa: F401
 from .nms import batched_nms, nms  # noqa: F401
@@ -29,5 +30,5 @@ from .structures import Boxes, Instances, pairwise_iou  # noqa: F401
 __all__ = [
     "Boxes", "Instances", "pairwise_iou", "Matcher", "Box2BoxTransform", "nms", "batched_nms",
     "RetinaNetDensePath", "GamblerLoss", "get_loss_upper_bound", "dense_train_step", "DenseLossConfig",
-    "StepResult", "DenseStepPlan", "ops", "DefaultAnchorGenerator", "detector_postprocess",
+    "StepResult", "DenseStepPlan", "dense_train_step_levels", "ops", "DefaultAnchorGenerator", "detector_postprocess",
 ]

@@ -104,6 +104,7 @@ PROTOTYPES = {
     ),
     "fsg_postprocess_boxes": (c_i32, [c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "fsg_grid_anchors": (c_i32, [ctypes.POINTER(AnchorLevel), c_i32, c_ptr, c_i64, c_ptr]),
+    "fsg_anchor_maps": (c_i32, [c_ptr, c_ptr, c_i32, c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "fsg_permute_level": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i64, c_i64, c_i64, c_i32, c_ptr]),
 }
 

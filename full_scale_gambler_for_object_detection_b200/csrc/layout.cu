@@ -55,6 +55,35 @@ __global__ void __launch_bounds__(256) permute_level_kernel(float* __restrict__ 
   }
 }
 
+// (N,R)-sized per-anchor maps between the flattened anchor order and the per-level (N, A, H, W) maps the
+// gambler produces / consumes (betting maps in, NAKHW_loss and d/d bets out; gambler_heads.py:91-101,291-318).
+// A few MB in total, so one launch covers all levels and up to three tensors; thread = one flat element.
+struct SmallMaps {
+  float* lvl[3][FSG_MAX_LEVELS];   // per tensor, per level: (N, A, H, W)
+  float* flat[3];                  // per tensor: (N, R)
+  int64_t off[FSG_MAX_LEVELS + 1];
+  int HW[FSG_MAX_LEVELS];
+  int num_levels, A, ntensors, to_levels;
+  int64_t R;
+};
+
+__global__ void __launch_bounds__(256) anchor_maps_kernel(const SmallMaps M) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int n = blockIdx.y;
+  if (r >= M.R) return;
+  int l = 0;
+  while (l + 1 < M.num_levels && r >= M.off[l + 1]) ++l;
+  const int64_t local = r - M.off[l];
+  const int64_t hw = local / M.A;
+  const int a = (int)(local - hw * M.A);
+  const int64_t src = ((int64_t)n * M.A + a) * M.HW[l] + hw;
+  const int64_t dst = (int64_t)n * M.R + r;
+  for (int t = 0; t < M.ntensors; ++t) {
+    if (M.to_levels) M.lvl[t][l][src] = M.flat[t][dst];
+    else M.flat[t][dst] = M.lvl[t][l][src];
+  }
+}
+
 // DefaultAnchorGenerator.grid_anchors (detectron2/modeling/anchor_generator.py:41-50,121-129): anchor
 // (level, y, x, a) = (x*stride, y*stride, x*stride, y*stride) + cell_anchor[a] in fp32, flattened in the order
 // (level, y, x, a) = the r index every other kernel uses.  x*stride is an exact fp32 integer (arange with an integer
@@ -120,6 +149,38 @@ extern "C" int fsg_permute_level(float* nchw, float* flat, int N, int C, int64_t
   dim3 grid((unsigned)ceil_div(HW, kTile), (unsigned)ceil_div(C, kTile), (unsigned)N);
   permute_level_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(nchw, flat, C, HW, flat_image_stride, flat_offset,
                                                                to_nchw);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" int fsg_anchor_maps(float* const* h_level_ptrs, float* const* h_flat_ptrs, int ntensors,
+                               const int32_t* h_HW, int num_levels, int A, int N, int to_levels,
+                               fsg_stream_t stream) {
+  if (!h_level_ptrs || !h_flat_ptrs || !h_HW || ntensors <= 0 || ntensors > 3 || num_levels <= 0 ||
+      num_levels > FSG_MAX_LEVELS || A <= 0 || N <= 0 || N > 65535)
+    return FSG_ERR_INVALID_ARG;
+  SmallMaps m;
+  int64_t off = 0;
+  for (int l = 0; l < FSG_MAX_LEVELS; ++l) {
+    m.off[l] = off;
+    m.HW[l] = l < num_levels ? h_HW[l] : 0;
+    if (l < num_levels) {
+      if (h_HW[l] < 0) return FSG_ERR_INVALID_ARG;
+      off += (int64_t)h_HW[l] * A;
+    }
+    for (int t = 0; t < 3; ++t) {
+      m.lvl[t][l] = (t < ntensors && l < num_levels) ? h_level_ptrs[t * num_levels + l] : nullptr;
+      if (t < ntensors && l < num_levels && h_HW[l] > 0 && !m.lvl[t][l]) return FSG_ERR_INVALID_ARG;
+    }
+  }
+  m.off[FSG_MAX_LEVELS] = off;
+  for (int t = 0; t < 3; ++t) {
+    m.flat[t] = t < ntensors ? h_flat_ptrs[t] : nullptr;
+    if (t < ntensors && !m.flat[t]) return FSG_ERR_INVALID_ARG;
+  }
+  m.num_levels = num_levels; m.A = A; m.ntensors = ntensors; m.to_levels = to_levels; m.R = off;
+  if (off == 0) return FSG_OK;
+  anchor_maps_kernel<<<dim3((unsigned)ceil_div(off, 256), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(m);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

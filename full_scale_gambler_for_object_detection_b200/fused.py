@@ -355,3 +355,71 @@ def dense_train_step(logits, pred_deltas, bets, anchors, gt, cfg, coeffs=(1.0, 1
     total, scalars, stats, ell, gtc, mask = res[:6]
     return StepResult(total=total, scalars=scalars, stats=stats, per_anchor_loss=ell, gt_classes=gtc, mask=mask,
                       weights=res[6] if len(res) > 6 else None)
+
+
+class _FusedStepLevels(torch.autograd.Function):
+    """The fused step on the head's native layout: every tensor argument is a per-level conv output."""
+
+    @staticmethod
+    def forward(ctx, anchors, gt, cfg, coeffs, detach_pred, group, L, *levels):
+        c_cls, c_reg, c_gam = coeffs
+        f32c = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+        xs = [f32c(t.detach()) for t in levels[:L]]
+        ds = [f32c(t.detach()) for t in levels[L:2 * L]]
+        bs = [f32c(t.detach()) for t in levels[2 * L:]]
+        params = cfg.loss_params(c_cls, c_reg, c_gam)
+        bets = ops.anchor_maps_to_flat([bs])[0]
+        m = ops.match_anchors(anchors, gt, cfg.num_classes, cfg.iou_thresholds, cfg.iou_labels,
+                              cfg.picky_thresholds, None, cfg.bbox_reg_weights,
+                              want=("gt_classes", "mask", "matched_idx32"), bets=bets,
+                              temperature=cfg.gambler_temperature)
+        stats = m["stats"]
+        if group is not None:
+            sharded.all_reduce_stats(stats, group)
+        need_gl, need_gd = not detach_pred, c_reg != 0.0
+        out = ops.loss_main_levels(xs, m["gt_classes"], params, stats, delta_levels=ds, anchors=anchors, gt=gt,
+                                   matched_idx32=m["matched_idx32"], mask=m["mask"], bets=bets,
+                                   want_grad_logits=need_gl, want_grad_deltas=need_gd)
+        scalars = out["scalars"]
+        if group is not None and cfg.norm_mode == _lib.NORM_BATCH:
+            sharded.all_reduce_batch_weighted_sum(scalars, group)
+        gb = ops.loss_post(bets, m["mask"], out["per_anchor_loss"], params, stats, scalars)
+        shapes = [tuple(b.shape[1:]) for b in bs]
+        gb_levels, ell_levels = ops.anchor_maps_to_levels([gb, out["per_anchor_loss"]], shapes)
+        saved = (out["grad_logits"] if need_gl else []) + (out["grad_deltas"] if need_gd else []) + gb_levels
+        ctx.save_for_backward(*saved)
+        ctx.cfg_ = (L, need_gl, need_gd)
+        nd = [scalars, stats, m["gt_classes"], m["mask"]] + ell_levels
+        ctx.mark_non_differentiable(*nd)
+        return (scalars[8].to(torch.float32),) + tuple(nd)
+
+    @staticmethod
+    def backward(ctx, g_total, *unused):
+        L, need_gl, need_gd = ctx.cfg_
+        saved = list(ctx.saved_tensors)
+        for t in saved:
+            ops.scale_(t, g_total)
+        gl = saved[:L] if need_gl else [None] * L
+        saved = saved[L:] if need_gl else saved
+        gd = saved[:L] if need_gd else [None] * L
+        saved = saved[L:] if need_gd else saved
+        return (None,) * 7 + tuple(gl) + tuple(gd) + tuple(saved)
+
+
+def dense_train_step_levels(logit_levels, delta_levels, bet_levels, anchors, gt, cfg, coeffs=(1.0, 1.0, -1.0),
+                            detach_pred=False, group=None):
+    """The fused match + loss step straight from the head outputs, no permute/cat copies in either direction.
+
+    logit_levels list[(N, A*K, H, W)], delta_levels list[(N, A*4, H, W)], bet_levels list[(N, A, H, W)] (the
+    gambler's betting maps); anchors (R,4) / (N,R,4) and gt as in :func:`dense_train_step`.
+    Returns a StepResult whose ``per_anchor_loss`` is the list of (N, A, H, W) NAKHW_loss maps
+    (gambler_heads.py:218); gradients arrive on the per-level inputs in their own layout.
+    Launches: bets gather, K1 (2), K2 on the native layout, K2 post, scatter of d/d bets + NAKHW_loss."""
+    L = len(logit_levels)
+    assert len(delta_levels) == L and len(bet_levels) == L
+    xs = [t.detach() for t in logit_levels] if detach_pred else list(logit_levels)
+    res = _FusedStepLevels.apply(anchors, gt, cfg, tuple(float(c) for c in coeffs), bool(detach_pred), group, L,
+                                 *(xs + list(delta_levels) + list(bet_levels)))
+    total, scalars, stats, gtc, mask = res[:5]
+    return StepResult(total=total, scalars=scalars, stats=stats, per_anchor_loss=list(res[5:]), gt_classes=gtc,
+                      mask=mask)

@@ -197,6 +197,46 @@ def flat_to_levels(flat, shapes):
     return outs
 
 
+def anchor_maps_to_flat(level_lists, out=None):
+    """Up to three lists of per-level (N, A, H, W) maps -> list of flat (N, R) tensors, one launch
+    (the betting maps' permute_all_weights_to_N_HWA_K_and_concat_, gambler_heads.py:291-318)."""
+    return _anchor_maps(level_lists, out, 0)
+
+
+def anchor_maps_to_levels(flats, shapes, out=None):
+    """Up to three flat (N, R) tensors -> lists of per-level (N, A, H, W) maps for ``shapes`` = [(A, H, W)],
+    one launch (NAKHW_loss / d-bets in the gambler's layout, gambler_heads.py:91-101)."""
+    N = flats[0].shape[0]
+    dev = flats[0].device
+    if out is None:
+        out = [[torch.empty((N, A, H, W), dtype=torch.float32, device=dev) for (A, H, W) in shapes] for _ in flats]
+    _anchor_maps(out, list(flats), 1)
+    return out
+
+
+def _anchor_maps(level_lists, flats, to_levels):
+    nt, nl = len(level_lists), len(level_lists[0])
+    first = level_lists[0]
+    N, A = first[0].shape[0], first[0].shape[1]
+    R = sum(A * x.shape[2] * x.shape[3] for x in first)
+    dev = first[0].device
+    if flats is None:
+        flats = [torch.empty((N, R), dtype=torch.float32, device=dev) for _ in range(nt)]
+    lp = (_lib.c_ptr * (nt * nl))()
+    fp = (_lib.c_ptr * nt)()
+    for t in range(nt):
+        assert flats[t].shape == (N, R) and flats[t].dtype == torch.float32
+        fp[t] = ptr(flats[t])
+        for l in range(nl):
+            x = level_lists[t][l]
+            assert x.dtype == torch.float32 and x.shape == first[l].shape
+            lp[t * nl + l] = ptr(x)
+    hw = (_lib.c_i32 * nl)(*[x.shape[2] * x.shape[3] for x in first])
+    check(lib().fsg_anchor_maps(lp, fp, nt, hw, nl, A, N, int(to_levels), stream()))
+    count_launches(1)
+    return flats
+
+
 # ------------------------------------------------------------------------------------------------
 # K2
 # ------------------------------------------------------------------------------------------------

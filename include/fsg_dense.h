@@ -156,6 +156,14 @@ FSG_API int fsg_permute_level(float* nchw, float* flat, int N, int C, int64_t HW
                               int64_t flat_image_stride, int64_t flat_offset, int to_nchw,
                               fsg_stream_t stream);
 
+/* The (N,R)-sized per-anchor maps in one launch for all levels and up to three tensors at once:
+ * per-level (N, A, H_l, W_l) maps (the gambler's betting maps, NAKHW_loss, d/d bets;
+ * gambler_heads.py:91-101,291-318)  <->  flat (N, R) with r = level_offset + (h*W+w)*A + a.
+ * h_level_ptrs[t*num_levels + l]: tensor t, level l; h_flat_ptrs[t]: tensor t flat; h_HW[l] = H_l*W_l.
+ * to_levels == 0 gathers levels -> flat, 1 scatters flat -> levels. */
+FSG_API int fsg_anchor_maps(float* const* h_level_ptrs, float* const* h_flat_ptrs, int ntensors,
+                    const int32_t* h_HW, int num_levels, int A, int N, int to_levels, fsg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K2 -- fused gambler-weighted sigmoid-focal / smooth-L1 loss, forward + backward
  * ---------------------------------------------------------------------------------------- */

@@ -568,3 +568,41 @@ def test_inference_with_fused_detector_postprocess(cuda):
         assert torch.equal(alone.pred_boxes.tensor, got[n].pred_boxes.tensor)
         dropped += len(plain[n]) - len(got[n])
     assert dropped > 0, "test inputs should make at least one detection empty after clipping"
+
+
+@pytest.mark.parametrize("detach,coeffs", [(False, (1.0, 1.0, -1.0)), (True, (0.0, 0.0, 1.0))])
+def test_fused_step_from_head_outputs(cuda, detach, coeffs):
+    """dense_train_step_levels: GT assignment + all three losses + backward from the per-level conv outputs and
+    betting maps, gradients delivered in the same per-level layout (no permute/cat copy anywhere)."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    N, K, A = 2, 80, 3
+    inp = synthetic.train_inputs(51, N, 256, 320, K, logits=False)
+    gen = torch.Generator().manual_seed(52)
+    cls_l = _levels(inp, K, N, gen, 1.0, synthetic.PRIOR_LOGIT)
+    reg_l = _levels(inp, 4, N, gen, 0.1)
+    bet_l = [torch.sigmoid(torch.randn((N, A, h, w), generator=gen) - 4.0) for (h, w) in inp["grids"]]
+    want = orc.train_step(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], orc.levels_to_flat(cls_l, K),
+                          orc.levels_to_flat(reg_l, 4), orc.levels_to_flat(bet_l, 1).reshape(N, -1), K, *coeffs,
+                          detach_pred=detach)
+    gx = [t.to(cuda).requires_grad_(True) for t in cls_l]
+    gd = [t.to(cuda).requires_grad_(True) for t in reg_l]
+    gb = [t.to(cuda).requires_grad_(True) for t in bet_l]
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    res = fsg.dense_train_step_levels(gx, gd, gb, inp["anchors"].to(cuda), gt, fsg.DenseLossConfig(num_classes=K),
+                                      coeffs, detach_pred=detach)
+    (res.total * 2.0).backward()
+    assert_equal_int(res.gt_classes, want["gt_classes"], "gt_classes")
+    assert_equal_int(res.mask, want["mask"], "mask")
+    assert_close_scalar(res.total.item(), want["total"], "total", rtol=2e-5)
+    assert_close_scalar(res.gambler_loss.item(), want["gambler_loss"], "gambler_loss")
+    for a, b in zip(res.per_anchor_loss, orc.flat_to_nahw(want["per_anchor_loss"], inp["grids"], A)):
+        assert_close_tensor(a, b, "NAKHW_loss")
+    if detach:
+        assert all(t.grad is None for t in gx)
+    else:
+        assert_close_tensor(orc.levels_to_flat([t.grad.cpu() for t in gx], K), 2.0 * want["grad_logits"], "grad_logits")
+    if coeffs[1] != 0:
+        assert_close_tensor(orc.levels_to_flat([t.grad.cpu() for t in gd], 4), 2.0 * want["grad_deltas"], "grad_deltas")
+    assert_close_tensor(orc.levels_to_flat([t.grad.cpu() for t in gb], 1).reshape(N, -1), 2.0 * want["grad_bets"],
+                        "grad_bets", atol_scale=1e-6)
