@@ -10,6 +10,8 @@ library is not built or a tensor is not on a CUDA device.
     nms            nms, batched_nms                        (detectron2/layers/nms.py)
     anchor_generator DefaultAnchorGenerator                (detectron2/modeling/anchor_generator.py)
     postprocessing detector_postprocess                    (detectron2/modeling/postprocessing.py)
+    proposals      find_top_rpn_proposals, rpn_ground_truth, subsample_labels, label_proposals,
+                   fast_rcnn_inference[_single_image]      (rpn_outputs.py, sampling.py, roi_heads.py, fast_rcnn.py)
     retinanet      RetinaNetDensePath                      (meta_arch/retinanet.py: GT, losses, inference)
     gambler        GamblerLoss, get_loss_upper_bound       (imbalancedetection/gambler_heads.py)
     fused          dense_train_step, DenseLossConfig       (the fused K1+K2 step)
@@ -24,6 +26,8 @@ from .gambler import GamblerLoss, get_loss_upper_bound  # noqa: F401
 from .matcher import Matcher  # noqa: F401
 from .nms import batched_nms, nms  # noqa: F401
 from .postprocessing import detector_postprocess  # noqa: F401
+from .proposals import (fast_rcnn_inference, fast_rcnn_inference_single_image,  # noqa: F401
+                        find_top_rpn_proposals, label_proposals, rpn_ground_truth, subsample_labels)
 from .retinanet import RetinaNetDensePath  # noqa: F401
 from .structures import Boxes, Instances, pairwise_iou  # noqa: F401
 
@@ -31,4 +35,6 @@ __all__ = [
     "Boxes", "Instances", "pairwise_iou", "Matcher", "Box2BoxTransform", "nms", "batched_nms",
     "RetinaNetDensePath", "GamblerLoss", "get_loss_upper_bound", "dense_train_step", "DenseLossConfig",
     "StepResult", "DenseStepPlan", "dense_train_step_levels", "ops", "DefaultAnchorGenerator", "detector_postprocess",
+    "find_top_rpn_proposals", "rpn_ground_truth", "subsample_labels", "label_proposals", "fast_rcnn_inference",
+    "fast_rcnn_inference_single_image",
 ]

@@ -104,6 +104,11 @@ PROTOTYPES = {
     ),
     "fsg_postprocess_boxes": (c_i32, [c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "fsg_grid_anchors": (c_i32, [ctypes.POINTER(AnchorLevel), c_i32, c_ptr, c_i64, c_ptr]),
+    "fsg_rpn_proposals_workspace_bytes": (c_size, [c_i32, c_ptr, c_i32, c_i32, c_i32]),
+    "fsg_rpn_proposals": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_i32, c_i32, c_f64, c_f32, c_ptr, c_ptr,
+                                  c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "fsg_score_filter": (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr,
+                                 c_ptr, c_ptr]),
     "fsg_anchor_maps": (c_i32, [c_ptr, c_ptr, c_i32, c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "fsg_permute_level": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i64, c_i64, c_i64, c_i32, c_ptr]),
 }

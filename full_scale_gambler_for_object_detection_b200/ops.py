@@ -487,3 +487,65 @@ def grid_anchors(grid_sizes, strides, cell_anchors, device):
     check(lib().fsg_grid_anchors(levels, nl, ptr(out) if offs[-1] else None, offs[-1], stream()))
     count_launches(1)
     return out, offs
+
+
+# ------------------------------------------------------------------------------------------------
+# RPN / ROI-head callers of the same kernels
+# ------------------------------------------------------------------------------------------------
+def rpn_proposals(level_proposals, level_logits, image_sizes, nms_thresh, pre_nms_topk, post_nms_topk,
+                  min_box_side_len=0.0):
+    """Batched find_top_rpn_proposals (rpn_outputs.py:52-151): level_proposals list[(N, S_l, 4)],
+    level_logits list[(N, S_l)], image_sizes [(h, w)] -> dict(boxes (N,post,4), logits (N,post),
+    levels (N,post) int64, count (N) int32).  Two launches for the whole batch, no host sync."""
+    nl = len(level_proposals)
+    ps = [_f32c(p) for p in level_proposals]
+    ls = [_f32c(x) for x in level_logits]
+    N = ls[0].shape[0]
+    dev = ls[0].device
+    sizes = host_i64([x.shape[1] for x in ls])
+    for p, x in zip(ps, ls):
+        assert p.shape == (N, x.shape[1], 4)
+    pp = (_lib.c_ptr * nl)(*[ptr(p) if p.numel() else None for p in ps])
+    lp = (_lib.c_ptr * nl)(*[ptr(x) if x.numel() else None for x in ls])
+    isz = torch.tensor([[float(h), float(w)] for (h, w) in image_sizes], dtype=torch.float32).to(dev)
+    assert isz.shape == (N, 2)
+    out = {
+        "boxes": torch.empty((N, post_nms_topk, 4), dtype=torch.float32, device=dev),
+        "logits": torch.empty((N, post_nms_topk), dtype=torch.float32, device=dev),
+        "levels": torch.empty((N, post_nms_topk), dtype=torch.int64, device=dev),
+        "count": torch.empty((N,), dtype=torch.int32, device=dev),
+    }
+    L = lib()
+    need = L.fsg_rpn_proposals_workspace_bytes(N, sizes, nl, int(pre_nms_topk), int(post_nms_topk))
+    if need == 0:
+        raise RuntimeError("fsg_rpn_proposals: shape outside what the kernels cover (pre_nms_topk <= 8192 per "
+                           "level, < 16384 candidates per image, post_nms_topk <= 8192)")
+    ws = _ws(need, dev)
+    check(L.fsg_rpn_proposals(pp, lp, sizes, nl, N, ptr(isz), int(pre_nms_topk), int(post_nms_topk),
+                              float(nms_thresh), float(min_box_side_len), ptr(out["boxes"]), ptr(out["logits"]),
+                              ptr(out["levels"]), ptr(out["count"]), ptr(ws), ws.numel(), stream()))
+    count_launches(2)
+    return out
+
+
+def score_filter(boxes, scores, image_shape, score_thresh):
+    """Candidate stage of fast_rcnn_inference_single_image (fast_rcnn.py:76-105).  boxes (R, C*4), scores
+    (R, K+1) -> (cand_boxes (n,4), cand_scores (n), cand_classes (n) int64, cand_rows (n) int64); the count is read
+    back once (the reference's ``nonzero`` synchronises at the same point)."""
+    sc = _f32c(scores)
+    R, K = sc.shape[0], sc.shape[1] - 1
+    b = _f32c(boxes).reshape(R, -1)
+    C = b.shape[1] // 4
+    dev = sc.device
+    cap = max(R * K, 1)
+    ob = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+    os_ = torch.empty((cap,), dtype=torch.float32, device=dev)
+    oc = torch.empty((cap,), dtype=torch.int64, device=dev)
+    orow = torch.empty((cap,), dtype=torch.int64, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    check(lib().fsg_score_filter(ptr(b) if R else None, C, ptr(sc) if R else None, R, K, float(image_shape[0]),
+                                 float(image_shape[1]), float(score_thresh), ptr(ob), ptr(os_), ptr(oc), ptr(orow),
+                                 ptr(cnt), stream()))
+    count_launches(1)
+    n = int(cnt.item())
+    return ob[:n], os_[:n], oc[:n], orow[:n]

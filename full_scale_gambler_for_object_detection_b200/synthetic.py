@@ -78,3 +78,42 @@ def matcher_stress_inputs(config_id, N, R, M):
         gt_boxes.append(torch.cat((g_xy, g_xy + g_wh), dim=1).to(torch.float32))
     gt_classes = [torch.randint(0, 80, (M,), generator=gen, dtype=torch.int64) for _ in range(N)]
     return dict(anchors=anchors, gt_boxes=gt_boxes, gt_classes=gt_classes, N=N, R=R, M=M)
+
+
+def rpn_inputs(config_id, N, level_counts, image_hw=(800, 1344), ties=True):
+    """RPN head outputs after decoding: per level proposals (N, S_l, 4) scattered over (and partly outside) the
+    image, some degenerate / tiny, and objectness logits ~ N(0, 2) with a few exact ties."""
+    gen = torch.Generator().manual_seed(BASE_SEED + config_id)
+    H, W = image_hw
+    props, logits = [], []
+    for l, cnt in enumerate(level_counts):
+        size = 32.0 * 2 ** l
+        cx = torch.rand((N, cnt), generator=gen) * (W + 100) - 50
+        cy = torch.rand((N, cnt), generator=gen) * (H + 100) - 50
+        w = size * torch.exp(torch.randn((N, cnt), generator=gen) * 0.5)
+        h = size * torch.exp(torch.randn((N, cnt), generator=gen) * 0.5)
+        w[:, ::37] = 2.0            # tiny boxes: dropped by min_box_side_len
+        h[:, 5::41] = 0.0           # empty boxes
+        p = torch.stack((cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2), dim=2).to(torch.float32)
+        lg = (torch.randn((N, cnt), generator=gen) * 2.0).to(torch.float32)
+        if ties and cnt > 64:
+            lg[:, 11] = lg[:, 3]
+            lg[:, cnt // 2] = lg[:, 3]
+            lg[:, 20:28] = lg[:, 20:21]
+        props.append(p.contiguous())
+        logits.append(lg.contiguous())
+    return dict(proposals=props, logits=logits, image_sizes=[(H, W)] * N, N=N)
+
+
+def fast_rcnn_inputs(config_id, R, K, class_specific=True, image_hw=(800, 1344)):
+    """Box-head outputs of one image: boxes (R, K*4) or (R, 4) around the image, softmax scores (R, K+1)."""
+    gen = torch.Generator().manual_seed(BASE_SEED + config_id)
+    H, W = image_hw
+    C = K if class_specific else 1
+    cx = torch.rand((R, 1), generator=gen) * (W + 60) - 30 + torch.randn((R, C), generator=gen) * 4
+    cy = torch.rand((R, 1), generator=gen) * (H + 60) - 30 + torch.randn((R, C), generator=gen) * 4
+    w = torch.exp(torch.rand((R, 1), generator=gen) * 3 + 2.5) * torch.exp(torch.randn((R, C), generator=gen) * 0.1)
+    h = torch.exp(torch.rand((R, 1), generator=gen) * 3 + 2.5) * torch.exp(torch.randn((R, C), generator=gen) * 0.1)
+    boxes = torch.stack((cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2), dim=2).reshape(R, C * 4).to(torch.float32)
+    scores = torch.softmax(torch.randn((R, K + 1), generator=gen) * 2.5, dim=1).to(torch.float32)
+    return dict(boxes=boxes.contiguous(), scores=scores.contiguous(), image_shape=(H, W))

@@ -301,6 +301,37 @@ FSG_API int fsg_detect(const float* logits, const float* deltas, const float* an
 FSG_API int fsg_postprocess_boxes(const float* boxes, int64_t n, float scale_x, float scale_y, float clip_w,
                           float clip_h, float* out_boxes, uint8_t* keep, fsg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Other callers of the same ops: RPN proposal selection
+ * ---------------------------------------------------------------------------------------- */
+
+/* find_top_rpn_proposals (proposal_generator/rpn_outputs.py:52-151) for the whole batch in two launches.
+ * Level l: proposals (N, S_l, 4) decoded boxes and objectness logits (N, S_l), S_l = h_level_sizes[l]
+ * (host arrays of device pointers).  image_sizes: device (N, 2) fp32 rows [height, width].
+ * Per (image, level): the min(pre_nms_topk, S_l) best logits (ties: lower index first), Boxes.clip to the image,
+ * boxes with a side <= min_box_side_len dropped; then per-level NMS (batched_nms with the level as class id,
+ * un-offset per-class algorithm) and the post_nms_topk best survivors by logit.
+ * Outputs: out_boxes (N, post_nms_topk, 4), out_logits (N, post_nms_topk), out_levels (N, post_nms_topk) int64
+ * (may be NULL), out_count (N) int32; rows >= out_count[n] are zero-filled.
+ * Limits: pre_nms_topk <= 8192 per level, fewer than 16384 candidates per image, post_nms_topk <= 8192. */
+FSG_API size_t fsg_rpn_proposals_workspace_bytes(int N, const int64_t* h_level_sizes, int num_levels,
+                                         int pre_nms_topk, int post_nms_topk);
+FSG_API int fsg_rpn_proposals(const float* const* h_level_proposals, const float* const* h_level_logits,
+                      const int64_t* h_level_sizes, int num_levels, int N, const float* image_sizes,
+                      int pre_nms_topk, int post_nms_topk, double nms_threshold, float min_box_side_len,
+                      float* out_boxes, float* out_logits, int64_t* out_levels, int32_t* out_count,
+                      void* workspace, size_t workspace_bytes, fsg_stream_t stream);
+
+/* Candidate stage of fast_rcnn_inference_single_image (roi_heads/fast_rcnn.py:76-105): scores (R, K+1) with the
+ * background column last, boxes (R, C*4) with C = num_bbox_reg_classes in {1, K}.  Boxes are clipped to the
+ * image; every (r, k) with scores[r,k] > score_thresh is emitted in row-major order (torch.nonzero order):
+ * out_boxes (cap,4), out_scores (cap), out_classes (cap) int64 = k, out_rows (cap) int64 = r, *out_count (device
+ * int32); cap = R*K in the worst case.  Follow with fsg_nms(class_ids = out_classes) for the per-class NMS. */
+FSG_API int fsg_score_filter(const float* boxes, int num_bbox_reg_classes, const float* scores, int64_t R, int K,
+                     float image_height, float image_width, float score_thresh, float* out_boxes,
+                     float* out_scores, int64_t* out_classes, int64_t* out_rows, int32_t* out_count,
+                     fsg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -421,3 +421,73 @@ def inference_single_image(box_cls, box_delta, anchors, num_classes, score_thres
     B, S, C = torch.cat(B), torch.cat(S), torch.cat(C)
     keep = batched_nms(B, S, C, nms_threshold)[:max_detections]
     return (B[keep], S[keep], C[keep]), (B, S, C), keep
+
+
+# ----------------------------------------------------------------------------------------
+# two-stage callers of the same ops
+# ----------------------------------------------------------------------------------------
+def find_top_rpn_proposals(proposals, logits, image_sizes, nms_thresh, pre_nms_topk, post_nms_topk,
+                           min_box_side_len):
+    """proposal_generator/rpn_outputs.py:52-151.  proposals list[(N,S_l,4)], logits list[(N,S_l)].
+    -> list over images of (boxes, logits, level ids).  Sort ties: lower index first (stable)."""
+    N = logits[0].shape[0]
+    tb, ts, lv = [], [], []
+    for level_id, (p_i, l_i) in enumerate(zip(proposals, logits)):
+        k = min(pre_nms_topk, l_i.shape[1])
+        sl, idx = torch.sort(l_i, descending=True, dim=1, stable=True)
+        idx = idx[:, :k]
+        tb.append(torch.gather(p_i, 1, idx[:, :, None].expand(-1, -1, 4)))
+        ts.append(sl[:, :k])
+        lv.append(torch.full((k,), level_id, dtype=torch.int64))
+    tb, ts, lv = torch.cat(tb, dim=1), torch.cat(ts, dim=1), torch.cat(lv)
+    out = []
+    for n, (h, w) in enumerate(image_sizes):
+        b = tb[n].clone()
+        b[:, 0].clamp_(min=0, max=w); b[:, 1].clamp_(min=0, max=h)
+        b[:, 2].clamp_(min=0, max=w); b[:, 3].clamp_(min=0, max=h)
+        keep = ((b[:, 2] - b[:, 0]) > min_box_side_len) & ((b[:, 3] - b[:, 1]) > min_box_side_len)
+        b, sc, l = b[keep], ts[n][keep], lv[keep]
+        k = batched_nms(b, sc, l, nms_thresh)[:post_nms_topk]
+        out.append((b[k], sc[k], l[k]))
+    return out
+
+
+def rpn_ground_truth(anchors, gt_boxes, thresholds=(0.3, 0.7), labels=(0, -1, 1), weights=(1.0, 1.0, 1.0, 1.0)):
+    """RPNOutputs._get_ground_truth (rpn_outputs.py:250-295, boundary_threshold < 0)."""
+    L, D = [], []
+    for g in gt_boxes:
+        m, lab = matcher(pairwise_iou(g, anchors), list(thresholds), list(labels), True)
+        L.append(lab)
+        D.append(torch.zeros_like(anchors) if g.shape[0] == 0 else get_deltas(anchors, g[m], weights))
+    return L, D
+
+
+def label_proposals(proposals, gt_boxes, gt_classes, num_classes, thresholds=(0.5,), labels=(0, 1)):
+    """roi_heads/roi_heads.py:233-246 + _sample_proposals relabelling (:178-186)."""
+    m, lab = matcher(pairwise_iou(gt_boxes, proposals), list(thresholds), list(labels), False)
+    if gt_classes.numel() > 0:
+        c = gt_classes[m].clone()
+        c[lab == 0] = num_classes
+        c[lab == -1] = -1
+    else:
+        c = torch.zeros_like(m) + num_classes
+    return m, lab, c
+
+
+def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, nms_thresh, topk_per_image):
+    """roi_heads/fast_rcnn.py:76-118 -> (boxes, scores, classes, kept row indices)."""
+    scores = scores[:, :-1]
+    C = boxes.shape[1] // 4
+    b = boxes.reshape(-1, 4).clone()
+    h, w = image_shape
+    b[:, 0].clamp_(min=0, max=w); b[:, 1].clamp_(min=0, max=h)
+    b[:, 2].clamp_(min=0, max=w); b[:, 3].clamp_(min=0, max=h)
+    b = b.view(-1, C, 4)
+    mask = scores > score_thresh
+    inds = mask.nonzero()
+    b = b[inds[:, 0], 0] if C == 1 else b[mask]
+    sc = scores[mask]
+    keep = batched_nms(b, sc, inds[:, 1], nms_thresh)
+    if topk_per_image >= 0:
+        keep = keep[:topk_per_image]
+    return b[keep], sc[keep], inds[keep, 1], inds[keep, 0]

@@ -308,12 +308,66 @@ def make_anchors(ref):
     print("[anchors] oracle == reference (bit-exact on CPU)")
 
 
+def make_rpn(ref):
+    """find_top_rpn_proposals / RPN ground truth / fast_rcnn_inference_single_image of the reference (its own
+    rpn_outputs.py, matcher.py, box_regression.py, fast_rcnn.py) against the oracle restatements."""
+    import types as _t
+    res = {}
+    cases = [(61, 2, [6000, 2500, 700, 200, 60], 1000, 1000, 0.7, 0.0),
+             (62, 1, [9000, 3000, 2000, 819], 2000, 1000, 0.7, 4.0)]
+    for ci, (cid, N, counts, pre, post, thr, min_side) in enumerate(cases):
+        # no exact logit ties here: the reference's sort is not stable (rpn_outputs.py:104 does not ask for it), so
+        # the order of tied proposals is implementation-defined there; ours is "lower index first" (tested
+        # against the oracle separately)
+        inp = synthetic.rpn_inputs(cid, N, counts, ties=False)
+        images = _t.SimpleNamespace(image_sizes=inp["image_sizes"])
+        want = ref.rpn_outputs.find_top_rpn_proposals([p.clone() for p in inp["proposals"]],
+                                                      [l.clone() for l in inp["logits"]], images, thr, pre, post,
+                                                      min_side, False)
+        got = orc.find_top_rpn_proposals(inp["proposals"], inp["logits"], inp["image_sizes"], thr, pre, post, min_side)
+        for n in range(N):
+            assert torch.equal(got[n][0], want[n].proposal_boxes.tensor), "oracle rpn proposals != reference"
+            assert torch.equal(got[n][1], want[n].objectness_logits)
+            res["rpn%d_boxes_%d" % (ci, n)] = want[n].proposal_boxes.tensor
+            res["rpn%d_logits_%d" % (ci, n)] = want[n].objectness_logits
+        res["rpn%d_params" % ci] = torch.tensor([cid, N, pre, post] + counts)
+        res["rpn%d_fparams" % ci] = torch.tensor([thr, min_side])
+    # RPN ground truth: Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=True) + get_deltas
+    inp = synthetic.train_inputs(63, 3, 256, 320, 80, M=6)
+    me = _t.SimpleNamespace(
+        anchors=[[ref.Boxes(inp["anchors"])] for _ in range(3)], gt_boxes=[ref.Boxes(b) for b in inp["gt_boxes"]],
+        image_sizes=[(256, 320)] * 3, boundary_threshold=-1,
+        anchor_matcher=ref.Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=True),
+        box2box_transform=ref.Box2BoxTransform(weights=(1.0, 1.0, 1.0, 1.0)))
+    wl, wd = ref.rpn_outputs.RPNOutputs._get_ground_truth(me)
+    ol, od = orc.rpn_ground_truth(inp["anchors"], inp["gt_boxes"])
+    for n in range(3):
+        assert torch.equal(wl[n], ol[n]) and torch.equal(wd[n], od[n]), "oracle rpn ground truth != reference"
+        res["rpngt_labels_%d" % n] = wl[n]
+        res["rpngt_deltas_%d" % n] = wd[n][::13].clone()
+    # fast_rcnn_inference_single_image: class-specific and class-agnostic boxes
+    for ci, (cid, R, K, spec, sthr) in enumerate([(64, 1000, 80, True, 0.05), (65, 700, 20, False, 0.02)]):
+        inp = synthetic.fast_rcnn_inputs(cid, R, K, spec)
+        r, rows = ref.fast_rcnn.fast_rcnn_inference_single_image(inp["boxes"].clone(), inp["scores"].clone(),
+                                                                 inp["image_shape"], sthr, 0.5, 100)
+        ob, os_, oc, orow = orc.fast_rcnn_inference_single_image(inp["boxes"], inp["scores"], inp["image_shape"],
+                                                                 sthr, 0.5, 100)
+        assert torch.equal(ob, r.pred_boxes.tensor) and torch.equal(os_, r.scores), "oracle fast_rcnn != reference"
+        assert torch.equal(oc, r.pred_classes) and torch.equal(orow, rows)
+        res.update({"frcnn%d_boxes" % ci: ob, "frcnn%d_scores" % ci: os_, "frcnn%d_classes" % ci: oc,
+                    "frcnn%d_rows" % ci: orow, "frcnn%d_params" % ci: torch.tensor([cid, R, K, int(spec)]),
+                    "frcnn%d_thr" % ci: torch.tensor([sthr])})
+    np.savez_compressed(os.path.join(OUT, "two_stage.npz"), **_np(res))
+    print("[two-stage callers] oracle == reference (bit-exact on CPU)")
+
+
 def main():
     assert rl.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     ref = rl.load_reference()
     make_postprocess(ref)
     make_anchors(ref)
+    make_rpn(ref)
     if "--only-new" in sys.argv:
         return
     make_matcher(ref)

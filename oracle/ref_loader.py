@@ -249,7 +249,20 @@ def load_reference():
     post_mod = _load("detectron2.modeling._postprocessing_real", "detectron2/modeling/postprocessing.py")
     ag_mod = _load("detectron2.modeling._anchor_generator_real", "detectron2/modeling/anchor_generator.py")
 
+    # two-stage callers: rpn_outputs.py and fast_rcnn.py are pure Python + torch
+    mem = _pkg("detectron2.utils.memory")
+    mem.retry_if_cuda_oom = lambda f: f
+    utils.memory = mem
+    _load("detectron2.modeling.sampling", "detectron2/modeling/sampling.py")
+    _pkg("detectron2.modeling.proposal_generator")
+    rpn_mod = _load("detectron2.modeling.proposal_generator.rpn_outputs",
+                    "detectron2/modeling/proposal_generator/rpn_outputs.py")
+    _pkg("detectron2.modeling.roi_heads")
+    frcnn_mod = _load("detectron2.modeling.roi_heads.fast_rcnn", "detectron2/modeling/roi_heads/fast_rcnn.py")
+
     ns = types.SimpleNamespace(
+        rpn_outputs=rpn_mod,
+        fast_rcnn=frcnn_mod,
         detector_postprocess=post_mod.detector_postprocess,
         anchor_generator=ag_mod,
         Boxes=boxes_mod.Boxes,

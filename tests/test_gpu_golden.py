@@ -160,3 +160,36 @@ def test_gpu_grid_anchors_vs_reference(cuda):
         feats = [torch.empty((2, 1, h, w), device=cuda) for h, w in grids]
         per_image = gen(feats)
         assert len(per_image) == 2 and len(per_image[0]) == 5 and len(per_image[0][0]) == offs[1]
+
+
+def test_gpu_two_stage_callers_vs_reference(cuda):
+    """find_top_rpn_proposals, RPN ground truth and fast_rcnn_inference_single_image on the GPU against the
+    reference's stored outputs: bit-exact (selection, clipping, NMS keep order, labels); deltas within 1e-5."""
+    import full_scale_gambler_for_object_detection_b200 as fsg
+    from full_scale_gambler_for_object_detection_b200 import proposals as P, synthetic
+
+    g = gu.load("two_stage")
+    for ci in range(2):
+        p = [int(v) for v in g["rpn%d_params" % ci]]
+        cid, N, pre, post, counts = p[0], p[1], p[2], p[3], p[4:]
+        thr, min_side = [float(v) for v in g["rpn%d_fparams" % ci]]
+        inp = synthetic.rpn_inputs(cid, N, counts, ties=False)
+        got = P.find_top_rpn_proposals([t.to(cuda) for t in inp["proposals"]], [t.to(cuda) for t in inp["logits"]],
+                                       inp["image_sizes"], thr, pre, post, min_side, False)
+        for n in range(N):
+            assert torch.equal(got[n].proposal_boxes.tensor.cpu(), g["rpn%d_boxes_%d" % (ci, n)])
+            assert torch.equal(got[n].objectness_logits.cpu(), g["rpn%d_logits_%d" % (ci, n)])
+    inp = synthetic.train_inputs(63, 3, 256, 320, 80, M=6)
+    gl, gd = P.rpn_ground_truth(inp["anchors"].to(cuda), [b.to(cuda) for b in inp["gt_boxes"]])
+    for n in range(3):
+        assert_equal_int(gl[n], g["rpngt_labels_%d" % n], "rpn labels")
+        assert_close_tensor(gd[n][::13], g["rpngt_deltas_%d" % n], "rpn deltas")
+    for ci in range(2):
+        cid, R, K, spec = [int(v) for v in g["frcnn%d_params" % ci]]
+        inp = synthetic.fast_rcnn_inputs(cid, R, K, bool(spec))
+        r, rows = P.fast_rcnn_inference_single_image(inp["boxes"].to(cuda), inp["scores"].to(cuda),
+                                                     inp["image_shape"], float(g["frcnn%d_thr" % ci][0]), 0.5, 100)
+        assert torch.equal(r.pred_boxes.tensor.cpu(), g["frcnn%d_boxes" % ci])
+        assert torch.equal(r.scores.cpu(), g["frcnn%d_scores" % ci])
+        assert_equal_int(r.pred_classes, g["frcnn%d_classes" % ci], "classes")
+        assert_equal_int(rows, g["frcnn%d_rows" % ci], "rows")

@@ -606,3 +606,80 @@ def test_fused_step_from_head_outputs(cuda, detach, coeffs):
         assert_close_tensor(orc.levels_to_flat([t.grad.cpu() for t in gd], 4), 2.0 * want["grad_deltas"], "grad_deltas")
     assert_close_tensor(orc.levels_to_flat([t.grad.cpu() for t in gb], 1).reshape(N, -1), 2.0 * want["grad_bets"],
                         "grad_bets", atol_scale=1e-6)
+
+
+# ------------------------------------------------------------------------------- two-stage callers (8f row 4)
+@pytest.mark.parametrize("N,counts,pre,post,thr,min_side", [
+    (2, [6000, 2500, 700, 200, 60], 1000, 1000, 0.7, 0.0),        # FPN test-time setting
+    (3, [20000, 5000, 2100, 819, 231], 2000, 1000, 0.7, 4.0),     # FPN train-time setting, min size filter
+    (1, [300, 40], 6000, 50, 0.5, 0.0),                           # levels shorter than pre_nms_topk
+    (2, [5000], 4096, 2000, 0.9, 0.0),                            # single level (C4-style), power-of-two k
+])
+def test_find_top_rpn_proposals(cuda, N, counts, pre, post, thr, min_side):
+    """Batched RPN proposal selection vs the oracle, with exact logit ties (lower index first)."""
+    from full_scale_gambler_for_object_detection_b200 import proposals as P, synthetic
+    inp = synthetic.rpn_inputs(70 + N + len(counts), N, counts, ties=True)
+    want = orc.find_top_rpn_proposals(inp["proposals"], inp["logits"], inp["image_sizes"], thr, pre, post, min_side)
+    res = _fsg().ops.rpn_proposals([t.to(cuda) for t in inp["proposals"]], [t.to(cuda) for t in inp["logits"]],
+                                   inp["image_sizes"], thr, pre, post, min_side)
+    for n in range(N):
+        c = int(res["count"][n].item())
+        assert c == want[n][0].shape[0], "image %d: %d vs %d proposals" % (n, c, want[n][0].shape[0])
+        assert torch.equal(res["boxes"][n, :c].cpu(), want[n][0])
+        assert torch.equal(res["logits"][n, :c].cpu(), want[n][1])
+        assert_equal_int(res["levels"][n, :c], want[n][2], "levels")
+        assert float(res["boxes"][n, c:].abs().sum()) == 0.0
+    got = P.find_top_rpn_proposals([t.to(cuda) for t in inp["proposals"]], [t.to(cuda) for t in inp["logits"]],
+                                   inp["image_sizes"], thr, pre, post, min_side, training=True)
+    assert all(len(got[n]) == want[n][0].shape[0] for n in range(N))
+
+
+def test_rpn_topk_all_equal_logits(cuda):
+    """Degenerate row: every logit equal -> the radix select runs through the index digits; lowest indices win."""
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    inp = synthetic.rpn_inputs(79, 1, [3000], ties=False)
+    inp["logits"][0][:] = 0.25
+    want = orc.find_top_rpn_proposals(inp["proposals"], inp["logits"], inp["image_sizes"], 0.7, 500, 500, 0.0)
+    res = _fsg().ops.rpn_proposals([t.to(cuda) for t in inp["proposals"]], [t.to(cuda) for t in inp["logits"]],
+                                   inp["image_sizes"], 0.7, 500, 500, 0.0)
+    c = int(res["count"][0].item())
+    assert c == want[0][0].shape[0] and torch.equal(res["boxes"][0, :c].cpu(), want[0][0])
+
+
+def test_rpn_and_roi_ground_truth(cuda):
+    """RPNOutputs._get_ground_truth and the matching part of label_and_sample_proposals vs the oracle; sampling
+    (random) checked through its invariants."""
+    from full_scale_gambler_for_object_detection_b200 import proposals as P, synthetic
+    inp = synthetic.train_inputs(81, 3, 320, 320, 80, M=7)
+    wl, wd = orc.rpn_ground_truth(inp["anchors"], inp["gt_boxes"])
+    gl, gd = P.rpn_ground_truth(inp["anchors"].to(cuda), [b.to(cuda) for b in inp["gt_boxes"]])
+    for n in range(3):
+        assert_equal_int(gl[n], wl[n], "rpn labels")
+        assert_close_tensor(gd[n], wd[n], "rpn deltas")
+    pos, neg = P.subsample_labels(gl[0], 256, 0.5, 0)
+    npos = int((wl[0] == 1).sum())
+    assert pos.numel() == min(npos, 128) and neg.numel() == 256 - pos.numel()
+    assert bool((gl[0][pos] == 1).all()) and bool((gl[0][neg] == 0).all())
+    assert pos.unique().numel() == pos.numel() and neg.unique().numel() == neg.numel()
+    # ROI heads: proposals (+ appended GT boxes) against the GT of one image, Matcher([0.5], [0, 1], no low-quality)
+    rp = synthetic.rpn_inputs(82, 1, [1500], image_hw=(320, 320), ties=False)["proposals"][0][0]
+    props = torch.cat([rp, inp["gt_boxes"][0]])
+    for gtb, gtc in ((inp["gt_boxes"][0], inp["gt_classes"][0]), (torch.zeros((0, 4)), torch.zeros(0, dtype=torch.int64))):
+        wm, wlab, wc = orc.label_proposals(props, gtb, gtc, 80)
+        gm, glab, gc = P.label_proposals(props.to(cuda), gtb.to(cuda), gtc.to(cuda), 80)
+        assert_equal_int(gm, wm, "matched idxs")
+        assert_equal_int(glab, wlab, "matched labels")
+        assert_equal_int(gc, wc, "gt classes")
+
+
+@pytest.mark.parametrize("R,K,spec,sthr,topk", [(1000, 80, True, 0.05, 100), (700, 20, False, 0.02, 100),
+                                                 (300, 1230, True, 0.0001, 300), (50, 5, True, 0.9999, -1)])
+def test_fast_rcnn_inference_single_image(cuda, R, K, spec, sthr, topk):
+    from full_scale_gambler_for_object_detection_b200 import proposals as P, synthetic
+    inp = synthetic.fast_rcnn_inputs(90 + K, R, K, spec)
+    wb, ws, wc, wr = orc.fast_rcnn_inference_single_image(inp["boxes"], inp["scores"], inp["image_shape"], sthr, 0.5, topk)
+    r, rows = P.fast_rcnn_inference_single_image(inp["boxes"].to(cuda), inp["scores"].to(cuda), inp["image_shape"],
+                                                 sthr, 0.5, topk)
+    assert torch.equal(r.pred_boxes.tensor.cpu(), wb) and torch.equal(r.scores.cpu(), ws)
+    assert_equal_int(r.pred_classes, wc, "classes")
+    assert_equal_int(rows, wr, "rows")

@@ -210,3 +210,32 @@ def test_grid_anchors_golden():
             assert flat.shape[0] == int(g["count_" + name][0])
             assert torch.equal(flat[::97], g["sample_" + name])
             assert torch.equal(flat.double().sum(dim=0), g["checksum_" + name])
+
+
+def test_two_stage_callers_golden():
+    """oracle find_top_rpn_proposals / rpn_ground_truth / fast_rcnn_inference_single_image == the reference's
+    stored outputs (rpn_outputs.py:52-151,250-295; fast_rcnn.py:76-118)."""
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    g = gu.load("two_stage")
+    for ci in range(2):
+        p = [int(v) for v in g["rpn%d_params" % ci]]
+        cid, N, pre, post, counts = p[0], p[1], p[2], p[3], p[4:]
+        thr, min_side = [float(v) for v in g["rpn%d_fparams" % ci]]
+        inp = synthetic.rpn_inputs(cid, N, counts, ties=False)
+        got = orc.find_top_rpn_proposals(inp["proposals"], inp["logits"], inp["image_sizes"], thr, pre, post, min_side)
+        for n in range(N):
+            assert torch.equal(got[n][0], g["rpn%d_boxes_%d" % (ci, n)])
+            assert torch.equal(got[n][1], g["rpn%d_logits_%d" % (ci, n)])
+    inp = synthetic.train_inputs(63, 3, 256, 320, 80, M=6)
+    ol, od = orc.rpn_ground_truth(inp["anchors"], inp["gt_boxes"])
+    for n in range(3):
+        assert torch.equal(ol[n], g["rpngt_labels_%d" % n]) and torch.equal(od[n][::13], g["rpngt_deltas_%d" % n])
+    for ci in range(2):
+        cid, R, K, spec = [int(v) for v in g["frcnn%d_params" % ci]]
+        inp = synthetic.fast_rcnn_inputs(cid, R, K, bool(spec))
+        ob, os_, oc, orow = orc.fast_rcnn_inference_single_image(inp["boxes"], inp["scores"], inp["image_shape"],
+                                                                 float(g["frcnn%d_thr" % ci][0]), 0.5, 100)
+        assert torch.equal(ob, g["frcnn%d_boxes" % ci]) and torch.equal(os_, g["frcnn%d_scores" % ci])
+        assert_equal_int(oc, g["frcnn%d_classes" % ci], "classes")
+        assert_equal_int(orow, g["frcnn%d_rows" % ci], "rows")
