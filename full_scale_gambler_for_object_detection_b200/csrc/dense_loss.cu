@@ -20,6 +20,9 @@
 
 namespace fsg {
 
+#ifndef LOSS_GENERIC_MINB
+#define LOSS_GENERIC_MINB 4
+#endif
 constexpr int kAnchorsPerGroup = 4;
 
 enum LossVariant { kFastWrite = 0, kFastNoWrite = 1, kGeneric = 2 };
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(256) loss_prepass_kernel(const int64_t* __rest
 // main pass
 // ------------------------------------------------------------------------------------------
 template <int V, int BATCH, int VARIANT, int GT>
-__global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : 3)) loss_main_kernel(const LossArgs A) {
+__global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) loss_main_kernel(const LossArgs A) {
   // GT > 0: "exact" instantiation, G == GT lanes per anchor and K == V*GT*BATCH (no predication in the
   // element loop); GT == 0: G and K are run-time values.
   constexpr bool kWrite = (VARIANT != kFastNoWrite);

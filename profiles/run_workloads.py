@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import full_scale_gambler_for_object_detection_b200 as fsg  # noqa: E402
 from full_scale_gambler_for_object_detection_b200 import synthetic  # noqa: E402
 
-ALL = ["train", "lvis", "detect", "match"]
+ALL = ["train", "lvis", "lvis_native", "detect", "match"]
 which = [a for a in sys.argv[1:] if a in ALL] or ALL
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 3
 warm = int(sys.argv[sys.argv.index("--warm") + 1]) if "--warm" in sys.argv else 2
@@ -47,6 +47,26 @@ if "train" in which:
     timed("train", train(80, 16, 2))
 if "lvis" in which:
     timed("lvis", train(1230, 8, 3))
+if "lvis_native" in which:
+    # config 3 shard on the head's native layout: K2 alone (fsg_loss_main_levels) and the whole step from head outputs
+    K, N = 1230, 8
+    inp = synthetic.train_inputs(3, N, 800, 1333, K, logits=False)
+    A, grids, R = inp["A"], inp["grids"], inp["R"]
+    g = torch.Generator(device=dev).manual_seed(3)
+    xs = [torch.randn((N, A * K, h, w), device=dev, generator=g) + synthetic.PRIOR_LOGIT for h, w in grids]
+    ds = [torch.randn((N, A * 4, h, w), device=dev, generator=g) * 0.1 for h, w in grids]
+    bs = [torch.sigmoid(torch.randn((N, A, h, w), device=dev, generator=g) - 4.6) for h, w in grids]
+    anchors = inp["anchors"].to(dev)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], dev)
+    cfg = fsg.DenseLossConfig(num_classes=K)
+    params = cfg.loss_params(1.0, 1.0, -1.0)
+    bets = fsg.ops.anchor_maps_to_flat([bs])[0]
+    m = fsg.ops.match_anchors(anchors, gt, K, bets=bets, temperature=0.1)
+    gl = [torch.empty_like(x) for x in xs]
+    timed("lvis_native_k2", lambda: fsg.ops.loss_main_levels(
+        xs, m["gt_classes"], params, m["stats"], delta_levels=ds, anchors=anchors, gt=gt,
+        matched_idx32=m["matched_idx32"], mask=m["mask"], bets=bets))
+    del gl
 if "detect" in which:
     inp = synthetic.inference_inputs(4, 1, [24000] * 5, 80)
     g = torch.Generator().manual_seed(4)
