@@ -28,6 +28,7 @@ constexpr int kStagePerWarp = 32;                   // raw (logit, index) candid
 constexpr int kSelTrigger = kSelCap - (kSelThreads / 32) * (256 + kStagePerWarp);
 constexpr int kMaxLevels = 8;
 constexpr int kNmsThreads = 1024;
+constexpr int kNmsBigSeg = 512;                     // class segments above this size are suppressed by the whole CTA
 constexpr int kNmsCap = 8192;                       // candidates per image the NMS kernel holds
 
 struct DetectLevels {
@@ -490,6 +491,15 @@ __device__ __forceinline__ float4 postprocess_box(float4 b, float4 pp) {
   return b;
 }
 
+// torchvision nms_kernel arithmetic: fp32 IoU of box i (area ai precomputed) and box j, in its op order
+__device__ __forceinline__ float nms_overlap(float4 bi, float ai, float4 bj) {
+  const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+  const float w = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+  const float h = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+}
+
 // ascending bitonic sort
 template <int NT>
 __device__ void bitonic_asc(uint64_t* a, int m) {
@@ -518,7 +528,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
   unsigned char* dead = smem_raw + (size_t)kNmsCap * 26;                        // kNmsCap
   __shared__ int s_pref[kMaxLevels + 1];
   __shared__ int s_warp[kNmsThreads / 32];
-  __shared__ int s_nseg, s_next, s_nkeep, s_mine;
+  __shared__ int s_nseg, s_next, s_nkeep, s_mine, s_nbatch;
+  __shared__ int s_batch[32];
   __shared__ bool s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -614,7 +625,48 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
   }
   const int nseg = s_nseg;
 
-  // ---- 3. greedy NMS, one warp per class segment (torchvision nms_kernel semantics)
+  // ---- 3a. big class segments (RPN levels: thousands of boxes in one class): the whole CTA works on one segment.
+  //      Batches of 32 boxes in score order: warp 0 runs the greedy pass inside the batch, then every thread
+  //      tests the boxes behind the batch against the batch's survivors.  Same result as the sequential greedy
+  //      pass (a box is suppressed iff an earlier KEPT box overlaps it), two barriers per 32 boxes.
+  for (int s = 0; s < nseg; ++s) {
+    const int b = seg[s];
+    const int e = (s + 1 < nseg) ? (int)seg[s + 1] : mc;
+    if (e - b <= kNmsBigSeg) continue;   // uniform
+    for (int i0 = b; i0 < e; i0 += 32) {
+      const int i1 = min(i0 + 32, e);
+      if (wid == 0) {
+        for (int i = i0; i < i1; ++i) {
+          if (dead[i]) continue;   // warp-uniform
+          const float4 bi = sbox[i];
+          const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+          const int j = i + 1 + lane;
+          if (j < i1 && !dead[j] && nms_overlap(bi, ai, sbox[j]) > A.thr) dead[j] = 1;
+          __syncwarp();
+        }
+        const bool alive = (i0 + lane < i1) && !dead[i0 + lane];
+        const unsigned bm = __ballot_sync(kFull, alive);
+        if (alive) s_batch[__popc(bm & ((1u << lane) - 1u))] = i0 + lane;
+        if (lane == 0) s_nbatch = __popc(bm);
+      }
+      __syncthreads();
+      const int nk = s_nbatch;
+      if (nk > 0) {
+        for (int j = i1 + tid; j < e; j += kNmsThreads) {
+          if (dead[j]) continue;
+          const float4 bj = sbox[j];
+          for (int q = 0; q < nk; ++q) {
+            const float4 bi = sbox[s_batch[q]];
+            const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+            if (nms_overlap(bi, ai, bj) > A.thr) { dead[j] = 1; break; }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- 3b. greedy NMS, one warp per (small) class segment (torchvision nms_kernel semantics)
   for (;;) {
     int s = 0;
     if (lane == 0) s = atomicAdd(&s_next, 1);
@@ -622,6 +674,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
     if (s >= nseg) break;
     const int b = seg[s];
     const int e = (s + 1 < nseg) ? (int)seg[s + 1] : mc;
+    if (e - b > kNmsBigSeg) continue;    // done above
     for (int i = b; i < e; ++i) {
       if (dead[i]) continue;   // warp-uniform (shared memory, synchronised below)
       const float4 bi = sbox[i];

@@ -8,8 +8,8 @@
 //                        key carries the index, so keys are unique) and a gather of boxes/classes into that order;
 //   2. nms_mask_kernel   upper-triangular suppression bit matrix, 64 x 64 tile per CTA (same fp32 IoU op order
 //                        and strict `>` as the small-n kernel; class equality folded in for batched_nms);
-//   3. nms_sweep_kernel  one CTA walks the 64-row blocks in order: resolves the diagonal word serially, then
-//                        ORs the kept rows into the `removed` bitset held in shared memory.
+//   3. nms_sweep_kernel  one CTA walks the rows in super-blocks of 1024: diagonal blocks resolved from shared
+//                        memory on warp shuffles, kept rows OR-ed into the `removed` bitset (see the kernel).
 #include <math.h>
 
 #include "common.cuh"
@@ -88,57 +88,113 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
   mask[(int64_t)i * nb + cb] = word;
 }
 
+// Sweep: one CTA walks the sorted boxes in super-blocks of kSB 64-row blocks (1024 rows).
+//   phase 0  the super-block's own kSB x kSB words of the bit matrix are loaded into shared memory (one row per
+//            thread, all loads independent);
+//   phase 1  warp 0 resolves the kSB diagonal blocks in order: the 64 diagonal words sit in registers and the
+//            serial keep / suppress chain runs on shuffles, then the kept rows of the block are OR-ed into the
+//            `removed` words of the later blocks of the super-block (shared memory only);
+//   phase 2  all threads OR the kept rows of the super-block into the `removed` words behind it, reading the bit
+//            matrix with batches of independent loads (rows split over thread groups when few words remain).
+constexpr int kSB = 16;
+constexpr int kTileStride = kSB + 1;   // words per tile row (+1: conflict-free column reads)
+
+__device__ __forceinline__ uint64_t warp_or64(uint64_t v) {
+  const unsigned lo = __reduce_or_sync(kFull, (unsigned)v);
+  const unsigned hi = __reduce_or_sync(kFull, (unsigned)(v >> 32));
+  return ((uint64_t)hi << 32) | lo;
+}
+
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const uint64_t* __restrict__ mask,
                                                                   const int* __restrict__ sidx, int n, int nb,
                                                                   int64_t* __restrict__ keep,
                                                                   int32_t* __restrict__ num_keep) {
-  extern __shared__ uint64_t removed[];  // nb words
-  __shared__ uint64_t s_diag[64];
-  __shared__ uint64_t s_kept;
-  __shared__ int s_count;
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) uint64_t smem64[];
+  uint64_t* removed = smem64;                                  // nb words
+  uint64_t* tile = smem64 + nb;                                // 1024 * kTileStride words
+  int* rowlist = reinterpret_cast<int*>(tile + 1024 * kTileStride);   // 1024 kept rows of the super-block
+  __shared__ int s_count, s_nrows;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int w = tid; w < nb; w += kSweepThreads) removed[w] = 0ull;
   if (tid == 0) s_count = 0;
   __syncthreads();
-  for (int rb = 0; rb < nb; ++rb) {
-    const int rows = min(64, n - rb * 64);
-    if (tid < 64) s_diag[tid] = (tid < rows) ? mask[(int64_t)(rb * 64 + tid) * nb + rb] : 0ull;
+  for (int sb0 = 0; sb0 < nb; sb0 += kSB) {
+    const int nblk = min(kSB, nb - sb0);
+    const int row0 = sb0 * 64;
+    const int rows = min(nblk * 64, n - row0);
+    // ---- phase 0
+    if (tid < rows) {
+      const uint64_t* src = mask + (int64_t)(row0 + tid) * nb + sb0;
+      uint64_t v[kSB];
+#pragma unroll
+      for (int j = 0; j < kSB; ++j) v[j] = (j < nblk && j >= (tid >> 6)) ? src[j] : 0ull;   // upper triangle only
+#pragma unroll
+      for (int j = 0; j < kSB; ++j) tile[tid * kTileStride + j] = v[j];
+    }
+    if (tid == 0) s_nrows = 0;
     __syncthreads();
-    if (tid == 0) {
-      uint64_t rem = removed[rb], kept = 0ull;
-      for (int t = 0; t < rows; ++t) {
-        if (!((rem >> t) & 1ull)) {
-          kept |= (1ull << t);
-          rem |= s_diag[t];
+    // ---- phase 1
+    if (wid == 0) {
+      int cnt = s_count, nrows = 0;
+      for (int b = 0; b < nblk; ++b) {
+        const int r_lo = b * 64 + lane, r_hi = r_lo + 32;
+        const uint64_t d_lo = (r_lo < rows) ? tile[r_lo * kTileStride + b] : 0ull;
+        const uint64_t d_hi = (r_hi < rows) ? tile[r_hi * kTileStride + b] : 0ull;
+        uint64_t rem = removed[sb0 + b];
+        const int rb_rows = min(64, rows - b * 64);
+        if (rb_rows < 64) rem |= ~0ull << rb_rows;             // rows past the end never survive
+        uint64_t kept = 0ull;
+#pragma unroll 8
+        for (int t = 0; t < 64; ++t) {
+          const uint64_t dt = __shfl_sync(kFull, (t < 32) ? d_lo : d_hi, t & 31);
+          if (!((rem >> t) & 1ull)) {
+            kept |= 1ull << t;
+            rem |= dt;
+          }
         }
+        const bool k_lo = (kept >> lane) & 1ull, k_hi = (kept >> (lane + 32)) & 1ull;
+        for (int j = b + 1; j < nblk; ++j) {
+          uint64_t v = (k_lo ? tile[r_lo * kTileStride + j] : 0ull) | (k_hi ? tile[r_hi * kTileStride + j] : 0ull);
+          v = warp_or64(v);
+          if (lane == 0) removed[sb0 + j] |= v;
+        }
+        __syncwarp();
+        const int p_lo = __popcll(kept & ((1ull << lane) - 1ull));
+        const int p_hi = __popcll(kept & ((1ull << (lane + 32)) - 1ull));
+        if (k_lo) { keep[cnt + p_lo] = (int64_t)sidx[row0 + r_lo]; rowlist[nrows + p_lo] = row0 + r_lo; }
+        if (k_hi) { keep[cnt + p_hi] = (int64_t)sidx[row0 + r_hi]; rowlist[nrows + p_hi] = row0 + r_hi; }
+        const int c = __popcll(kept);
+        cnt += c;
+        nrows += c;
       }
-      s_kept = kept;
+      if (lane == 0) { s_count = cnt; s_nrows = nrows; }
     }
     __syncthreads();
-    const uint64_t kept = s_kept;
-    const int base = s_count;
-    // kept rows -> output (score-descending order = sorted order) and into the bitset of later blocks
-    if (tid < 64 && ((kept >> tid) & 1ull)) {
-      const int pos = base + __popcll(kept & ((1ull << tid) - 1ull));
-      keep[pos] = (int64_t)sidx[rb * 64 + tid];
-    }
-    if (kept != 0ull) {
-      for (int w = rb + 1 + tid; w < nb; w += kSweepThreads) {
+    // ---- phase 2
+    const int w0 = sb0 + nblk;
+    const int W = nb - w0;
+    const int K = s_nrows;
+    if (W > 0 && K > 0) {
+      int span = 1;                      // threads along the word axis (power of two)
+      while (span < W && span < kSweepThreads) span <<= 1;
+      const int groups = kSweepThreads / span;   // thread groups along the row axis
+      const int g = tid / span, wi = tid - g * span;
+      for (int w = w0 + wi; w < nb; w += span) {
         uint64_t acc = 0ull;
-        uint64_t k = kept;
-        while (k) {
-          const int t = __ffsll((long long)k) - 1;
-          k &= k - 1ull;
-          acc |= mask[(int64_t)(rb * 64 + t) * nb + w];
+        int q = g;
+        for (; q + 7 * groups < K; q += 8 * groups) {
+          uint64_t v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = mask[(int64_t)rowlist[q + u * groups] * nb + w];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc |= v[u];
         }
-        removed[w] |= acc;
+        for (; q < K; q += groups) acc |= mask[(int64_t)rowlist[q] * nb + w];
+        if (acc) atomicOr(reinterpret_cast<unsigned long long*>(&removed[w]), (unsigned long long)acc);
       }
     }
     __syncthreads();
-    if (tid == 0) s_count = base + __popcll(kept);
-    // the next iteration's first barrier orders this write before any read of s_count
   }
-  __syncthreads();
   if (tid == 0) *num_keep = s_count;
 }
 
@@ -170,7 +226,9 @@ int nms_large(const float* boxes, const float* scores, const int64_t* class_ids,
   FSG_LAUNCH_CHECK();
   nms_mask_kernel<<<dim3((unsigned)nb, (unsigned)nb), 64, 0, s>>>(sbox, scls, (int)n, nb, thr, mask);
   FSG_LAUNCH_CHECK();
-  nms_sweep_kernel<<<1, kSweepThreads, sizeof(uint64_t) * (size_t)nb, s>>>(mask, sidx, (int)n, nb, keep, num_keep);
+  const size_t sweep_smem = sizeof(uint64_t) * ((size_t)nb + 1024 * kTileStride) + sizeof(int) * 1024;
+  FSG_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem));
+  nms_sweep_kernel<<<1, kSweepThreads, sweep_smem, s>>>(mask, sidx, (int)n, nb, keep, num_keep);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import full_scale_gambler_for_object_detection_b200 as fsg  # noqa: E402
 from full_scale_gambler_for_object_detection_b200 import synthetic  # noqa: E402
 
-ALL = ["train", "lvis", "lvis_native", "detect", "match"]
+ALL = ["train", "lvis", "lvis_native", "detect", "match", "rpn", "nms_large"]
 which = [a for a in sys.argv[1:] if a in ALL] or ALL
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 3
 warm = int(sys.argv[sys.argv.index("--warm") + 1]) if "--warm" in sys.argv else 2
@@ -75,6 +75,21 @@ if "detect" in which:
     deltas = (torch.randn((N4, inp["R"], 4), generator=g) * 0.2).to(dev)
     anchors = inp["anchors"].to(dev)
     timed("detect", lambda: fsg.ops.detect(logits, deltas, anchors, inp["level_offsets"]))
+if "rpn" in which:
+    # find_top_rpn_proposals, FPN Faster R-CNN training setting (Base-RCNN-FPN.yaml): 16 images, P2..P6 of an
+    # 800x1333 input with A = 3, pre_nms_topk 2000 per level, post_nms_topk 1000, NMS 0.7
+    counts = [200 * 336 * 3, 100 * 168 * 3, 50 * 84 * 3, 25 * 42 * 3, 13 * 21 * 3]
+    ri = synthetic.rpn_inputs(6, 16, counts, ties=False)
+    P = [t.to(dev) for t in ri["proposals"]]
+    Lg = [t.to(dev) for t in ri["logits"]]
+    timed("rpn", lambda: fsg.ops.rpn_proposals(P, Lg, ri["image_sizes"], 0.7, 2000, 1000, 0.0))
+if "nms_large" in which:
+    g = torch.Generator().manual_seed(8)
+    n = 20000
+    xy = torch.rand((n, 2), generator=g) * 2000
+    wh = torch.rand((n, 2), generator=g) * 90 + 10
+    bx, sc = torch.cat([xy, xy + wh], 1).to(dev), torch.rand(n, generator=g).to(dev)
+    timed("nms20k", lambda: fsg.ops.nms_raw(bx, sc, None, 0.5))
 if "match" in which:
     inp5 = synthetic.matcher_stress_inputs(5, 8, 1000000, 200)
     a5 = inp5["anchors"].to(dev)
