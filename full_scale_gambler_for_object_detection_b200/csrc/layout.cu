@@ -57,30 +57,43 @@ __global__ void __launch_bounds__(256) permute_level_kernel(float* __restrict__ 
 
 // (N,R)-sized per-anchor maps between the flattened anchor order and the per-level (N, A, H, W) maps the
 // gambler produces / consumes (betting maps in, NAKHW_loss and d/d bets out; gambler_heads.py:91-101,291-318).
-// A few MB in total, so one launch covers all levels and up to three tensors; thread = one flat element.
+// A few MB in total, so one launch covers all levels and up to three tensors.
 struct SmallMaps {
   float* lvl[3][FSG_MAX_LEVELS];   // per tensor, per level: (N, A, H, W)
   float* flat[3];                  // per tensor: (N, R)
   int64_t off[FSG_MAX_LEVELS + 1];
   int HW[FSG_MAX_LEVELS];
+  int tile_base[FSG_MAX_LEVELS + 1];   // tiles of 256 hw positions per level
   int num_levels, A, ntensors, to_levels;
   int64_t R;
 };
 
 __global__ void __launch_bounds__(256) anchor_maps_kernel(const SmallMaps M) {
-  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const int n = blockIdx.y;
-  if (r >= M.R) return;
+  // one CTA: 256 consecutive hw positions of one level and image, all A anchor slots, staged through shared
+  // memory so that both the per-plane side and the flat side are accessed with consecutive addresses
+  __shared__ float s_t[FSG_MAX_CELL_ANCHORS][257];
+  const int n = blockIdx.y, tid = threadIdx.x;
   int l = 0;
-  while (l + 1 < M.num_levels && r >= M.off[l + 1]) ++l;
-  const int64_t local = r - M.off[l];
-  const int64_t hw = local / M.A;
-  const int a = (int)(local - hw * M.A);
-  const int64_t src = ((int64_t)n * M.A + a) * M.HW[l] + hw;
-  const int64_t dst = (int64_t)n * M.R + r;
+  while (l + 1 < M.num_levels && (int)blockIdx.x >= M.tile_base[l + 1]) ++l;
+  const int64_t hw0 = (int64_t)((int)blockIdx.x - M.tile_base[l]) * 256;
+  const int HW = M.HW[l], A = M.A;
+  const int cnt = (int)min((int64_t)256, HW - hw0);          // hw positions in this tile
+  const int64_t fbase = (int64_t)n * M.R + M.off[l] + hw0 * A;
   for (int t = 0; t < M.ntensors; ++t) {
-    if (M.to_levels) M.lvl[t][l][src] = M.flat[t][dst];
-    else M.flat[t][dst] = M.lvl[t][l][src];
+    float* lv = M.lvl[t][l] + (int64_t)n * A * HW + hw0;
+    float* fl = M.flat[t] + fbase;
+    if (!M.to_levels) {
+      if (tid < cnt)
+        for (int a = 0; a < A; ++a) s_t[a][tid] = lv[(int64_t)a * HW + tid];
+      __syncthreads();
+      for (int i = tid; i < cnt * A; i += 256) fl[i] = s_t[i % A][i / A];
+    } else {
+      for (int i = tid; i < cnt * A; i += 256) s_t[i % A][i / A] = fl[i];
+      __syncthreads();
+      if (tid < cnt)
+        for (int a = 0; a < A; ++a) lv[(int64_t)a * HW + tid] = s_t[a][tid];
+    }
+    __syncthreads();
   }
 }
 
@@ -157,12 +170,15 @@ extern "C" int fsg_anchor_maps(float* const* h_level_ptrs, float* const* h_flat_
                                const int32_t* h_HW, int num_levels, int A, int N, int to_levels,
                                fsg_stream_t stream) {
   if (!h_level_ptrs || !h_flat_ptrs || !h_HW || ntensors <= 0 || ntensors > 3 || num_levels <= 0 ||
-      num_levels > FSG_MAX_LEVELS || A <= 0 || N <= 0 || N > 65535)
+      num_levels > FSG_MAX_LEVELS || A <= 0 || A > FSG_MAX_CELL_ANCHORS || N <= 0 || N > 65535)
     return FSG_ERR_INVALID_ARG;
   SmallMaps m;
   int64_t off = 0;
+  int tiles = 0;
   for (int l = 0; l < FSG_MAX_LEVELS; ++l) {
     m.off[l] = off;
+    m.tile_base[l] = tiles;
+    if (l < num_levels && h_HW[l] > 0) tiles += (int)ceil_div(h_HW[l], 256);
     m.HW[l] = l < num_levels ? h_HW[l] : 0;
     if (l < num_levels) {
       if (h_HW[l] < 0) return FSG_ERR_INVALID_ARG;
@@ -174,13 +190,14 @@ extern "C" int fsg_anchor_maps(float* const* h_level_ptrs, float* const* h_flat_
     }
   }
   m.off[FSG_MAX_LEVELS] = off;
+  m.tile_base[FSG_MAX_LEVELS] = tiles;
   for (int t = 0; t < 3; ++t) {
     m.flat[t] = t < ntensors ? h_flat_ptrs[t] : nullptr;
     if (t < ntensors && !m.flat[t]) return FSG_ERR_INVALID_ARG;
   }
   m.num_levels = num_levels; m.A = A; m.ntensors = ntensors; m.to_levels = to_levels; m.R = off;
   if (off == 0) return FSG_OK;
-  anchor_maps_kernel<<<dim3((unsigned)ceil_div(off, 256), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(m);
+  anchor_maps_kernel<<<dim3((unsigned)tiles, (unsigned)N), 256, 0, (cudaStream_t)stream>>>(m);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

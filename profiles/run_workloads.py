@@ -74,7 +74,8 @@ if "detect" in which:
     logits = (torch.randn((N4, inp["R"], 80), generator=g) * 1.5 + synthetic.PRIOR_LOGIT).to(dev)
     deltas = (torch.randn((N4, inp["R"], 4), generator=g) * 0.2).to(dev)
     anchors = inp["anchors"].to(dev)
-    timed("detect", lambda: fsg.ops.detect(logits, deltas, anchors, inp["level_offsets"]))
+    thr = float(os.environ.get("FSG_DETECT_THR", "0.05"))   # e.g. 0.9999: nothing passes -> cost of the bare scan
+    timed("detect", lambda: fsg.ops.detect(logits, deltas, anchors, inp["level_offsets"], score_threshold=thr))
 if "rpn" in which:
     # find_top_rpn_proposals, FPN Faster R-CNN training setting (Base-RCNN-FPN.yaml): 16 images, P2..P6 of an
     # 800x1333 input with A = 3, pre_nms_topk 2000 per level, post_nms_topk 1000, NMS 0.7
