@@ -20,7 +20,13 @@
 namespace fsg {
 
 constexpr int kSelThreads = 256;
-constexpr int kSelCap = 4096;                       // candidate buffer entries (u64 keys): 32 KB -> 4 CTAs/SM
+#ifndef SEL_CAP
+#define SEL_CAP 4096
+#endif
+#ifndef SEL_CTAS
+#define SEL_CTAS 4
+#endif
+constexpr int kSelCap = SEL_CAP;                       // candidate buffer entries (u64 keys): 32 KB -> 4 CTAs/SM
 constexpr int kSelIter = kSelThreads * 8;           // elements consumed per block iteration
 constexpr int kStagePerWarp = 32;                   // raw (logit, index) candidates a warp collects before it
                                                     // evaluates their sigmoids as one dense batch
@@ -58,8 +64,11 @@ __device__ __forceinline__ uint32_t key_index(uint64_t k) { return 0xffffffffu -
 // top digits put almost every key in one bin and un-aggregated shared atomics would serialise 32-fold.
 constexpr int kDigitBits = 10;
 constexpr int kBins = 1 << kDigitBits;
+// slack > 0: an in-stream prune may stop after two digits once the selected bin holds at most `slack` keys more than
+// needed -- the threshold then keeps a few extra keys (at most k + slack), which the next prune sorts out.
 template <int NT>
-__device__ uint64_t select_kth(const uint64_t* buf, int count, int k, unsigned* hist /*kBins*/, int* s_tmp /*4*/) {
+__device__ uint64_t select_kth(const uint64_t* buf, int count, int k, unsigned* hist /*kBins*/, int* s_tmp /*4*/,
+                               int slack = 0) {
   const int tid = threadIdx.x, lane = tid & 31;
   uint64_t prefix = 0;
   int need = k;
@@ -112,6 +121,7 @@ __device__ uint64_t select_kth(const uint64_t* buf, int count, int k, unsigned* 
     prefix |= (uint64_t)digit << shift;
     __syncthreads();
     if (inbin == need) break;  // the whole bin is taken: low bits of the threshold stay zero
+    if (slack > 0 && top <= 64 - kDigitBits && inbin - need <= slack) break;   // good enough for now
   }
   return prefix;
 }
@@ -155,10 +165,10 @@ __device__ uint64_t block_min_u64(const uint64_t* buf, int count, uint64_t* s_re
 }
 
 template <int NT>
-__device__ void prune_topk(uint64_t* buf, int* s_count, int k, unsigned* hist, int* s_tmp) {
+__device__ void prune_topk(uint64_t* buf, int* s_count, int k, unsigned* hist, int* s_tmp, int slack = 0) {
   const int count = *s_count;  // caller synchronised
   if (count <= k) return;
-  const uint64_t T = select_kth<NT>(buf, count, k, hist, s_tmp);
+  const uint64_t T = select_kth<NT>(buf, count, k, hist, s_tmp, slack);
   compact_ge<NT>(buf, s_count, T);
 }
 
@@ -286,7 +296,7 @@ __device__ __forceinline__ void stage_candidates(const float* v, uint32_t idx0, 
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kSelThreads, 4) detect_select_kernel(const SelectArgs A, const DetectLevels LV) {
+__global__ void __launch_bounds__(kSelThreads, SEL_CTAS) detect_select_kernel(const SelectArgs A, const DetectLevels LV) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);  // kSelCap
   __shared__ unsigned hist[kBins];
@@ -343,7 +353,8 @@ __global__ void __launch_bounds__(kSelThreads, 4) detect_select_kernel(const Sel
     }
     __syncthreads();
     if (s_count > kSelTrigger) {   // uniform: read after the barrier
-      prune_topk<kSelThreads>(buf, &s_count, k, hist, s_tmp);
+      // in-stream prunes may keep up to 64 keys too many when that still leaves the buffer well under the trigger
+      prune_topk<kSelThreads>(buf, &s_count, k, hist, s_tmp, (k + 64 <= kSelTrigger / 2 + 256) ? 64 : 0);
       const int now = s_count;
       if (now >= k) {
         // buffer now holds exactly the k best so far: raise the bar.  A later element (higher index)
@@ -862,7 +873,7 @@ static DetectLevels plan_levels(const int64_t* off, int num_levels, int K, int t
     int parts = (int)ceil_div(E > 0 ? E : 1, (int64_t)64 * kSelIter);  // ~256K elements per CTA
     // a longer stream per CTA tightens its running threshold (pass rate ~ k/n_seen) and needs fewer prunes:
     // only split a slab as far as one wave of resident CTAs (4 per SM) can take
-    int want = (4 * 148) / (N * num_levels);   // 4 resident CTAs per SM: keep every stream in the first wave
+    int want = (SEL_CTAS * 148) / (N * num_levels);   // 4 resident CTAs per SM: keep every stream in the first wave
     if (want < 1) want = 1;
     if (parts > want) parts = want;
     if (parts > 16) parts = 16;

@@ -109,3 +109,83 @@ def test_config5_full_image_size(cuda):
     for k in ("matches", "match_labels", "picky_labels", "gt_classes", "mask"):
         assert_equal_int(got[k], want[k], k)
     assert int((want["match_labels"] == 1).sum()) >= 200
+
+
+def test_config2_full_batch_native_layout(cuda):
+    """Config 2 at full size on the head's native layout: the step from per-level conv outputs must give, element
+    for element, the gradients of the (N, R, K) step on the permuted copy (same arithmetic per element), the same
+    integer outputs, and losses equal up to the order of the K-reduction."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    N, K = 16, 80
+    inp = synthetic.train_inputs(2, N, 800, 1333, K, logits=False)
+    A, grids = inp["A"], inp["grids"]
+    g = torch.Generator(device=cuda).manual_seed(9)
+    xs = [(torch.randn((N, A * K, h, w), device=cuda, generator=g) + synthetic.PRIOR_LOGIT).requires_grad_(True)
+          for h, w in grids]
+    ds = [(torch.randn((N, A * 4, h, w), device=cuda, generator=g) * 0.1).requires_grad_(True) for h, w in grids]
+    bs = [torch.sigmoid(torch.randn((N, A, h, w), device=cuda, generator=g) + synthetic.PRIOR_LOGIT).requires_grad_(True)
+          for h, w in grids]
+    anchors = inp["anchors"].to(cuda)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    cfg = fsg.DenseLossConfig(num_classes=K)
+    res = fsg.dense_train_step_levels(xs, ds, bs, anchors, gt, cfg)
+    res.total.backward()
+    # the same step on the permuted copy
+    xf = fsg.ops.levels_to_flat([t.detach() for t in xs], K).requires_grad_(True)
+    df = fsg.ops.levels_to_flat([t.detach() for t in ds], 4).requires_grad_(True)
+    bf = fsg.ops.anchor_maps_to_flat([[t.detach() for t in bs]])[0].requires_grad_(True)
+    ref = fsg.dense_train_step(xf, df, bf, anchors, gt, cfg)
+    ref.total.backward()
+    assert torch.equal(res.gt_classes, ref.gt_classes) and torch.equal(res.mask, ref.mask)
+    assert torch.equal(res.stats, ref.stats)
+    assert torch.equal(fsg.ops.levels_to_flat([t.grad for t in xs], K), xf.grad)
+    assert torch.equal(fsg.ops.levels_to_flat([t.grad for t in ds], 4), df.grad)
+    for k in (5, 6, 7, 8):
+        assert_close_scalar(res.scalars[k].item(), ref.scalars[k].item(), "scalar %d" % k, rtol=1e-6)
+    assert_close_tensor(fsg.ops.anchor_maps_to_flat([[t.grad for t in bs]])[0], bf.grad, "grad_bets", rtol=1e-5,
+                        atol_scale=1e-6)
+    ell = fsg.ops.anchor_maps_to_flat([res.per_anchor_loss])[0]
+    assert_close_tensor(ell, ref.per_anchor_loss, "per_anchor_loss", rtol=2e-6)
+    # the generated anchors are the ones the synthetic batch was built with
+    gen = fsg.DefaultAnchorGenerator([list(s) for s in fsg.anchor_generator.RETINANET_SIZES], [[1.0]],
+                                     fsg.anchor_generator.RETINANET_STRIDES, cuda)
+    flat, offs = gen.flat(xs)
+    assert torch.equal(flat, anchors) and offs == inp["level_offsets"]
+
+
+def test_rpn_full_size_properties(cuda):
+    """find_top_rpn_proposals at the FPN training size (P2..P6 of 800x1333, A = 3, 2000 -> 1000): size-independent
+    properties on 4 images -- sorted logits, boxes inside the image and larger than the minimum side, every kept
+    proposal among its level's top-k, no kept pair of one level above the NMS threshold; image 0 against the oracle."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    counts = [200 * 336 * 3, 100 * 168 * 3, 50 * 84 * 3, 25 * 42 * 3, 13 * 21 * 3]
+    N, pre, post, thr, min_side = 4, 2000, 1000, 0.7, 2.5
+    inp = synthetic.rpn_inputs(7, N, counts, ties=False)
+    res = fsg.ops.rpn_proposals([t.to(cuda) for t in inp["proposals"]], [t.to(cuda) for t in inp["logits"]],
+                                inp["image_sizes"], thr, pre, post, min_side)
+    H, W = inp["image_sizes"][0]
+    for n in range(N):
+        c = int(res["count"][n])
+        assert 0 < c <= post
+        b, lg, lv = res["boxes"][n, :c], res["logits"][n, :c], res["levels"][n, :c]
+        assert bool((lg[:-1] >= lg[1:]).all())
+        assert bool((b[:, 0] >= 0).all() and (b[:, 1] >= 0).all() and (b[:, 2] <= W).all() and (b[:, 3] <= H).all())
+        assert bool(((b[:, 2] - b[:, 0]) > min_side).all() and ((b[:, 3] - b[:, 1]) > min_side).all())
+        for l in range(len(counts)):
+            sel = lv == l
+            if int(sel.sum()) == 0:
+                continue
+            kth = torch.topk(inp["logits"][l][n].to(cuda), min(pre, counts[l])).values[-1]
+            assert bool((lg[sel] >= kth).all())
+            iou = fsg.ops.pairwise_iou(b[sel], b[sel])
+            iou.fill_diagonal_(0.0)
+            assert float(iou.max()) <= thr
+    want = orc.find_top_rpn_proposals([p[:1] for p in inp["proposals"]], [x[:1] for x in inp["logits"]],
+                                      inp["image_sizes"][:1], thr, pre, post, min_side)
+    c0 = int(res["count"][0])
+    assert c0 == want[0][0].shape[0]
+    assert torch.equal(res["boxes"][0, :c0].cpu(), want[0][0]) and torch.equal(res["logits"][0, :c0].cpu(), want[0][1])
