@@ -78,3 +78,43 @@ def test_no_cpu_fallback():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_argument_validation_needs_no_device(lib_path):
+    """Every entry point validates its arguments before touching the device: bad calls come back with a status
+    (1 = invalid argument, 2 = workspace, 3 = unsupported shape) instead of launching anything."""
+    import ctypes as C
+    from full_scale_gambler_for_object_detection_b200 import _lib
+
+    L = _lib.lib()
+    INVALID, WORKSPACE, UNSUPPORTED = 1, 2, 3
+    null = None
+    assert L.fsg_pairwise_iou(null, -1, null, 1, null, null) == INVALID
+    assert L.fsg_nms(null, null, null, -1, 0.5, null, null, null, 0, null) == INVALID
+    assert L.fsg_nms_workspace_bytes(300000) == 0                       # beyond the general-n cap
+    assert L.fsg_nms_workspace_bytes(20000) > 20000 * (20000 // 64) * 8  # bit matrix for the large path
+    assert L.fsg_box2box_get_deltas(null, null, -1, null, null, null) == INVALID
+    assert L.fsg_permute_level(null, null, 1, 0, 4, 0, 0, 0, null) == INVALID
+    assert L.fsg_scale_inplace(null, -1, null, 1.0, null) == INVALID
+    assert L.fsg_postprocess_boxes(null, -1, 1.0, 1.0, 1.0, 1.0, null, null, null) == INVALID
+    assert L.fsg_score_filter(null, 3, null, 10, 80, 1.0, 1.0, 0.5, null, null, null, null, C.c_void_p(16), null) == INVALID
+    lv = (_lib.AnchorLevel * 1)()
+    lv[0].H, lv[0].W, lv[0].stride, lv[0].A = 4, 4, 8, 17                # more cell anchors than the table holds
+    assert L.fsg_grid_anchors(lv, 1, null, 4 * 4 * 17, null) == INVALID
+    lv[0].A = 3
+    assert L.fsg_grid_anchors(lv, 1, null, 5, null) == INVALID           # R does not match the grid
+    sizes = _lib.host_i64([100, 50])
+    assert L.fsg_rpn_proposals_workspace_bytes(2, sizes, 2, 9000, 1000) > 0      # k clipped to the level sizes
+    big = _lib.host_i64([20000, 20000])
+    assert L.fsg_rpn_proposals_workspace_bytes(2, big, 2, 9000, 1000) == 0       # pre_nms_topk > 8192 per level
+    hl = (_lib.HeadLevel * 1)()
+    hl[0].H, hl[0].W = 0, 4
+    assert L.fsg_loss_main_levels_workspace_bytes(2, hl, 1, 3) == 0
+    p = _lib.LossParams()
+    p.num_classes = 80
+    assert L.fsg_loss_main(null, null, null, null, 0, null, null, null, null, null, null, 1, 10, C.byref(p), null, null,
+                           null, null, null, null, null, 0, null) == INVALID
+    assert L.fsg_detect(null, null, null, 0, 1, 10, 80, null, 1, 0.05, 1000, 0.5, 100, null, 4.0, null, null, null,
+                        null, null, null, null, null, null, null, null, 0, null) == INVALID
+    assert b"invalid" in L.fsg_status_string(INVALID).lower() or b"argument" in L.fsg_status_string(INVALID).lower()
+    assert L.fsg_status_string(UNSUPPORTED) and L.fsg_status_string(WORKSPACE)
