@@ -111,6 +111,59 @@ def test_fused_match_stress_slice(cuda):
         assert_equal_int(got[k], want[k], k)
 
 
+@pytest.mark.parametrize("Ms", [(65, 256), (130, 200), (256, 65), (257, 64), (100, 0, 180)])
+def test_fused_match_crowded_images_spatial_prefilter(cuda, Ms):
+    """Crowded images (64..257 GT per image, mixed with a GT-free one) on the shared-memory GT path.  Includes: anchors far outside the GT extent,
+    anchors covering the whole extent, GT that touch nothing (zero maximum: every anchor becomes a low-quality
+    match), duplicated anchors and GT (ties -> lowest GT index), degenerate and identical GT boxes."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    N, R = len(Ms), 30000
+    g = torch.Generator().manual_seed(500 + sum(Ms))
+    base = synthetic.matcher_stress_inputs(7, N, R, 300)
+    anchors = base["anchors"]
+    gt_boxes, gt_classes = [], []
+    for n, M in enumerate(Ms):
+        b = base["gt_boxes"][n][:M].clone()
+        if M > 10:
+            b[3] = b[2]                                           # duplicated GT: the lower index must win
+            b[5] = torch.tensor([5000.0, 5000.0, 5100.0, 5100.0]) if n == 0 else b[5]   # touches no anchor
+            b[7, 2:] = b[7, :2]                                   # zero-area GT
+            anchors[n, 11] = b[4]                                 # IoU exactly 1 with GT 4
+            anchors[n, 12] = anchors[n, 11]
+            anchors[n, 13] = torch.tensor([-5000.0, -5000.0, -4000.0, -4900.0])          # far outside the extent
+            anchors[n, 14] = torch.tensor([-100.0, -100.0, 9000.0, 9000.0])              # covers everything
+            anchors[n, 15] = torch.tensor([b[:, 0].min(), b[:, 1].min(), b[:, 0].min() + 1, b[:, 1].min() + 1])
+        gt_boxes.append(b)
+        gt_classes.append(torch.randint(0, 80, (M,), generator=g))
+    want = orc.ground_truth([anchors[n] for n in range(N)], gt_boxes, gt_classes, 80)
+    gt = fsg.ops.PackedGT.from_lists(gt_boxes, gt_classes, cuda)
+    got = fsg.ops.match_anchors(anchors.to(cuda), gt, 80,
+                                want=("matches", "match_labels", "picky_labels", "gt_classes", "mask"))
+    for k in ("matches", "match_labels", "picky_labels", "gt_classes", "mask"):
+        assert_equal_int(got[k], want[k], k)
+    if Ms[0] > 10:
+        assert bool((want["match_labels"][0] == 1).all())        # the untouched GT of image 0 flips every anchor
+
+
+def test_fused_match_crowded_identical_gt(cuda):
+    """100 identical GT boxes (every anchor ties on all of them: index 0 must win) and a row of GT sharing one y
+    interval."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    base = synthetic.matcher_stress_inputs(8, 2, 20000, 100)
+    box = torch.tensor([[300.0, 300.0, 420.0, 380.0]])
+    gt_boxes = [box.repeat(100, 1), base["gt_boxes"][1].clone()]
+    gt_boxes[1][:, 1] = 200.0
+    gt_boxes[1][:, 3] = 260.0
+    gt_classes = base["gt_classes"]
+    want = orc.ground_truth([base["anchors"][n] for n in range(2)], gt_boxes, gt_classes, 80)
+    gt = fsg.ops.PackedGT.from_lists(gt_boxes, gt_classes, cuda)
+    got = fsg.ops.match_anchors(base["anchors"].to(cuda), gt, 80, want=("matches", "match_labels", "mask"))
+    for k in ("matches", "match_labels", "mask"):
+        assert_equal_int(got[k], want[k], k)
+
+
 def test_fused_match_many_gt_chunks(cuda):
     """More GT than one shared-memory chunk (1024)."""
     fsg = _fsg()
