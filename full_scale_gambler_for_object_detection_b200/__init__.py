@@ -20,8 +20,8 @@ library is not built or a tensor is not on a CUDA device.
 from . import _lib, ops  # noqa: F401
 from .anchor_generator import DefaultAnchorGenerator  # noqa: F401
 from .box_regression import Box2BoxTransform  # noqa: F401
-from .fused import (DenseLossConfig, DenseStepPlan, StepResult, dense_train_step,  # noqa: F401
-                    dense_train_step_levels)
+from .fused import (DenseLossConfig, DenseStepPlan, DenseStepPlanLevels, StepResult,  # noqa: F401
+                    dense_train_step, dense_train_step_levels)
 from .gambler import GamblerLoss, get_loss_upper_bound  # noqa: F401
 from .matcher import Matcher  # noqa: F401
 from .nms import batched_nms, nms  # noqa: F401
@@ -34,7 +34,7 @@ from .structures import Boxes, Instances, pairwise_iou  # noqa: F401
 __all__ = [
     "Boxes", "Instances", "pairwise_iou", "Matcher", "Box2BoxTransform", "nms", "batched_nms",
     "RetinaNetDensePath", "GamblerLoss", "get_loss_upper_bound", "dense_train_step", "DenseLossConfig",
-    "StepResult", "DenseStepPlan", "dense_train_step_levels", "ops", "DefaultAnchorGenerator", "detector_postprocess",
+    "StepResult", "DenseStepPlan", "DenseStepPlanLevels", "dense_train_step_levels", "ops", "DefaultAnchorGenerator", "detector_postprocess",
     "find_top_rpn_proposals", "rpn_ground_truth", "subsample_labels", "label_proposals", "fast_rcnn_inference",
     "fast_rcnn_inference_single_image",
 ]

@@ -423,3 +423,68 @@ def dense_train_step_levels(logit_levels, delta_levels, bet_levels, anchors, gt,
     total, scalars, stats, gtc, mask = res[:5]
     return StepResult(total=total, scalars=scalars, stats=stats, per_anchor_loss=list(res[5:]), gt_classes=gtc,
                       mask=mask)
+
+
+class DenseStepPlanLevels:
+    """``DenseStepPlan`` for the head's native layout: pre-allocated outputs and (optionally) one CUDA graph for
+    bets gather -> K1 (2 launches) -> K2 on the per-level conv outputs -> K2 post -> scatter of d/d bets and
+    NAKHW_loss.  Single process (a sharded run uses :func:`dense_train_step_levels` with ``group``).
+
+    ``level_shapes``: [(H, W)] per level; the head outputs are (N, A*K, H, W), (N, A*4, H, W), (N, A, H, W).
+    Outputs (owned by the plan, overwritten by the next run/replay): ``grad_logits`` / ``grad_deltas`` /
+    ``grad_bets`` / ``nakhw_loss`` (lists, per-level layout), ``gt_classes``, ``mask``, ``stats``, ``scalars``."""
+
+    def __init__(self, N, level_shapes, A, K, cfg, device, coeffs=(1.0, 1.0, -1.0), detach_pred=False):
+        assert K == cfg.num_classes
+        self.N, self.A, self.K, self.cfg, self.device = N, A, K, cfg, torch.device(device)
+        self.shapes = [(int(h), int(w)) for h, w in level_shapes]
+        self.R = sum(h * w * A for h, w in self.shapes)
+        self.coeffs = tuple(float(c) for c in coeffs)
+        self.params = cfg.loss_params(*self.coeffs)
+        self.need_gl, self.need_gd = not detach_pred, self.coeffs[1] != 0.0
+        dev, f32 = self.device, torch.float32
+        mk = lambda c: [torch.empty((N, c, h, w), dtype=f32, device=dev) for h, w in self.shapes]
+        self.grad_logits = mk(A * K) if self.need_gl else None
+        self.grad_deltas = mk(A * 4) if self.need_gd else None
+        self.grad_bets, self.nakhw_loss = mk(A), mk(A)
+        self.bets_flat = torch.empty((N, self.R), dtype=f32, device=dev)
+        self.graph, self._static, self._last = None, None, None
+
+    def run(self, logit_levels, delta_levels, bet_levels, anchors, gt):
+        cfg, K = self.cfg, self.K
+        ops.anchor_maps_to_flat([bet_levels], [self.bets_flat])
+        m = ops.match_anchors(anchors, gt, K, cfg.iou_thresholds, cfg.iou_labels, cfg.picky_thresholds, None,
+                              cfg.bbox_reg_weights, want=("gt_classes", "mask", "matched_idx32"),
+                              bets=self.bets_flat, temperature=cfg.gambler_temperature)
+        out = ops.loss_main_levels(logit_levels, m["gt_classes"], self.params, m["stats"], delta_levels=delta_levels,
+                                   anchors=anchors, gt=gt, matched_idx32=m["matched_idx32"], mask=m["mask"],
+                                   bets=self.bets_flat, want_grad_logits=self.need_gl,
+                                   want_grad_deltas=self.need_gd, grad_logits_out=self.grad_logits,
+                                   grad_deltas_out=self.grad_deltas)
+        gb = ops.loss_post(self.bets_flat, m["mask"], out["per_anchor_loss"], self.params, m["stats"], out["scalars"])
+        ops.anchor_maps_to_levels([gb, out["per_anchor_loss"]], None, [self.grad_bets, self.nakhw_loss])
+        self._last = StepResult(total=out["scalars"][8], scalars=out["scalars"], stats=m["stats"],
+                                per_anchor_loss=self.nakhw_loss, gt_classes=m["gt_classes"], mask=m["mask"],
+                                extras={"grad_logits": self.grad_logits, "grad_deltas": self.grad_deltas,
+                                        "grad_bets": self.grad_bets})
+        return self._last
+
+    def capture(self, logit_levels, delta_levels, bet_levels, anchors, gt, warmup=2):
+        """Capture the step reading from exactly these tensors (refresh them in place between replays)."""
+        self._static = (list(logit_levels), list(delta_levels), list(bet_levels), anchors, gt)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.run(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.run(*self._static)      # intermediates live in the graph's private pool
+        return self
+
+    def replay(self):
+        self.graph.replay()
+        _lib.count_launches(6)
+        return self._last

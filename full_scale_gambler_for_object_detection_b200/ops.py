@@ -304,7 +304,7 @@ def loss_main(logits, gt_classes, params, stats, pred_deltas=None, gt_deltas=Non
 
 def loss_main_levels(logit_levels, gt_classes, params, stats, delta_levels=None, gt_deltas=None, anchors=None,
                      gt=None, matched_idx32=None, mask=None, bets=None, want_grad_logits=True,
-                     want_grad_deltas=True, want_weights=False):
+                     want_grad_deltas=True, want_weights=False, grad_logits_out=None, grad_deltas_out=None):
     """The fused main pass on the head's native layout: ``logit_levels`` list[(N, A*K, H, W)],
     ``delta_levels`` list[(N, A*4, H, W)]; gradients come back as lists of the same shapes.  The
     (N,R)-sized arguments are as in :func:`loss_main`.  No permute/cat copy of the logits is made."""
@@ -319,9 +319,9 @@ def loss_main_levels(logit_levels, gt_classes, params, stats, delta_levels=None,
         ds = [d if (d.dtype == torch.float32 and d.is_contiguous()) else _f32c(d) for d in delta_levels]
     out = {}
     if want_grad_logits:
-        out["grad_logits"] = [torch.empty_like(x) for x in xs]
+        out["grad_logits"] = grad_logits_out if grad_logits_out is not None else [torch.empty_like(x) for x in xs]
     if ds is not None and want_grad_deltas:
-        out["grad_deltas"] = [torch.empty_like(d) for d in ds]
+        out["grad_deltas"] = grad_deltas_out if grad_deltas_out is not None else [torch.empty_like(d) for d in ds]
     R = sum(x.shape[2] * x.shape[3] * A for x in xs)
     assert gt_classes.shape == (N, R), "gt_classes %s vs (N=%d, R=%d)" % (tuple(gt_classes.shape), N, R)
     levels = (_lib.HeadLevel * nl)()

@@ -736,3 +736,49 @@ def test_fast_rcnn_inference_single_image(cuda, R, K, spec, sthr, topk):
     assert torch.equal(r.pred_boxes.tensor.cpu(), wb) and torch.equal(r.scores.cpu(), ws)
     assert_equal_int(r.pred_classes, wc, "classes")
     assert_equal_int(rows, wr, "rows")
+
+
+def test_native_layout_plan_and_graph(cuda):
+    """DenseStepPlanLevels: direct run and CUDA-graph replay (with refreshed inputs) equal dense_train_step_levels."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    N, K, A = 2, 80, 3
+    inp = synthetic.train_inputs(61, N, 256, 320, K, logits=False)
+    gen = torch.Generator().manual_seed(62)
+    mk = lambda: ([t.to(cuda) for t in _levels(inp, K, N, gen, 1.0, synthetic.PRIOR_LOGIT)],
+                  [t.to(cuda) for t in _levels(inp, 4, N, gen, 0.1)],
+                  [torch.sigmoid(torch.randn((N, A, h, w), generator=gen) - 4.0).to(cuda) for (h, w) in inp["grids"]])
+    xs, ds, bs = mk()
+    anchors = inp["anchors"].to(cuda)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    cfg = fsg.DenseLossConfig(num_classes=K)
+    plan = fsg.DenseStepPlanLevels(N, inp["grids"], A, K, cfg, cuda)
+
+    def reference(xs, ds, bs):
+        gx = [t.clone().requires_grad_(True) for t in xs]
+        gd = [t.clone().requires_grad_(True) for t in ds]
+        gb = [t.clone().requires_grad_(True) for t in bs]
+        r = fsg.dense_train_step_levels(gx, gd, gb, anchors, gt, cfg)
+        r.total.backward()
+        return r, gx, gd, gb
+
+    def check(res, ref):
+        r, gx, gd, gb = ref
+        assert torch.equal(res.scalars, r.scalars) and torch.equal(res.gt_classes, r.gt_classes)
+        for a, b in zip(plan.grad_logits, gx):
+            assert torch.equal(a, b.grad)
+        for a, b in zip(plan.grad_deltas, gd):
+            assert torch.equal(a, b.grad)
+        for a, b in zip(plan.grad_bets, gb):
+            assert torch.equal(a, b.grad)
+        for a, b in zip(plan.nakhw_loss, r.per_anchor_loss):
+            assert torch.equal(a, b)
+
+    check(plan.run(xs, ds, bs, anchors, gt), reference(xs, ds, bs))
+    plan.capture(xs, ds, bs, anchors, gt)
+    xs2, ds2, bs2 = mk()                       # new values, same storage: refresh in place and replay
+    for dst, src in zip(xs + ds + bs, xs2 + ds2 + bs2):
+        dst.copy_(src)
+    res = plan.replay()
+    torch.cuda.synchronize()
+    check(res, reference(xs, ds, bs))
