@@ -806,10 +806,19 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
   const float wx = h_box_weights ? h_box_weights[0] : 1.f, wy = h_box_weights ? h_box_weights[1] : 1.f;
   const float ww = h_box_weights ? h_box_weights[2] : 1.f, wh = h_box_weights ? h_box_weights[3] : 1.f;
 
-  constexpr int U = 4;
-  dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
-  match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
-                                                        (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
+  // anchors per thread in pass A: 2 for the few-GT training case (more CTAs in flight for a latency-bound pass:
+  // 33.3 vs 35.6 us for K1 on config 2), 4 when the batch is crowded (each staged GT box is reused more)
+  if (sum_M <= (int64_t)N * kSmallM) {
+    constexpr int U = 2;
+    dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
+    match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
+                                                          (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
+  } else {
+    constexpr int U = 4;
+    dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
+    match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
+                                                          (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
+  }
   FSG_LAUNCH_CHECK();
   MatchOut out{matches, match_labels, picky_labels, gt_classes_out, mask_out, (float4*)gt_deltas, matched_idx32};
   dim3 grid_b((unsigned)w.nb, (unsigned)N);
