@@ -224,12 +224,11 @@ def native_layout_step(dev, fsg):
     shapes = [tuple(b.shape[1:]) for b in bs]
 
     def native():
-        bets = ops.anchor_maps_to_flat([bs])[0]
-        m = ops.match_anchors(anchors, gt, K, bets=bets, temperature=cfg.gambler_temperature)
+        m = ops.match_anchors(anchors, gt, K, bet_levels=bs, temperature=cfg.gambler_temperature)
+        ell = [torch.empty_like(b) for b in bs]
         o = ops.loss_main_levels(xs, m["gt_classes"], params, m["stats"], delta_levels=ds, anchors=anchors, gt=gt,
-                                 matched_idx32=m["matched_idx32"], mask=m["mask"], bets=bets)
-        gb = ops.loss_post(bets, m["mask"], o["per_anchor_loss"], params, m["stats"], o["scalars"])
-        return o, ops.anchor_maps_to_levels([gb, o["per_anchor_loss"]], shapes)
+                                 matched_idx32=m["matched_idx32"], mask=m["mask"], bet_levels=bs, ell_levels_out=ell)
+        return o, ops.loss_post_levels(bs, m["mask"], ell, params, m["stats"], o["scalars"])
 
     def permuted():
         x, d = ops.levels_to_flat(xs, K), ops.levels_to_flat(ds, 4)
@@ -270,7 +269,7 @@ def native_layout_step(dev, fsg):
     step_bytes = (8 * K + 76) * N * R
     return {"anchors_per_s": N * R / (ms_n * 1e-3), "ms_per_step": ms_n,
             "step_hbm_frac": step_bytes / (ms_n * 1e-3) / 1e9 / hbm,
-            "launches": "bets gather, K1 x2, K2 native, K2 post, scatter (CUDA graph)",
+            "launches": "K1 x2, K2 native, K2 post native (CUDA graph)",
             "permute_cat_flow_ms_per_step": ms_p, "speedup_vs_permute_cat_flow": ms_p / ms_n}
 
 

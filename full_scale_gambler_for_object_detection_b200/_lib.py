@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FSG_DENSE_LIB") or os.path.join(_HERE, "libfsg_dense.so")  # override: kernel experiments
-ABI_VERSION = 2
+ABI_VERSION = 3
 STATS_HEADER = 2
 SCALARS_HEADER = 10
 
@@ -44,7 +44,19 @@ class HeadLevel(ctypes.Structure):
     """``struct fsg_head_level``."""
 
     _fields_ = [("logits", c_ptr), ("grad_logits", c_ptr), ("pred_deltas", c_ptr), ("grad_deltas", c_ptr),
-                ("H", c_i32), ("W", c_i32)]
+                ("bets", c_ptr), ("per_anchor_loss", c_ptr), ("H", c_i32), ("W", c_i32)]
+
+
+class BetLevels(ctypes.Structure):
+    """``struct fsg_bet_levels``."""
+
+    _fields_ = [("bets", c_ptr * 8), ("H", c_i32 * 8), ("W", c_i32 * 8), ("num_levels", c_i32), ("A", c_i32)]
+
+
+class PostLevel(ctypes.Structure):
+    """``struct fsg_post_level``."""
+
+    _fields_ = [("bets", c_ptr), ("per_anchor_loss", c_ptr), ("grad_bets", c_ptr), ("H", c_i32), ("W", c_i32)]
 
 
 class AnchorLevel(ctypes.Structure):
@@ -73,7 +85,7 @@ PROTOTYPES = {
     "fsg_match_anchors": (
         c_i32,
         [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr,
-         c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr,
+         c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(BetLevels), c_f32, c_ptr,
          ctypes.POINTER(PeerCtx), c_ptr, c_size, c_ptr],
     ),
     "fsg_box2box_get_deltas": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
@@ -92,6 +104,8 @@ PROTOTYPES = {
         [ctypes.POINTER(HeadLevel), c_i32, c_i32, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
          c_i32, c_i64, ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
     ),
+    "fsg_loss_post_levels": (c_i32, [ctypes.POINTER(PostLevel), c_i32, c_i32, c_ptr, c_i32, c_i64,
+                                     ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr]),
     "fsg_loss_post": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i64, ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr, c_ptr]),
     "fsg_scale_inplace": (c_i32, [c_ptr, c_i64, c_ptr, c_f32, c_ptr]),
     "fsg_nms_workspace_bytes": (c_size, [c_i64]),

@@ -32,6 +32,8 @@ struct LevelTable {
   float* grad_logits[kLvMax];
   const float* pred_deltas[kLvMax];
   float* grad_deltas[kLvMax];
+  const float* bets[kLvMax];  // per-level (N, A, H, W) betting maps / NAKHW_loss, or NULL: the flat (N, R) arrays
+  float* ell[kLvMax];
   int64_t off[kLvMax + 1];   // first anchor index of the level
   int HW[kLvMax];
   int vec[kLvMax];           // hw positions per thread (2 when every plane of the level is 8-byte aligned)
@@ -98,9 +100,10 @@ __device__ __forceinline__ void level_body(const LevelLossArgs& A, const LevelTa
     const int64_t o = o0 + (int64_t)v * LT.A;
     cls[v] = in ? (int)A.gt_classes[o] : -1;
     w_hat[v] = 0.f;
-    if (A.bets && in) {
+    if ((A.bets || LT.bets[l]) && in) {
       const float m = A.mask ? (float)A.mask[o] : 1.f;
-      const float w = __fadd_rn(__fmul_rn(A.bets[o], m), A.T);   // gambler_heads.py:569,304
+      const float b = LT.bets[l] ? LT.bets[l][((int64_t)n * LT.A + a) * HW + hw0 + v] : A.bets[o];
+      const float w = __fadd_rn(__fmul_rn(b, m), A.T);           // gambler_heads.py:569,304
       w_hat[v] = w * inv_S;                                      // :308-311
     }
     valid[v] = cls[v] >= 0;
@@ -175,7 +178,8 @@ __device__ __forceinline__ void level_body(const LevelLossArgs& A, const LevelTa
     }
     const float lf = valid[v] ? sum_f[v] : 0.f;                                   // gambler_heads.py:554-555
     const float lg = (A.gmode == FSG_CLS_FOCAL) ? lf : (valid[v] ? sum_b[v] : 0.f);
-    if (A.ell) A.ell[o] = lg;
+    if (LT.ell[l]) LT.ell[l][((int64_t)n * LT.A + a) * HW + hw0 + v] = lg;
+    else if (A.ell) A.ell[o] = lg;
     if (A.wout) A.wout[o] = w_hat[v];
     S.cls += lf;
     S.wl = fmaf(wg[v], lg, S.wl);
@@ -251,6 +255,52 @@ __global__ void __launch_bounds__(kLvBlock, LV_MINB) loss_main_levels_kernel(con
                         A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam);
 }
 
+// d(c_gam * G)/d bets on the gambler's own layout (see fsg_loss_post for the formula): thread = one (n, a, hw).
+struct PostTable {
+  const float* bets[kLvMax];
+  const float* ell[kLvMax];
+  float* grad[kLvMax];
+  int64_t off[kLvMax + 1];
+  int HW[kLvMax];
+  int tile_base[kLvMax + 1];   // tiles of 256 hw positions, A slots each
+  int num_levels, A;
+};
+
+__global__ void __launch_bounds__(256) loss_post_levels_kernel(const PostTable PT, const int64_t* __restrict__ mask,
+                                                               int64_t R, float T, float ggamma, int nmode, float c_gam,
+                                                               const double* __restrict__ stats,
+                                                               const double* __restrict__ scalars) {
+  const int n = blockIdx.y;
+  int l = 0;
+  while (l + 1 < PT.num_levels && (int)blockIdx.x >= PT.tile_base[l + 1]) ++l;
+  const int local = (int)blockIdx.x - PT.tile_base[l];
+  const int chunks = (PT.HW[l] + 255) / 256;
+  const int a = local / chunks;
+  const int hw = (local - a * chunks) * 256 + threadIdx.x;
+  if (hw >= PT.HW[l]) return;
+  float inv_S = 1.f, Asum = 0.f;
+  if (nmode != FSG_NORM_NONE) {
+    const double S = (nmode == FSG_NORM_IMAGE) ? stats[FSG_STATS_HEADER + n] : stats[1];
+    const double Av = (nmode == FSG_NORM_IMAGE) ? scalars[FSG_SCALARS_HEADER + n] : scalars[2];
+    inv_S = __frcp_rn((float)S);
+    Asum = (float)Av;
+  }
+  const int64_t i = ((int64_t)n * PT.A + a) * PT.HW[l] + hw;
+  const float m = mask ? (float)mask[(int64_t)n * R + PT.off[l] + (int64_t)hw * PT.A + a] : 1.f;
+  const float b = PT.bets[l][i], e = PT.ell[l][i];
+  const float w = __fadd_rn(__fmul_rn(b, m), T);
+  float g;
+  if (nmode == FSG_NORM_NONE) {
+    const float pw = (ggamma == 1.f) ? 1.f : powf(w, ggamma - 1.f);
+    g = -m * ggamma * pw * e;
+  } else {
+    const float w_hat = w * inv_S;
+    const float pw = (ggamma == 1.f) ? 1.f : powf(w_hat, ggamma - 1.f);
+    g = -(m * inv_S) * ggamma * (pw * e - Asum);
+  }
+  PT.grad[l][i] = c_gam * g;
+}
+
 static int build_table(const fsg_head_level* h, int num_levels, int A, LevelTable* t, int64_t* R_out) {
   if (!h || num_levels <= 0 || num_levels > kLvMax || A <= 0) return FSG_ERR_INVALID_ARG;
   t->num_levels = num_levels;
@@ -264,6 +314,7 @@ static int build_table(const fsg_head_level* h, int num_levels, int A, LevelTabl
       if (hw > (1 << 30)) return FSG_ERR_UNSUPPORTED;
       t->logits[l] = h[l].logits; t->grad_logits[l] = h[l].grad_logits;
       t->pred_deltas[l] = h[l].pred_deltas; t->grad_deltas[l] = h[l].grad_deltas;
+      t->bets[l] = h[l].bets; t->ell[l] = h[l].per_anchor_loss;
       // two hw per thread when every (channel) plane of the level starts 8-byte aligned
       const bool al8 = (hw % 2 == 0) && !(((uintptr_t)h[l].logits | (uintptr_t)h[l].grad_logits |
                                            (uintptr_t)h[l].pred_deltas | (uintptr_t)h[l].grad_deltas) & 7);
@@ -276,6 +327,7 @@ static int build_table(const fsg_head_level* h, int num_levels, int A, LevelTabl
       tiles += A * t->chunks[l];
     } else {
       t->logits[l] = nullptr; t->grad_logits[l] = nullptr; t->pred_deltas[l] = nullptr; t->grad_deltas[l] = nullptr;
+      t->bets[l] = nullptr; t->ell[l] = nullptr;
       t->off[l] = off; t->HW[l] = 0; t->vec[l] = 1; t->chunks[l] = 1; t->tile_base[l] = tiles;
     }
   }
@@ -339,7 +391,11 @@ extern "C" int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_leve
     any_pred = any_pred || t.pred_deltas[l];
   }
   if (any_pred && !gt_deltas && (!anchors || !gt_boxes || !gt_offsets || !matched_idx32)) return FSG_ERR_INVALID_ARG;
-  if (!bets && (hp->c_gam != 0.f || weights_out)) return FSG_ERR_INVALID_ARG;
+  int native_bets = 0;
+  for (int l = 0; l < num_levels; ++l) native_bets += t.bets[l] ? 1 : 0;
+  if (native_bets != 0 && (native_bets != num_levels || bets)) return FSG_ERR_INVALID_ARG;   // all levels, or flat
+  const bool have_bets = bets || native_bets;
+  if (!have_bets && (hp->c_gam != 0.f || weights_out)) return FSG_ERR_INVALID_ARG;
   if (hp->gambler_mode != FSG_CLS_FOCAL && hp->gambler_mode != FSG_CLS_SIGMOID) return FSG_ERR_INVALID_ARG;
   if (hp->norm_mode < FSG_NORM_NONE || hp->norm_mode > FSG_NORM_BATCH) return FSG_ERR_INVALID_ARG;
   const size_t need = 16 + align_up(sizeof(float) * kPartialStride * (size_t)N * t.tile_base[kLvMax], 16);
@@ -355,7 +411,7 @@ extern "C" int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_leve
   a.a0 = hp->focal_alpha >= 0.f ? 1.f - hp->focal_alpha : 1.f;
   a.a1 = hp->focal_alpha >= 0.f ? hp->focal_alpha : 1.f;
   a.gamma = hp->focal_gamma; a.beta = hp->smooth_l1_beta; a.T = hp->temperature; a.ggamma = hp->gambler_gamma;
-  a.gmode = hp->gambler_mode; a.nmode = bets ? hp->norm_mode : FSG_NORM_NONE;
+  a.gmode = hp->gambler_mode; a.nmode = have_bets ? hp->norm_mode : FSG_NORM_NONE;
   a.c_cls = hp->c_cls; a.c_reg = hp->c_reg; a.c_gam = hp->c_gam;
   a.wx = hp->box_weights[0]; a.wy = hp->box_weights[1]; a.ww = hp->box_weights[2]; a.wh = hp->box_weights[3];
   a.stats = stats; a.ell = per_anchor_loss; a.wout = weights_out;
@@ -369,6 +425,39 @@ extern "C" int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_leve
   for (int l = 0; l < num_levels; ++l)
     if (write && !t.grad_logits[l]) return FSG_ERR_INVALID_ARG;   // gradients for all levels or for none
   launch_levels(a.K, fast, write, grid, s, a, t);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+extern "C" int fsg_loss_post_levels(const fsg_post_level* h_levels, int num_levels, int A, const int64_t* mask, int N,
+                                    int64_t R, const fsg_loss_params* hp, const double* stats, const double* scalars,
+                                    fsg_stream_t stream) {
+  if (!hp || !h_levels || num_levels <= 0 || num_levels > kLvMax || A <= 0 || N <= 0 || !stats || !scalars)
+    return FSG_ERR_INVALID_ARG;
+  if (N > 65535) return FSG_ERR_UNSUPPORTED;
+  PostTable t;
+  int64_t off = 0;
+  int tiles = 0;
+  for (int l = 0; l < kLvMax; ++l) {
+    t.off[l] = off;
+    t.tile_base[l] = tiles;
+    if (l < num_levels) {
+      const int64_t hw = (int64_t)h_levels[l].H * h_levels[l].W;
+      if (h_levels[l].H <= 0 || h_levels[l].W <= 0 || hw > (1 << 30)) return FSG_ERR_INVALID_ARG;
+      if (!h_levels[l].bets || !h_levels[l].per_anchor_loss || !h_levels[l].grad_bets) return FSG_ERR_INVALID_ARG;
+      t.bets[l] = h_levels[l].bets; t.ell[l] = h_levels[l].per_anchor_loss; t.grad[l] = h_levels[l].grad_bets;
+      t.HW[l] = (int)hw;
+      off += hw * A;
+      tiles += A * (int)ceil_div(hw, 256);
+    } else {
+      t.bets[l] = nullptr; t.ell[l] = nullptr; t.grad[l] = nullptr; t.HW[l] = 0;
+    }
+  }
+  t.off[kLvMax] = off; t.tile_base[kLvMax] = tiles;
+  t.num_levels = num_levels; t.A = A;
+  if (off != R) return FSG_ERR_INVALID_ARG;
+  loss_post_levels_kernel<<<dim3((unsigned)tiles, (unsigned)N), 256, 0, (cudaStream_t)stream>>>(
+      t, mask, R, hp->temperature, hp->gambler_gamma, hp->norm_mode, hp->c_gam, stats, scalars);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

@@ -313,6 +313,22 @@ struct MatchOut {
   int32_t* matched_idx32;
 };
 
+// the gambler's betting maps in their own per-level (N, A, H, W) layout (read in place by pass B)
+struct BetLevels {
+  const float* ptr[FSG_MAX_LEVELS];
+  int64_t off[FSG_MAX_LEVELS + 1];
+  int HW[FSG_MAX_LEVELS];
+  int A, num_levels;
+};
+__device__ __forceinline__ float bet_at(const BetLevels& lv, int n, int64_t r) {
+  int l = 0;
+  while (l + 1 < lv.num_levels && r >= lv.off[l + 1]) ++l;
+  const int local = (int)(r - lv.off[l]);
+  const int hw = local / lv.A;
+  const int a = local - hw * lv.A;
+  return lv.ptr[l][((int64_t)n * lv.A + a) * lv.HW[l] + hw];
+}
+
 constexpr int kPassBU = 4;  // anchors per thread in pass B
 constexpr int kWarpsPerBlock = kMatchBlock / 32;
 
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     const int32_t* __restrict__ best_idx, const unsigned* __restrict__ gt_max, MatchOut out,
     const float* __restrict__ bets, float temperature, int* __restrict__ part_cnt,
     float* __restrict__ part_s, double* __restrict__ img_cnt, unsigned* __restrict__ done_counter,
-    double* __restrict__ stats, const fsg_peer_ctx peer, const BandsReg br, const BandsReg pbr) {
+    double* __restrict__ stats, const fsg_peer_ctx peer, const BandsReg br, const BandsReg pbr, const BetLevels lv) {
   constexpr int U = kPassBU;
   __shared__ __align__(16) float4 s_gt[kGtChunk];
   __shared__ float s_area[kGtChunk];
@@ -520,6 +536,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     if (o_idx32) out.matched_idx32[o] = id;
     fg += (cls >= 0 && cls != num_classes) ? 1 : 0;
     if (has_bets) w_part += __fadd_rn(__fmul_rn(bets[o], (float)msk), temperature);  // gambler_heads.py:569,304
+    else if (lv.num_levels > 0 && msk != 0) w_part += __fmul_rn(bet_at(lv, n, r), (float)msk);  // + R*T at the fold
   }
 
   if (stats == nullptr) return;
@@ -564,6 +581,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
   if (tid == 0) {
     double c = 0.0, sacc = 0.0;
     for (int w = 0; w < kWarpsPerBlock; ++w) { c += s_tc[w]; sacc += s_ts[w]; }
+    if (lv.num_levels > 0) sacc += (double)R * (double)temperature;   // per-level bets: S[n] = R*T + sum bet*mask
     stats[FSG_STATS_HEADER + n] = sacc;
     img_cnt[n] = c;
     done_counter[1 + n] = 0u;   // self-reset for the next call
@@ -763,10 +781,33 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
                                  int num_picky_thresholds,
                                  const float* h_box_weights, int64_t* matches, int8_t* match_labels,
                                  int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
-                                 float* gt_deltas, int32_t* matched_idx32, const float* bets, float temperature,
+                                 float* gt_deltas, int32_t* matched_idx32, const float* bets,
+                                 const fsg_bet_levels* h_bet_levels, float temperature,
                                  double* stats, const fsg_peer_ctx* h_peer, void* workspace,
                                  size_t workspace_bytes, fsg_stream_t stream) {
   if (N <= 0 || R < 0 || sum_M < 0 || !gt_offsets) return FSG_ERR_INVALID_ARG;
+  BetLevels lv = {};
+  if (h_bet_levels) {
+    if (bets || !stats || h_bet_levels->num_levels <= 0 || h_bet_levels->num_levels > FSG_MAX_LEVELS ||
+        h_bet_levels->A <= 0)
+      return FSG_ERR_INVALID_ARG;
+    int64_t off = 0;
+    lv.A = h_bet_levels->A;
+    lv.num_levels = h_bet_levels->num_levels;
+    for (int l = 0; l < FSG_MAX_LEVELS; ++l) {
+      lv.off[l] = off;
+      if (l < lv.num_levels) {
+        const int64_t hw = (int64_t)h_bet_levels->H[l] * h_bet_levels->W[l];
+        if (h_bet_levels->H[l] < 0 || h_bet_levels->W[l] < 0 || hw > (1 << 30) || (hw > 0 && !h_bet_levels->bets[l]))
+          return FSG_ERR_INVALID_ARG;
+        lv.ptr[l] = h_bet_levels->bets[l];
+        lv.HW[l] = (int)hw;
+        off += hw * lv.A;
+      }
+    }
+    lv.off[FSG_MAX_LEVELS] = off;
+    if (off != R) return FSG_ERR_INVALID_ARG;
+  }
   if (R == 0) return FSG_OK;
   if (!anchors || (sum_M > 0 && !gt_boxes)) return FSG_ERR_INVALID_ARG;
   if (N > 65535) return FSG_ERR_UNSUPPORTED;
@@ -827,7 +868,7 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
       num_classes, mb, pmb, allow_lq ? 1 : 0, wx, wy, ww, wh, bval, bidx, gtmax, out, bets, temperature,
       (int*)(ws + w.off_pcnt), (float*)(ws + w.off_ps), (double*)(ws + w.off_icnt), counter, stats, peer,
       make_bands_reg(mb),
-      make_bands_reg(pmb));
+      make_bands_reg(pmb), lv);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

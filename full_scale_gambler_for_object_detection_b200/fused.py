@@ -170,7 +170,7 @@ class DenseStepPlan:
         _lib.check(L.fsg_match_anchors(
             P(anchors), R, a_stride, P(gt.boxes), P(gt.classes), P(gt.offsets), N, gt.total, cfg.num_classes,
             self._thr, self._lab, len(cfg.iou_thresholds), 1, self._pthr, self._lab, len(cfg.picky_thresholds),
-            self._bw, None, None, None, P(self.gt_classes), P(self.mask), None, P(self.matched), P(bets),
+            self._bw, None, None, None, P(self.gt_classes), P(self.mask), None, P(self.matched), P(bets), None,
             float(cfg.gambler_temperature), P(self.stats), self.peer.ctx if self.peer is not None else None,
             P(self.ws_match), self.ws_match.numel(), _lib.stream()))
         _lib.count_launches(2)
@@ -368,24 +368,22 @@ class _FusedStepLevels(torch.autograd.Function):
         ds = [f32c(t.detach()) for t in levels[L:2 * L]]
         bs = [f32c(t.detach()) for t in levels[2 * L:]]
         params = cfg.loss_params(c_cls, c_reg, c_gam)
-        bets = ops.anchor_maps_to_flat([bs])[0]
         m = ops.match_anchors(anchors, gt, cfg.num_classes, cfg.iou_thresholds, cfg.iou_labels,
                               cfg.picky_thresholds, None, cfg.bbox_reg_weights,
-                              want=("gt_classes", "mask", "matched_idx32"), bets=bets,
+                              want=("gt_classes", "mask", "matched_idx32"), bet_levels=bs,
                               temperature=cfg.gambler_temperature)
         stats = m["stats"]
         if group is not None:
             sharded.all_reduce_stats(stats, group)
         need_gl, need_gd = not detach_pred, c_reg != 0.0
+        ell_levels = [torch.empty_like(b) for b in bs]
         out = ops.loss_main_levels(xs, m["gt_classes"], params, stats, delta_levels=ds, anchors=anchors, gt=gt,
-                                   matched_idx32=m["matched_idx32"], mask=m["mask"], bets=bets,
-                                   want_grad_logits=need_gl, want_grad_deltas=need_gd)
+                                   matched_idx32=m["matched_idx32"], mask=m["mask"], bet_levels=bs,
+                                   ell_levels_out=ell_levels, want_grad_logits=need_gl, want_grad_deltas=need_gd)
         scalars = out["scalars"]
         if group is not None and cfg.norm_mode == _lib.NORM_BATCH:
             sharded.all_reduce_batch_weighted_sum(scalars, group)
-        gb = ops.loss_post(bets, m["mask"], out["per_anchor_loss"], params, stats, scalars)
-        shapes = [tuple(b.shape[1:]) for b in bs]
-        gb_levels, ell_levels = ops.anchor_maps_to_levels([gb, out["per_anchor_loss"]], shapes)
+        gb_levels = ops.loss_post_levels(bs, m["mask"], ell_levels, params, stats, scalars)
         saved = (out["grad_logits"] if need_gl else []) + (out["grad_deltas"] if need_gd else []) + gb_levels
         ctx.save_for_backward(*saved)
         ctx.cfg_ = (L, need_gl, need_gd)
@@ -414,7 +412,7 @@ def dense_train_step_levels(logit_levels, delta_levels, bet_levels, anchors, gt,
     gambler's betting maps); anchors (R,4) / (N,R,4) and gt as in :func:`dense_train_step`.
     Returns a StepResult whose ``per_anchor_loss`` is the list of (N, A, H, W) NAKHW_loss maps
     (gambler_heads.py:218); gradients arrive on the per-level inputs in their own layout.
-    Launches: bets gather, K1 (2), K2 on the native layout, K2 post, scatter of d/d bets + NAKHW_loss."""
+    Launches: K1 (2), K2 on the native layout, K2 post on the native layout -- no layout adapter of any size."""
     L = len(logit_levels)
     assert len(delta_levels) == L and len(bet_levels) == L
     xs = [t.detach() for t in logit_levels] if detach_pred else list(logit_levels)
@@ -427,8 +425,8 @@ def dense_train_step_levels(logit_levels, delta_levels, bet_levels, anchors, gt,
 
 class DenseStepPlanLevels:
     """``DenseStepPlan`` for the head's native layout: pre-allocated outputs and (optionally) one CUDA graph for
-    bets gather -> K1 (2 launches) -> K2 on the per-level conv outputs -> K2 post -> scatter of d/d bets and
-    NAKHW_loss.  Single process (a sharded run uses :func:`dense_train_step_levels` with ``group``).
+    K1 (2 launches, betting maps read in place) -> K2 on the per-level conv outputs -> K2 post on the per-level
+    maps.  Single process (a sharded run uses :func:`dense_train_step_levels` with ``group``).
 
     ``level_shapes``: [(H, W)] per level; the head outputs are (N, A*K, H, W), (N, A*4, H, W), (N, A, H, W).
     Outputs (owned by the plan, overwritten by the next run/replay): ``grad_logits`` / ``grad_deltas`` /
@@ -447,22 +445,20 @@ class DenseStepPlanLevels:
         self.grad_logits = mk(A * K) if self.need_gl else None
         self.grad_deltas = mk(A * 4) if self.need_gd else None
         self.grad_bets, self.nakhw_loss = mk(A), mk(A)
-        self.bets_flat = torch.empty((N, self.R), dtype=f32, device=dev)
         self.graph, self._static, self._last = None, None, None
 
     def run(self, logit_levels, delta_levels, bet_levels, anchors, gt):
         cfg, K = self.cfg, self.K
-        ops.anchor_maps_to_flat([bet_levels], [self.bets_flat])
         m = ops.match_anchors(anchors, gt, K, cfg.iou_thresholds, cfg.iou_labels, cfg.picky_thresholds, None,
                               cfg.bbox_reg_weights, want=("gt_classes", "mask", "matched_idx32"),
-                              bets=self.bets_flat, temperature=cfg.gambler_temperature)
+                              bet_levels=bet_levels, temperature=cfg.gambler_temperature)
         out = ops.loss_main_levels(logit_levels, m["gt_classes"], self.params, m["stats"], delta_levels=delta_levels,
                                    anchors=anchors, gt=gt, matched_idx32=m["matched_idx32"], mask=m["mask"],
-                                   bets=self.bets_flat, want_grad_logits=self.need_gl,
-                                   want_grad_deltas=self.need_gd, grad_logits_out=self.grad_logits,
-                                   grad_deltas_out=self.grad_deltas)
-        gb = ops.loss_post(self.bets_flat, m["mask"], out["per_anchor_loss"], self.params, m["stats"], out["scalars"])
-        ops.anchor_maps_to_levels([gb, out["per_anchor_loss"]], None, [self.grad_bets, self.nakhw_loss])
+                                   bet_levels=bet_levels, ell_levels_out=self.nakhw_loss,
+                                   want_grad_logits=self.need_gl, want_grad_deltas=self.need_gd,
+                                   grad_logits_out=self.grad_logits, grad_deltas_out=self.grad_deltas)
+        ops.loss_post_levels(bet_levels, m["mask"], self.nakhw_loss, self.params, m["stats"], out["scalars"],
+                             out=self.grad_bets)
         self._last = StepResult(total=out["scalars"][8], scalars=out["scalars"], stats=m["stats"],
                                 per_anchor_loss=self.nakhw_loss, gt_classes=m["gt_classes"], mask=m["mask"],
                                 extras={"grad_logits": self.grad_logits, "grad_deltas": self.grad_deltas,
@@ -486,5 +482,5 @@ class DenseStepPlanLevels:
 
     def replay(self):
         self.graph.replay()
-        _lib.count_launches(6)
+        _lib.count_launches(4)
         return self._last

@@ -87,12 +87,13 @@ class PackedGT:
 def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1, 1),
                   picky_thresholds=(0.4, 0.9), picky_labels=None, box_weights=(1.0, 1.0, 1.0, 1.0),
                   want=("gt_classes", "mask", "matched_idx32"), bets=None, temperature=0.0,
-                  allow_low_quality_matches=True):
+                  allow_low_quality_matches=True, bet_levels=None):
     """Fused IoU + Matcher(s) + GT assignment (retinanet.py:339-363, 400-425) for a batch.
 
     anchors: (R,4) shared by all images or (N,R,4) per image.  gt: PackedGT.
     want: subset of {matches, match_labels, picky_labels, gt_classes, mask, gt_deltas, matched_idx32}.
     bets (N,R): when given, the loss pre-pass is fused in and ``stats`` is returned too.
+    bet_levels list[(N, A, H, W)]: the same with the betting maps read in their own layout (no flattened copy).
     Returns a dict of the requested (N,R[,4]) tensors (+ "stats").
     """
     a = _f32c(anchors)
@@ -118,7 +119,12 @@ def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1
     if bets is not None:
         bets = _f32c(bets)
         assert bets.shape == (N, R)
-    if bets is not None or "stats" in want:
+    lv = None
+    if bet_levels is not None:
+        assert bets is None
+        lv = bet_levels_struct(bet_levels)
+        assert sum(b.shape[1] * b.shape[2] * b.shape[3] for b in bet_levels) == R and bet_levels[0].shape[0] == N
+    if bets is not None or lv is not None or "stats" in want:
         stats = torch.empty(_lib.STATS_HEADER + N, dtype=torch.float64, device=dev)
     L = lib()
     ws = _ws(L.fsg_match_workspace_bytes(N, R, gt.total), dev)
@@ -131,12 +137,23 @@ def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1
             len(picky_thresholds) if picky_thresholds is not None else 0,
             host_f32(box_weights), ptr(out.get("matches")), ptr(out.get("match_labels")),
             ptr(out.get("picky_labels")), ptr(out.get("gt_classes")), ptr(out.get("mask")),
-            ptr(out.get("gt_deltas")), ptr(out.get("matched_idx32")), ptr(bets), float(temperature), ptr(stats),
+            ptr(out.get("gt_deltas")), ptr(out.get("matched_idx32")), ptr(bets), lv, float(temperature), ptr(stats),
             None, ptr(ws), ws.numel(), stream()))
         count_launches(2)
     if stats is not None:
         out["stats"] = stats
     return out
+
+
+def bet_levels_struct(bet_levels):
+    """list[(N, A, H, W)] contiguous fp32 CUDA tensors -> ``fsg_bet_levels`` (keeps no reference: the caller must)."""
+    lv = _lib.BetLevels()
+    lv.num_levels, lv.A = len(bet_levels), bet_levels[0].shape[1]
+    for i, b in enumerate(bet_levels):
+        assert b.dtype == torch.float32 and b.shape[1] == lv.A
+        lv.bets[i] = ptr(b)
+        lv.H[i], lv.W[i] = b.shape[2], b.shape[3]
+    return lv
 
 
 def get_deltas(src_boxes, target_boxes, weights):
@@ -304,10 +321,13 @@ def loss_main(logits, gt_classes, params, stats, pred_deltas=None, gt_deltas=Non
 
 def loss_main_levels(logit_levels, gt_classes, params, stats, delta_levels=None, gt_deltas=None, anchors=None,
                      gt=None, matched_idx32=None, mask=None, bets=None, want_grad_logits=True,
-                     want_grad_deltas=True, want_weights=False, grad_logits_out=None, grad_deltas_out=None):
+                     want_grad_deltas=True, want_weights=False, grad_logits_out=None, grad_deltas_out=None,
+                     bet_levels=None, ell_levels_out=None):
     """The fused main pass on the head's native layout: ``logit_levels`` list[(N, A*K, H, W)],
     ``delta_levels`` list[(N, A*4, H, W)]; gradients come back as lists of the same shapes.  The
-    (N,R)-sized arguments are as in :func:`loss_main`.  No permute/cat copy of the logits is made."""
+    (N,R)-sized arguments are as in :func:`loss_main`.  No permute/cat copy of the logits is made.
+    bet_levels list[(N, A, H, W)] (instead of flat ``bets``) and ell_levels_out (same shapes; the NAKHW_loss is then
+    written there and ``per_anchor_loss`` in the result is that list) keep the gambler side in its own layout too."""
     K = params.num_classes
     N = logit_levels[0].shape[0]
     A = logit_levels[0].shape[1] // K
@@ -334,7 +354,14 @@ def loss_main_levels(logit_levels, gt_classes, params, stats, delta_levels=None,
         levels[i].H, levels[i].W = x.shape[2], x.shape[3]
         if ds is not None:
             assert ds[i].shape == (N, A * 4, x.shape[2], x.shape[3])
-    out["per_anchor_loss"] = torch.empty((N, R), dtype=torch.float32, device=dev)
+        if bet_levels is not None:
+            assert bets is None and bet_levels[i].shape == (N, A, x.shape[2], x.shape[3])
+            levels[i].bets = ptr(bet_levels[i])
+        if ell_levels_out is not None:
+            assert ell_levels_out[i].shape == (N, A, x.shape[2], x.shape[3])
+            levels[i].per_anchor_loss = ptr(ell_levels_out[i])
+    out["per_anchor_loss"] = (ell_levels_out if ell_levels_out is not None
+                              else torch.empty((N, R), dtype=torch.float32, device=dev))
     if want_weights:
         out["weights"] = torch.empty((N, R), dtype=torch.float32, device=dev)
     scalars = torch.empty(_lib.SCALARS_HEADER + N, dtype=torch.float64, device=dev)
@@ -348,8 +375,27 @@ def loss_main_levels(logit_levels, gt_classes, params, stats, delta_levels=None,
     check(L.fsg_loss_main_levels(
         levels, nl, A, ptr(gt_deltas), a_ptr, a_stride, ptr(gt.boxes) if gt is not None else None,
         ptr(gt.offsets) if gt is not None else None, ptr(matched_idx32), ptr(gt_classes), ptr(mask), ptr(bets),
-        N, R, params, ptr(stats), ptr(out["per_anchor_loss"]), ptr(out.get("weights")), ptr(scalars), ptr(ws),
-        ws.numel(), stream()))
+        N, R, params, ptr(stats), ptr(out["per_anchor_loss"]) if ell_levels_out is None else None,
+        ptr(out.get("weights")), ptr(scalars), ptr(ws), ws.numel(), stream()))
+    count_launches(1)
+    return out
+
+
+def loss_post_levels(bet_levels, mask, ell_levels, params, stats, scalars, out=None):
+    """d(c_gam * gambler_loss)/d bets with everything in the gambler's per-level (N, A, H, W) layout; mask is the
+    flat (N, R) K1 output.  -> list of gradients (same shapes)."""
+    nl = len(bet_levels)
+    N, A = bet_levels[0].shape[0], bet_levels[0].shape[1]
+    if out is None:
+        out = [torch.empty_like(b) for b in bet_levels]
+    lv = (_lib.PostLevel * nl)()
+    R = 0
+    for i, (b, e, g) in enumerate(zip(bet_levels, ell_levels, out)):
+        assert b.shape == e.shape == g.shape and b.dtype == torch.float32
+        lv[i].bets, lv[i].per_anchor_loss, lv[i].grad_bets = ptr(b), ptr(e), ptr(g)
+        lv[i].H, lv[i].W = b.shape[2], b.shape[3]
+        R += A * b.shape[2] * b.shape[3]
+    check(lib().fsg_loss_post_levels(lv, nl, A, ptr(mask), N, R, params, ptr(stats), ptr(scalars), stream()))
     count_launches(1)
     return out
 

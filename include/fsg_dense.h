@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FSG_ABI_VERSION 2
+#define FSG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FSG_API __attribute__((visibility("default")))
@@ -92,6 +92,15 @@ typedef struct fsg_peer_ctx {
   int32_t rank, world; /* world <= 8 */
 } fsg_peer_ctx;
 
+/* The gambler's betting maps in their own layout (level l: (N, A, H_l, W_l), gambler_heads.py:463-470), for the
+ * entry points that can read them in place instead of a flattened (N, R) copy. */
+#define FSG_MAX_LEVELS 8
+typedef struct fsg_bet_levels {
+  const float* bets[FSG_MAX_LEVELS];
+  int32_t H[FSG_MAX_LEVELS], W[FSG_MAX_LEVELS];
+  int32_t num_levels, A;
+} fsg_bet_levels;
+
 /* Fused IoU + Matcher(s) + GT assignment for a batch of images, never materialising the
  * (M, R) matrix.  Replaces, per image, retinanet.py:339-363 and :400-425:
  *   pairwise_iou -> Matcher(thresholds) [-> picky Matcher(picky_thresholds)] ->
@@ -110,7 +119,8 @@ typedef struct fsg_peer_ctx {
  *   mask_out int64 (1 iff picky label == 1; image without GT -> all K, retinanet.py:425),
  *   gt_deltas (N,R,4) fp32 (zeros for an image without GT),
  *   matched_idx32 (N,R) int32 copy of matches for the loss kernel.
- * Optional fused loss pre-pass (bets != NULL): stats as defined by fsg_loss_prepass.
+ * Optional fused loss pre-pass (bets != NULL, or h_bet_levels != NULL for per-level betting maps read in place --
+ * not both): stats as defined by fsg_loss_prepass.
  * workspace: fsg_match_workspace_bytes(N, R, sum_M) bytes, 16-byte aligned. */
 FSG_API size_t fsg_match_workspace_bytes(int N, int64_t R, int64_t sum_M);
 FSG_API int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor_image_stride,
@@ -121,6 +131,7 @@ FSG_API int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor_im
                       int num_picky_thresholds, const float* h_box_weights /* 4 */, int64_t* matches, int8_t* match_labels,
                       int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
                       float* gt_deltas, int32_t* matched_idx32, const float* bets,
+                      const fsg_bet_levels* h_bet_levels /* NULL: flat bets or none */,
                       float temperature, double* stats, const fsg_peer_ctx* h_peer /* NULL: no exchange */,
                       void* workspace, size_t workspace_bytes, fsg_stream_t stream);
 
@@ -136,7 +147,6 @@ FSG_API int fsg_box2box_apply_deltas(const float* deltas, const float* boxes, in
  * levels: anchors[r] for r = level_offset + (y*W + x)*A + a is (x*stride, y*stride, x*stride, y*stride) +
  * cell[a] in fp32 (bit-exact with the reference).  cell = generate_cell_anchors(sizes, aspect_ratios)
  * (:131-168, host arithmetic in double, rounded to fp32).  R must equal sum_l H*W*A. */
-#define FSG_MAX_LEVELS 8
 #define FSG_MAX_CELL_ANCHORS 16
 typedef struct fsg_anchor_level {
   int32_t H, W, stride, A;
@@ -237,6 +247,8 @@ typedef struct fsg_head_level {
   float* grad_logits;
   const float* pred_deltas;
   float* grad_deltas;
+  const float* bets;        /* (N, A, H, W) betting map of the level, or NULL: the flat `bets` argument is used   */
+  float* per_anchor_loss;   /* (N, A, H, W) NAKHW_loss of the level, or NULL: the flat `per_anchor_loss` argument */
   int32_t H, W;
 } fsg_head_level;
 FSG_API size_t fsg_loss_main_levels_workspace_bytes(int N, const fsg_head_level* h_levels, int num_levels, int A);
@@ -254,6 +266,18 @@ FSG_API int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_levels,
 FSG_API int fsg_loss_post(const float* bets, const int64_t* mask, const float* per_anchor_loss, int N,
                   int64_t R, const fsg_loss_params* h_params, const double* stats,
                   const double* scalars, float* grad_bets, fsg_stream_t stream);
+
+/* fsg_loss_post on the gambler's own layout: betting maps, NAKHW_loss and d/d bets per level as (N, A, H, W);
+ * mask stays the flat (N, R) K1 output (may be NULL). */
+typedef struct fsg_post_level {
+  const float* bets;
+  const float* per_anchor_loss;
+  float* grad_bets;
+  int32_t H, W;
+} fsg_post_level;
+FSG_API int fsg_loss_post_levels(const fsg_post_level* h_levels, int num_levels, int A, const int64_t* mask, int N,
+                         int64_t R, const fsg_loss_params* h_params, const double* stats, const double* scalars,
+                         fsg_stream_t stream);
 
 /* in-place x *= *scale_dev or x *= scale_host (backward with a non-unit upstream gradient) */
 FSG_API int fsg_scale_inplace(float* x, int64_t n, const float* scale_dev, float scale_host,

@@ -112,9 +112,9 @@ def test_config5_full_image_size(cuda):
 
 
 def test_config2_full_batch_native_layout(cuda):
-    """Config 2 at full size on the head's native layout: the step from per-level conv outputs must give, element
-    for element, the gradients of the (N, R, K) step on the permuted copy (same arithmetic per element), the same
-    integer outputs, and losses equal up to the order of the K-reduction."""
+    """Config 2 at full size on the head's native layout: the step from per-level conv outputs against the (N, R, K)
+    step on the permuted copy -- same integer outputs; gradients and losses equal up to the order of the
+    K-reduction and of the bet normaliser's sum (the in-place form adds R*T once instead of T per anchor)."""
     fsg = _fsg()
     from full_scale_gambler_for_object_detection_b200 import synthetic
 
@@ -139,8 +139,9 @@ def test_config2_full_batch_native_layout(cuda):
     ref = fsg.dense_train_step(xf, df, bf, anchors, gt, cfg)
     ref.total.backward()
     assert torch.equal(res.gt_classes, ref.gt_classes) and torch.equal(res.mask, ref.mask)
-    assert torch.equal(res.stats, ref.stats)
-    assert torch.equal(fsg.ops.levels_to_flat([t.grad for t in xs], K), xf.grad)
+    assert float(res.stats[0]) == float(ref.stats[0])
+    assert_close_tensor(res.stats, ref.stats, "stats", rtol=1e-6)
+    assert_close_tensor(fsg.ops.levels_to_flat([t.grad for t in xs], K), xf.grad, "grad_logits", rtol=2e-6)
     assert torch.equal(fsg.ops.levels_to_flat([t.grad for t in ds], 4), df.grad)
     for k in (5, 6, 7, 8):
         assert_close_scalar(res.scalars[k].item(), ref.scalars[k].item(), "scalar %d" % k, rtol=1e-6)
