@@ -95,6 +95,24 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
       : "memory");
 }
 
+// ---- NMS pair test ------------------------------------------------------------------------
+// `fl(inter / uni) > thr` (torchvision's test) without the IEEE division whenever the answer is clear: a correctly
+// rounded quotient q satisfies |q - inter/uni| <= 2^-24 * inter/uni, so inter outside thr*uni*(1 +- 2^-20) decides it;
+// only pairs inside that band (and the degenerate uni <= 0 / NaN cases) take the exact division.
+__device__ __forceinline__ bool nms_suppresses(float4 bi, float ai, float4 bj, float thr) {
+  const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+  const float w = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+  const float h = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+  const float inter = __fmul_rn(w, h);
+  const float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+  if (uni > 0.f && thr >= 0.f) {
+    const float c = thr * uni;
+    if (inter < c * 0.999999f) return false;
+    if (inter > c * 1.000001f && c > 1e-30f) return true;
+  }
+  return __fdiv_rn(inter, uni) > thr;
+}
+
 // ---- reductions ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

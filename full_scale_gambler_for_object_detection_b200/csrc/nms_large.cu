@@ -77,13 +77,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
   uint64_t word = 0;
   const int start = (cb == rb) ? t + 1 : 0;
   for (int j = start; j < ncol; ++j) {
-    const float4 bj = cbox[j];
-    const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-    const float w = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
-    const float h = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
-    const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
-    if (ovr > thr && ccls[j] == ci) word |= (1ull << j);
+    if (ccls[j] == ci && nms_suppresses(bi, ai, cbox[j], thr)) word |= (1ull << j);
   }
   mask[(int64_t)i * nb + cb] = word;
 }
