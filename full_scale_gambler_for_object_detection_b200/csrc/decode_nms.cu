@@ -746,20 +746,28 @@ __global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A)
 
   // ---- 4. this CTA's survivors by score descending (ties: lower concat index first)
   uint64_t* k2 = reinterpret_cast<uint64_t*>(sbox);  // the sorted boxes are no longer needed
-  for (int i = tid; i < m; i += kNmsThreads) {
-    uint64_t key = ~0ull;
-    if (i < mc && !dead[i]) key = keys[i] & ((1ull << 46) - 1ull);  // drop the class field
-    k2[i] = key;
+  //      (compacted first: only the survivors are sorted, not the whole padded candidate list)
+  for (int i0 = 0; i0 < mc; i0 += kNmsThreads) {
+    const int i = i0 + tid;
+    const bool alive = (i < mc) && !dead[i];
+    const unsigned bm = __ballot_sync(kFull, alive);
+    if (bm != 0u) {
+      int base = 0;
+      const int leader = __ffs(bm) - 1;
+      if (lane == leader) base = atomicAdd(&s_nkeep, __popc(bm));
+      base = __shfl_sync(kFull, base, leader);
+      if (alive) k2[base + __popc(bm & ((1u << lane) - 1u))] = keys[i] & ((1ull << 46) - 1ull);  // class field dropped
+    }
   }
   __syncthreads();
   {
-    int c = 0;
-    for (int i = tid; i < mc; i += kNmsThreads) c += (k2[i] != ~0ull) ? 1 : 0;
-    c = __reduce_add_sync(kFull, c);
-    if (lane == 0 && c) atomicAdd(&s_nkeep, c);
+    const int nk0 = s_nkeep;
+    int m4 = 1;
+    while (m4 < nk0) m4 <<= 1;
+    for (int i = nk0 + tid; i < m4; i += kNmsThreads) k2[i] = ~0ull;
+    __syncthreads();
+    bitonic_asc<kNmsThreads>(k2, m4);
   }
-  __syncthreads();
-  bitonic_asc<kNmsThreads>(k2, m);
   int mine_keep = s_nkeep;
   if (mine_keep > A.part_cap) mine_keep = A.part_cap;
   uint64_t* pk = A.part_keys + ((int64_t)n * S + part) * A.part_cap;
