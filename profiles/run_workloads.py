@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import full_scale_gambler_for_object_detection_b200 as fsg  # noqa: E402
 from full_scale_gambler_for_object_detection_b200 import synthetic  # noqa: E402
 
-ALL = ["train", "lvis", "lvis_native", "detect", "match", "rpn", "nms_large"]
+ALL = ["train", "train_native", "lvis", "lvis_native", "detect", "match", "rpn", "nms_large"]
 which = [a for a in sys.argv[1:] if a in ALL] or ALL
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 3
 warm = int(sys.argv[sys.argv.index("--warm") + 1]) if "--warm" in sys.argv else 2
@@ -45,6 +45,20 @@ def train(K, N, cid):
 
 if "train" in which:
     timed("train", train(80, 16, 2))
+if "train_native" in which:
+    # config 2 from the per-level head outputs (K1 with in-place betting maps, K2 and post on the native layout)
+    K, N = 80, 16
+    inp = synthetic.train_inputs(2, N, 800, 1333, K, logits=False)
+    A, grids = inp["A"], inp["grids"]
+    g = torch.Generator(device=dev).manual_seed(2)
+    xs = [torch.randn((N, A * K, h, w), device=dev, generator=g) + synthetic.PRIOR_LOGIT for h, w in grids]
+    ds = [torch.randn((N, A * 4, h, w), device=dev, generator=g) * 0.1 for h, w in grids]
+    bs = [torch.sigmoid(torch.randn((N, A, h, w), device=dev, generator=g) - 4.6) for h, w in grids]
+    anchors = inp["anchors"].to(dev)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], dev)
+    planl = fsg.DenseStepPlanLevels(N, grids, A, K, fsg.DenseLossConfig(num_classes=K), dev)
+    timed("train_native", lambda: planl.run(xs, ds, bs, anchors, gt))
+    del xs, ds, bs, planl
 if "lvis" in which:
     timed("lvis", train(1230, 8, 3))
 if "lvis_native" in which:
