@@ -12,6 +12,11 @@ followed by ``loss.backward()`` through all of it.
     [sharded] all-reduce(SUM) of [num_foreground, S_batch] over the process group
     launch 3  K2 main     focal + smooth-L1 + gambler weighting, fwd + bwd (logits read once, grads written once)
     launch 4  K2 post     d/d bets
+
+Two layouts: ``dense_train_step`` / ``DenseStepPlan`` take the reference's flattened (N, sum HWA, K) tensors;
+``dense_train_step_levels`` / ``DenseStepPlanLevels`` take what the heads and the gambler actually produce -- per-level
+(N, A*K, H, W), (N, A*4, H, W) and (N, A, H, W) tensors -- and run the same four launches on them in place
+(SURVEY.md section 8f row 2), returning gradients and NAKHW_loss in that layout.
 """
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
