@@ -4,7 +4,6 @@ torchvision semantics: stable score-descending greedy NMS, suppress when IoU > t
 is the per-class (un-offset) algorithm; the result is sorted by score descending.  The whole thing runs in
 one CUDA kernel; the only host synchronisation is reading the number of kept boxes to size the result
 (the reference has the same variable-length return)."""
-import torch
 
 from . import ops
 
