@@ -357,13 +357,15 @@ __global__ void __launch_bounds__(kSelThreads, SEL_CTAS) detect_select_kernel(co
       prune_topk<kSelThreads>(buf, &s_count, k, hist, s_tmp, (k + 64 <= kSelTrigger / 2 + 256) ? 64 : 0);
       const int now = s_count;
       if (now >= k) {
-        // buffer now holds exactly the k best so far: raise the bar.  A later element (higher index)
-        // must beat the current minimum strictly (ties lose on index).
+        // buffer now holds the k best so far: raise the bar to their minimum.  A candidate that is still waiting
+        // in a warp's staging queue can have a LOWER index than keys already in the buffer (the queues of the
+        // eight warps drain at different times), so an equal score must still be admitted (`score >= minimum`);
+        // the exact (score, index) order is settled by the next prune.
         const uint64_t mn = block_min_u64<kSelThreads>(buf, now, s_red64);
         if (tid == 0) {
-          const float t = key_score(mn);
+          const float t = nextafterf(key_score(mn), 0.f);  // `score > t`  <=>  `score >= minimum`
           s_ts = t;
-          const float lg = logf(t / (1.f - t));            // +inf when t == 1: nothing can beat it
+          const float lg = logf(t / (1.f - t));
           s_xb = fmaxf(A.xpre, lg - 1e-4f * (1.f + fabsf(lg)));
         }
       }

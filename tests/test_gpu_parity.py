@@ -578,6 +578,59 @@ def test_detect_multi_part_levels(cuda):
     _detect_case(cuda, 1, [24000, 6000, 1500], 80, 42)
 
 
+def test_detect_saturated_score_ties(cuda):
+    """Thousands of logits so large that their fp32 sigmoid is exactly 1.0, and a block of equal mid-range logits
+    straddling the top-k boundary: the selection among equal scores must go to the lowest indices (the reference's
+    stable sort), including for candidates that wait in a warp queue while later ones are already in the buffer."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    K = 80
+    inp = synthetic.inference_inputs(44, 2, [24000, 3000], K)
+    g = torch.Generator().manual_seed(45)
+    flat0 = inp["logits"][0].view(-1)
+    sat = torch.randperm(400000, generator=g)[:3500]               # all inside the first CTA's stream of level 0
+    flat0[sat] = 30.0                                             # sigmoid == 1.0f: 3500 exact ties, top-k is 1000
+    flat1 = inp["logits"][1].view(-1)
+    flat1[torch.randperm(flat1.numel(), generator=g)[:900]] = 6.0   # 900 clear winners ...
+    flat1[torch.randperm(flat1.numel(), generator=g)[:5000]] = 2.5  # ... and 5000 tied at the boundary
+    res = fsg.ops.detect(inp["logits"].to(cuda), inp["deltas"].to(cuda), inp["anchors"].to(cuda),
+                         inp["level_offsets"], want_candidates=True)
+    offs = inp["level_offsets"]
+    for n in range(2):
+        cls = [inp["logits"][n, offs[i]:offs[i + 1]] for i in range(2)]
+        reg = [inp["deltas"][n, offs[i]:offs[i + 1]] for i in range(2)]
+        anc = [inp["anchors"][offs[i]:offs[i + 1]] for i in range(2)]
+        _, (cb, cs, cc), _ = orc.inference_single_image(cls, reg, anc, K)
+        cnt = int(res["cand_count"][n].item())
+        assert cnt == cb.shape[0]
+        assert_equal_int(res["cand_classes"][n, :cnt], cc, "cand classes")
+        assert_close_tensor(res["cand_boxes"][n, :cnt], cb, "cand boxes", atol_scale=1e-6)
+        assert_close_tensor(res["cand_scores"][n, :cnt], cs, "cand scores")
+
+
+@pytest.mark.parametrize("seed", [46, 47, 48])
+def test_detect_tie_boundary_inside_one_stream(cuda, seed):
+    """A single-CTA slab (1500 anchors x 80) with 300 clear winners and 3000 logits tied exactly at the top-k
+    boundary: 700 of the tied ones must be kept, the ones with the lowest indices -- also when a lower-index
+    candidate is still waiting in a warp's queue while higher-index ones already sit in the key buffer."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    K = 80
+    inp = synthetic.inference_inputs(seed, 1, [1500], K)
+    g = torch.Generator().manual_seed(seed)
+    flat = inp["logits"][0].view(-1)
+    perm = torch.randperm(flat.numel(), generator=g)
+    flat[perm[:3000]] = 2.5
+    flat[perm[3000:3300]] = 6.0
+    res = fsg.ops.detect(inp["logits"].to(cuda), inp["deltas"].to(cuda), inp["anchors"].to(cuda),
+                         inp["level_offsets"], want_candidates=True)
+    _, (cb, cs, cc), _ = orc.inference_single_image([inp["logits"][0]], [inp["deltas"][0]], [inp["anchors"]], K)
+    cnt = int(res["cand_count"][0].item())
+    assert cnt == cb.shape[0] == 1000
+    assert_equal_int(res["cand_classes"][0, :cnt], cc, "cand classes")
+    assert_close_tensor(res["cand_boxes"][0, :cnt], cb, "cand boxes", atol_scale=1e-6)
+
+
 def test_detect_small_topk_and_lvis_classes(cuda):
     _detect_case(cuda, 1, [900, 300], 1230, 43, topk=100)
 
