@@ -88,6 +88,13 @@ PROTOTYPES = {
          c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(BetLevels), c_f32, c_ptr,
          ctypes.POINTER(PeerCtx), c_ptr, c_size, c_ptr],
     ),
+    "fsg_match_anchors_ex": (
+        c_i32,
+        [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr,
+         c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(BetLevels), c_f32, c_ptr,
+         ctypes.POINTER(PeerCtx), c_ptr, c_size, c_i32, c_ptr],
+    ),
+    "fsg_match_gt_max_offset": (c_size, [c_i32, c_i64, c_i64]),
     "fsg_box2box_get_deltas": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "fsg_box2box_apply_deltas": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_f32, c_ptr, c_ptr]),
     "fsg_loss_prepass_workspace_bytes": (c_size, [c_i32, c_i64]),

@@ -773,7 +773,7 @@ extern "C" size_t fsg_match_workspace_bytes(int N, int64_t R, int64_t sum_M) {
   return match_ws_layout(N, R, sum_M).total;
 }
 
-extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor_image_stride,
+extern "C" int fsg_match_anchors_ex(const float* anchors, int64_t R, int64_t anchor_image_stride,
                                  const float* gt_boxes, const int64_t* gt_class_ids, const int32_t* gt_offsets,
                                  int N, int64_t sum_M, int num_classes, const float* h_thresholds,
                                  const int8_t* h_labels, int num_thresholds, int allow_lq,
@@ -784,8 +784,9 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
                                  float* gt_deltas, int32_t* matched_idx32, const float* bets,
                                  const fsg_bet_levels* h_bet_levels, float temperature,
                                  double* stats, const fsg_peer_ctx* h_peer, void* workspace,
-                                 size_t workspace_bytes, fsg_stream_t stream) {
+                                 size_t workspace_bytes, int phases, fsg_stream_t stream) {
   if (N <= 0 || R < 0 || sum_M < 0 || !gt_offsets) return FSG_ERR_INVALID_ARG;
+  if (phases < 1 || phases > 3) return FSG_ERR_INVALID_ARG;
   BetLevels lv = {};
   if (h_bet_levels) {
     if (bets || !stats || h_bet_levels->num_levels <= 0 || h_bet_levels->num_levels > FSG_MAX_LEVELS ||
@@ -842,25 +843,29 @@ extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor
   unsigned* gtmax = (unsigned*)(ws + w.off_gtmax);
   float* bval = (float*)(ws + w.off_val);
   int32_t* bidx = (int32_t*)(ws + w.off_idx);
-  // counter + gt_max are contiguous: one memset node
-  FSG_CUDA_TRY(cudaMemsetAsync(ws, 0, w.off_val, s));
+  // counter + gt_max are contiguous: one memset node (phase 1 only: phase 2 consumes the -- possibly all-reduced --
+  // per-GT maxima that phase 1 left in the workspace)
+  if (phases & 1) FSG_CUDA_TRY(cudaMemsetAsync(ws, 0, w.off_val, s));
   const float wx = h_box_weights ? h_box_weights[0] : 1.f, wy = h_box_weights ? h_box_weights[1] : 1.f;
   const float ww = h_box_weights ? h_box_weights[2] : 1.f, wh = h_box_weights ? h_box_weights[3] : 1.f;
 
-  // anchors per thread in pass A: 2 for the few-GT training case (more CTAs in flight for a latency-bound pass:
-  // 33.3 vs 35.6 us for K1 on config 2), 4 when the batch is crowded (each staged GT box is reused more)
-  if (sum_M <= (int64_t)N * kSmallM) {
-    constexpr int U = 2;
-    dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
-    match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
-                                                          (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
-  } else {
-    constexpr int U = 4;
-    dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
-    match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
-                                                          (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
+  if (phases & 1) {
+    // anchors per thread in pass A: 2 for the few-GT training case (more CTAs in flight for a latency-bound pass:
+    // 33.3 vs 35.6 us for K1 on config 2), 4 when the batch is crowded (each staged GT box is reused more)
+    if (sum_M <= (int64_t)N * kSmallM) {
+      constexpr int U = 2;
+      dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
+      match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
+                                                            (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
+    } else {
+      constexpr int U = 4;
+      dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
+      match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
+                                                            (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
+    }
+    FSG_LAUNCH_CHECK();
   }
-  FSG_LAUNCH_CHECK();
+  if (!(phases & 2)) return FSG_OK;
   MatchOut out{matches, match_labels, picky_labels, gt_classes_out, mask_out, (float4*)gt_deltas, matched_idx32};
   dim3 grid_b((unsigned)w.nb, (unsigned)N);
   match_pass_b_kernel<<<grid_b, kMatchBlock, 0, s>>>(
@@ -896,4 +901,27 @@ extern "C" int fsg_box2box_apply_deltas(const float* deltas, const float* boxes,
       scale_clamp, (float4*)out);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
+}
+
+extern "C" int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor_image_stride,
+                                 const float* gt_boxes, const int64_t* gt_class_ids, const int32_t* gt_offsets,
+                                 int N, int64_t sum_M, int num_classes, const float* h_thresholds,
+                                 const int8_t* h_labels, int num_thresholds, int allow_lq,
+                                 const float* h_picky_thresholds, const int8_t* h_picky_labels,
+                                 int num_picky_thresholds, const float* h_box_weights, int64_t* matches,
+                                 int8_t* match_labels, int8_t* picky_labels, int64_t* gt_classes_out,
+                                 int64_t* mask_out, float* gt_deltas, int32_t* matched_idx32, const float* bets,
+                                 const fsg_bet_levels* h_bet_levels, float temperature, double* stats,
+                                 const fsg_peer_ctx* h_peer, void* workspace, size_t workspace_bytes,
+                                 fsg_stream_t stream) {
+  return fsg_match_anchors_ex(anchors, R, anchor_image_stride, gt_boxes, gt_class_ids, gt_offsets, N, sum_M,
+                              num_classes, h_thresholds, h_labels, num_thresholds, allow_lq, h_picky_thresholds,
+                              h_picky_labels, num_picky_thresholds, h_box_weights, matches, match_labels,
+                              picky_labels, gt_classes_out, mask_out, gt_deltas, matched_idx32, bets, h_bet_levels,
+                              temperature, stats, h_peer, workspace, workspace_bytes, 3, stream);
+}
+
+extern "C" size_t fsg_match_gt_max_offset(int N, int64_t R, int64_t sum_M) {
+  if (N <= 0 || R < 0 || sum_M < 0) return 0;
+  return match_ws_layout(N, R, sum_M).off_gtmax;
 }

@@ -87,13 +87,16 @@ class PackedGT:
 def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1, 1),
                   picky_thresholds=(0.4, 0.9), picky_labels=None, box_weights=(1.0, 1.0, 1.0, 1.0),
                   want=("gt_classes", "mask", "matched_idx32"), bets=None, temperature=0.0,
-                  allow_low_quality_matches=True, bet_levels=None):
+                  allow_low_quality_matches=True, bet_levels=None, phases=3, workspace=None, out=None):
     """Fused IoU + Matcher(s) + GT assignment (retinanet.py:339-363, 400-425) for a batch.
 
     anchors: (R,4) shared by all images or (N,R,4) per image.  gt: PackedGT.
     want: subset of {matches, match_labels, picky_labels, gt_classes, mask, gt_deltas, matched_idx32}.
     bets (N,R): when given, the loss pre-pass is fused in and ``stats`` is returned too.
     bet_levels list[(N, A, H, W)]: the same with the betting maps read in their own layout (no flattened copy).
+    phases / workspace / out: the two-phase form for anchors sharded by range over ranks (see
+    ``sharded.match_anchor_range``): phases=1 runs pass A only, phases=2 pass B on the same ``workspace`` after the
+    per-GT maxima in it (``out["gt_max_bits"]``, an int32 view) were all-reduced with MAX.
     Returns a dict of the requested (N,R[,4]) tensors (+ "stats").
     """
     a = _f32c(anchors)
@@ -111,11 +114,12 @@ def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1
         "gt_classes": (torch.int64, ()), "mask": (torch.int64, ()), "gt_deltas": (torch.float32, (4,)),
         "matched_idx32": (torch.int32, ()),
     }
-    out = {}
-    for k in want:
-        dt, tail = kinds[k]
-        out[k] = torch.empty((N, R) + tail, dtype=dt, device=dev)
-    stats = None
+    if out is None:
+        out = {}
+        for k in want:
+            dt, tail = kinds[k]
+            out[k] = torch.empty((N, R) + tail, dtype=dt, device=dev)
+    stats = out.get("stats")
     if bets is not None:
         bets = _f32c(bets)
         assert bets.shape == (N, R)
@@ -124,12 +128,12 @@ def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1
         assert bets is None
         lv = bet_levels_struct(bet_levels)
         assert sum(b.shape[1] * b.shape[2] * b.shape[3] for b in bet_levels) == R and bet_levels[0].shape[0] == N
-    if bets is not None or lv is not None or "stats" in want:
+    if stats is None and (bets is not None or lv is not None or "stats" in want):
         stats = torch.empty(_lib.STATS_HEADER + N, dtype=torch.float64, device=dev)
     L = lib()
-    ws = _ws(L.fsg_match_workspace_bytes(N, R, gt.total), dev)
+    ws = workspace if workspace is not None else _ws(L.fsg_match_workspace_bytes(N, R, gt.total), dev)
     if R > 0:
-        check(L.fsg_match_anchors(
+        check(L.fsg_match_anchors_ex(
             ptr(a), R, stride, ptr(gt.boxes), ptr(gt.classes), ptr(gt.offsets), N, gt.total, int(num_classes),
             host_f32(thresholds), host_i8(labels), len(thresholds), int(bool(allow_low_quality_matches)),
             host_f32(picky_thresholds) if picky_thresholds is not None else None,
@@ -138,10 +142,14 @@ def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1
             host_f32(box_weights), ptr(out.get("matches")), ptr(out.get("match_labels")),
             ptr(out.get("picky_labels")), ptr(out.get("gt_classes")), ptr(out.get("mask")),
             ptr(out.get("gt_deltas")), ptr(out.get("matched_idx32")), ptr(bets), lv, float(temperature), ptr(stats),
-            None, ptr(ws), ws.numel(), stream()))
-        count_launches(2)
+            None, ptr(ws), ws.numel(), int(phases), stream()))
+        count_launches(2 if phases == 3 else 1)
     if stats is not None:
         out["stats"] = stats
+    if phases != 3:
+        off = L.fsg_match_gt_max_offset(N, R, gt.total)
+        out["workspace"] = ws
+        out["gt_max_bits"] = ws[off:off + 4 * max(gt.total, 1)].view(torch.int32)   # fp32 bit patterns, all >= 0
     return out
 
 

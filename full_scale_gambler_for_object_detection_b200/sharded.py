@@ -118,3 +118,29 @@ class PeerExchange:
         """Host-synchronising: raise if a peer failed to arrive within the kernel's time-out."""
         if int(self.error.item()) != 0:
             raise RuntimeError("peer exchange timed out: a rank did not enqueue the matching step")
+
+
+def all_reduce_gt_max(gt_max_bits, group=None):
+    """All-reduce(MAX) of the per-GT maxima between the two matching passes when ONE image's anchors are sharded by
+    range over the ranks.  ``gt_max_bits``: int32 view of the fp32 bit patterns; IoU values
+    are non-negative, so their bit patterns order like integers and MAX on the view is MAX on the floats."""
+    dist.all_reduce(gt_max_bits, op=dist.ReduceOp.MAX, group=group)
+    return gt_max_bits
+
+
+def anchor_range(num_anchors, world_size, rank):
+    """Contiguous anchor range [lo, hi) of ``rank`` (sizes differ by at most one)."""
+    base, extra = divmod(num_anchors, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def match_anchor_range(local_anchors, gt, num_classes, group=None, want=("matches", "match_labels"), **kw):
+    """Matcher (with low-quality matches) for images whose anchors are sharded by range: every rank holds the same
+    GT and its own slice ``local_anchors`` ((R_local,4) or (N,R_local,4)).  Pass A locally, all-reduce(MAX) of the
+    M per-GT maxima, pass B locally; the concatenation of the ranks' outputs equals the unsharded result."""
+    from . import ops
+    first = ops.match_anchors(local_anchors, gt, num_classes, want=want, phases=1, **kw)
+    all_reduce_gt_max(first["gt_max_bits"], group)
+    return ops.match_anchors(local_anchors, gt, num_classes, want=want, phases=2, workspace=first["workspace"],
+                             out={k: first[k] for k in want}, **kw)

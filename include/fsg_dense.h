@@ -135,6 +135,26 @@ FSG_API int fsg_match_anchors(const float* anchors, int64_t R, int64_t anchor_im
                       float temperature, double* stats, const fsg_peer_ctx* h_peer /* NULL: no exchange */,
                       void* workspace, size_t workspace_bytes, fsg_stream_t stream);
 
+/* The same in two phases, for ONE image (or a few) whose ANCHORS are sharded by range over the GPUs (SURVEY section
+ * 8e, the matcher stress with fewer images than GPUs): phases = 1 runs pass A on the local anchors (per-anchor
+ * best/argmax and the per-GT maxima over the local anchors), phases = 2 runs pass B with whatever per-GT maxima are
+ * in the workspace, phases = 3 is fsg_match_anchors.  Between the two calls the caller all-reduces (MAX) the
+ * sum_M uint32 words at workspace + fsg_match_gt_max_offset(N, R, sum_M) over the ranks: they hold the per-GT
+ * maxima as fp32 bit patterns, which order like unsigned integers for the non-negative IoU values.  The same
+ * workspace must be passed to both calls; stats, if requested, are partial sums over the local anchors. */
+FSG_API int fsg_match_anchors_ex(const float* anchors, int64_t R, int64_t anchor_image_stride,
+                         const float* gt_boxes, const int64_t* gt_class_ids, const int32_t* gt_offsets,
+                         int N, int64_t sum_M, int num_classes, const float* h_thresholds,
+                         const int8_t* h_labels, int num_thresholds, int allow_low_quality_matches,
+                         const float* h_picky_thresholds, const int8_t* h_picky_labels,
+                         int num_picky_thresholds, const float* h_box_weights, int64_t* matches,
+                         int8_t* match_labels, int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
+                         float* gt_deltas, int32_t* matched_idx32, const float* bets,
+                         const fsg_bet_levels* h_bet_levels, float temperature, double* stats,
+                         const fsg_peer_ctx* h_peer, void* workspace, size_t workspace_bytes, int phases,
+                         fsg_stream_t stream);
+FSG_API size_t fsg_match_gt_max_offset(int N, int64_t R, int64_t sum_M);
+
 /* box_regression.py:34-67 / :69-107.  h_weights = (wx, wy, ww, wh).
  * apply_deltas: deltas (n, 4k) -> out (n, 4k), dw/dh clamped to scale_clamp (max only). */
 FSG_API int fsg_box2box_get_deltas(const float* src_boxes, const float* target_boxes, int64_t n,

@@ -78,10 +78,22 @@ def main():
                 r = plan.run(x, d, b, anchors, gt)
             assert float(r.stats[0]) == float(want["nf"])
             peer.check()
+    # ---- one image, anchors sharded by range (matcher stress with fewer images than GPUs): pass A, NCCL
+    #      all-reduce(MAX) of the per-GT maxima, pass B; every rank's slice must equal the unsharded result
+    ms = synthetic.matcher_stress_inputs(35, 1, 300001, 200)
+    a_all = ms["anchors"][0]
+    gts = fsg.ops.PackedGT.from_lists(ms["gt_boxes"], ms["gt_classes"], dev)
+    keys = ("matches", "match_labels", "gt_classes")
+    whole = fsg.ops.match_anchors(a_all.to(dev), gts, 80, want=keys, picky_thresholds=None)
+    lo, hi = sharded.anchor_range(a_all.shape[0], world, rank)
+    mine = sharded.match_anchor_range(a_all[lo:hi].to(dev), gts, 80, group=dist.group.WORLD, want=keys,
+                                      picky_thresholds=None)
+    for k in keys:
+        assert torch.equal(mine[k], whole[k][:, lo:hi]), "anchor-range sharded %s" % k
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
-        print("SHARDED_OK world=%d" % world, flush=True)
+        print("SHARDED_OK world=%d (image shards, peer exchange, anchor-range shards)" % world, flush=True)
     t = threading.Timer(20.0, lambda: os._exit(0))
     t.daemon = True
     t.start()

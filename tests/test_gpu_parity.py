@@ -835,3 +835,37 @@ def test_native_layout_plan_and_graph(cuda):
     res = plan.replay()
     torch.cuda.synchronize()
     check(res, reference(xs, ds, bs))
+
+
+@pytest.mark.parametrize("M,shards", [(200, 3), (8, 2), (1500, 2)])
+def test_match_with_anchors_sharded_by_range(cuda, M, shards):
+    """one image whose anchors are split by range over `shards` ranks.  Emulated in one process:
+    phase 1 (pass A) per shard with its own workspace, MAX of the per-GT maxima over the shards (what
+    sharded.all_reduce_gt_max does over NCCL), phase 2 (pass B) per shard; the concatenation must equal the
+    unsharded call and the oracle, bit for bit."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import sharded, synthetic
+    R = 40001
+    inp = synthetic.matcher_stress_inputs(33, 1, R, M)
+    anchors = inp["anchors"][0]
+    anchors[7] = inp["gt_boxes"][0][3]                              # IoU 1 with GT 3, lives in shard 0
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    want_keys = ("matches", "match_labels", "gt_classes")
+    whole = fsg.ops.match_anchors(anchors.to(cuda), gt, 80, want=want_keys, picky_thresholds=None)
+    firsts = []
+    for r in range(shards):
+        lo, hi = sharded.anchor_range(R, shards, r)
+        firsts.append(fsg.ops.match_anchors(anchors[lo:hi].to(cuda), gt, 80, want=want_keys, picky_thresholds=None,
+                                            phases=1))
+    gmax = torch.stack([f["gt_max_bits"] for f in firsts]).max(dim=0).values
+    parts = []
+    for r, f in enumerate(firsts):
+        lo, hi = sharded.anchor_range(R, shards, r)
+        f["gt_max_bits"].copy_(gmax)
+        parts.append(fsg.ops.match_anchors(anchors[lo:hi].to(cuda), gt, 80, want=want_keys, picky_thresholds=None,
+                                           phases=2, workspace=f["workspace"], out={k: f[k] for k in want_keys}))
+    oracle = orc.ground_truth([anchors], inp["gt_boxes"], inp["gt_classes"], 80)
+    for k in want_keys:
+        got = torch.cat([p[k] for p in parts], dim=1)
+        assert torch.equal(got, whole[k]), k
+        assert_equal_int(got, oracle[k], k)

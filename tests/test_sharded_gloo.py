@@ -118,3 +118,51 @@ def test_sharded_step_equals_single_process(output):
             g = torch.from_numpy(g)
             w = want[name][a:b]
             assert float((g - w).abs().max()) <= 1e-5 * float(want[name].abs().max()) + 1e-12, name
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one image, anchors sharded by range (the matcher stress with fewer images than GPUs)
+# ---------------------------------------------------------------------------------------------------------
+def _range_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from full_scale_gambler_for_object_detection_b200 import sharded, synthetic
+
+        torch.set_num_threads(1)
+        inp = synthetic.matcher_stress_inputs(31, 1, 6001, 37)
+        anchors, gt = inp["anchors"][0], inp["gt_boxes"][0]
+        lo, hi = sharded.anchor_range(anchors.shape[0], world, rank)
+        iou = orc.pairwise_iou(gt, anchors[lo:hi])                         # pass A on the local anchors
+        local_max = iou.max(dim=1).values
+        bits = local_max.contiguous().view(torch.int32).clone()            # fp32 bit patterns, all >= 0
+        sharded.all_reduce_gt_max(bits, dist.group.WORLD)                  # the exchange between the passes
+        gmax = bits.view(torch.float32)
+        best, idx = iou.max(dim=0)                                         # pass B on the local anchors
+        labels = torch.full_like(idx, 1, dtype=torch.int8)
+        labels[best < 0.5] = -1
+        labels[best < 0.4] = 0
+        labels[(iou == gmax[:, None]).any(dim=0)] = 1                      # matcher.py:99-132 with the GLOBAL maxima
+        ret[rank] = dict(lo=lo, hi=hi, matches=idx.numpy(), labels=labels.numpy(), gmax=gmax.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_anchor_range_sharded_matching_equals_single_process():
+    from full_scale_gambler_for_object_detection_b200 import sharded, synthetic
+
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_range_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    inp = synthetic.matcher_stress_inputs(31, 1, 6001, 37)
+    iou = orc.pairwise_iou(inp["gt_boxes"][0], inp["anchors"][0])
+    want_m, want_l = orc.matcher(iou, [0.4, 0.5], [0, -1, 1], True)
+    covered = 0
+    for rank in range(world):
+        r = ret[rank]
+        assert (r["lo"], r["hi"]) == sharded.anchor_range(6001, world, rank)
+        assert torch.equal(torch.from_numpy(r["gmax"]), iou.max(dim=1).values)      # every rank sees the global maxima
+        assert torch.equal(torch.from_numpy(r["matches"]), want_m[r["lo"]:r["hi"]])
+        assert torch.equal(torch.from_numpy(r["labels"]), want_l[r["lo"]:r["hi"]])
+        covered += r["hi"] - r["lo"]
+    assert covered == 6001
