@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------------
-def secondary_metrics(dev, fsg):
+def secondary_metrics(dev, fsg, with_cpu=True):
     """NMS images/s (config 4) and the matcher stress (config 5), short runs; reported beside the headline."""
     from full_scale_gambler_for_object_detection_b200 import synthetic
 
@@ -180,6 +180,16 @@ def secondary_metrics(dev, fsg):
     scan_bytes = 4.0 * K_CLASSES * inp["R"] * N4
     out["detect_config4"] = {"images_per_s": N4 / (ms * 1e-3), "ms_per_batch": ms, "batch": N4,
                              "scan_hbm_frac": scan_bytes / (ms * 1e-3) / (hbm * 1e9)}
+    if with_cpu:
+        # the reference's inference_single_image (oracle port) on ONE image of the same shape, host cores
+        from oracle import dense_oracle as orc
+        lg, dl, an = logits[0].cpu(), deltas[0].cpu(), inp["anchors"]
+        cls = [lg[offs[i]:offs[i + 1]] for i in range(5)]
+        reg = [dl[offs[i]:offs[i + 1]] for i in range(5)]
+        anc = [an[offs[i]:offs[i + 1]] for i in range(5)]
+        ts = time_cpu(lambda: orc.inference_single_image(cls, reg, anc, K_CLASSES), 2, 1)
+        out["detect_config4"]["cpu_baseline"] = {"images_per_s": 1.0 / min(ts), "cores": torch.get_num_threads(),
+                                                 "kind": "port", "sample": "1 image of the batch, min of 2"}
     del logits, deltas
     out["native_layout_step_config2"] = native_layout_step(dev, fsg)
     # config 5: 200 GT x 1M anchors per image, 8 images, allow_low_quality_matches
@@ -196,9 +206,22 @@ def secondary_metrics(dev, fsg):
     e1.record()
     torch.cuda.synchronize()
     ms5 = e0.elapsed_time(e1) / reps
+    props = torch.cuda.get_device_properties(dev)
+    fp32_peak = props.multi_processor_count * 128 * 1.965e9          # lanes x max SM clock (instr/s)
+    pairs = 8e6 * 200 / (ms5 * 1e-3)
     out["match_config5"] = {"anchors_per_s": 8e6 / (ms5 * 1e-3), "ms_per_batch": ms5,
-                            "iou_pairs_per_s": 8e6 * 200 / (ms5 * 1e-3),
-                            "hbm_frac": 25.0 * 8e6 / (ms5 * 1e-3) / (hbm * 1e9)}
+                            "iou_pairs_per_s": pairs,
+                            "hbm_frac": 25.0 * 8e6 / (ms5 * 1e-3) / (hbm * 1e9),
+                            # SURVEY 8d model: ~16 fp32 instructions + 1 IEEE divide per pair
+                            "fp32_issue_frac_model": pairs * 17.0 / fp32_peak,
+                            "bound": "fp32 issue (ncu: 90% of issue slots busy in pass A, 33 instr/pair)"}
+    if with_cpu:
+        from oracle import dense_oracle as orc
+        a_cpu, g_cpu, c_cpu = inp5["anchors"][0][:100000], inp5["gt_boxes"][:1], inp5["gt_classes"][:1]
+        ts = time_cpu(lambda: orc.ground_truth([a_cpu], g_cpu, c_cpu, 80), 2, 1)
+        out["match_config5"]["cpu_baseline"] = {"anchors_per_s": 1e5 / min(ts), "cores": torch.get_num_threads(),
+                                                "kind": "port",
+                                                "sample": "200 GT x 100k anchors of one image (both matchers), min of 2"}
     return out
 
 
@@ -414,7 +437,7 @@ def run_ours(args, rank, local_rank, world):
 
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
-        secondary = secondary_metrics(dev, fsg)
+        secondary = secondary_metrics(dev, fsg, with_cpu=not args.no_cpu)
 
     clocks = sampler.stop() if rank == 0 else None
 
