@@ -504,15 +504,6 @@ __device__ __forceinline__ float4 postprocess_box(float4 b, float4 pp) {
   return b;
 }
 
-// torchvision nms_kernel arithmetic: fp32 IoU of box i (area ai precomputed) and box j, in its op order
-__device__ __forceinline__ float nms_overlap(float4 bi, float ai, float4 bj) {
-  const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-  const float w = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
-  const float h = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
-  const float inter = __fmul_rn(w, h);
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
-}
-
 // ascending bitonic sort of m (power of two) keys in shared memory, block-wide
 template <int NT>
 __device__ void bitonic_asc_smem(uint64_t* a, int m) {
