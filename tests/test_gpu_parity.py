@@ -869,3 +869,38 @@ def test_match_with_anchors_sharded_by_range(cuda, M, shards):
         got = torch.cat([p[k] for p in parts], dim=1)
         assert torch.equal(got, whole[k]), k
         assert_equal_int(got, oracle[k], k)
+
+
+def test_native_layout_with_nine_anchors_per_cell(cuda):
+    """Upstream RetinaNet geometry (3 scales x 3 aspect ratios, A = 9): K1 + K2 on the native layout against the
+    oracle, with the anchors produced by the device-side generator."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import anchor_generator as ag, synthetic
+    N, K, A, H, W = 2, 80, 9, 224, 288
+    gen_a = fsg.DefaultAnchorGenerator([list(s) for s in ag.RETINANET_SIZES], [[0.5, 1.0, 2.0]], ag.RETINANET_STRIDES, cuda)
+    grids = ag.retinanet_grid_sizes(H, W)
+    anchors, offs = gen_a.flat_for_grids(grids)
+    want_anchors, _, _ = ag.retinanet_anchors(H, W, aspect_ratios=((0.5, 1.0, 2.0),) * 5)
+    assert torch.equal(anchors.cpu(), want_anchors)
+    R = anchors.shape[0]
+    g = torch.Generator().manual_seed(71)
+    base = synthetic.train_inputs(71, N, H, W, K, M=6, logits=False)
+    cls_l = [torch.randn((N, A * K, h, w), generator=g) + synthetic.PRIOR_LOGIT for h, w in grids]
+    reg_l = [torch.randn((N, A * 4, h, w), generator=g) * 0.1 for h, w in grids]
+    bet_l = [torch.sigmoid(torch.randn((N, A, h, w), generator=g) - 4.0) for h, w in grids]
+    bets_flat = orc.levels_to_flat(bet_l, 1).reshape(N, R)
+    want = orc.train_step(want_anchors, base["gt_boxes"], base["gt_classes"], orc.levels_to_flat(cls_l, K),
+                          orc.levels_to_flat(reg_l, 4), bets_flat, K, 1.0, 1.0, -1.0)
+    gx = [t.to(cuda).requires_grad_(True) for t in cls_l]
+    gd = [t.to(cuda).requires_grad_(True) for t in reg_l]
+    gb = [t.to(cuda).requires_grad_(True) for t in bet_l]
+    gt = fsg.ops.PackedGT.from_lists(base["gt_boxes"], base["gt_classes"], cuda)
+    res = fsg.dense_train_step_levels(gx, gd, gb, anchors, gt, fsg.DenseLossConfig(num_classes=K))
+    res.total.backward()
+    assert_equal_int(res.gt_classes, want["gt_classes"], "gt_classes")
+    assert_equal_int(res.mask, want["mask"], "mask")
+    assert_close_scalar(res.total.item(), want["total"], "total", rtol=2e-5)
+    assert_close_tensor(orc.levels_to_flat([t.grad.cpu() for t in gx], K), want["grad_logits"], "grad_logits")
+    assert_close_tensor(orc.levels_to_flat([t.grad.cpu() for t in gd], 4), want["grad_deltas"], "grad_deltas")
+    assert_close_tensor(orc.levels_to_flat([t.grad.cpu() for t in gb], 1).reshape(N, R), want["grad_bets"], "grad_bets",
+                        atol_scale=1e-6)
