@@ -229,6 +229,55 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) 
           pos_fix = f1 * A.a1 - l0 * A.a0;
           if (write_grad) A.grad_logits[o * A.K + cls] = fg1 * (coef_f * A.a1);
         }
+      } else if (kFast) {
+        // any K, fast variants: whole batches without predication, one predicated tail batch, the positive class
+        // patched afterwards (no per-vector test, no register double buffer: 4 CTAs/SM hide the load latency)
+        const float cf = coef_f * A.a0;
+        const int span = G * BATCH;
+        // y holds the batch being evaluated, z the next one (in flight meanwhile); a batch is "full" when every
+        // lane of the group has all BATCH vectors in range, only the last one is predicated
+        Vec<V> y[BATCH], z[BATCH];
+        int j0 = gl;
+        auto load_batch = [&](Vec<V>* dst, int jb) {
+          if (jb + span - gl <= nvec) {
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) dst[b].load(xrow + (int64_t)(jb - gl + b * G) * V);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b)
+              if (jb + b * G < nvec) dst[b].load(xrow + (int64_t)(jb - gl + b * G) * V);
+          }
+        };
+        load_batch(y, j0);
+#pragma unroll 1
+        for (; j0 - gl < nvec; j0 += span) {
+          if (j0 - gl + span < nvec) load_batch(z, j0 + span);
+          const bool full = (j0 + span - gl <= nvec);
+#pragma unroll
+          for (int b = 0; b < BATCH; ++b) {
+            if (full || j0 + b * G < nvec) {
+              Vec<V> g;
+#pragma unroll
+              for (int k = 0; k < V; ++k) {
+                float l, d;
+                focal_neg_g2(y[b].v[k], l, d);
+                sum_f += l;
+                g.v[k] = d * cf;
+              }
+              if (write_grad) g.store(grow + (int64_t)(j0 - gl + b * G) * V);
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < BATCH; ++b) y[b] = z[b];
+        }
+        if (fgc && (jpos & (G - 1)) == gl) {   // rare: this lane owns the positive class
+          const float xv = A.logits[o * A.K + cls];
+          float l0, d0, f1, fg1, b1, bg1;
+          focal_neg_g2(xv, l0, d0);
+          cls_elem_general(xv, true, 2.f, f1, fg1, b1, bg1);
+          pos_fix = f1 * A.a1 - l0 * A.a0;
+          if (write_grad) A.grad_logits[o * A.K + cls] = fg1 * (coef_f * A.a1);
+        }
       } else {
         // double-buffered: the next batch of row pieces is in flight while this one is evaluated
         Vec<V> y[BATCH], z[BATCH];
