@@ -37,7 +37,7 @@ IMG_H, IMG_W, K_CLASSES, IMGS_PER_GPU, GT_PER_IMG = 800, 1333, 80, 16, 8
 WORKLOAD = ("config2: RetinaNet R50-FPN + gambler, synthetic 800x1333 (padded 800x1344), %d img/GPU, K=%d, A=3, "
             "R=67200 anchors/img, %d GT/img (one GT-free image), L_BAHW, focal(0.25,2), T=0.1"
             % (IMGS_PER_GPU, K_CLASSES, GT_PER_IMG))
-CPU_SAMPLE_IMAGES = 2
+CPU_SAMPLE_IMAGES = 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one loss_main_kernel<4,5,0,4> launch on this workload, from
 # the committed `ncu --set full` capture profiles/r1c_ncu_full_raw.csv (366.09 MB read + 313.57 MB written);
 # the algorithmic figure is (8K+72)*N*R = 765.5 MB -- the (N,R)-sized side inputs mostly hit L2
