@@ -102,3 +102,41 @@ def test_get_loss_upper_bound_matches_oracle_definition():
     assert torch.allclose(got, want)
     with pytest.raises(AssertionError):
         fsg.get_loss_upper_bound(levels[:4], N, 0.1, 1.0)
+
+
+def test_anchor_range_partitions_exactly():
+    """sharded.anchor_range: contiguous, disjoint, covering, sizes differing by at most one."""
+    for R, world in ((1000000, 8), (6001, 2), (7, 8), (0, 3), (67200, 5)):
+        ranges = [sharded.anchor_range(R, world, r) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == R
+        for (lo, hi), (lo2, _) in zip(ranges[:-1], ranges[1:]):
+            assert hi == lo2 and lo <= hi
+        sizes = [hi - lo for lo, hi in ranges]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_postprocess_rows_and_struct_sizes():
+    """The (N,4) table detect() takes for the fused detector_postprocess (postprocessing.py:27: scale = out / in)."""
+    import ctypes
+
+    rows = fsg.ops.postprocess_rows([(800, 1344), (512, 512)], [(480, 640), (1024, 768)], "cpu")
+    want = torch.tensor([[640 / 1344, 480 / 800, 640.0, 480.0], [768 / 512, 1024 / 512, 768.0, 1024.0]])
+    assert torch.equal(rows, want.to(torch.float32))
+    # ctypes mirrors of the header's structs (include/fsg_dense.h)
+    assert ctypes.sizeof(_lib.HeadLevel) == 6 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.BetLevels) == 8 * 8 + 2 * 8 * 4 + 2 * 4
+    assert ctypes.sizeof(_lib.PostLevel) == 3 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.AnchorLevel) == 4 * 4 + 16 * 4 * 4
+
+
+def test_default_anchor_generator_host_side():
+    """Cell anchors and broadcasting of sizes / ratios over levels (anchor_generator.py:83-96,131-168); the grid
+    itself is produced on the device (GPU test)."""
+    gen = fsg.DefaultAnchorGenerator([[32, 64]], [[0.25, 1, 4]], [4, 8], device="cpu")
+    assert gen.num_cell_anchors == [6, 6] and gen.box_dim == 4
+    want = torch.tensor([[-32.0, -8.0, 32.0, 8.0], [-16.0, -16.0, 16.0, 16.0], [-8.0, -32.0, 8.0, 32.0],
+                         [-64.0, -16.0, 64.0, 16.0], [-32.0, -32.0, 32.0, 32.0], [-16.0, -64.0, 16.0, 64.0]])
+    assert torch.allclose(gen.cell_anchors[0], want)          # tests/test_anchor_generator.py:14-43 (cell part)
+    gen2 = fsg.DefaultAnchorGenerator(anchor_generator.RETINANET_SIZES, ((1.0,),), anchor_generator.RETINANET_STRIDES,
+                                      device="cpu")
+    assert gen2.num_cell_anchors == [3] * 5
