@@ -17,7 +17,7 @@ __device__ __forceinline__ float4 postprocess_box(float4 b, float4 pp) {
 }
 
 // ascending bitonic sort of m (power of two) keys in shared memory, block-wide
-__global__ void __launch_bounds__(kNmsThreads) nms_image_kernel(const NmsArgs A) {
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const NmsArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                      // kNmsCap * 8
   float4* sbox = reinterpret_cast<float4*>(smem_raw + (size_t)kNmsCap * 8);     // kNmsCap * 16
