@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FSG_DENSE_LIB") or os.path.join(_HERE, "libfsg_dense.so")  # override: kernel experiments
-ABI_VERSION = 3
+ABI_VERSION = 4
 STATS_HEADER = 2
 SCALARS_HEADER = 10
 
@@ -63,6 +63,12 @@ class AnchorLevel(ctypes.Structure):
     """``struct fsg_anchor_level``."""
 
     _fields_ = [("H", c_i32), ("W", c_i32), ("stride", c_i32), ("A", c_i32), ("cell", (c_f32 * 4) * 16)]
+
+
+class DetectLevel(ctypes.Structure):
+    """``struct fsg_detect_level``."""
+
+    _fields_ = [("logits", c_ptr), ("deltas", c_ptr), ("H", c_i32), ("W", c_i32)]
 
 
 class PeerCtx(ctypes.Structure):
@@ -118,10 +124,16 @@ PROTOTYPES = {
     "fsg_nms_workspace_bytes": (c_size, [c_i64]),
     "fsg_nms": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_f64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "fsg_detect_workspace_bytes": (c_size, [c_i32, c_i64, c_i32, c_i32, c_i32]),
+    "fsg_detect_status_offset": (c_size, [c_i32, c_i32, c_i32]),
     "fsg_detect": (
         c_i32,
         [c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i64, c_i32, c_ptr, c_i32, c_f32, c_i32, c_f64, c_i32, c_ptr, c_f32,
          c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
+    ),
+    "fsg_detect_levels": (
+        c_i32,
+        [ctypes.POINTER(DetectLevel), c_i32, c_i32, c_i32, c_ptr, c_i64, c_i32, c_i64, c_f32, c_i32, c_f64, c_i32,
+         c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
     ),
     "fsg_postprocess_boxes": (c_i32, [c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "fsg_grid_anchors": (c_i32, [ctypes.POINTER(AnchorLevel), c_i32, c_ptr, c_i64, c_ptr]),
@@ -136,6 +148,7 @@ PROTOTYPES = {
 
 _LIB = None
 LAUNCHES = 0  # kernels enqueued through this binding (bench.py reports it as gpu_launches)
+_CALL_DEVICE = None  # device of the tensor arguments marshalled for the call being assembled (see ptr / stream)
 
 
 def build(verbose=False):
@@ -159,15 +172,39 @@ def lib():
                 "libfsg_dense.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or csrc/build.sh. There is no CPU fallback for this path." % LIB_PATH
             )
-        L = ctypes.CDLL(LIB_PATH)
+        cdll = ctypes.CDLL(LIB_PATH)
+        L = _Guarded()
         for name, (res, args) in PROTOTYPES.items():
-            fn = getattr(L, name)  # AttributeError if the header and the library diverge
+            fn = getattr(cdll, name)  # AttributeError if the header and the library diverge
             fn.restype = res
             fn.argtypes = args
+            setattr(L, name, _guard(fn) if (args and args[-1] is c_ptr and res is c_i32) else fn)
         if L.fsg_abi_version() != ABI_VERSION:
             raise RuntimeError("libfsg_dense.so ABI %d != binding ABI %d" % (L.fsg_abi_version(), ABI_VERSION))
         _LIB = L
     return _LIB
+
+
+class _Guarded:
+    """Namespace of the library's entry points; the launching ones run under a device guard."""
+
+
+def _guard(fn):
+    """The library never changes the current device (include/fsg_dense.h) and launches on the stream it is given, so
+    the binding makes the tensors' device current for the duration of the call when it is not already: tensors on
+    cuda:1 with cuda:0 current would otherwise be launched on a stream of the wrong device.  ``ptr`` records the
+    device of every tensor argument (and refuses a mix), ``stream`` picks that device's current stream."""
+
+    def call(*args):
+        global _CALL_DEVICE
+        dev, _CALL_DEVICE = _CALL_DEVICE, None
+        if dev is None or dev == torch.cuda.current_device():
+            return fn(*args)
+        with torch.cuda.device(dev):
+            return fn(*args)
+
+    call.__name__ = fn.__name__
+    return call
 
 
 def check(status):
@@ -177,18 +214,30 @@ def check(status):
 
 
 def ptr(t):
-    """Device pointer of a CUDA tensor (None -> NULL)."""
+    """Device pointer of a CUDA tensor (None -> NULL).  All tensors of one call must live on one device."""
+    global _CALL_DEVICE
     if t is None:
         return None
     if not t.is_cuda:
+        _CALL_DEVICE = None
         raise RuntimeError("fsg_dense kernels take CUDA tensors only (no CPU path); got %s" % t.device)
     if not t.is_contiguous():
+        _CALL_DEVICE = None
         raise RuntimeError("fsg_dense kernels take contiguous tensors")
+    idx = t.device.index
+    if _CALL_DEVICE is None:
+        _CALL_DEVICE = idx
+    elif _CALL_DEVICE != idx:
+        was, _CALL_DEVICE = _CALL_DEVICE, None
+        raise RuntimeError("fsg_dense: tensor arguments on different devices (cuda:%d and cuda:%d)" % (was, idx))
     return t.data_ptr()
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Current stream of the device the call's tensors live on (the current device when there are none)."""
+    if _CALL_DEVICE is None:
+        return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(_CALL_DEVICE).cuda_stream
 
 
 def host_f32(vals):

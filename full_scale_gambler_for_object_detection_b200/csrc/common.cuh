@@ -113,6 +113,26 @@ __device__ __forceinline__ bool nms_suppresses(float4 bi, float ai, float4 bj, f
   return __fdiv_rn(inter, uni) > thr;
 }
 
+// ---- shared-memory histogram update of one warp round ---------------------------------------
+// Radix-select digits of score keys are either almost all equal inside a warp (the leading digits: keys share sign
+// and exponent) or almost all different (the trailing digits).  Up to two groups of equal bins are added with one
+// aggregated atomic each; whatever is left goes through plain shared-memory atomics, where distinct bins do not
+// conflict.  (match.any resolves one distinct value per step -- 32 steps for a warp of distinct bins.)
+__device__ __forceinline__ void warp_hist_add(unsigned* hist, unsigned bin, bool ok) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const unsigned act = __ballot_sync(kFull, ok);
+    if (act == 0u) return;
+    const int leader = __ffs(act) - 1;
+    const unsigned b0 = __shfl_sync(kFull, bin, leader);
+    const unsigned same = __ballot_sync(kFull, ok && bin == b0);
+    if (lane == leader) atomicAdd(&hist[b0], (unsigned)__popc(same));
+    ok = ok && bin != b0;
+  }
+  if (ok) atomicAdd(&hist[bin], 1u);
+}
+
 // ---- reductions ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

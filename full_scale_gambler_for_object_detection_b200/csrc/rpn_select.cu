@@ -75,11 +75,7 @@ __global__ void __launch_bounds__(kRpnThreads) rpn_select_kernel(const RpnArgs A
           digit = (unsigned)((key >> sh) & ((1u << width) - 1u));
         }
         // warp-aggregated histogram update (objectness logits crowd a few exponent bins)
-        const unsigned act = __ballot_sync(kFull, in);
-        if (in) {
-          const unsigned peers = __match_any_sync(act, digit);
-          if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
-        }
+        warp_hist_add(hist, digit, in);
       }
       __syncthreads();
       // ascending scan over the bins: thread t owns bins 2t, 2t+1

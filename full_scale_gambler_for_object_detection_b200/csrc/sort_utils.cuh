@@ -10,7 +10,7 @@ __device__ void bitonic_desc(uint64_t* a, int m) {
   for (int size = 2; size <= m; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = threadIdx.x; t < (m >> 1); t += NT) {
-        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1))   /* stride is a power of two */;
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
         const uint64_t x = a[lo], y = a[hi];
@@ -26,7 +26,7 @@ __device__ void bitonic_asc_smem(uint64_t* a, int m) {
   for (int size = 2; size <= m; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = threadIdx.x; t < (m >> 1); t += NT) {
-        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1))   /* stride is a power of two */;
         const int hi = lo + stride;
         const bool asc = ((lo & size) == 0);
         const uint64_t x = a[lo], y = a[hi];
@@ -58,7 +58,7 @@ __device__ void bitonic_asc(uint64_t* a, int m) {
       __syncthreads();
       for (; stride >= 64; stride >>= 1) {
         if (act) {
-          const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+          const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1))   /* stride is a power of two */;
           const int hi = lo + stride;
           const bool up = ((lo & size) == 0);
           const uint64_t x = a[lo], y = a[hi];

@@ -429,15 +429,18 @@ def dense_train_step_levels(logit_levels, delta_levels, bet_levels, anchors, gt,
 
 
 class DenseStepPlanLevels:
-    """``DenseStepPlan`` for the head's native layout: pre-allocated outputs and (optionally) one CUDA graph for
+    """``DenseStepPlan`` for the head's native layout: pre-allocated outputs and (optionally) CUDA graph(s) for
     K1 (2 launches, betting maps read in place) -> K2 on the per-level conv outputs -> K2 post on the per-level
-    maps.  Single process (a sharded run uses :func:`dense_train_step_levels` with ``group``).
+    maps.  ``group`` / ``peer`` as in ``DenseStepPlan``: a batch sharded by image over ranks exchanges
+    [num_foreground, S_batch] between K1 and K2 -- inside K1's second kernel over NVLink peer memory (``peer``, one
+    graph), else with an eager NCCL all-reduce between two graphs.
 
     ``level_shapes``: [(H, W)] per level; the head outputs are (N, A*K, H, W), (N, A*4, H, W), (N, A, H, W).
     Outputs (owned by the plan, overwritten by the next run/replay): ``grad_logits`` / ``grad_deltas`` /
     ``grad_bets`` / ``nakhw_loss`` (lists, per-level layout), ``gt_classes``, ``mask``, ``stats``, ``scalars``."""
 
-    def __init__(self, N, level_shapes, A, K, cfg, device, coeffs=(1.0, 1.0, -1.0), detach_pred=False):
+    def __init__(self, N, level_shapes, A, K, cfg, device, coeffs=(1.0, 1.0, -1.0), detach_pred=False, group=None,
+                 peer=None, max_total_gt=4096):
         assert K == cfg.num_classes
         self.N, self.A, self.K, self.cfg, self.device = N, A, K, cfg, torch.device(device)
         self.shapes = [(int(h), int(w)) for h, w in level_shapes]
@@ -445,34 +448,69 @@ class DenseStepPlanLevels:
         self.coeffs = tuple(float(c) for c in coeffs)
         self.params = cfg.loss_params(*self.coeffs)
         self.need_gl, self.need_gd = not detach_pred, self.coeffs[1] != 0.0
-        dev, f32 = self.device, torch.float32
+        self.group = group
+        self.peer = peer if (peer is not None and group is not None) else None
+        self.max_total_gt = int(max_total_gt)
+        dev, f32, i64 = self.device, torch.float32, torch.int64
         mk = lambda c: [torch.empty((N, c, h, w), dtype=f32, device=dev) for h, w in self.shapes]
         self.grad_logits = mk(A * K) if self.need_gl else None
         self.grad_deltas = mk(A * 4) if self.need_gd else None
         self.grad_bets, self.nakhw_loss = mk(A), mk(A)
+        R = self.R
+        self.m = {"gt_classes": torch.empty((N, R), dtype=i64, device=dev),
+                  "mask": torch.empty((N, R), dtype=i64, device=dev),
+                  "matched_idx32": torch.empty((N, R), dtype=torch.int32, device=dev),
+                  "stats": torch.zeros(_lib.STATS_HEADER + N, dtype=torch.float64, device=dev)}
+        self.scalars = torch.zeros(_lib.SCALARS_HEADER + N, dtype=torch.float64, device=dev)
+        L = ops.lib()
+        self.ws_match = torch.empty(max(16, L.fsg_match_workspace_bytes(N, R, self.max_total_gt)), dtype=torch.uint8,
+                                    device=dev)
         self.graph, self._static, self._last = None, None, None
 
-    def run(self, logit_levels, delta_levels, bet_levels, anchors, gt):
-        cfg, K = self.cfg, self.K
-        m = ops.match_anchors(anchors, gt, K, cfg.iou_thresholds, cfg.iou_labels, cfg.picky_thresholds, None,
-                              cfg.bbox_reg_weights, want=("gt_classes", "mask", "matched_idx32"),
-                              bet_levels=bet_levels, temperature=cfg.gambler_temperature)
-        out = ops.loss_main_levels(logit_levels, m["gt_classes"], self.params, m["stats"], delta_levels=delta_levels,
-                                   anchors=anchors, gt=gt, matched_idx32=m["matched_idx32"], mask=m["mask"],
-                                   bet_levels=bet_levels, ell_levels_out=self.nakhw_loss,
-                                   want_grad_logits=self.need_gl, want_grad_deltas=self.need_gd,
-                                   grad_logits_out=self.grad_logits, grad_deltas_out=self.grad_deltas)
-        ops.loss_post_levels(bet_levels, m["mask"], self.nakhw_loss, self.params, m["stats"], out["scalars"],
+    # ---- stages ---------------------------------------------------------------------------------------
+    def stage_match(self, bet_levels, anchors, gt):
+        cfg = self.cfg
+        if gt.total > self.max_total_gt:
+            raise RuntimeError("DenseStepPlanLevels: %d GT boxes > max_total_gt %d" % (gt.total, self.max_total_gt))
+        ops.match_anchors(anchors, gt, self.K, cfg.iou_thresholds, cfg.iou_labels, cfg.picky_thresholds, None,
+                          cfg.bbox_reg_weights, bet_levels=bet_levels, temperature=cfg.gambler_temperature,
+                          workspace=self.ws_match, out=self.m, peer=self.peer)
+
+    def stage_main(self, logit_levels, delta_levels, bet_levels, anchors, gt):
+        m = self.m
+        ops.loss_main_levels(logit_levels, m["gt_classes"], self.params, m["stats"], delta_levels=delta_levels,
+                             anchors=anchors, gt=gt, matched_idx32=m["matched_idx32"], mask=m["mask"],
+                             bet_levels=bet_levels, ell_levels_out=self.nakhw_loss,
+                             want_grad_logits=self.need_gl, want_grad_deltas=self.need_gd,
+                             grad_logits_out=self.grad_logits, grad_deltas_out=self.grad_deltas,
+                             scalars_out=self.scalars)
+
+    def stage_post(self, bet_levels):
+        ops.loss_post_levels(bet_levels, self.m["mask"], self.nakhw_loss, self.params, self.m["stats"], self.scalars,
                              out=self.grad_bets)
-        self._last = StepResult(total=out["scalars"][8], scalars=out["scalars"], stats=m["stats"],
+
+    def result(self):
+        m = self.m
+        self._last = StepResult(total=self.scalars[8], scalars=self.scalars, stats=m["stats"],
                                 per_anchor_loss=self.nakhw_loss, gt_classes=m["gt_classes"], mask=m["mask"],
                                 extras={"grad_logits": self.grad_logits, "grad_deltas": self.grad_deltas,
                                         "grad_bets": self.grad_bets})
         return self._last
 
+    def run(self, logit_levels, delta_levels, bet_levels, anchors, gt):
+        self.stage_match(bet_levels, anchors, gt)
+        if self.group is not None and self.peer is None:
+            sharded.all_reduce_stats(self.m["stats"], self.group)
+        self.stage_main(logit_levels, delta_levels, bet_levels, anchors, gt)
+        if self.group is not None and self.cfg.norm_mode == _lib.NORM_BATCH:
+            sharded.all_reduce_batch_weighted_sum(self.scalars, self.group)
+        self.stage_post(bet_levels)
+        return self.result()
+
     def capture(self, logit_levels, delta_levels, bet_levels, anchors, gt, warmup=2):
         """Capture the step reading from exactly these tensors (refresh them in place between replays)."""
-        self._static = (list(logit_levels), list(delta_levels), list(bet_levels), anchors, gt)
+        xs, ds, bs = list(logit_levels), list(delta_levels), list(bet_levels)
+        self._static = (xs, ds, bs, anchors, gt)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -480,12 +518,38 @@ class DenseStepPlanLevels:
                 self.run(*self._static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.run(*self._static)      # intermediates live in the graph's private pool
+
+        def cap(fn):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return g
+
+        batch_norm = self.cfg.norm_mode == _lib.NORM_BATCH
+        if self.group is None or (self.peer is not None and not batch_norm):
+            self.graph = [cap(lambda: self.run(*self._static))]
+        else:
+            g1 = cap(lambda: self.stage_match(bs, anchors, gt))
+            if batch_norm:
+                self.graph = [g1, cap(lambda: self.stage_main(xs, ds, bs, anchors, gt)), cap(lambda: self.stage_post(bs))]
+            else:
+                self.graph = [g1, cap(lambda: (self.stage_main(xs, ds, bs, anchors, gt), self.stage_post(bs)))]
+        self.result()
         return self
 
     def replay(self):
-        self.graph.replay()
+        g = self.graph
+        g[0].replay()
+        if len(g) > 1:
+            if self.peer is None:
+                sharded.all_reduce_stats(self.m["stats"], self.group)
+            g[1].replay()
+            if len(g) == 3:
+                sharded.all_reduce_batch_weighted_sum(self.scalars, self.group)
+                g[2].replay()
         _lib.count_launches(4)
         return self._last
+
+    def release_graphs(self):
+        self.graph = None
+        self._static = None

@@ -87,13 +87,15 @@ class PackedGT:
 def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1, 1),
                   picky_thresholds=(0.4, 0.9), picky_labels=None, box_weights=(1.0, 1.0, 1.0, 1.0),
                   want=("gt_classes", "mask", "matched_idx32"), bets=None, temperature=0.0,
-                  allow_low_quality_matches=True, bet_levels=None, phases=3, workspace=None, out=None):
+                  allow_low_quality_matches=True, bet_levels=None, phases=3, workspace=None, out=None, peer=None):
     """Fused IoU + Matcher(s) + GT assignment (retinanet.py:339-363, 400-425) for a batch.
 
     anchors: (R,4) shared by all images or (N,R,4) per image.  gt: PackedGT.
     want: subset of {matches, match_labels, picky_labels, gt_classes, mask, gt_deltas, matched_idx32}.
     bets (N,R): when given, the loss pre-pass is fused in and ``stats`` is returned too.
     bet_levels list[(N, A, H, W)]: the same with the betting maps read in their own layout (no flattened copy).
+    peer: ``sharded.PeerExchange`` -- the all-reduce of [num_foreground, S_batch] over the ranks then happens inside
+    the second kernel over NVLink peer memory (every rank must enqueue the same call).
     phases / workspace / out: the two-phase form for anchors sharded by range over ranks (see
     ``sharded.match_anchor_range``): phases=1 runs pass A only, phases=2 pass B on the same ``workspace`` after the
     per-GT maxima in it (``out["gt_max_bits"]``, an int32 view) were all-reduced with MAX.
@@ -142,7 +144,7 @@ def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1
             host_f32(box_weights), ptr(out.get("matches")), ptr(out.get("match_labels")),
             ptr(out.get("picky_labels")), ptr(out.get("gt_classes")), ptr(out.get("mask")),
             ptr(out.get("gt_deltas")), ptr(out.get("matched_idx32")), ptr(bets), lv, float(temperature), ptr(stats),
-            None, ptr(ws), ws.numel(), int(phases), stream()))
+            peer.ctx if peer is not None else None, ptr(ws), ws.numel(), int(phases), stream()))
         count_launches(2 if phases == 3 else 1)
     if stats is not None:
         out["stats"] = stats
@@ -330,7 +332,7 @@ def loss_main(logits, gt_classes, params, stats, pred_deltas=None, gt_deltas=Non
 def loss_main_levels(logit_levels, gt_classes, params, stats, delta_levels=None, gt_deltas=None, anchors=None,
                      gt=None, matched_idx32=None, mask=None, bets=None, want_grad_logits=True,
                      want_grad_deltas=True, want_weights=False, grad_logits_out=None, grad_deltas_out=None,
-                     bet_levels=None, ell_levels_out=None):
+                     bet_levels=None, ell_levels_out=None, scalars_out=None, workspace=None):
     """The fused main pass on the head's native layout: ``logit_levels`` list[(N, A*K, H, W)],
     ``delta_levels`` list[(N, A*4, H, W)]; gradients come back as lists of the same shapes.  The
     (N,R)-sized arguments are as in :func:`loss_main`.  No permute/cat copy of the logits is made.
@@ -372,14 +374,15 @@ def loss_main_levels(logit_levels, gt_classes, params, stats, delta_levels=None,
                               else torch.empty((N, R), dtype=torch.float32, device=dev))
     if want_weights:
         out["weights"] = torch.empty((N, R), dtype=torch.float32, device=dev)
-    scalars = torch.empty(_lib.SCALARS_HEADER + N, dtype=torch.float64, device=dev)
+    scalars = scalars_out if scalars_out is not None else torch.empty(_lib.SCALARS_HEADER + N, dtype=torch.float64,
+                                                                      device=dev)
     out["scalars"] = scalars
     a_ptr, a_stride = None, 0
     if anchors is not None:
         a_ptr = ptr(anchors)
         a_stride = anchors.shape[1] * 4 if anchors.dim() == 3 else 0
     L = lib()
-    ws = _ws(L.fsg_loss_main_levels_workspace_bytes(N, levels, nl, A), dev)
+    ws = workspace if workspace is not None else _ws(L.fsg_loss_main_levels_workspace_bytes(N, levels, nl, A), dev)
     check(L.fsg_loss_main_levels(
         levels, nl, A, ptr(gt_deltas), a_ptr, a_stride, ptr(gt.boxes) if gt is not None else None,
         ptr(gt.offsets) if gt is not None else None, ptr(matched_idx32), ptr(gt_classes), ptr(mask), ptr(bets),
@@ -433,6 +436,7 @@ def scale_(x, scale):
 # ------------------------------------------------------------------------------------------------
 # K3
 # ------------------------------------------------------------------------------------------------
+DETECT_LAUNCHES = 5        # sample bar, scan, finalize, streaming top-k (exact fallback, usually idle), NMS
 NMS_SMEM_BOXES = 8192      # up to here one CTA (or 8, split by class) does the whole call in shared memory
 NMS_MAX_BOXES = 262144     # beyond: rank / bit-matrix / sweep kernels (csrc/nms_large.cu), 8.6 GB mask at the cap
 
@@ -491,7 +495,61 @@ def detect(logits, deltas, anchors, level_offsets, score_threshold=0.05, topk=10
         float(scale_clamp), ptr(out["boxes"]), ptr(out["scores"]), ptr(out["classes"]), ptr(out["count"]),
         ptr(out.get("cand_boxes")), ptr(out.get("cand_scores")), ptr(out.get("cand_classes")),
         ptr(out.get("cand_count")), ptr(out.get("keep_idx")), ptr(postprocess), ptr(ws), ws.numel(), stream()))
-    count_launches(2)
+    count_launches(DETECT_LAUNCHES)
+    if want_candidates:   # diagnostics: how each (image, level) slab was selected (see fsg_detect_status_offset)
+        off = L.fsg_detect_status_offset(N, nl, int(topk))
+        out["slab_status"] = ws[off:off + 4 * N * nl].view(torch.int32).view(N, nl)
+    return out
+
+
+def detect_levels(logit_levels, delta_levels, anchors, num_classes, score_threshold=0.05, topk=1000, nms_threshold=0.5,
+                  max_det=100, box_weights=(1.0, 1.0, 1.0, 1.0), scale_clamp=SCALE_CLAMP, want_candidates=False,
+                  postprocess=None):
+    """:func:`detect` straight from the head outputs: ``logit_levels`` list[(N, A*K, H, W)], ``delta_levels``
+    list[(N, A*4, H, W)] are read in place (no permute/cat copy, retinanet.py:444-447); anchors (R,4) or (N,R,4) in
+    the reference's flattened order.  Same result dict as :func:`detect`, bit-identical to running it on the permuted
+    copy."""
+    K = int(num_classes)
+    xs = [x if (x.dtype == torch.float32 and x.is_contiguous()) else _f32c(x) for x in logit_levels]
+    ds = [d if (d.dtype == torch.float32 and d.is_contiguous()) else _f32c(d) for d in delta_levels]
+    a = _f32c(anchors)
+    N = xs[0].shape[0]
+    A = xs[0].shape[1] // K
+    dev = xs[0].device
+    nl = len(xs)
+    levels = (_lib.DetectLevel * nl)()
+    R = 0
+    for i, (x, d) in enumerate(zip(xs, ds)):
+        assert x.shape[0] == N and x.shape[1] == A * K and d.shape == (N, A * 4, x.shape[2], x.shape[3])
+        levels[i].logits, levels[i].deltas = ptr(x), ptr(d)
+        levels[i].H, levels[i].W = x.shape[2], x.shape[3]
+        R += A * x.shape[2] * x.shape[3]
+    assert a.shape[-2] == R, "anchors (%d) do not match the levels (%d)" % (a.shape[-2], R)
+    out = {
+        "boxes": torch.empty((N, max_det, 4), dtype=torch.float32, device=dev),
+        "scores": torch.empty((N, max_det), dtype=torch.float32, device=dev),
+        "classes": torch.empty((N, max_det), dtype=torch.int64, device=dev),
+        "count": torch.empty((N,), dtype=torch.int32, device=dev),
+    }
+    if want_candidates:
+        cap = nl * topk
+        out["cand_boxes"] = torch.zeros((N, cap, 4), dtype=torch.float32, device=dev)
+        out["cand_scores"] = torch.zeros((N, cap), dtype=torch.float32, device=dev)
+        out["cand_classes"] = torch.zeros((N, cap), dtype=torch.int64, device=dev)
+        out["cand_count"] = torch.empty((N,), dtype=torch.int32, device=dev)
+        out["keep_idx"] = torch.empty((N, max_det), dtype=torch.int64, device=dev)
+    L = lib()
+    ws = _ws(L.fsg_detect_workspace_bytes(N, R, K, nl, topk), dev)
+    check(L.fsg_detect_levels(
+        levels, nl, A, K, ptr(a), a.shape[1] * 4 if a.dim() == 3 else 0, N, R, float(score_threshold), int(topk),
+        float(nms_threshold), int(max_det), host_f32(box_weights), float(scale_clamp), ptr(out["boxes"]),
+        ptr(out["scores"]), ptr(out["classes"]), ptr(out["count"]), ptr(out.get("cand_boxes")),
+        ptr(out.get("cand_scores")), ptr(out.get("cand_classes")), ptr(out.get("cand_count")),
+        ptr(out.get("keep_idx")), ptr(postprocess), ptr(ws), ws.numel(), stream()))
+    count_launches(DETECT_LAUNCHES)
+    if want_candidates:   # diagnostics: how each (image, level) slab was selected (see fsg_detect_status_offset)
+        off = L.fsg_detect_status_offset(N, nl, int(topk))
+        out["slab_status"] = ws[off:off + 4 * N * nl].view(torch.int32).view(N, nl)
     return out
 
 

@@ -173,13 +173,20 @@ class RetinaNetDensePath:
                           postprocess)
 
     @staticmethod
-    def _to_instances(res, n, image_size):
-        c = int(res["count"][n].item())
+    def _to_instances(res, n, image_size, count=None):
+        c = int(res["count"][n].item()) if count is None else count
         r = Instances(tuple(image_size))
         r.pred_boxes = Boxes(res["boxes"][n, :c])
         r.scores = res["scores"][n, :c]
         r.pred_classes = res["classes"][n, :c]
         return r
+
+    @staticmethod
+    def _to_instances_batch(res, image_sizes):
+        """One device->host read of the N detection counts for the whole batch (the reference's per-image
+        variable-length Instances need the lengths on the host), not one ``.item()`` per image."""
+        counts = res["count"].tolist()
+        return [RetinaNetDensePath._to_instances(res, n, image_sizes[n], counts[n]) for n in range(len(counts))]
 
     @torch.no_grad()
     def inference(self, box_cls, box_delta, anchors, image_sizes, output_sizes=None):
@@ -189,18 +196,25 @@ class RetinaNetDensePath:
         what RetinaNet.forward applies to every result, retinanet.py:150-157) is then fused into the NMS
         epilogue and the returned Instances are at the output resolution."""
         assert len(anchors) == len(image_sizes)
-        x = ops.levels_to_flat([t.detach() for t in box_cls], self.num_classes)
-        d = ops.levels_to_flat([t.detach() for t in box_delta], 4)
-        offs = [0]
-        for a in anchors[0]:
-            offs.append(offs[-1] + len(a))
         post = None
         if output_sizes is not None:
             assert len(output_sizes) == len(image_sizes)
-            post = ops.postprocess_rows(image_sizes, output_sizes, x.device)
+            post = ops.postprocess_rows(image_sizes, output_sizes, box_cls[0].device)
             image_sizes = [tuple(s) for s in output_sizes]
-        res = self._detect(x, d, self._anchor_tensor(anchors), offs, postprocess=post)
-        return [self._to_instances(res, n, image_sizes[n]) for n in range(len(anchors))]
+        a = self._anchor_tensor(anchors)
+        if self.native_layout:   # the (N, A*K, H, W) / (N, A*4, H, W) head outputs are read in place
+            res = ops.detect_levels([t.detach() for t in box_cls], [t.detach() for t in box_delta], a,
+                                    self.num_classes, self.score_threshold, self.topk_candidates, self.nms_threshold,
+                                    self.max_detections_per_image, self.box2box_transform.weights,
+                                    self.box2box_transform.scale_clamp, postprocess=post)
+        else:                    # the reference's data flow: permute + cat per level (retinanet.py:444-447)
+            x = ops.levels_to_flat([t.detach() for t in box_cls], self.num_classes)
+            d = ops.levels_to_flat([t.detach() for t in box_delta], 4)
+            offs = [0]
+            for lvl in anchors[0]:
+                offs.append(offs[-1] + len(lvl))
+            res = self._detect(x, d, a, offs, postprocess=post)
+        return self._to_instances_batch(res, image_sizes)
 
     @torch.no_grad()
     def inference_single_image(self, box_cls, box_delta, anchors, image_size):

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FSG_ABI_VERSION 3
+#define FSG_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define FSG_API __attribute__((visibility("default")))
@@ -331,6 +331,11 @@ FSG_API int fsg_nms(const float* boxes, const float* scores, const int64_t* clas
  * are scaled (Boxes.scale), clipped to the output size (Boxes.clip) and the ones that became empty
  * (Boxes.nonempty) are dropped, stable; out_count / keep_idx then describe the filtered list. */
 FSG_API size_t fsg_detect_workspace_bytes(int N, int64_t R, int K, int num_levels, int topk);
+/* Diagnostics: after fsg_detect / fsg_detect_levels, the (N, num_levels) int32 words at workspace + this offset say
+ * how each (image, level) slab was selected: 1 = sampled bar + one scan, 2 = the sampled bar could not be proven
+ * safe (score ties at the top-k boundary, a plateau overflowing the candidate list, an unlucky sample) and the exact
+ * streaming top-k kernel redid the slab.  The result is the same either way. */
+FSG_API size_t fsg_detect_status_offset(int N, int num_levels, int topk);
 FSG_API int fsg_detect(const float* logits, const float* deltas, const float* anchors,
                int64_t anchor_image_stride, int N, int64_t R, int K,
                const int64_t* h_level_offsets, int num_levels, float score_threshold, int topk,
@@ -339,6 +344,24 @@ FSG_API int fsg_detect(const float* logits, const float* deltas, const float* an
                float* cand_boxes, float* cand_scores, int64_t* cand_classes, int32_t* cand_count,
                int64_t* keep_idx, const float* postprocess, void* workspace, size_t workspace_bytes,
                fsg_stream_t stream);
+
+/* fsg_detect on the head's NATIVE layout (SURVEY section 8f row 2 for K3): level l's logits (N, A*K, H_l, W_l) and
+ * deltas (N, A*4, H_l, W_l) are read in place (channel a*K+k / a*4+j, retinanet.py:40-43) -- the permute + cat that
+ * RetinaNet.inference does per level (retinanet.py:444-447) is never materialised.  Results are identical to
+ * fsg_detect on the permuted copy: candidates are ranked by (score, index in the reference's (h, w, a, k) order).
+ * anchors: flat (R,4) / (N,R,4) in the reference's order, R = sum_l H_l*W_l*A.  Workspace: fsg_detect_workspace_bytes. */
+typedef struct fsg_detect_level {
+  const float* logits;
+  const float* deltas;
+  int32_t H, W;
+} fsg_detect_level;
+FSG_API int fsg_detect_levels(const fsg_detect_level* h_levels, int num_levels, int A, int K, const float* anchors,
+                      int64_t anchor_image_stride, int N, int64_t R, float score_threshold, int topk,
+                      double nms_threshold, int max_det, const float* h_box_weights, float scale_clamp,
+                      float* out_boxes, float* out_scores, int64_t* out_classes, int32_t* out_count,
+                      float* cand_boxes, float* cand_scores, int64_t* cand_classes, int32_t* cand_count,
+                      int64_t* keep_idx, const float* postprocess, void* workspace, size_t workspace_bytes,
+                      fsg_stream_t stream);
 
 /* detector_postprocess on an arbitrary box list (e.g. an Instances of another detector head):
  * out_boxes[i] = clip(scale(boxes[i])), keep[i] = 1 iff the result is non-empty (width > 0 and height > 0). */

@@ -635,6 +635,79 @@ def test_detect_small_topk_and_lvis_classes(cuda):
     _detect_case(cuda, 1, [900, 300], 1230, 43, topk=100)
 
 
+def test_detect_select_paths(cuda):
+    """Which select path served each slab: ordinary data goes through the sampled bar + one scan (status 1);
+    plateaus of equal scores at the top-k boundary cannot be proven safe from a sample and are redone by the exact
+    streaming kernel (status 2).  Both are checked against the oracle by the tests above/below; here only the routing."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    K = 80
+    inp = synthetic.inference_inputs(49, 2, [24000, 3000, 300], K)
+    res = fsg.ops.detect(inp["logits"].to(cuda), inp["deltas"].to(cuda), inp["anchors"].to(cuda),
+                         inp["level_offsets"], want_candidates=True)
+    assert res["slab_status"].tolist() == [[1, 1, 1], [1, 1, 1]]
+    x = inp["logits"].clone()
+    x[1, :24000].view(-1)[::7] = 2.5                  # a plateau far larger than top-k in image 1, level 0
+    res = fsg.ops.detect(x.to(cuda), inp["deltas"].to(cuda), inp["anchors"].to(cuda), inp["level_offsets"],
+                         want_candidates=True)
+    st = res["slab_status"].tolist()
+    assert st[1][0] == 2 and st[0] == [1, 1, 1] and st[1][1:] == [1, 1]
+    offs = inp["level_offsets"]
+    cls = [x[1, offs[i]:offs[i + 1]] for i in range(3)]
+    reg = [inp["deltas"][1, offs[i]:offs[i + 1]] for i in range(3)]
+    anc = [inp["anchors"][offs[i]:offs[i + 1]] for i in range(3)]
+    _, (cb, cs, cc), _ = orc.inference_single_image(cls, reg, anc, K)
+    cnt = int(res["cand_count"][1].item())
+    assert cnt == cb.shape[0]
+    assert_equal_int(res["cand_classes"][1, :cnt], cc, "cand classes")
+    assert_close_tensor(res["cand_boxes"][1, :cnt], cb, "cand boxes", atol_scale=1e-6)
+
+
+@pytest.mark.parametrize("K,counts,A", [(80, [(20, 28), (10, 14), (5, 7), (3, 4), (2, 2)], 3),
+                                        (7, [(33, 21), (9, 5)], 3), (3, [(41, 37), (5, 3)], 9)])
+def test_detect_native_layout_equals_flat(cuda, K, counts, A):
+    """fsg_detect_levels on the head's (N, A*K, H, W) / (N, A*4, H, W) outputs == fsg_detect on the permuted copy,
+    bit for bit (candidates, order, detections); odd K / H*W make slabs that do not start on 16-byte boundaries.
+    Includes a block of tied logits so that index order in the reference's (h, w, a, k) flattening matters."""
+    fsg = _fsg()
+    N = 3
+    g = torch.Generator().manual_seed(50 + K)
+    xs = [torch.randn((N, A * K, h, w), generator=g) * 1.5 - 2.0 for h, w in counts]
+    ds = [torch.randn((N, A * 4, h, w), generator=g) * 0.2 for h, w in counts]
+    xs[0].view(-1)[torch.randperm(xs[0].numel(), generator=g)[:4000]] = 1.25     # ties across planes
+    R = sum(h * w * A for h, w in counts)
+    cx, cy = torch.rand(R, generator=g) * 600, torch.rand(R, generator=g) * 400
+    sz = torch.rand(R, generator=g) * 100 + 16
+    anchors = torch.stack((cx - sz / 2, cy - sz / 2, cx + sz / 2, cy + sz / 2), dim=1).to(torch.float32)
+    xs_c, ds_c, an = [t.to(cuda) for t in xs], [t.to(cuda) for t in ds], anchors.to(cuda)
+    got = fsg.ops.detect_levels(xs_c, ds_c, an, K, topk=300, want_candidates=True)
+    offs = [0]
+    for h, w in counts:
+        offs.append(offs[-1] + h * w * A)
+    want = fsg.ops.detect(fsg.ops.levels_to_flat(xs_c, K), fsg.ops.levels_to_flat(ds_c, 4), an, offs, topk=300,
+                          want_candidates=True)
+    for k in ("count", "cand_count"):
+        assert torch.equal(got[k], want[k]), k
+    for n in range(N):
+        c, d = int(want["cand_count"][n]), int(want["count"][n])
+        for k in ("cand_boxes", "cand_scores", "cand_classes"):
+            assert torch.equal(got[k][n, :c], want[k][n, :c]), k
+        for k in ("boxes", "scores", "classes", "keep_idx"):
+            assert torch.equal(got[k][n, :d], want[k][n, :d]), k
+    if K != 80:
+        return   # (tiny K: thousands of near-equal scores, whose order may differ by one ulp of the CPU's / GPU's expf)
+    # and the flat result against the oracle for image 0
+    flat_x, flat_d = orc.levels_to_flat(xs, K), orc.levels_to_flat(ds, 4)
+    cls = [flat_x[0, offs[i]:offs[i + 1]] for i in range(len(counts))]
+    reg = [flat_d[0, offs[i]:offs[i + 1]] for i in range(len(counts))]
+    anc = [anchors[offs[i]:offs[i + 1]] for i in range(len(counts))]
+    _, (cb, cs, cc), _ = orc.inference_single_image(cls, reg, anc, K, topk_candidates=300)
+    c = int(got["cand_count"][0])
+    assert c == cb.shape[0]
+    assert_equal_int(got["cand_classes"][0, :c], cc, "cand classes")
+    assert_close_tensor(got["cand_boxes"][0, :c], cb, "cand boxes", atol_scale=1e-6)
+
+
 def test_inference_with_fused_detector_postprocess(cuda):
     """RetinaNet.forward's inference tail (retinanet.py:150-157): inference -> detector_postprocess per image, with
     the post-processing fused into the NMS epilogue; against oracle inference + oracle detector_postprocess."""
