@@ -75,7 +75,25 @@ class PeerCtx(ctypes.Structure):
     """``struct fsg_peer_ctx``."""
 
     _fields_ = [("mailbox", ctypes.c_uint64 * 8), ("epoch", ctypes.c_uint64), ("error", ctypes.c_uint64),
-                ("rank", c_i32), ("world", c_i32)]
+                ("rank", c_i32), ("world", c_i32), ("timeout_cycles", ctypes.c_uint64)]
+
+
+class StepIO(ctypes.Structure):
+    """``struct fsg_step_io``."""
+
+    _fields_ = [("logits", c_ptr), ("pred_deltas", c_ptr), ("bets", c_ptr), ("anchors", c_ptr),
+                ("anchor_image_stride", c_i64), ("gt_boxes", c_ptr), ("gt_class_ids", c_ptr), ("gt_offsets", c_ptr),
+                ("sum_M", c_i64), ("gt_classes", c_ptr), ("mask", c_ptr), ("matched_idx32", c_ptr), ("stats", c_ptr),
+                ("scalars", c_ptr), ("grad_logits", c_ptr), ("grad_deltas", c_ptr), ("grad_bets", c_ptr),
+                ("per_anchor_loss", c_ptr), ("weights_out", c_ptr)]
+
+
+class MatchConfig(ctypes.Structure):
+    """``struct fsg_match_config``."""
+
+    _fields_ = [("thresholds", c_f32 * 4), ("picky_thresholds", c_f32 * 4), ("labels", ctypes.c_int8 * 8),
+                ("picky_labels", ctypes.c_int8 * 8), ("num_thresholds", c_i32), ("num_picky_thresholds", c_i32),
+                ("allow_low_quality_matches", c_i32), ("reserved", c_i32)]
 
 
 CLS_MODES = {"focal": 0, "sigmoid": 1}
@@ -120,6 +138,9 @@ PROTOTYPES = {
     "fsg_loss_post_levels": (c_i32, [ctypes.POINTER(PostLevel), c_i32, c_i32, c_ptr, c_i32, c_i64,
                                      ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr]),
     "fsg_loss_post": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i64, ctypes.POINTER(LossParams), c_ptr, c_ptr, c_ptr, c_ptr]),
+    "fsg_dense_step_workspace_bytes": (c_size, [c_i32, c_i64, c_i32, c_i64]),
+    "fsg_dense_step": (c_i32, [ctypes.POINTER(StepIO), c_i32, c_i64, ctypes.POINTER(MatchConfig),
+                               ctypes.POINTER(LossParams), ctypes.POINTER(PeerCtx), c_ptr, c_size, c_ptr]),
     "fsg_scale_inplace": (c_i32, [c_ptr, c_i64, c_ptr, c_f32, c_ptr]),
     "fsg_nms_workspace_bytes": (c_size, [c_i64]),
     "fsg_nms": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_f64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),

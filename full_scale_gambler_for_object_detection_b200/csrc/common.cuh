@@ -113,6 +113,39 @@ __device__ __forceinline__ bool nms_suppresses(float4 bi, float ai, float4 bj, f
   return __fdiv_rn(inter, uni) > thr;
 }
 
+// ---- programmatic dependent launch: device side --------------------------------------------------
+// No-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void grid_dependency_sync() {
+#if __CUDA_ARCH__ >= 900
+  cudaGridDependencySynchronize();
+#endif
+}
+__device__ __forceinline__ void grid_launch_dependents() {
+#if __CUDA_ARCH__ >= 900
+  cudaTriggerProgrammaticLaunchCompletion();
+#endif
+}
+
+// ---- launch with or without programmatic dependent launch -------------------------------------
+// pdl: the kernel may be scheduled while the kernel in front of it in the stream is still draining; it must call
+// cudaGridDependencySynchronize() before touching anything that kernel wrote (captured into CUDA graphs as a
+// programmatic dependency edge).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- shared-memory histogram update of one warp round ---------------------------------------
 // Radix-select digits of score keys are either almost all equal inside a warp (the leading digits: keys share sign
 // and exponent) or almost all different (the trailing digits).  Up to two groups of equal bins are added with one

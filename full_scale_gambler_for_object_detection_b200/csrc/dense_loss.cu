@@ -17,6 +17,7 @@
 // A[n] = sum_r w_hat*l afterwards (post pass over (N,R)-sized data).
 #include "common.cuh"
 #include "loss_math.cuh"
+#include "step_internal.cuh"
 
 namespace fsg {
 
@@ -60,6 +61,10 @@ struct LossArgs {
   float* partials;
   unsigned* counter;
   double* scalars;
+  // sharded batch, fsg_dense_step: K1 only POSTED this rank's [num_foreground, S_batch] into the peers' mailboxes;
+  // every CTA of this kernel polls its own rank's mailbox (local memory, L2 hits once the peers have arrived) and
+  // sums the slots in rank order -- the NVLink latency hides behind the first logit loads already in flight
+  PeerPoll peer;
 };
 
 
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) 
   // element loop); GT == 0: G and K are run-time values.
   constexpr bool kWrite = (VARIANT != kFastNoWrite);
   constexpr bool kFast = (VARIANT != kGeneric);
+  grid_launch_dependents();   // the post pass may be scheduled as this grid's CTAs retire; it waits for the whole grid
   const int tid = threadIdx.x;
   const int n = blockIdx.y;
   const int G = GT > 0 ? GT : A.G;
@@ -141,14 +147,23 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) 
   const int ngrp = kLossBlock >> logG;
   const int64_t tile_base = (int64_t)blockIdx.x * A.anchors_per_tile;
 
+  // Everything K1 produced is read from here on (under programmatic dependent launch this grid may have been
+  // scheduled while K1 was still draining).
+  grid_dependency_sync();
   // normalisers: every thread derives them itself from two broadcast loads (no block barrier behind one
   // thread's fp64 divide).  num_foreground is an integer < 2^24, so the fp32 reciprocal of max(1, nf) is the
   // reference's own fp32 division; S[n] is rounded to fp32 like the reference's fp32 sum.
-  const double nf_d = A.stats[0];
+  double nf_d = A.stats[0];
+  float s_batch = (A.nmode == FSG_NORM_BATCH) ? (float)A.stats[1] : 1.f;
+  if (A.peer.world > 1) {   // sharded batch: the global sums arrive through the peer mailboxes (fsg_dense_step)
+    double sb;
+    peer_poll_sum(A.peer, nf_d, sb);
+    s_batch = (float)sb;
+  }
   const float inv_nf = __frcp_rn(fmaxf((float)nf_d, 1.f));
   float inv_S = 1.f;
   if (A.nmode == FSG_NORM_IMAGE) inv_S = __frcp_rn((float)A.stats[FSG_STATS_HEADER + n]);
-  else if (A.nmode == FSG_NORM_BATCH) inv_S = __frcp_rn((float)A.stats[1]);
+  else if (A.nmode == FSG_NORM_BATCH) inv_S = __frcp_rn(s_batch);
   const int m0 = A.gt_offsets ? A.gt_offsets[n] : 0;
   const bool write_grad = kWrite && (A.grad_logits != nullptr);
 
@@ -377,7 +392,7 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) 
   acc_cls = warp_sum(acc_cls); acc_reg = warp_sum(acc_reg); acc_wl = warp_sum(acc_wl);
   acc_l = warp_sum(acc_l); max_l = warp_max(max_l);
   finish_tile(acc_cls, acc_reg, acc_wl, acc_l, max_l, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
-              A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam);
+              A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam, A.peer);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -403,6 +418,7 @@ __global__ void __launch_bounds__(256) loss_post_kernel(const float* __restrict_
                                                         const double* __restrict__ scalars,
                                                         float* __restrict__ grad_bets) {
   const int n = blockIdx.y;
+  grid_dependency_sync();   // (programmatic dependent launch behind the main pass)
   // every thread derives the two per-image constants itself (broadcast loads, one fp32 reciprocal): a block
   // barrier behind one thread's fp64 divide cost more than the whole rest of this kernel
   float inv_S = 1.f, Asum = 0.f;
@@ -494,10 +510,10 @@ static LossWs loss_ws_layout(int N, const LossPlan& p) {
 }
 
 template <int V, int BATCH, int GT>
-static void launch_main(int variant, dim3 grid, cudaStream_t s, const LossArgs& a) {
-  if (variant == kFastWrite) loss_main_kernel<V, BATCH, kFastWrite, GT><<<grid, kLossBlock, 0, s>>>(a);
-  else if (variant == kFastNoWrite) loss_main_kernel<V, BATCH, kFastNoWrite, GT><<<grid, kLossBlock, 0, s>>>(a);
-  else loss_main_kernel<V, BATCH, kGeneric, GT><<<grid, kLossBlock, 0, s>>>(a);
+static void launch_main(int variant, dim3 grid, cudaStream_t s, const LossArgs& a, bool pdl) {
+  if (variant == kFastWrite) launch_pdl(loss_main_kernel<V, BATCH, kFastWrite, GT>, grid, dim3(kLossBlock), 0, s, pdl, a);
+  else if (variant == kFastNoWrite) launch_pdl(loss_main_kernel<V, BATCH, kFastNoWrite, GT>, grid, dim3(kLossBlock), 0, s, pdl, a);
+  else launch_pdl(loss_main_kernel<V, BATCH, kGeneric, GT>, grid, dim3(kLossBlock), 0, s, pdl, a);
 }
 
 }  // namespace fsg
@@ -536,13 +552,15 @@ extern "C" size_t fsg_loss_main_workspace_bytes(int N, int64_t R, int K) {
   return loss_ws_layout(N, plan_loss(R, K)).total;
 }
 
-extern "C" int fsg_loss_main(const float* logits, const float* pred_deltas, const float* gt_deltas,
-                             const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
-                             const int32_t* gt_offsets, const int32_t* matched_idx32, const int64_t* gt_classes,
-                             const int64_t* mask, const float* bets, int N, int64_t R,
-                             const fsg_loss_params* hp, const double* stats, float* grad_logits,
-                             float* grad_deltas, float* per_anchor_loss, float* weights_out, double* scalars,
-                             void* workspace, size_t workspace_bytes, fsg_stream_t stream) {
+namespace fsg {
+int loss_main_enqueue(const float* logits, const float* pred_deltas, const float* gt_deltas,
+                      const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
+                      const int32_t* gt_offsets, const int32_t* matched_idx32, const int64_t* gt_classes,
+                      const int64_t* mask, const float* bets, int N, int64_t R,
+                      const fsg_loss_params* hp, double* stats, float* grad_logits,
+                      float* grad_deltas, float* per_anchor_loss, float* weights_out, double* scalars,
+                      void* workspace, size_t workspace_bytes, const fsg_peer_ctx* h_peer, int flags,
+                      fsg_stream_t stream) {
   if (!hp || N <= 0 || R <= 0 || hp->num_classes <= 0) return FSG_ERR_INVALID_ARG;
   if (!logits || !gt_classes || !stats || !scalars) return FSG_ERR_INVALID_ARG;
   if (N > 65535) return FSG_ERR_UNSUPPORTED;
@@ -578,32 +596,56 @@ extern "C" int fsg_loss_main(const float* logits, const float* pred_deltas, cons
   a.stats = stats; a.grad_logits = grad_logits; a.grad_deltas = grad_deltas; a.ell = per_anchor_loss;
   a.wout = weights_out; a.partials = (float*)(ws + w.off_partials); a.counter = (unsigned*)(ws + w.off_counter);
   a.scalars = scalars;
+  a.peer = make_peer_poll(h_peer, stats);
 
-  FSG_CUDA_TRY(cudaMemsetAsync(a.counter, 0, 16, s));
+  const bool pdl = (flags & kLossPdl) != 0;
+  if (!(flags & kLossCounterZeroed)) FSG_CUDA_TRY(cudaMemsetAsync(a.counter, 0, 16, s));
   const bool fast = (hp->focal_gamma == 2.f) && (hp->gambler_mode == FSG_CLS_FOCAL);
   const int variant = fast ? (grad_logits ? kFastWrite : kFastNoWrite) : kGeneric;
   dim3 grid((unsigned)p.tiles_per_image, (unsigned)N);
   const bool exact = (p.nvec == p.G * p.batch);
-  if (p.V == 4 && p.G == 4 && p.batch == 5 && exact && variant != kGeneric) launch_main<4, 5, 4>(variant, grid, s, a);  // K = 80
-  else if (p.V == 4) { if (p.batch == 5) launch_main<4, 5, 0>(variant, grid, s, a); else launch_main<4, 4, 0>(variant, grid, s, a); }
-  else if (p.V == 2) { if (p.batch == 5) launch_main<2, 5, 0>(variant, grid, s, a); else launch_main<2, 4, 0>(variant, grid, s, a); }
-  else { if (p.batch == 5) launch_main<1, 5, 0>(variant, grid, s, a); else launch_main<1, 4, 0>(variant, grid, s, a); }
+  if (p.V == 4 && p.G == 4 && p.batch == 5 && exact && variant != kGeneric) launch_main<4, 5, 4>(variant, grid, s, a, pdl);  // K = 80
+  else if (p.V == 4) { if (p.batch == 5) launch_main<4, 5, 0>(variant, grid, s, a, pdl); else launch_main<4, 4, 0>(variant, grid, s, a, pdl); }
+  else if (p.V == 2) { if (p.batch == 5) launch_main<2, 5, 0>(variant, grid, s, a, pdl); else launch_main<2, 4, 0>(variant, grid, s, a, pdl); }
+  else { if (p.batch == 5) launch_main<1, 5, 0>(variant, grid, s, a, pdl); else launch_main<1, 4, 0>(variant, grid, s, a, pdl); }
   FSG_LAUNCH_CHECK();
   return FSG_OK;
+}
+
+int loss_post_enqueue(const float* bets, const int64_t* mask, const float* per_anchor_loss, int N,
+                      int64_t R, const fsg_loss_params* hp, const double* stats, const double* scalars,
+                      float* grad_bets, int flags, fsg_stream_t stream) {
+  if (!hp || N <= 0 || R <= 0 || !bets || !per_anchor_loss || !stats || !scalars || !grad_bets)
+    return FSG_ERR_INVALID_ARG;
+  if (N > 65535) return FSG_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)ceil_div(R, 1024), (unsigned)N);
+  launch_pdl(loss_post_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (flags & kLossPdl) != 0, bets, mask,
+             per_anchor_loss, N, R, hp->temperature, hp->gambler_gamma, (int)hp->norm_mode, hp->c_gam, stats, scalars,
+             grad_bets);
+  FSG_LAUNCH_CHECK();
+  return FSG_OK;
+}
+
+size_t loss_main_ws_bytes(int N, int64_t R, int K) { return loss_ws_layout(N, plan_loss(R, K)).total; }
+}  // namespace fsg
+
+extern "C" int fsg_loss_main(const float* logits, const float* pred_deltas, const float* gt_deltas,
+                             const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
+                             const int32_t* gt_offsets, const int32_t* matched_idx32, const int64_t* gt_classes,
+                             const int64_t* mask, const float* bets, int N, int64_t R,
+                             const fsg_loss_params* hp, const double* stats, float* grad_logits,
+                             float* grad_deltas, float* per_anchor_loss, float* weights_out, double* scalars,
+                             void* workspace, size_t workspace_bytes, fsg_stream_t stream) {
+  return loss_main_enqueue(logits, pred_deltas, gt_deltas, anchors, anchor_image_stride, gt_boxes, gt_offsets,
+                           matched_idx32, gt_classes, mask, bets, N, R, hp, const_cast<double*>(stats), grad_logits,
+                           grad_deltas, per_anchor_loss, weights_out, scalars, workspace, workspace_bytes, nullptr, 0,
+                           stream);
 }
 
 extern "C" int fsg_loss_post(const float* bets, const int64_t* mask, const float* per_anchor_loss, int N,
                              int64_t R, const fsg_loss_params* hp, const double* stats, const double* scalars,
                              float* grad_bets, fsg_stream_t stream) {
-  if (!hp || N <= 0 || R <= 0 || !bets || !per_anchor_loss || !stats || !scalars || !grad_bets)
-    return FSG_ERR_INVALID_ARG;
-  if (N > 65535) return FSG_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)ceil_div(R, 1024), (unsigned)N);
-  loss_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bets, mask, per_anchor_loss, N, R, hp->temperature,
-                                                           hp->gambler_gamma, hp->norm_mode, hp->c_gam, stats,
-                                                           scalars, grad_bets);
-  FSG_LAUNCH_CHECK();
-  return FSG_OK;
+  return loss_post_enqueue(bets, mask, per_anchor_loss, N, R, hp, stats, scalars, grad_bets, 0, stream);
 }
 
 extern "C" int fsg_scale_inplace(float* x, int64_t n, const float* scale_dev, float scale_host,

@@ -1,0 +1,75 @@
+// The fused training step as one entry point (include/fsg_dense.h: fsg_dense_step).
+//
+// What the reference does across RetinaNet.get_ground_truth / get_picky_ground_truth / losses
+// (detectron2/modeling/meta_arch/retinanet.py:201-248, 309-429), LayeredUnetGambler.gambler_loss
+// (ImbalanceDetection/imbalancedetection/gambler_heads.py:502-602) and loss.backward() becomes
+//
+//   memset (every completion counter and the per-GT maxima of the step)
+//   K1 A     per-anchor best / argmax with warp-level GT culling, per-GT maxima, and everything that depends only
+//            on the anchor's own best IoU: labels, gt_classes, mask, partial pre-pass sums
+//   K1 B     low-quality rule as a patch pass, sums folded; the peer sums are only posted       (PDL)
+//   K2 main  polls the peer mailboxes itself, in every CTA                                      (PDL)
+//   K2 post                                                                                     (PDL)
+// PDL = programmatic dependent launch: the kernel is scheduled while its predecessor drains and waits on the device.
+//
+// Nothing here computes: the kernels live in iou_match.cu and dense_loss.cu.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "step_internal.cuh"
+
+using namespace fsg;
+
+namespace {
+// FSG_STEP_NO_PDL=1: plain stream-ordered launches (A/B timing of the programmatic dependent launch)
+bool step_no_pdl() {
+  static const int v = [] {
+    const char* e = getenv("FSG_STEP_NO_PDL");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return v != 0;
+}
+}  // namespace
+
+extern "C" size_t fsg_dense_step_workspace_bytes(int N, int64_t R, int K, int64_t sum_M) {
+  if (N <= 0 || R <= 0 || K <= 0 || sum_M < 0) return 0;
+  return align_up(fsg_match_workspace_bytes(N, R, sum_M), 256) + loss_main_ws_bytes(N, R, K);
+}
+
+extern "C" int fsg_dense_step(const fsg_step_io* io, int N, int64_t R, const fsg_match_config* mc,
+                              const fsg_loss_params* hp, const fsg_peer_ctx* h_peer, void* workspace,
+                              size_t workspace_bytes, fsg_stream_t stream) {
+  if (!io || !mc || !hp || N <= 0 || R <= 0) return FSG_ERR_INVALID_ARG;
+  if (!io->logits || !io->pred_deltas || !io->bets || !io->anchors || !io->gt_offsets || !io->gt_classes ||
+      !io->mask || !io->matched_idx32 || !io->stats || !io->scalars || !io->grad_bets || !io->per_anchor_loss)
+    return FSG_ERR_INVALID_ARG;
+  if (mc->num_thresholds < 1 || mc->num_thresholds > 4 || mc->num_picky_thresholds < 1 || mc->num_picky_thresholds > 4)
+    return FSG_ERR_INVALID_ARG;
+  const bool sharded = h_peer && h_peer->world > 1;
+  if (sharded && hp->norm_mode == FSG_NORM_BATCH) return FSG_ERR_UNSUPPORTED;
+  const int K = hp->num_classes;
+  const size_t off_loss = align_up(fsg_match_workspace_bytes(N, R, io->sum_M), 256);
+  const size_t need = off_loss + loss_main_ws_bytes(N, R, K);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  // the loss kernel's completion counter; K1 zeroes its own workspace head (one more memset node) -- both sit in
+  // front of K1, so nothing separates K1 from the main pass
+  FSG_CUDA_TRY(cudaMemsetAsync(ws + off_loss, 0, 16, s));
+  int st = match_enqueue(io->anchors, R, io->anchor_image_stride, io->gt_boxes, io->gt_class_ids, io->gt_offsets, N,
+                         io->sum_M, K, mc->thresholds, mc->labels, mc->num_thresholds,
+                         mc->allow_low_quality_matches, mc->picky_thresholds, mc->picky_labels,
+                         mc->num_picky_thresholds, hp->box_weights, nullptr, nullptr, nullptr, io->gt_classes, io->mask,
+                         nullptr, io->matched_idx32, io->bets, nullptr, hp->temperature, io->stats,
+                         sharded ? h_peer : nullptr, ws, off_loss, 3,
+                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl), nullptr, 0, stream);
+  if (st != FSG_OK) return st;
+  const int pdl = step_no_pdl() ? 0 : kLossPdl;
+  st = loss_main_enqueue(io->logits, io->pred_deltas, nullptr, io->anchors, io->anchor_image_stride, io->gt_boxes,
+                         io->gt_offsets, io->matched_idx32, io->gt_classes, io->mask, io->bets, N, R, hp, io->stats,
+                         io->grad_logits, io->grad_deltas, io->per_anchor_loss, io->weights_out, io->scalars,
+                         ws + off_loss, need - off_loss, sharded ? h_peer : nullptr, pdl | kLossCounterZeroed, stream);
+  if (st != FSG_OK) return st;
+  return loss_post_enqueue(io->bets, io->mask, io->per_anchor_loss, N, R, hp, io->stats, io->scalars, io->grad_bets,
+                           pdl, stream);
+}

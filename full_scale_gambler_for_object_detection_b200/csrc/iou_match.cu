@@ -12,7 +12,10 @@
 // mbarrier); every thread owns U anchors and walks the GT table with shared-memory broadcast
 // reads; per-GT maxima are reduced with redux.sync and merged with atomicMax on the
 // float-as-uint pattern (valid because IoU >= 0).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "step_internal.cuh"
 
 namespace fsg {
 
@@ -190,49 +193,143 @@ __global__ void __launch_bounds__(256) matrix_match_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------
 // Fused path, pass A: per-anchor max/argmax over the image's GT + per-GT max over anchors
 // ------------------------------------------------------------------------------------------
-constexpr int kSmallM = 32;  // images with at most this many GT skip the shared-memory staging entirely
+constexpr int kSmallM = 32;  // images with at most this many GT: boxes staged by one parallel load, warp-level culling
+
+struct MatchOut {
+  int64_t* matches;
+  int8_t* match_labels;
+  int8_t* picky_labels;
+  int64_t* gt_classes;
+  int64_t* mask;
+  float4* gt_deltas;
+  int32_t* matched_idx32;
+};
+
+// the gambler's betting maps in their own per-level (N, A, H, W) layout (read in place)
+struct BetLevels {
+  const float* ptr[FSG_MAX_LEVELS];
+  int64_t off[FSG_MAX_LEVELS + 1];
+  int HW[FSG_MAX_LEVELS];
+  int A, num_levels;
+};
+__device__ __forceinline__ float bet_at(const BetLevels& lv, int n, int64_t r) {
+  int l = 0;
+  while (l + 1 < lv.num_levels && r >= lv.off[l + 1]) ++l;
+  const int local = (int)(r - lv.off[l]);
+  const int hw = local / lv.A;
+  const int a = local - hw * lv.A;
+  return lv.ptr[l][((int64_t)n * lv.A + a) * lv.HW[l] + hw];
+}
+
+constexpr int kWarpsPerBlock = kMatchBlock / 32;
+
+// (count, sum) of the CTA into slot `slot`: warp shuffles, one barrier, warps summed in a fixed order
+__device__ __forceinline__ void block_partial(int cnt, float sum, int* part_cnt, float* part_s, int64_t slot) {
+  __shared__ int s_pi[kWarpsPerBlock];
+  __shared__ float s_pf[kWarpsPerBlock];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int cw = __reduce_add_sync(kFull, cnt);
+  const float sw = warp_sum(sum);
+  if (lane == 0) { s_pi[wid] = cw; s_pf[wid] = sw; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ci = 0;
+    float cs = 0.f;
+    for (int w = 0; w < kWarpsPerBlock; ++w) { ci += s_pi[w]; cs += s_pf[w]; }
+    part_cnt[slot] = ci;
+    part_s[slot] = cs;
+  }
+}
+
+// Every thread of pass A has seen ALL ground truth of its image when its loop ends, so its best IoU / argmax are
+// final and the threshold bands (matcher.py:88-92), the class relabel (retinanet.py:354-360), the picky mask
+// (:417-425), get_deltas and the loss pre-pass sums can be produced right there.  What pass A cannot know is the
+// low-quality rule (matcher.py:99-132: needs the per-GT maxima over all anchors): pass B revisits only the anchors
+// that can be affected and patches their labels and the sums.
+struct PassAEpi {
+  const int64_t* gt_class_ids;
+  int num_classes;
+  int8_t lab0, plab0;        // labels of an image without ground truth (matcher.py:70-80)
+  int has_picky;
+  BandsReg br, pbr;
+  float wx, wy, ww, wh;
+  MatchOut out;
+  const float* bets;
+  float temperature;
+  int* part_cnt;             // (N, gridDim.x) or NULL: no pre-pass sums
+  float* part_s;
+};
 
 template <int U>
-__global__ void __launch_bounds__(kMatchBlock) match_pass_a_kernel(
+__global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
     const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
     const float4* __restrict__ gt_boxes, const int32_t* __restrict__ gt_offsets,
-    float* __restrict__ best_val, int32_t* __restrict__ best_idx, unsigned* __restrict__ gt_max) {
+    float* __restrict__ best_val, int32_t* __restrict__ best_idx, unsigned* __restrict__ gt_max,
+    const PassAEpi E, const BetLevels lv) {
   __shared__ __align__(16) float4 s_gt[kGtChunk];
   __shared__ float s_area[kGtChunk];
   __shared__ unsigned s_max[kGtChunk];
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int64_t s_cls[kSmallM];
+  grid_launch_dependents();   // pass B may be scheduled as this grid's CTAs retire (it waits for the whole grid)
 
   const int n = blockIdx.y;
   const int m0 = gt_offsets[n];
   const int M = gt_offsets[n + 1] - m0;
   const int tid = threadIdx.x;
-  const int lane = tid & 31;
+  const int lane = tid & 31, wid = tid >> 5;
   const int64_t base = (int64_t)blockIdx.x * (kMatchBlock * U);
   const float4* a_img = anchors + (int64_t)n * anchor_stride4;
 
   float4 a[U];
-  float aa[U], bv[U];
+  float aa[U], bv[U], bet[U];
   int bi[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     int64_t r = base + u * kMatchBlock + tid;
     a[u] = (r < R) ? a_img[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // the bet is only needed by the epilogue; loading it now hides its HBM latency behind the GT loop
+    bet[u] = (E.bets != nullptr && r < R) ? E.bets[(int64_t)n * R + r] : 0.f;
     aa[u] = box_area(a[u]);
     bv[u] = 0.f;   // running best starts at (IoU 0, GT 0): exactly torch's argmax of an all-zero column,
     bi[u] = 0;     // and strict '>' keeps the lowest GT index among ties (matcher.py:86)
   }
 
   if (M <= kSmallM) {
-    // ---- few GT (the detection-training case): GT boxes by broadcast loads straight from global/L1 (no
-    //      TMA round trip); per-GT maxima are still merged per CTA in shared memory first, because
-    //      same-address atomics serialise in L2 (~27 cycles each) and every overlapping warp would hit
-    //      the same M words
-    if (tid < kSmallM) s_max[tid] = 0u;
+    // ---- few GT (the detection-training case).  The M boxes and areas arrive by one parallel load (M broadcast
+    //      loads inside the loop would each expose a full L2 latency); per-GT maxima are merged per CTA in shared
+    //      memory first, because same-address atomics serialise in L2 (~27 cycles each).
+    if (tid < kSmallM) {
+      s_max[tid] = 0u;
+      if (tid < M) {
+        const float4 G = gt_boxes[m0 + tid];
+        s_gt[tid] = G;
+        s_area[tid] = box_area(G);
+        s_cls[tid] = E.gt_class_ids ? E.gt_class_ids[m0 + tid] : 0;
+      }
+    }
+    // warp-level culling: consecutive anchors are neighbouring cells of one pyramid level, so the warp's anchors
+    // span a small rectangle, and a ground truth that does not reach into it has IoU exactly 0 with every lane --
+    // it can neither beat a running best (which starts at 0) nor raise a per-GT maximum.  Exact, not a heuristic.
+    float bx0 = __int_as_float(0x7f800000), by0 = bx0, bx1 = -bx0, by1 = -bx0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * kMatchBlock + tid < R) {
+        bx0 = fminf(bx0, a[u].x); by0 = fminf(by0, a[u].y);
+        bx1 = fmaxf(bx1, a[u].z); by1 = fmaxf(by1, a[u].w);
+      }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      bx0 = fminf(bx0, __shfl_xor_sync(kFull, bx0, sft)); by0 = fminf(by0, __shfl_xor_sync(kFull, by0, sft));
+      bx1 = fmaxf(bx1, __shfl_xor_sync(kFull, bx1, sft)); by1 = fmaxf(by1, __shfl_xor_sync(kFull, by1, sft));
+    }
     __syncthreads();
     for (int g = 0; g < M; ++g) {
-      const float4 G = gt_boxes[m0 + g];
-      const float ga = box_area(G);
-      const float known = __uint_as_float(gt_max[m0 + g]);  // may be stale: only makes the filter looser
+      const float4 G = s_gt[g];
+      if (G.z <= bx0 || G.x >= bx1 || G.w <= by0 || G.y >= by1) continue;   // warp-uniform; NaN never culls
+      const float ga = s_area[g];
+      const float known = __uint_as_float(s_max[g]);  // what this CTA found so far: only makes the filter looser
       float m = 0.f;
 #pragma unroll
       for (int u = 0; u < U; ++u) pair_update(G, ga, a[u], aa[u], known, g, bv[u], bi[u], m);
@@ -290,58 +387,76 @@ __global__ void __launch_bounds__(kMatchBlock) match_pass_a_kernel(
     }
   }
 
+
+  // ---- epilogue: everything that depends only on this anchor's own best IoU
+  const bool need_deltas = (E.out.gt_deltas != nullptr);
+  const bool o_matches = E.out.matches != nullptr, o_labels = E.out.match_labels != nullptr;
+  const bool o_picky = E.out.picky_labels != nullptr, o_cls = E.out.gt_classes != nullptr;
+  const bool o_mask = E.out.mask != nullptr, o_idx32 = E.out.matched_idx32 != nullptr;
+  const bool has_ids = E.gt_class_ids != nullptr, has_bets = E.bets != nullptr;
+  int fg = 0;
+  float w_part = 0.f;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    int64_t r = base + u * kMatchBlock + tid;
-    if (r < R) {
-      best_val[(int64_t)n * R + r] = (M > 0) ? bv[u] : 0.f;
-      best_idx[(int64_t)n * R + r] = bi[u];
+    const int64_t r = base + u * kMatchBlock + tid;
+    if (r >= R) continue;
+    const int64_t o = (int64_t)n * R + r;
+    const float val = (M > 0) ? bv[u] : 0.f;
+    best_val[o] = val;
+    best_idx[o] = bi[u];
+    int8_t l1, l2 = 0;
+    int64_t cls, msk = 0;
+    int id = bi[u];
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (M > 0) {
+      l1 = band_label_reg(E.br, val);
+      if (E.has_picky) l2 = band_label_reg(E.pbr, val);
+      cls = (M <= kSmallM) ? s_cls[id] : (has_ids ? E.gt_class_ids[m0 + id] : 0);
+      if (l1 == 0) cls = E.num_classes;   // retinanet.py:356
+      if (l1 == -1) cls = -1;             // :360
+      msk = (l2 == 1) ? 1 : 0;            // :417-423
+      if (need_deltas) d = encode_deltas(a[u], gt_boxes[m0 + id], E.wx, E.wy, E.ww, E.wh);
+    } else {                              // matcher.py:70-80, retinanet.py:362-363, :425
+      l1 = E.lab0;
+      l2 = E.plab0;
+      cls = E.num_classes;
+      msk = E.num_classes;
+      id = 0;
     }
+    if (o_matches) E.out.matches[o] = id;
+    if (o_labels) E.out.match_labels[o] = l1;
+    if (o_picky) E.out.picky_labels[o] = l2;
+    if (o_cls) E.out.gt_classes[o] = cls;
+    if (o_mask) E.out.mask[o] = msk;
+    if (need_deltas) E.out.gt_deltas[o] = d;
+    if (o_idx32) E.out.matched_idx32[o] = id;
+    fg += (cls >= 0 && cls != E.num_classes) ? 1 : 0;
+    if (has_bets) w_part += __fadd_rn(__fmul_rn(bet[u], (float)msk), E.temperature);  // gambler_heads.py:569,304
+    else if (lv.num_levels > 0 && msk != 0) w_part += __fmul_rn(bet_at(lv, n, r), (float)msk);  // + R*T at the fold
   }
+  if (E.part_cnt == nullptr) return;
+  // one partial per CTA in a fixed slot; the fold kernel sums the slots in a fixed order => run-to-run deterministic
+  block_partial(fg, w_part, E.part_cnt, E.part_s, (int64_t)n * gridDim.x + blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
-// Fused path, pass B: low-quality pass, labels, class relabel, picky mask, encode, loss pre-pass
+// Fused path, pass B: the low-quality rule (matcher.py:99-132) as a patch pass, and the fold of the pre-pass sums.
+// An anchor can equal some GT's maximum only if its own best IoU reaches the smallest per-GT maximum of its image
+// (IoU(g,a) <= best(a)), so all but a handful of anchors are dismissed after one 4-byte load.
 // ------------------------------------------------------------------------------------------
-struct MatchOut {
-  int64_t* matches;
-  int8_t* match_labels;
-  int8_t* picky_labels;
-  int64_t* gt_classes;
-  int64_t* mask;
-  float4* gt_deltas;
-  int32_t* matched_idx32;
-};
+constexpr int kPassBU = 4;  // anchors per thread in pass B (8 was measured slower: 17 vs 13 us on config 2)
 
-// the gambler's betting maps in their own per-level (N, A, H, W) layout (read in place by pass B)
-struct BetLevels {
-  const float* ptr[FSG_MAX_LEVELS];
-  int64_t off[FSG_MAX_LEVELS + 1];
-  int HW[FSG_MAX_LEVELS];
-  int A, num_levels;
-};
-__device__ __forceinline__ float bet_at(const BetLevels& lv, int n, int64_t r) {
-  int l = 0;
-  while (l + 1 < lv.num_levels && r >= lv.off[l + 1]) ++l;
-  const int local = (int)(r - lv.off[l]);
-  const int hw = local / lv.A;
-  const int a = local - hw * lv.A;
-  return lv.ptr[l][((int64_t)n * lv.A + a) * lv.HW[l] + hw];
-}
-
-constexpr int kPassBU = 4;  // anchors per thread in pass B
-constexpr int kWarpsPerBlock = kMatchBlock / 32;
-
+template <int U>
 __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
     const float4* __restrict__ gt_boxes, const int64_t* __restrict__ gt_class_ids,
-    const int32_t* __restrict__ gt_offsets, int N, int num_classes, MatcherBands mb, MatcherBands pmb, int allow_lq,
-    float wx, float wy, float ww, float wh, const float* __restrict__ best_val,
+    const int32_t* __restrict__ gt_offsets, int N, int allow_lq, int has_picky, const float* __restrict__ best_val,
     const int32_t* __restrict__ best_idx, const unsigned* __restrict__ gt_max, MatchOut out,
-    const float* __restrict__ bets, float temperature, int* __restrict__ part_cnt,
-    float* __restrict__ part_s, double* __restrict__ img_cnt, unsigned* __restrict__ done_counter,
-    double* __restrict__ stats, const fsg_peer_ctx peer, const BandsReg br, const BandsReg pbr, const BetLevels lv) {
-  constexpr int U = kPassBU;
+    const float* __restrict__ bets, float temperature, int* __restrict__ part_cnt, float* __restrict__ part_s,
+    const BandsReg br, const BandsReg pbr, const BetLevels lv) {
+  static_assert(U % 4 == 0, "runs of 4 consecutive anchors per thread");
+  grid_launch_dependents();
+  grid_dependency_sync();     // (programmatic dependent launch behind pass A in fsg_dense_step)
   __shared__ __align__(16) float4 s_gt[kGtChunk];
   __shared__ float s_area[kGtChunk];
   __shared__ float s_max[kGtChunk];
@@ -357,26 +472,36 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
   const int64_t base = (int64_t)blockIdx.x * (kMatchBlock * U);
   const int64_t img = (int64_t)n * R;
   const float4* a_img = anchors + (int64_t)n * anchor_stride4;
-  const bool need_anchor = (out.gt_deltas != nullptr);
 
+  // thread t owns two runs of 4 consecutive anchors: base + j*1024 + 4t .. +3 (16-byte loads of the best IoUs)
+  auto r_of = [&](int u) -> int64_t { return base + (int64_t)(u >> 2) * (kMatchBlock * 4) + tid * 4 + (u & 3); };
   float val[U];
-  int idx[U];
   bool live[U], lq[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int64_t r = base + u * kMatchBlock + tid;
-    live[u] = r < R;
-    val[u] = live[u] ? best_val[img + r] : -1.f;
-    idx[u] = live[u] ? best_idx[img + r] : 0;
-    lq[u] = false;
+  for (int j = 0; j < U / 4; ++j) {
+    const int64_t r0 = r_of(4 * j);
+    if (r0 + 4 <= R && ((img + r0) & 3) == 0) {
+      const float4 v = *reinterpret_cast<const float4*>(best_val + img + r0);
+      val[4 * j] = v.x; val[4 * j + 1] = v.y; val[4 * j + 2] = v.z; val[4 * j + 3] = v.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) live[4 * j + q] = true;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        live[4 * j + q] = r0 + q < R;
+        val[4 * j + q] = live[4 * j + q] ? best_val[img + r0 + q] : -1.f;
+      }
+    }
   }
+#pragma unroll
+  for (int u = 0; u < U; ++u) lq[u] = false;
 
-  // An anchor can equal some GT's maximum only if its own best IoU reaches the smallest per-GT maximum
-  // (IoU(g,a) <= best(a)); and it needs checking only against GTs whose maximum is <= its best IoU.
   if (allow_lq && M > 0 && M <= kSmallM) {
-    // ---- few GT: everything from global/L1 with broadcast loads, warp-level control flow, no barriers
-    float mn = __int_as_float(0x7f800000);
-    for (int g = 0; g < M; ++g) mn = fminf(mn, __uint_as_float(gt_max[m0 + g]));
+    // ---- few GT: lane g holds GT g's maximum and box (one parallel load, then shuffles), warp-level control flow
+    const float my_gm = (lane < M) ? __uint_as_float(gt_max[m0 + lane]) : __int_as_float(0x7f800000);
+    float mn = my_gm;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, sft));
     bool any_cand = false;
     bool cand[U];
 #pragma unroll
@@ -385,22 +510,20 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
       any_cand |= cand[u];
     }
     if (__any_sync(kFull, any_cand)) {
-      float4 a[U];
-      float aa[U];
+      float4 myG = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < M) myG = gt_boxes[m0 + lane];
+      // candidates are rare: one anchor slot at a time keeps a single box live instead of U of them
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        a[u] = cand[u] ? a_img[base + u * kMatchBlock + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
-        aa[u] = box_area(a[u]);
-      }
-      for (int g = 0; g < M; ++g) {
-        const float gm = __uint_as_float(gt_max[m0 + g]);
-        const float4 G = gt_boxes[m0 + g];
-        const float ga = box_area(G);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (cand[u] && gm <= val[u]) {
-            if (iou_exact(G, ga, a[u], aa[u]) == gm) lq[u] = true;  // matcher.py:114-116 (ties included)
-          }
+        if (!__any_sync(kFull, cand[u])) continue;
+        const float4 a = cand[u] ? a_img[r_of(u)] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float aa = box_area(a);
+        for (int g = 0; g < M; ++g) {
+          const float gm = __shfl_sync(kFull, my_gm, g);
+          float4 G;
+          G.x = __shfl_sync(kFull, myG.x, g); G.y = __shfl_sync(kFull, myG.y, g);
+          G.z = __shfl_sync(kFull, myG.z, g); G.w = __shfl_sync(kFull, myG.w, g);
+          if (cand[u] && gm <= val[u] && iou_exact(G, box_area(G), a, aa) == gm) lq[u] = true;  // matcher.py:114-116
         }
       }
     }
@@ -432,12 +555,17 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
       if (cand[u]) vmax = fmaxf(vmax, val[u]);
     }
     if (__syncthreads_or(any_cand)) {
-      float4 a[U];
-      float aa[U];
+      // U <= 4 (the instantiation crowded batches get): the candidates' boxes stay in registers; U = 8 (a few-GT
+      // batch with one crowded image in it): they are re-read from L1 where needed, which keeps the common path lean
+      constexpr int UA = (U <= 4) ? U : 1;
+      float4 a[UA];
+      float aa[UA];
+      if (U <= 4) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        a[u] = cand[u] ? a_img[base + u * kMatchBlock + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
-        aa[u] = box_area(a[u]);
+        for (int u = 0; u < UA; ++u) {
+          a[u] = cand[u] ? a_img[r_of(u)] : make_float4(0.f, 0.f, 0.f, 0.f);
+          aa[u] = box_area(a[u]);
+        }
       }
       uint32_t phase = 0;
       for (int c = 0; c < M; c += kGtChunk) {
@@ -486,7 +614,11 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               if (cand[u] && gm <= val[u]) {
-                if (iou_exact(s_gt[g], s_area[g], a[u], aa[u]) == gm) lq[u] = true;
+                float4 au;
+                float aau;
+                if (U <= 4) { au = a[u < UA ? u : 0]; aau = aa[u < UA ? u : 0]; }
+                else { au = a_img[r_of(u)]; aau = box_area(au); }
+                if (iou_exact(s_gt[g], s_area[g], au, aau) == gm) lq[u] = true;
               }
             }
           }
@@ -496,82 +628,62 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     }
   }
 
-  int fg = 0;
-  float w_part = 0.f;
-  const bool has_picky = pmb.n != 0;
-  const bool o_matches = out.matches != nullptr, o_labels = out.match_labels != nullptr;
-  const bool o_picky = out.picky_labels != nullptr, o_cls = out.gt_classes != nullptr;
-  const bool o_mask = out.mask != nullptr, o_idx32 = out.matched_idx32 != nullptr;
-  const bool has_ids = gt_class_ids != nullptr, has_bets = bets != nullptr;
+
+  // ---- patch the anchors the low-quality rule promotes (label 1 whatever their band said; `matches` is never
+  //      changed, matcher.py:131-132) and note what that does to num_foreground and to the bet normaliser
+  int dfg = 0;
+  float dw = 0.f;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    if (!live[u]) continue;
-    const int64_t r = base + u * kMatchBlock + tid;
+    if (!lq[u]) continue;   // (lq implies live)
+    const int64_t r = r_of(u);
     const int64_t o = img + r;
-    int8_t l1, l2 = 0;
-    int64_t cls, msk = 0;
-    int id = idx[u];
-    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (M > 0) {
-      l1 = lq[u] ? (int8_t)1 : band_label_reg(br, val[u]);
-      if (has_picky) l2 = lq[u] ? (int8_t)1 : band_label_reg(pbr, val[u]);
-      cls = has_ids ? gt_class_ids[m0 + id] : 0;
-      if (l1 == 0) cls = num_classes;   // retinanet.py:356
-      if (l1 == -1) cls = -1;           // :360
-      msk = (l2 == 1) ? 1 : 0;          // :417-423
-      if (need_anchor) d = encode_deltas(a_img[r], gt_boxes[m0 + id], wx, wy, ww, wh);
-    } else {                            // matcher.py:70-80, retinanet.py:362-363, :425
-      l1 = mb.lab[0];
-      l2 = pmb.n ? pmb.lab[0] : 0;
-      cls = num_classes;
-      msk = num_classes;
-      id = 0;
+    if (band_label_reg(br, val[u]) != 1) {
+      if (out.match_labels) out.match_labels[o] = 1;
+      if (out.gt_classes) out.gt_classes[o] = gt_class_ids ? gt_class_ids[m0 + best_idx[o]] : 0;
+      dfg += 1;             // was background or ignored, is foreground now
     }
-    if (o_matches) out.matches[o] = id;
-    if (o_labels) out.match_labels[o] = l1;
-    if (o_picky) out.picky_labels[o] = l2;
-    if (o_cls) out.gt_classes[o] = cls;
-    if (o_mask) out.mask[o] = msk;
-    if (need_anchor) out.gt_deltas[o] = d;
-    if (o_idx32) out.matched_idx32[o] = id;
-    fg += (cls >= 0 && cls != num_classes) ? 1 : 0;
-    if (has_bets) w_part += __fadd_rn(__fmul_rn(bets[o], (float)msk), temperature);  // gambler_heads.py:569,304
-    else if (lv.num_levels > 0 && msk != 0) w_part += __fmul_rn(bet_at(lv, n, r), (float)msk);  // + R*T at the fold
+    if (has_picky && band_label_reg(pbr, val[u]) != 1) {
+      if (out.picky_labels) out.picky_labels[o] = 1;
+      if (out.mask) out.mask[o] = 1;
+      if (bets) dw += __fadd_rn(bets[o], temperature) - temperature;   // (bet*1 + T) - (bet*0 + T)
+      else if (lv.num_levels > 0) dw += bet_at(lv, n, r);
+    }
   }
 
-  if (stats == nullptr) return;
-  // ---- loss pre-pass: num_foreground and S[n] = sum_r (bet*mask + T).  One partial per CTA in a fixed
-  //      slot, the last CTA to finish folds them in a fixed order => run-to-run deterministic.
-  __shared__ int s_redi[kWarpsPerBlock];
-  __shared__ float s_redf[kWarpsPerBlock];
+  if (part_cnt == nullptr) return;
+  // corrections of this CTA in its fixed slot (zero for almost every CTA); folded by match_fold_kernel
+  block_partial(dfg, dw, part_cnt, part_s, (int64_t)n * gridDim.x + blockIdx.x);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fold of the loss pre-pass sums: num_foreground and S[n] = sum_r (bet*mask + T).  One CTA per image adds pass A's
+// per-warp partials and pass B's corrections in a fixed order (run-to-run deterministic); the last CTA to finish
+// adds the images up in image order and runs the peer exchange.  A kernel of its own because 1000+ CTAs each
+// ending in fence + atomic + barrier cost pass B more than all of its real work.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMatchBlock) match_fold_kernel(
+    int N, int64_t R, const int* __restrict__ part_cnt_a, const float* __restrict__ part_s_a, int slots_a,
+    const int* __restrict__ part_cnt_b, const float* __restrict__ part_s_b, int slots_b, float temperature,
+    int levels_mode, double* __restrict__ img_cnt, unsigned* __restrict__ done_counter, double* __restrict__ stats,
+    const fsg_peer_ctx peer, const int peer_wait) {
+  grid_launch_dependents();
+  grid_dependency_sync();
   __shared__ double s_tc[kWarpsPerBlock], s_ts[kWarpsPerBlock];
   __shared__ bool s_last;
-  const int fg_w = __reduce_add_sync(kFull, fg);
-  const float s_w = warp_sum(w_part);
-  if (lane == 0) { s_redi[wid] = fg_w; s_redf[wid] = s_w; }
-  __syncthreads();
-  const int nb = gridDim.x;
-  // two-level completion counters (per image, then over images): 1000+ CTAs bumping ONE word and waiting for
-  // the returned value serialise in L2; with a counter per image the chains are N times shorter and the
-  // per-image folds run in parallel.  done_counter[0] = images finished, done_counter[1+n] = CTAs of image n.
-  if (tid == 0) {
-    int ci = 0;
-    float cs = 0.f;
-    for (int w = 0; w < kWarpsPerBlock; ++w) { ci += s_redi[w]; cs += s_redf[w]; }
-    part_cnt[n * nb + blockIdx.x] = ci;
-    part_s[n * nb + blockIdx.x] = cs;
-    __threadfence();
-    s_last = (atomicAdd(&done_counter[1 + n], 1u) == (unsigned)nb - 1u);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // ---- last CTA of image n: fold the image's partials in a fixed order
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   {
     double c = 0.0, sacc = 0.0;
-    for (int b = tid; b < nb; b += kMatchBlock) {
-      c += (double)__ldcg(&part_cnt[n * nb + b]);
-      sacc += (double)__ldcg(&part_s[n * nb + b]);
+    for (int b = tid; b < slots_a; b += kMatchBlock) {
+      c += (double)part_cnt_a[(int64_t)n * slots_a + b];
+      sacc += (double)part_s_a[(int64_t)n * slots_a + b];
+    }
+    if (part_cnt_b != nullptr) {
+      for (int b = tid; b < slots_b; b += kMatchBlock) {
+        c += (double)part_cnt_b[(int64_t)n * slots_b + b];
+        sacc += (double)part_s_b[(int64_t)n * slots_b + b];
+      }
     }
     c = warp_sum_d(c);
     sacc = warp_sum_d(sacc);
@@ -581,10 +693,9 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
   if (tid == 0) {
     double c = 0.0, sacc = 0.0;
     for (int w = 0; w < kWarpsPerBlock; ++w) { c += s_tc[w]; sacc += s_ts[w]; }
-    if (lv.num_levels > 0) sacc += (double)R * (double)temperature;   // per-level bets: S[n] = R*T + sum bet*mask
+    if (levels_mode) sacc += (double)R * (double)temperature;   // per-level bets: S[n] = R*T + sum bet*mask
     stats[FSG_STATS_HEADER + n] = sacc;
     img_cnt[n] = c;
-    done_counter[1 + n] = 0u;   // self-reset for the next call
     __threadfence();
     s_last = (atomicAdd(&done_counter[0], 1u) == (unsigned)N - 1u);
   }
@@ -630,21 +741,33 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     __threadfence_system();
     unsigned long long* fl = reinterpret_cast<unsigned long long*>(dst + 2);
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(ep) : "memory");
+  }
+  if (!peer_wait) {
+    // fsg_dense_step: the sums are only POSTED here; every CTA of the loss main pass polls this rank's mailbox
+    // (stats[0..1] stay local until that kernel's last CTA stores the global sums)
+    __syncthreads();
+    if (tid == 0) *epoch_ptr = ep;
+    return;
+  }
+  if (tid < peer.world) {
     const int slot_in = (int)(ep & 1ull) * 8 + tid;
     const double* src = reinterpret_cast<const double*>(peer.mailbox[peer.rank]) + slot_in * 4;
     const unsigned long long* fin = reinterpret_cast<const unsigned long long*>(src + 2);
     const long long t0 = clock64();
     unsigned long long seen = 0ull;
+    const long long limit = peer.timeout_cycles > 0 ? (long long)peer.timeout_cycles : 120000000000ll;   // ~60 s
+    bool arrived = true;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fin) : "memory");
       if (seen == ep) break;
-      if (clock64() - t0 > 6000000000ll) {   // ~3 s: a peer never arrived; fail loudly instead of hanging
-        *reinterpret_cast<int*>(peer.error) = 1;
+      if (clock64() - t0 > limit) {   // a peer never arrived: raise the flag AND poison the sums (NaN losses and
+        *reinterpret_cast<int*>(peer.error) = 1;   // gradients), so the step cannot be used silently
+        arrived = false;
         break;
       }
     }
-    s_px[tid] = *reinterpret_cast<const volatile double*>(src);
-    s_py[tid] = *reinterpret_cast<const volatile double*>(src + 1);
+    s_px[tid] = arrived ? *reinterpret_cast<const volatile double*>(src) : __longlong_as_double(0x7ff8000000000000ll);
+    s_py[tid] = arrived ? *reinterpret_cast<const volatile double*>(src + 1) : __longlong_as_double(0x7ff8000000000000ll);
   }
   __syncthreads();
   if (tid == 0) {
@@ -749,19 +872,24 @@ extern "C" int fsg_matcher(const float* mqm, int64_t M, int64_t N, const float* 
 
 namespace {
 struct MatchWs {
-  size_t off_counter, off_gtmax, off_val, off_idx, off_pcnt, off_ps, off_icnt, total;
+  size_t off_counter, off_gtmax, off_val, off_idx, off_pcnt, off_ps, off_pcnt_a, off_ps_a, off_icnt, total;
   int nb;
 };
 MatchWs match_ws_layout(int N, int64_t R, int64_t sum_M) {
   MatchWs w;
   w.nb = (int)ceil_div(R > 0 ? R : 1, kMatchBlock * kPassBU);
+  // per-CTA partial-sum slots of pass B and of pass A (at most: 2 anchors per thread)
+  const size_t slots = (size_t)N * w.nb;
+  const size_t slots_a = (size_t)N * (size_t)ceil_div(R > 0 ? R : 1, kMatchBlock * 2);
   size_t o = 0;
   w.off_counter = o; o += align_up(sizeof(unsigned) * (size_t)(N + 1), 16);
   w.off_gtmax = o;   o += align_up(sizeof(unsigned) * (size_t)(sum_M > 0 ? sum_M : 1), 16);
   w.off_val = o;     o += align_up(sizeof(float) * (size_t)N * (size_t)R, 16);
   w.off_idx = o;     o += align_up(sizeof(int32_t) * (size_t)N * (size_t)R, 16);
-  w.off_pcnt = o;    o += align_up(sizeof(int) * (size_t)N * w.nb, 16);
-  w.off_ps = o;      o += align_up(sizeof(float) * (size_t)N * w.nb, 16);
+  w.off_pcnt = o;    o += align_up(sizeof(int) * slots, 16);
+  w.off_ps = o;      o += align_up(sizeof(float) * slots, 16);
+  w.off_pcnt_a = o;  o += align_up(sizeof(int) * slots_a, 16);
+  w.off_ps_a = o;    o += align_up(sizeof(float) * slots_a, 16);
   w.off_icnt = o;    o += align_up(sizeof(double) * (size_t)N, 16);
   w.total = o;
   return w;
@@ -773,18 +901,20 @@ extern "C" size_t fsg_match_workspace_bytes(int N, int64_t R, int64_t sum_M) {
   return match_ws_layout(N, R, sum_M).total;
 }
 
-extern "C" int fsg_match_anchors_ex(const float* anchors, int64_t R, int64_t anchor_image_stride,
-                                 const float* gt_boxes, const int64_t* gt_class_ids, const int32_t* gt_offsets,
-                                 int N, int64_t sum_M, int num_classes, const float* h_thresholds,
-                                 const int8_t* h_labels, int num_thresholds, int allow_lq,
-                                 const float* h_picky_thresholds, const int8_t* h_picky_labels,
-                                 int num_picky_thresholds,
-                                 const float* h_box_weights, int64_t* matches, int8_t* match_labels,
-                                 int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
-                                 float* gt_deltas, int32_t* matched_idx32, const float* bets,
-                                 const fsg_bet_levels* h_bet_levels, float temperature,
-                                 double* stats, const fsg_peer_ctx* h_peer, void* workspace,
-                                 size_t workspace_bytes, int phases, fsg_stream_t stream) {
+namespace fsg {
+int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
+                  const float* gt_boxes, const int64_t* gt_class_ids, const int32_t* gt_offsets,
+                  int N, int64_t sum_M, int num_classes, const float* h_thresholds,
+                  const int8_t* h_labels, int num_thresholds, int allow_lq,
+                  const float* h_picky_thresholds, const int8_t* h_picky_labels,
+                  int num_picky_thresholds,
+                  const float* h_box_weights, int64_t* matches, int8_t* match_labels,
+                  int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
+                  float* gt_deltas, int32_t* matched_idx32, const float* bets,
+                  const fsg_bet_levels* h_bet_levels, float temperature,
+                  double* stats, const fsg_peer_ctx* h_peer, void* workspace,
+                  size_t workspace_bytes, int phases, int flags, const void* prefetch, size_t prefetch_bytes,
+                  fsg_stream_t stream) {
   if (N <= 0 || R < 0 || sum_M < 0 || !gt_offsets) return FSG_ERR_INVALID_ARG;
   if (phases < 1 || phases > 3) return FSG_ERR_INVALID_ARG;
   BetLevels lv = {};
@@ -849,33 +979,75 @@ extern "C" int fsg_match_anchors_ex(const float* anchors, int64_t R, int64_t anc
   const float wx = h_box_weights ? h_box_weights[0] : 1.f, wy = h_box_weights ? h_box_weights[1] : 1.f;
   const float ww = h_box_weights ? h_box_weights[2] : 1.f, wh = h_box_weights ? h_box_weights[3] : 1.f;
 
+  (void)prefetch; (void)prefetch_bytes;
+  // anchors per thread in pass A: 2 for the few-GT training case (more CTAs in flight), 4 when the batch is crowded
+  // (each staged GT box is reused more); the same choice sizes pass A's partial-sum slots in both phases
+  const bool few_gt = sum_M <= (int64_t)N * kSmallM;
+  const int nb_a = (int)ceil_div(R, kMatchBlock * (few_gt ? 2 : 4));
+  MatchOut out{matches, match_labels, picky_labels, gt_classes_out, mask_out, (float4*)gt_deltas, matched_idx32};
   if (phases & 1) {
-    // anchors per thread in pass A: 2 for the few-GT training case (more CTAs in flight for a latency-bound pass:
-    // 33.3 vs 35.6 us for K1 on config 2), 4 when the batch is crowded (each staged GT box is reused more)
-    if (sum_M <= (int64_t)N * kSmallM) {
-      constexpr int U = 2;
-      dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
-      match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
-                                                            (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
-    } else {
-      constexpr int U = 4;
-      dim3 grid_a((unsigned)ceil_div(R, kMatchBlock * U), (unsigned)N);
-      match_pass_a_kernel<U><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
-                                                            (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax);
-    }
+    PassAEpi e;
+    e.gt_class_ids = gt_class_ids; e.num_classes = num_classes;
+    e.lab0 = mb.lab[0]; e.plab0 = pmb.n ? pmb.lab[0] : (int8_t)0; e.has_picky = pmb.n != 0;
+    e.br = make_bands_reg(mb); e.pbr = make_bands_reg(pmb);
+    e.wx = wx; e.wy = wy; e.ww = ww; e.wh = wh;
+    e.out = out; e.bets = bets; e.temperature = temperature;
+    e.part_cnt = stats ? (int*)(ws + w.off_pcnt_a) : nullptr;
+    e.part_s = (float*)(ws + w.off_ps_a);
+    dim3 grid_a((unsigned)nb_a, (unsigned)N);
+    if (few_gt)
+      match_pass_a_kernel<2><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
+                                                            (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax, e, lv);
+    else
+      match_pass_a_kernel<4><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
+                                                            (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax, e, lv);
     FSG_LAUNCH_CHECK();
   }
   if (!(phases & 2)) return FSG_OK;
-  MatchOut out{matches, match_labels, picky_labels, gt_classes_out, mask_out, (float4*)gt_deltas, matched_idx32};
-  dim3 grid_b((unsigned)w.nb, (unsigned)N);
-  match_pass_b_kernel<<<grid_b, kMatchBlock, 0, s>>>(
-      (const float4*)anchors, R, anchor_image_stride / 4, (const float4*)gt_boxes, gt_class_ids, gt_offsets, N,
-      num_classes, mb, pmb, allow_lq ? 1 : 0, wx, wy, ww, wh, bval, bidx, gtmax, out, bets, temperature,
-      (int*)(ws + w.off_pcnt), (float*)(ws + w.off_ps), (double*)(ws + w.off_icnt), counter, stats, peer,
-      make_bands_reg(mb),
-      make_bands_reg(pmb), lv);
+  const bool pdl = (flags & kMatchPdl) != 0 && phases == 3;
+  const bool patch = allow_lq != 0;
+  const int nb_b = w.nb;
+  if (patch) {
+    dim3 grid_b((unsigned)nb_b, (unsigned)N);
+    auto go = [&](auto kern) {
+      return launch_pdl(kern, grid_b, dim3(kMatchBlock), 0, s, pdl,
+                        (const float4*)anchors, R, anchor_image_stride / 4, (const float4*)gt_boxes, gt_class_ids,
+                        gt_offsets, N, 1, pmb.n != 0 ? 1 : 0, (const float*)bval, (const int32_t*)bidx,
+                        (const unsigned*)gtmax, out, bets, temperature,
+                        stats ? (int*)(ws + w.off_pcnt) : (int*)nullptr, (float*)(ws + w.off_ps),
+                        make_bands_reg(mb), make_bands_reg(pmb), lv);
+    };
+    go(match_pass_b_kernel<kPassBU>);
+    FSG_LAUNCH_CHECK();
+  }
+  if (!stats) return FSG_OK;
+  launch_pdl(match_fold_kernel, dim3((unsigned)N), dim3(kMatchBlock), 0, s, pdl, N, R,
+             (const int*)(ws + w.off_pcnt_a), (const float*)(ws + w.off_ps_a), nb_a,
+             patch ? (const int*)(ws + w.off_pcnt) : (const int*)nullptr, (const float*)(ws + w.off_ps),
+             nb_b, temperature, lv.num_levels > 0 ? 1 : 0, (double*)(ws + w.off_icnt), counter, stats,
+             peer, (flags & kMatchPeerPolled) ? 0 : 1);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
+}
+}  // namespace fsg
+
+extern "C" int fsg_match_anchors_ex(const float* anchors, int64_t R, int64_t anchor_image_stride,
+                                 const float* gt_boxes, const int64_t* gt_class_ids, const int32_t* gt_offsets,
+                                 int N, int64_t sum_M, int num_classes, const float* h_thresholds,
+                                 const int8_t* h_labels, int num_thresholds, int allow_lq,
+                                 const float* h_picky_thresholds, const int8_t* h_picky_labels,
+                                 int num_picky_thresholds,
+                                 const float* h_box_weights, int64_t* matches, int8_t* match_labels,
+                                 int8_t* picky_labels, int64_t* gt_classes_out, int64_t* mask_out,
+                                 float* gt_deltas, int32_t* matched_idx32, const float* bets,
+                                 const fsg_bet_levels* h_bet_levels, float temperature,
+                                 double* stats, const fsg_peer_ctx* h_peer, void* workspace,
+                                 size_t workspace_bytes, int phases, fsg_stream_t stream) {
+  return match_enqueue(anchors, R, anchor_image_stride, gt_boxes, gt_class_ids, gt_offsets, N, sum_M, num_classes,
+                       h_thresholds, h_labels, num_thresholds, allow_lq, h_picky_thresholds, h_picky_labels,
+                       num_picky_thresholds, h_box_weights, matches, match_labels, picky_labels, gt_classes_out,
+                       mask_out, gt_deltas, matched_idx32, bets, h_bet_levels, temperature, stats, h_peer, workspace,
+                       workspace_bytes, phases, 0, nullptr, 0, stream);
 }
 
 extern "C" int fsg_box2box_get_deltas(const float* src_boxes, const float* target_boxes, int64_t n,

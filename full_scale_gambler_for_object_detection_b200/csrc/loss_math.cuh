@@ -117,6 +117,62 @@ __device__ __forceinline__ void smooth_l1_elem(float pd, float gd, float beta, f
   }
 }
 
+// ---- peer exchange polled by the consumer ------------------------------------------------------------
+struct PeerPoll {
+  const double* mailbox;              // this rank's own mailbox (2 parities x 8 senders x {v0, v1, flag, pad})
+  const unsigned long long* epoch;    // written by K1's last CTA: the epoch of this step
+  int* error;
+  double* stats_out;                  // stats[0..1] receive the global sums (written once, by the last CTA)
+  long long timeout_cycles;
+  int world;
+};
+inline PeerPoll make_peer_poll(const fsg_peer_ctx* h, double* stats) {
+  PeerPoll p = {};
+  p.world = 1;
+  if (h && h->world > 1) {
+    p.mailbox = reinterpret_cast<const double*>(h->mailbox[h->rank]);
+    p.epoch = reinterpret_cast<const unsigned long long*>(h->epoch);
+    p.error = reinterpret_cast<int*>(h->error);
+    p.stats_out = stats;
+    p.timeout_cycles = h->timeout_cycles > 0 ? (long long)h->timeout_cycles : 120000000000ll;   // ~60 s
+    p.world = h->world;
+  }
+  return p;
+}
+// All threads of the CTA call this (it contains a barrier).  v0 / v1 come back as the sums over the ranks, in rank
+// order (identical on every rank and in every CTA).  A peer that does not arrive within the time-out poisons the
+// result with NaN (the step's losses and gradients become NaN: it cannot be used silently) and raises *error.
+__device__ __forceinline__ void peer_poll_sum(const PeerPoll& P, double& v0, double& v1) {
+  __shared__ double s_p0[8], s_p1[8];
+  const int tid = threadIdx.x;
+  if (tid < P.world) {
+    const unsigned long long ep = *reinterpret_cast<const volatile unsigned long long*>(P.epoch);
+    const double* src = P.mailbox + ((int)(ep & 1ull) * 8 + tid) * 4;
+    const unsigned long long* fin = reinterpret_cast<const unsigned long long*>(src + 2);
+    const long long t0 = clock64();
+    unsigned long long seen = 0ull;
+    bool ok = true;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fin) : "memory");
+      if (seen == ep) break;
+      if (clock64() - t0 > P.timeout_cycles) { ok = false; break; }
+    }
+    if (ok) {
+      s_p0[tid] = *reinterpret_cast<const volatile double*>(src);
+      s_p1[tid] = *reinterpret_cast<const volatile double*>(src + 1);
+    } else {
+      *P.error = 1;
+      s_p0[tid] = __longlong_as_double(0x7ff8000000000000ll);
+      s_p1[tid] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+  }
+  __syncthreads();
+  double a = 0.0, b = 0.0;
+  for (int p = 0; p < P.world; ++p) { a += s_p0[p]; b += s_p1[p]; }
+  v0 = a;
+  v1 = b;
+}
+
 // ---- per-tile partials -> scalars --------------------------------------------------------------
 // Called by every thread of an NT-thread CTA after it has reduced its own five sums into registers of
 // warp lane 0 (acc_* already warp-reduced).  Writes the tile's slot, elects the last CTA of the grid and lets it
@@ -124,7 +180,8 @@ __device__ __forceinline__ void smooth_l1_elem(float pd, float gd, float beta, f
 template <int NT = kLossBlock>
 __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float acc_wl, float acc_l, float max_l,
                                             int n, int tile, int T, int N, float* partials, unsigned* counter,
-                                            double* scalars, double nf_d, float c_cls, float c_reg, float c_gam) {
+                                            double* scalars, double nf_d, float c_cls, float c_reg, float c_gam,
+                                            const PeerPoll peer = PeerPoll{nullptr, nullptr, nullptr, nullptr, 0, 1}) {
   __shared__ float s_part[NT / 32][5];
   __shared__ double s_tot[NT / 32][5];
   __shared__ bool s_last;
@@ -179,6 +236,14 @@ __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float 
     scalars[7] = -v[2];
     scalars[8] = (double)c_cls * scalars[5] + (double)c_reg * scalars[6] + (double)c_gam * scalars[7];
     scalars[9] = nf_d;
+    if (peer.world > 1) {   // the polled global sums become stats[0..1] (every peer has arrived: no waiting here)
+      const unsigned long long ep = *reinterpret_cast<const volatile unsigned long long*>(peer.epoch);
+      double sb = 0.0;
+      for (int p = 0; p < peer.world; ++p)
+        sb += *reinterpret_cast<const volatile double*>(peer.mailbox + ((int)(ep & 1ull) * 8 + p) * 4 + 1);
+      peer.stats_out[0] = nf_d;
+      peer.stats_out[1] = sb;
+    }
     *counter = 0u;
   }
 }

@@ -18,6 +18,7 @@ Two layouts: ``dense_train_step`` / ``DenseStepPlan`` take the reference's flatt
 (N, A*K, H, W), (N, A*4, H, W) and (N, A, H, W) tensors -- and run the same four launches on them in place
 (SURVEY.md section 8f row 2), returning gradients and NAKHW_loss in that layout.
 """
+import os
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -156,6 +157,23 @@ class DenseStepPlan:
         self._bw = _lib.host_f32(cfg.bbox_reg_weights)
         self.graph = None
         self._static = None
+        # one-call form of the step (fsg_dense_step: persistent K1, K2 under programmatic dependent launch, the peer
+        # exchange polled by K2): everything except a sharded run that still needs an NCCL collective in the middle
+        self.one_call = (os.environ.get("FSG_STEP_STAGED", "0") != "1") and (
+            group is None or (self.peer is not None and cfg.norm_mode != _lib.NORM_BATCH))
+        self.ws_step = torch.empty(max(16, L.fsg_dense_step_workspace_bytes(N, R, K, self.max_total_gt)),
+                                   dtype=torch.uint8, device=dev) if self.one_call else None
+        mc = _lib.MatchConfig()
+        mc.num_thresholds, mc.num_picky_thresholds = len(cfg.iou_thresholds), len(cfg.picky_thresholds)
+        mc.allow_low_quality_matches = 1
+        for i, v in enumerate(cfg.iou_thresholds):
+            mc.thresholds[i] = float(v)
+        for i, v in enumerate(cfg.picky_thresholds):
+            mc.picky_thresholds[i] = float(v)
+        for i, v in enumerate(cfg.iou_labels):
+            mc.labels[i] = int(v)
+            mc.picky_labels[i] = int(v)
+        self._mc = mc
 
     def _check(self, logits, deltas, bets, anchors, gt):
         N, R, K = self.N, self.R, self.K
@@ -196,9 +214,28 @@ class DenseStepPlan:
                                         P(self.stats), P(self.scalars), P(self.grad_bets), _lib.stream()))
         _lib.count_launches(1)
 
+    def step_one_call(self, logits, deltas, bets, anchors, gt):
+        """The whole step through ``fsg_dense_step`` (one ctypes call, 2 memset nodes + 3 kernels)."""
+        P = _lib.ptr
+        io = _lib.StepIO()
+        io.logits, io.pred_deltas, io.bets, io.anchors = P(logits), P(deltas), P(bets), P(anchors)
+        io.anchor_image_stride = self.R * 4 if anchors.dim() == 3 else 0
+        io.gt_boxes, io.gt_class_ids, io.gt_offsets, io.sum_M = P(gt.boxes), P(gt.classes), P(gt.offsets), gt.total
+        io.gt_classes, io.mask, io.matched_idx32 = P(self.gt_classes), P(self.mask), P(self.matched)
+        io.stats, io.scalars = P(self.stats), P(self.scalars)
+        io.grad_logits, io.grad_deltas, io.grad_bets = P(self.grad_logits), P(self.grad_deltas), P(self.grad_bets)
+        io.per_anchor_loss, io.weights_out = P(self.ell), P(self.weights)
+        _lib.check(self.L.fsg_dense_step(io, self.N, self.R, self._mc, self.params,
+                                         self.peer.ctx if self.peer is not None else None, P(self.ws_step),
+                                         self.ws_step.numel(), _lib.stream()))
+        _lib.count_launches(3)
+
     def run(self, logits, deltas, bets, anchors, gt):
         """Enqueue the step on the current stream.  Inputs: detached contiguous CUDA fp32 tensors."""
         self._check(logits, deltas, bets, anchors, gt)
+        if self.one_call:
+            self.step_one_call(logits, deltas, bets, anchors, gt)
+            return self.result()
         self.stage_match(bets, anchors, gt)
         if self.group is not None and self.peer is None:
             sharded.all_reduce_stats(self.stats, self.group)
@@ -238,7 +275,7 @@ class DenseStepPlan:
                 fn()
             return g
 
-        if self.group is None or (self.peer is not None and self.cfg.norm_mode != _lib.NORM_BATCH):
+        if self.one_call or self.group is None or (self.peer is not None and self.cfg.norm_mode != _lib.NORM_BATCH):
             self.graph = [cap(lambda: self.run(*self._static))]
         else:
             batch_norm = self.cfg.norm_mode == _lib.NORM_BATCH
@@ -263,7 +300,7 @@ class DenseStepPlan:
             if len(g) == 3:
                 sharded.all_reduce_batch_weighted_sum(self.scalars, self.group)
                 g[2].replay()
-        _lib.count_launches(4)
+        _lib.count_launches(3 if self.one_call else 4)
         return self.result()
 
     def release_graphs(self):
@@ -271,11 +308,28 @@ class DenseStepPlan:
         self._static = None
 
 
+_single_use = ops.single_use
+
+
+def _grad_mul(group, grad_reduction):
+    """Gradients of a sharded step are those of the WHOLE-batch loss (global num_foreground) w.r.t. this rank's
+    inputs.  Under DistributedDataParallel the parameter gradients are then AVERAGED over ranks, which would leave
+    1/world of the single-process whole-batch gradient (and of the reference's own DDP result); 'mean' therefore
+    multiplies the outgoing gradients by world_size.  'sum': leave them for a SUM reduction."""
+    if grad_reduction not in ("mean", "sum"):
+        raise ValueError("grad_reduction must be 'mean' (DDP averages gradients) or 'sum'")
+    if group is None or grad_reduction == "sum":
+        return 1.0
+    import torch.distributed as dist
+    return float(dist.get_world_size(group))
+
+
 class _FusedStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, pred_deltas, bets, anchors, gt, cfg, coeffs, detach_pred, group, want_weights,
-                plan=None):
+                plan=None, grad_mul=1.0):
         c_cls, c_reg, c_gam = coeffs
+        ctx.grad_mul, ctx.used = float(grad_mul), False
         if plan is not None:
             x = logits.detach()
             x = x if (x.dtype == torch.float32 and x.is_contiguous()) else x.to(torch.float32).contiguous()
@@ -329,18 +383,19 @@ class _FusedStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, *unused):
+        _single_use(ctx)
         gl, gd, gb = ctx.saved_tensors
         # grads were produced for a unit upstream gradient; rescale on the device (no-op kernel when 1.0)
         if gl is not None:
-            ops.scale_(gl, g_total)
+            ops.scale_(gl, g_total, ctx.grad_mul)
         if gd is not None:
-            ops.scale_(gd, g_total)
-        ops.scale_(gb, g_total)
-        return gl if ctx.has_gl else None, gd, gb, None, None, None, None, None, None, None, None
+            ops.scale_(gd, g_total, ctx.grad_mul)
+        ops.scale_(gb, g_total, ctx.grad_mul)
+        return gl if ctx.has_gl else None, gd, gb, None, None, None, None, None, None, None, None, None
 
 
 def dense_train_step(logits, pred_deltas, bets, anchors, gt, cfg, coeffs=(1.0, 1.0, -1.0), detach_pred=False,
-                     group=None, want_weights=False, plan=None):
+                     group=None, want_weights=False, plan=None, grad_reduction="mean"):
     """Fused match + loss step.
 
     logits (N,R,K), pred_deltas (N,R,4), bets (N,R): CUDA fp32, the flattened (N, sum HWA, .) layout;
@@ -349,14 +404,19 @@ def dense_train_step(logits, pred_deltas, bets, anchors, gt, cfg, coeffs=(1.0, 1
     ``c_cls*loss_cls + c_reg*loss_box_reg + c_gam*gambler_loss``; the detector phase of the reference is
     (1, lambda_reg, -lambda_out*kappa), the gambler phase (detach_pred=True) is (0, 0, kappa).
     group: a torch.distributed process group when the batch is sharded by image over ranks.
+    grad_reduction (with ``group``): how the caller reduces parameter gradients over ranks -- 'mean'
+    (DistributedDataParallel, the reference's deployment: the gradients leaving this node are multiplied by
+    world_size so that the averaged parameter gradient equals the single-process whole-batch one) or 'sum'.
+    The loss values are unaffected.
     plan: a DenseStepPlan built for these shapes/coefficients: no allocation, outputs live in the plan.
+    The autograd node is single-use (see ``_single_use``).
     """
     if plan is not None:
         assert plan.coeffs == tuple(float(c) for c in coeffs) and plan.detach_pred == bool(detach_pred)
     if detach_pred:
         logits = logits.detach()
     res = _FusedStep.apply(logits, pred_deltas, bets, anchors, gt, cfg, tuple(float(c) for c in coeffs),
-                           bool(detach_pred), group, bool(want_weights), plan)
+                           bool(detach_pred), group, bool(want_weights), plan, _grad_mul(group, grad_reduction))
     total, scalars, stats, ell, gtc, mask = res[:6]
     return StepResult(total=total, scalars=scalars, stats=stats, per_anchor_loss=ell, gt_classes=gtc, mask=mask,
                       weights=res[6] if len(res) > 6 else None)
@@ -366,8 +426,9 @@ class _FusedStepLevels(torch.autograd.Function):
     """The fused step on the head's native layout: every tensor argument is a per-level conv output."""
 
     @staticmethod
-    def forward(ctx, anchors, gt, cfg, coeffs, detach_pred, group, L, *levels):
+    def forward(ctx, anchors, gt, cfg, coeffs, detach_pred, group, L, grad_mul, *levels):
         c_cls, c_reg, c_gam = coeffs
+        ctx.grad_mul, ctx.used = float(grad_mul), False
         f32c = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
         xs = [f32c(t.detach()) for t in levels[:L]]
         ds = [f32c(t.detach()) for t in levels[L:2 * L]]
@@ -398,19 +459,20 @@ class _FusedStepLevels(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, *unused):
+        _single_use(ctx)
         L, need_gl, need_gd = ctx.cfg_
         saved = list(ctx.saved_tensors)
         for t in saved:
-            ops.scale_(t, g_total)
+            ops.scale_(t, g_total, ctx.grad_mul)
         gl = saved[:L] if need_gl else [None] * L
         saved = saved[L:] if need_gl else saved
         gd = saved[:L] if need_gd else [None] * L
         saved = saved[L:] if need_gd else saved
-        return (None,) * 7 + tuple(gl) + tuple(gd) + tuple(saved)
+        return (None,) * 8 + tuple(gl) + tuple(gd) + tuple(saved)
 
 
 def dense_train_step_levels(logit_levels, delta_levels, bet_levels, anchors, gt, cfg, coeffs=(1.0, 1.0, -1.0),
-                            detach_pred=False, group=None):
+                            detach_pred=False, group=None, grad_reduction="mean"):
     """The fused match + loss step straight from the head outputs, no permute/cat copies in either direction.
 
     logit_levels list[(N, A*K, H, W)], delta_levels list[(N, A*4, H, W)], bet_levels list[(N, A, H, W)] (the
@@ -422,7 +484,7 @@ def dense_train_step_levels(logit_levels, delta_levels, bet_levels, anchors, gt,
     assert len(delta_levels) == L and len(bet_levels) == L
     xs = [t.detach() for t in logit_levels] if detach_pred else list(logit_levels)
     res = _FusedStepLevels.apply(anchors, gt, cfg, tuple(float(c) for c in coeffs), bool(detach_pred), group, L,
-                                 *(xs + list(delta_levels) + list(bet_levels)))
+                                 _grad_mul(group, grad_reduction), *(xs + list(delta_levels) + list(bet_levels)))
     total, scalars, stats, gtc, mask = res[:5]
     return StepResult(total=total, scalars=scalars, stats=stats, per_anchor_loss=list(res[5:]), gt_classes=gtc,
                       mask=mask)

@@ -40,6 +40,7 @@ class _GamblerLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, *unused):
+        ops.single_use(ctx)
         gl, gb = ctx.saved_tensors
         if gl is not None:
             ops.scale_(gl, g)
@@ -67,6 +68,7 @@ class _GamblerLossLevelsFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, *unused):
+        ops.single_use(ctx)
         saved = ctx.saved_tensors
         gb, gls = saved[0], saved[1:]
         for t in gls:

@@ -420,15 +420,27 @@ def loss_post(bets, mask, per_anchor_loss, params, stats, scalars):
     return g
 
 
-def scale_(x, scale):
-    """In-place x *= scale; scale is a python float or a 0-d CUDA tensor (no host sync)."""
+def single_use(ctx):
+    """The fused kernels write the gradients for a UNIT upstream gradient at forward time; backward rescales those
+    buffers in place (through raw pointers, so autograd's version counters never see it; no extra pass over 344 MB
+    when the upstream gradient is 1) and hands them to autograd.  A second backward through the same node
+    (retain_graph=True, two losses sharing the node) would scale them twice, and with a plan they alias storage the
+    next ``plan.run`` overwrites -- so every autograd node of this package is single-use and says so."""
+    if getattr(ctx, "used", False):
+        raise RuntimeError("fsg_dense: backward() ran twice through the same node; its gradient buffers are scaled in "
+                           "place and handed out once (call the op again instead of retain_graph=True)")
+    ctx.used = True
+
+
+def scale_(x, scale, mul=1.0):
+    """In-place x *= scale * mul; scale is a python float or a 0-d CUDA tensor (no host sync), mul a python float."""
     if isinstance(scale, torch.Tensor):
         s = scale.detach().to(torch.float32).reshape(1).contiguous()
-        check(lib().fsg_scale_inplace(ptr(x), x.numel(), ptr(s), 1.0, stream()))
+        check(lib().fsg_scale_inplace(ptr(x), x.numel(), ptr(s), float(mul), stream()))
     else:
-        if float(scale) == 1.0:
+        if float(scale) * float(mul) == 1.0:
             return x
-        check(lib().fsg_scale_inplace(ptr(x), x.numel(), None, float(scale), stream()))
+        check(lib().fsg_scale_inplace(ptr(x), x.numel(), None, float(scale) * float(mul), stream()))
     count_launches(1)
     return x
 

@@ -54,6 +54,7 @@ class _RetinaLosses(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_cls, g_reg):
+        ops.single_use(ctx)
         gl, gd = ctx.saved_tensors
         # loss_cls depends only on the logits and loss_box_reg only on the deltas, so the gradients saved
         # for unit coefficients just need scaling by the upstream scalars (on the device, no sync)
@@ -79,6 +80,7 @@ class _RetinaLossesLevels(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_cls, g_reg):
+        ops.single_use(ctx)
         saved = ctx.saved_tensors
         for t in saved[:ctx.L]:
             ops.scale_(t, g_cls)

@@ -78,12 +78,16 @@ class PeerExchange:
 
     MAILBOX_BYTES = 1024
 
-    def __init__(self, handle, mailbox, epoch, error, rank, world):
+    def __init__(self, handle, mailbox, epoch, error, rank, world, timeout_s=60.0):
         from . import _lib
 
         self._handle, self.mailbox, self.epoch, self.error = handle, mailbox, epoch, error
         self.rank, self.world = rank, world
         ctx = _lib.PeerCtx()
+        # SM cycles a kernel waits for a peer before it raises `error` and poisons the exchanged sums with NaN
+        khz = torch.cuda.get_device_properties(mailbox.device).clock_rate if hasattr(
+            torch.cuda.get_device_properties(mailbox.device), "clock_rate") else 1965000
+        ctx.timeout_cycles = int(float(timeout_s) * khz * 1e3)
         ptrs = list(handle.buffer_ptrs)
         for p in range(world):
             ctx.mailbox[p] = int(ptrs[p])
@@ -93,7 +97,10 @@ class PeerExchange:
         self.ctx = ctx
 
     @staticmethod
-    def create(group, device):
+    def create(group, device, timeout_s=60.0):
+        """timeout_s: how long a kernel waits for a peer (a rank stalled in its data loader, a checkpoint on rank 0,
+        first-step autotuning ...) before the step is declared dead: the error flag is raised and the exchanged
+        sums become NaN, so the step's losses and gradients are NaN and ``check()`` raises."""
         try:
             import torch.distributed._symmetric_memory as symm_mem
 
@@ -107,7 +114,7 @@ class PeerExchange:
             error = torch.zeros(1, dtype=torch.int32, device=device)
             torch.cuda.synchronize(device)
             dist.barrier(group)     # every mailbox is zeroed before anyone may write into it
-            return PeerExchange(handle, buf, epoch, error, dist.get_rank(group), world)
+            return PeerExchange(handle, buf, epoch, error, dist.get_rank(group), world, timeout_s)
         except Exception as e:  # noqa: BLE001 -- any failure means "not available here"
             import sys
 

@@ -90,6 +90,9 @@ typedef struct fsg_peer_ctx {
   uint64_t epoch;      /* device pointer to a local uint64 counter, zero-initialised                */
   uint64_t error;      /* device pointer to a local int32 flag, set to 1 if a peer never showed up  */
   int32_t rank, world; /* world <= 8 */
+  uint64_t timeout_cycles; /* SM clock cycles a kernel waits for a peer; 0 = default (about 60 s).  On time-out
+                              *error is raised AND the exchanged sums become NaN, so the step's losses and
+                              gradients are NaN: a step with a missing peer can never be used silently. */
 } fsg_peer_ctx;
 
 /* The gambler's betting maps in their own layout (level l: (N, A, H_l, W_l), gambler_heads.py:463-470), for the
@@ -298,6 +301,51 @@ typedef struct fsg_post_level {
 FSG_API int fsg_loss_post_levels(const fsg_post_level* h_levels, int num_levels, int A, const int64_t* mask, int N,
                          int64_t R, const fsg_loss_params* h_params, const double* stats, const double* scalars,
                          fsg_stream_t stream);
+
+/* The whole fused training step in one call: K1 (as one persistent launch when the batch averages <= 32 GT per
+ * image) -> K2 main pass -> K2 post pass, the last two under programmatic dependent launch (each kernel issues its
+ * first loads while the kernel in front of it drains and waits on the device for its completion), one memset node
+ * in front.  Same arithmetic and outputs as fsg_match_anchors + fsg_loss_main + fsg_loss_post on the flattened
+ * layout (the regression targets are encoded on the fly).  Capturable in a CUDA graph.
+ * h_peer (batch sharded by image over ranks): K1 only posts this rank's [num_foreground, S_batch] into the peers'
+ * mailboxes; every CTA of the main pass polls its own mailbox and sums in rank order, so the NVLink round trip
+ * hides behind the first logit loads.  stats[0..1] hold the global sums afterwards.  FSG_NORM_BATCH needs a second
+ * exchange before the post pass and is not supported together with h_peer (status FSG_ERR_UNSUPPORTED). */
+typedef struct fsg_step_io {
+  const float* logits;      /* (N,R,K) */
+  const float* pred_deltas; /* (N,R,4) */
+  const float* bets;        /* (N,R)   */
+  const float* anchors;     /* (R,4), or (N,R,4) with anchor_image_stride = R*4 */
+  int64_t anchor_image_stride;
+  const float* gt_boxes;    /* packed (sum_M,4) */
+  const int64_t* gt_class_ids;
+  const int32_t* gt_offsets; /* (N+1) */
+  int64_t sum_M;
+  /* outputs */
+  int64_t* gt_classes;      /* (N,R) */
+  int64_t* mask;            /* (N,R) */
+  int32_t* matched_idx32;   /* (N,R) */
+  double* stats;            /* [2+N] */
+  double* scalars;          /* [10+N] */
+  float* grad_logits;       /* (N,R,K) or NULL (gambler phase, detach_pred) */
+  float* grad_deltas;       /* (N,R,4) or NULL */
+  float* grad_bets;         /* (N,R) */
+  float* per_anchor_loss;   /* (N,R) */
+  float* weights_out;       /* (N,R) or NULL */
+} fsg_step_io;
+typedef struct fsg_match_config {
+  float thresholds[4];
+  float picky_thresholds[4];
+  int8_t labels[8];         /* num_thresholds + 1 used */
+  int8_t picky_labels[8];
+  int32_t num_thresholds, num_picky_thresholds; /* num_picky_thresholds == 0: invalid here (the mask is needed) */
+  int32_t allow_low_quality_matches;
+  int32_t reserved;
+} fsg_match_config;
+FSG_API size_t fsg_dense_step_workspace_bytes(int N, int64_t R, int K, int64_t sum_M);
+FSG_API int fsg_dense_step(const fsg_step_io* h_io, int N, int64_t R, const fsg_match_config* h_match,
+                   const fsg_loss_params* h_params, const fsg_peer_ctx* h_peer, void* workspace,
+                   size_t workspace_bytes, fsg_stream_t stream);
 
 /* in-place x *= *scale_dev or x *= scale_host (backward with a non-unit upstream gradient) */
 FSG_API int fsg_scale_inplace(float* x, int64_t n, const float* scale_dev, float scale_host,

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""profiles/traffic.json from an `ncu --set full` capture: DRAM bytes of ONE launch of the dominant kernel.
+
+    python profiles/ncu_traffic.py gpurun_out/<capture>.ncu-rep loss_main_kernel [profiles/<committed summary name>]
+
+bench.py reports the numbers as roofline.traffic together with the capture they came from."""
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+rep, pat = sys.argv[1], sys.argv[2]
+name = sys.argv[3] if len(sys.argv) > 3 else os.path.basename(rep)
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units = rows[0], rows[1]
+kn, rd, wr, du = (hdr.index(k) for k in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                                         "gpu__time_duration.sum"))
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+for r in rows[2:]:
+    if pat in r[kn]:
+        res = {"capture": name, "kernel": r[kn][:100], "grid": r[hdr.index("Grid Size")],
+               "dram_bytes_read": int(float(r[rd]) * scale[units[rd]]),
+               "dram_bytes_write": int(float(r[wr]) * scale[units[wr]]),
+               "duration_us_under_ncu": float(r[du]) * (1e-3 if units[du] in ("ns", "nsecond") else 1.0)}
+        here = os.path.dirname(os.path.abspath(__file__))
+        with open(os.path.join(here, "traffic.json"), "w") as f:
+            json.dump(res, f, indent=1)
+        print(json.dumps(res))
+        break
+else:
+    sys.exit("no kernel matching %r in %s" % (pat, rep))

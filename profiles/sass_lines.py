@@ -33,7 +33,7 @@ for r in rows:
     elif hdr and len(r) == len(hdr):
         sass.append(r)
 si, ii = hdr.index("# Samples"), hdr.index("Instructions Executed")
-mangled_hint = re.sub(r"\(.*", "", kname).split("::")[-1]
+mangled_hint = re.sub(r"[<(].*", "", kname.replace("void ", "")).split("::")[-1]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "full_scale_gambler_for_object_detection_b200",
                                                           "libfsg_dense.so")], cwd=tmp, capture_output=True)
@@ -56,8 +56,28 @@ for cub in glob.glob(os.path.join(tmp, "*.cubin")):
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             per.append(cur)
-    if per:
+    if per and abs(len(per) - len(sass)) <= 4:
         lines = per
+        break
+    # several instantiations of a template live in one cubin: take the one whose length matches
+    cur, infn, per, best = None, False, [], None
+    for ln in dis.splitlines() + [".text.END:"]:
+        m = re.match(r"\s*\.text\.(\S+):", ln)
+        if m:
+            if infn and abs(len(per) - len(sass)) <= 4:
+                best = per
+            infn, per = mangled_hint in m.group(1), []
+            continue
+        if not infn:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
+            per.append(cur)
+    if best:
+        lines = best
         break
 if lines is None or abs(len(lines) - len(sass)) > 4:
     print("could not align SASS (%d) with the line table (%s)" % (len(sass), None if lines is None else len(lines)))

@@ -27,7 +27,7 @@ def lib_path():
 
 def test_header_declares_the_expected_surface():
     syms = declared_symbols()
-    assert len(syms) == 32, syms
+    assert len(syms) == 34, syms
     for s in ("fsg_pairwise_iou", "fsg_matcher", "fsg_match_anchors", "fsg_box2box_get_deltas",
               "fsg_box2box_apply_deltas", "fsg_loss_main", "fsg_loss_post", "fsg_nms", "fsg_detect",
               "fsg_permute_level", "fsg_loss_main_levels", "fsg_grid_anchors", "fsg_postprocess_boxes"):
@@ -54,7 +54,8 @@ def test_ctypes_prototypes_cover_the_header(lib_path):
     assert L.fsg_detect_workspace_bytes(2, 1000, 80, 5, 1000) > 0
     assert L.fsg_nms_workspace_bytes(100) > 0
     assert ctypes.sizeof(_lib.LossParams) == 64
-    assert ctypes.sizeof(_lib.PeerCtx) == 88
+    assert ctypes.sizeof(_lib.PeerCtx) == 96
+    assert ctypes.sizeof(_lib.StepIO) == 19 * 8 and ctypes.sizeof(_lib.MatchConfig) == 64
 
 
 def test_header_is_plain_c():

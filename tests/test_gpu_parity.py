@@ -280,6 +280,54 @@ def test_step_run_to_run_deterministic(cuda):
         assert torch.equal(s, outs[0][0]) and torch.equal(g, outs[0][1])
 
 
+def test_one_call_step_equals_staged_step(cuda):
+    """fsg_dense_step (persistent K1 + K2 under programmatic dependent launch, what DenseStepPlan runs) against the
+    staged entry points on the same inputs: integer outputs bit-identical, floats equal up to the order in which the
+    bet normaliser S[n] is summed (per-CTA partials are grouped differently); also through a CUDA graph, twice."""
+    fsg = _fsg()
+    inp = _train_inputs(61, 5, 320, 448, 80, M=7)
+    N, R, K = inp["N"], inp["R"], 80
+    x, d, b = (inp[k].to(cuda) for k in ("logits", "deltas", "bets"))
+    anchors = inp["anchors"].to(cuda)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    for kw in (dict(), dict(gambler_output="L_BAHW_extendtobatch"), dict(normalize=False)):
+        cfg = fsg.DenseLossConfig(num_classes=K, **kw)
+        a = fsg.DenseStepPlan(N, R, K, cfg, cuda, (1.0, 0.5, -2.0), want_weights=True)
+        assert a.one_call
+        s = fsg.DenseStepPlan(N, R, K, cfg, cuda, (1.0, 0.5, -2.0), want_weights=True)
+        s.one_call = False
+        ra, rs = a.run(x, d, b, anchors, gt), s.run(x, d, b, anchors, gt)
+        assert torch.equal(ra.gt_classes, rs.gt_classes) and torch.equal(ra.mask, rs.mask)
+        assert torch.equal(a.matched, s.matched) and float(ra.stats[0]) == float(rs.stats[0])
+        assert_close_tensor(ra.stats, rs.stats, "stats", rtol=1e-6)
+        assert_close_tensor(ra.scalars, rs.scalars, "scalars", rtol=1e-6)
+        assert_close_tensor(a.grad_logits, s.grad_logits, "grad_logits", rtol=2e-6)
+        assert torch.equal(a.grad_deltas, s.grad_deltas)
+        assert_close_tensor(a.grad_bets, s.grad_bets, "grad_bets", rtol=1e-5, atol_scale=1e-6)
+        assert_close_tensor(a.weights, s.weights, "weights", rtol=2e-6)
+        keep = [t.clone() for t in (a.grad_logits, a.grad_deltas, a.grad_bets, a.scalars, a.gt_classes)]
+        a.capture(x, d, b, anchors, gt)
+        for _ in range(2):
+            a.replay()
+            torch.cuda.synchronize()
+            for t, u in zip(keep, (a.grad_logits, a.grad_deltas, a.grad_bets, a.scalars, a.gt_classes)):
+                assert torch.equal(t, u)      # the graph replays the very same launches: bit-identical
+        a.release_graphs()
+
+
+def test_backward_is_single_use(cuda):
+    fsg = _fsg()
+    inp = _train_inputs(62, 2, 128, 128, 80, M=3)
+    x = inp["logits"].to(cuda).requires_grad_(True)
+    d = inp["deltas"].to(cuda).requires_grad_(True)
+    b = inp["bets"].to(cuda).requires_grad_(True)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    res = fsg.dense_train_step(x, d, b, inp["anchors"].to(cuda), gt, fsg.DenseLossConfig(num_classes=80))
+    res.total.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="twice"):
+        res.total.backward()
+
+
 def test_upstream_gradient_scaling(cuda):
     fsg = _fsg()
     inp = _train_inputs(1, 1, 128, 128, 80, M=3)
