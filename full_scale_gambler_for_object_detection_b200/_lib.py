@@ -141,6 +141,9 @@ PROTOTYPES = {
     "fsg_dense_step_workspace_bytes": (c_size, [c_i32, c_i64, c_i32, c_i64]),
     "fsg_dense_step": (c_i32, [ctypes.POINTER(StepIO), c_i32, c_i64, ctypes.POINTER(MatchConfig),
                                ctypes.POINTER(LossParams), ctypes.POINTER(PeerCtx), c_ptr, c_size, c_ptr]),
+    "fsg_bet_stats_workspace_bytes": (c_size, []),
+    "fsg_bet_stats": (c_i32, [c_ptr, ctypes.POINTER(BetLevels), c_ptr, c_i32, c_i64, ctypes.POINTER(LossParams), c_ptr,
+                              c_ptr, c_ptr, c_size, c_ptr]),
     "fsg_scale_inplace": (c_i32, [c_ptr, c_i64, c_ptr, c_f32, c_ptr]),
     "fsg_nms_workspace_bytes": (c_size, [c_i64]),
     "fsg_nms": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_f64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),

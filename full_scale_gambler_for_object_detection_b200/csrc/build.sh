@@ -6,7 +6,7 @@ set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="${FSG_OUT:-${here}/../libfsg_dense.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-srcs=(abi nms_large iou_match dense_loss dense_step dense_loss_levels detect_select nms_image rpn_select layout)
+srcs=(abi nms_large iou_match dense_loss dense_step bet_stats dense_loss_levels detect_select nms_image rpn_select layout)
 objdir="$(mktemp -d "${TMPDIR:-/tmp}/fsg_build.XXXXXX")"
 trap 'rm -rf "${objdir}"' EXIT
 flags=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC

@@ -126,6 +126,11 @@ __device__ __forceinline__ void grid_launch_dependents() {
 #endif
 }
 
+// L2 prefetch of one 128-byte line (fire and forget: no register, no scoreboard entry)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---- launch with or without programmatic dependent launch -------------------------------------
 // pdl: the kernel may be scheduled while the kernel in front of it in the stream is still draining; it must call
 // cudaGridDependencySynchronize() before touching anything that kernel wrote (captured into CUDA graphs as a

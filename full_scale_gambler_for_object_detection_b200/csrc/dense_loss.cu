@@ -147,8 +147,16 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) 
   const int ngrp = kLossBlock >> logG;
   const int64_t tile_base = (int64_t)blockIdx.x * A.anchors_per_tile;
 
-  // Everything K1 produced is read from here on (under programmatic dependent launch this grid may have been
-  // scheduled while K1 was still draining).
+  // Sharded run: this CTA is about to wait for the peers' sums to cross NVLink.  The logits are not produced by K1,
+  // so it pulls its tile's rows into L2 first and the HBM latency of the first wave hides behind the exchange.
+  // (Not done on one GPU: with nothing to hide, the extra L2 requests cost the main pass 2 %.)
+  if (A.peer.world > 1) {
+    const char* rows = reinterpret_cast<const char*>(A.logits + ((int64_t)n * A.R + tile_base) * A.K);
+    int64_t bytes = (min((int64_t)A.anchors_per_tile, A.R - tile_base)) * A.K * (int64_t)sizeof(float);
+    if (bytes > 96 * 1024) bytes = 96 * 1024;
+    for (int64_t off = (int64_t)tid * 128; off < bytes; off += kLossBlock * 128) prefetch_l2(rows + off);
+  }
+  // Everything K1 produced is read from here on.
   grid_dependency_sync();
   // normalisers: every thread derives them itself from two broadcast loads (no block barrier behind one
   // thread's fp64 divide).  num_foreground is an integer < 2^24, so the fp32 reciprocal of max(1, nf) is the

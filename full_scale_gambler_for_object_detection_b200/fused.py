@@ -94,13 +94,36 @@ class StepResult:
         """gambler_heads.py:589-594."""
         if mode == "focal":
             return self.scalars[3] / torch.clamp(self.stats[0], min=1.0)
-        return self.scalars[3] / self.per_anchor_loss.numel()
+        return self.scalars[3] / self.gt_classes.numel()
 
     def lower_bound(self, temperature, kappa=1.0):
         """-get_loss_upper_bound (gambler_heads.py:17-31, 583-587)."""
         N, R = self.per_anchor_loss.shape
         w_max = (1 + temperature) / (R * temperature + 1)
         return -(kappa * w_max * N) * self.scalars[4]
+
+    def log_metrics(self, bets, cfg, lambda_reg=1.0, kappa=1.0, lambda_out=1.0, mode="cls+reg-gambler"):
+        """GANTrainer.calc_log_metrics (train_net.py:1089-1124) as a dict of device scalars, no host sync: the loss
+        combination plus the bet / weight statistics (sum / max / mean of the masked betting maps, sum / max / mean /
+        median of the normalised weights).  ``bets``: the (N,R) tensor or the list of per-level (N, A, H, W) maps the
+        step was given (unmasked; the step's picky mask is applied here as gambler_loss applies it in place)."""
+        params = cfg.loss_params(1.0, 1.0, 1.0)
+        if isinstance(bets, (list, tuple)):
+            st = ops.bet_stats(None, self.mask, params, self.stats, bet_levels=[b.detach() for b in bets])
+        else:
+            st = ops.bet_stats(bets.detach().to(torch.float32).contiguous(), self.mask, params, self.stats)
+        d = {"loss_cls": self.loss_cls, "loss_box_reg": self.loss_box_reg * lambda_reg,
+             "loss_gambler": self.gambler_loss * kappa,
+             "loss_before_weighting": self.loss_before_weighting(cfg.gambler_loss_mode)}
+        if mode == "cls+reg-gambler":
+            d["loss_detector"] = d["loss_box_reg"] + d["loss_cls"] - lambda_out * d["loss_gambler"]
+        elif mode == "weighted_cls_with_gambler+reg":
+            d["loss_detector"] = d["loss_box_reg"] - lambda_out * d["loss_gambler"]
+        else:
+            raise ValueError("unknown DETECTOR_LOSS_MODE %r" % (mode,))
+        for i, name in enumerate(ops.BET_STAT_NAMES):
+            d[name] = st[i]
+        return d
 
     def per_level_loss(self, grids, A):
         """(N,R) -> list[(N,A,H,W)] views, the NAKHW_loss layout (gambler_heads.py:91-101, :218)."""

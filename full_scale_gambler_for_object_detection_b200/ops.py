@@ -420,6 +420,32 @@ def loss_post(bets, mask, per_anchor_loss, params, stats, scalars):
     return g
 
 
+BET_STAT_NAMES = ("gambler_bets/sum", "gambler_bets/max", "gambler_bets/mean", "visualized weights/sum",
+                  "visualized weights/max", "visualized weights/mean", "visualized weights/median")
+
+
+def bet_stats(bets, mask, params, stats, bet_levels=None):
+    """The bet / weight statistics of GANTrainer.calc_log_metrics (train_net.py:1104-1121) as a (8,) double device
+    tensor (names: ``BET_STAT_NAMES``) -- no host sync, no sort.  bets (N,R) flat, or bet_levels list[(N, A, H, W)]
+    (the UNMASKED maps; the picky ``mask`` (N,R) is applied here exactly like gambler_loss applies it)."""
+    L = lib()
+    lv = None
+    if bet_levels is not None:
+        assert bets is None
+        lv = bet_levels_struct(bet_levels)
+        N = bet_levels[0].shape[0]
+        R = sum(b.shape[1] * b.shape[2] * b.shape[3] for b in bet_levels)
+        dev = bet_levels[0].device
+    else:
+        N, R = bets.shape
+        dev = bets.device
+    out = torch.zeros(8, dtype=torch.float64, device=dev)
+    ws = _ws(L.fsg_bet_stats_workspace_bytes(), dev)
+    check(L.fsg_bet_stats(ptr(bets), lv, ptr(mask), N, R, params, ptr(stats), ptr(out), ptr(ws), ws.numel(), stream()))
+    count_launches(3)
+    return out
+
+
 def single_use(ctx):
     """The fused kernels write the gradients for a UNIT upstream gradient at forward time; backward rescales those
     buffers in place (through raw pointers, so autograd's version counters never see it; no extra pass over 344 MB

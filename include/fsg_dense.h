@@ -347,6 +347,18 @@ FSG_API int fsg_dense_step(const fsg_step_io* h_io, int N, int64_t R, const fsg_
                    const fsg_loss_params* h_params, const fsg_peer_ctx* h_peer, void* workspace,
                    size_t workspace_bytes, fsg_stream_t stream);
 
+/* Bet / weight statistics of GANTrainer.calc_log_metrics (ImbalanceDetection/train_net.py:1104-1121) without a
+ * host sync or a sort: out[0..2] = sum, max, mean of the MASKED betting maps bet*mask (the maps as gambler_loss
+ * leaves them, gambler_heads.py:568-569; the max starts at 0 like the reference's running maximum), out[3..5] = sum,
+ * max, mean of the normalised weights w_hat (N*R values, computed as the loss kernel computes them), out[6] =
+ * torch.median(w_hat) (the lower median, by a 3-pass radix select that never materialises w_hat), out[7] reserved.
+ * bets: flat (N,R), or h_bet_levels for the per-level (N, A, H, W) maps read in place -- exactly one of the two.
+ * mask (N,R) int64 may be NULL (= 1).  stats: the step's [num_foreground, S_batch, S[n]...].  Three launches. */
+FSG_API size_t fsg_bet_stats_workspace_bytes(void);
+FSG_API int fsg_bet_stats(const float* bets, const fsg_bet_levels* h_bet_levels, const int64_t* mask, int N, int64_t R,
+                  const fsg_loss_params* h_params, const double* stats, double* out /* 8 */, void* workspace,
+                  size_t workspace_bytes, fsg_stream_t stream);
+
 /* in-place x *= *scale_dev or x *= scale_host (backward with a non-unit upstream gradient) */
 FSG_API int fsg_scale_inplace(float* x, int64_t n, const float* scale_dev, float scale_host,
                       fsg_stream_t stream);

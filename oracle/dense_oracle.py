@@ -278,6 +278,31 @@ def train_step(anchors, gt_boxes, gt_classes_list, logits, pred_deltas, bets, nu
     return out
 
 
+def calc_log_metrics(masked_bet_levels, weights, loss_cls, loss_box_reg, gambler_loss_value, loss_before_weighting,
+                     lambda_reg=1.0, kappa=1.0, lambda_out=1.0, mode="cls+reg-gambler"):
+    """GANTrainer.calc_log_metrics (ImbalanceDetection/train_net.py:1089-1124).  ``masked_bet_levels``: the betting
+    maps as gambler_loss left them (multiplied by the picky mask in place, gambler_heads.py:568-569);
+    ``weights``: the normalised weights it returned.  Returns the reference's loss_dict entries."""
+    d = {"loss_cls": loss_cls, "loss_box_reg": loss_box_reg * lambda_reg, "loss_gambler": gambler_loss_value * kappa,
+         "loss_before_weighting": loss_before_weighting}
+    if mode == "cls+reg-gambler":
+        d["loss_detector"] = d["loss_box_reg"] + d["loss_cls"] - lambda_out * d["loss_gambler"]
+    else:
+        d["loss_detector"] = d["loss_box_reg"] - lambda_out * d["loss_gambler"]
+    s, mx, n = 0, 0, 0
+    for b in masked_bet_levels:          # :1104-1111
+        s = s + torch.sum(b)
+        n = n + torch.numel(b)
+        if torch.max(b) > mx:
+            mx = torch.max(b)
+    d["gambler_bets/sum"], d["gambler_bets/max"], d["gambler_bets/mean"] = s, mx, s / n
+    d["visualized weights/sum"] = torch.sum(weights)
+    d["visualized weights/max"] = torch.max(weights)
+    d["visualized weights/mean"] = torch.mean(weights)
+    d["visualized weights/median"] = torch.median(weights)   # lower median
+    return d
+
+
 # ----------------------------------------------------------------------------------------
 # layout helpers (retinanet.py:24-54, gambler_heads.py:34-101)
 # ----------------------------------------------------------------------------------------

@@ -361,6 +361,73 @@ def make_rpn(ref):
     print("[two-stage callers] oracle == reference (bit-exact on CPU)")
 
 
+def reference_calc_log_metrics():
+    """GANTrainer.calc_log_metrics (ImbalanceDetection/train_net.py:1089-1124) as the reference wrote it: the module
+    imports half of detectron2 (engine, data, evaluation), so the method's own source is cut out of the file with
+    `ast` and compiled stand-alone -- it only needs `torch` and a `self` with five attributes."""
+    import ast
+    import types
+
+    path = os.path.join(rl.REF_ROOT, "ImbalanceDetection", "train_net.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    fn = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == "GANTrainer":
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name == "calc_log_metrics":
+                    fn = item
+    assert fn is not None, "calc_log_metrics not found in %s" % path
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ns = {"torch": torch}
+    exec(compile(mod, path, "exec"), ns)
+    return ns["calc_log_metrics"], types.SimpleNamespace
+
+
+def make_log_metrics(ref):
+    """calc_log_metrics on the outputs of a reference training step (config-1 shape and a GT-free image)."""
+    calc, NS = reference_calc_log_metrics()
+    cid, N, H, W, K, M = 6, 3, 256, 320, 80, 5
+    inp = synthetic.train_inputs(cid, N, H, W, K, M=M)
+    cfg = rl.make_cfg(NUM_CLASSES=K, IN_LAYERS=[g[0] for g in inp["grids"]])
+    cfg.MODEL.RETINANET.NUM_CLASSES = K
+    rl.set_global_cfg(ref, cfg)
+    me = rl.retinanet_self(ref, num_classes=K)
+    anchors, targets = ref_anchor_lists(ref, inp), ref_targets(ref, inp, (H, W))
+    gt_classes, gt_deltas = ref.RetinaNet.get_ground_truth(me, anchors, targets)
+    mask = ref.RetinaNet.get_picky_ground_truth(me, anchors, targets)
+    A = inp["A"]
+    cls_levels = flat_to_levels_nchw(inp["logits"], inp["grids"], A)
+    reg_levels = flat_to_levels_nchw(inp["deltas"], inp["grids"], A)
+    bet_levels = [t.reshape(t.shape[0], A, t.shape[2], t.shape[3])
+                  for t in flat_to_levels_nchw(inp["bets"][..., None], inp["grids"], A)]
+    losses = ref.RetinaNet.losses(me, gt_classes, gt_deltas, cls_levels, reg_levels)
+    g = rl.gambler_self(ref, cfg)
+    bets_in = list(bet_levels)
+    gdict, weights = g.gambler_loss(cls_levels, bets_in, gt_classes, mask, detach_pred=False)
+    lam_reg, kappa, lam_out = 0.7, 1.3, 0.9
+    me2 = NS(cfg=_AttrNS(MODEL=_AttrNS(GAMBLER_HEAD=_AttrNS(DETECTOR_LOSS_MODE="cls+reg-gambler"))),
+             regression_loss_lambda=lam_reg, gambler_loss_kappa=kappa, gambler_outside_lambda=lam_out,
+             _detect_anomaly=lambda *a, **k: None)
+    out = calc(me2, bets_in, weights, dict(losses), gdict, 0.0)      # bets_in is the MASKED list now (:568-569)
+    names = ["loss_cls", "loss_box_reg", "loss_gambler", "loss_before_weighting", "loss_detector",
+             "gambler_bets/sum", "gambler_bets/max", "gambler_bets/mean", "visualized weights/sum",
+             "visualized weights/max", "visualized weights/mean", "visualized weights/median"]
+    want = np.asarray([float(out[k]) for k in names], dtype=np.float64)
+    got = orc.calc_log_metrics(bets_in, weights, losses["loss_cls"], losses["loss_box_reg"], gdict["gambler_loss"],
+                               gdict["loss_before_weighting"], lam_reg, kappa, lam_out)
+    for k, w in zip(names, want):
+        assert abs(float(got[k]) - w) <= 1e-6 * max(abs(w), 1e-30), (k, float(got[k]), w)
+    np.savez_compressed(os.path.join(OUT, "log_metrics.npz"), params=np.asarray([cid, N, H, W, K, M]),
+                        lambdas=np.asarray([lam_reg, kappa, lam_out]), names=np.asarray(names), values=want)
+    print("[log_metrics] oracle == reference (calc_log_metrics source executed): %d scalars" % len(names))
+
+
+class _AttrNS(dict):
+    def __getattr__(self, k):
+        return self[k]
+
+
 def main():
     assert rl.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -375,6 +442,7 @@ def main():
     make_nms(ref)
     make_inference(ref)
     make_train(ref)
+    make_log_metrics(ref)
 
 
 if __name__ == "__main__":

@@ -45,6 +45,70 @@ def test_train_step_vs_reference(cuda, name):
     assert_close_tensor(b.grad, g["grad_bets"], "grad_bets", atol_scale=floor)
 
 
+@pytest.mark.parametrize("native", [False, True])
+def test_log_metrics_vs_reference(cuda, native):
+    """StepResult.log_metrics (fsg_bet_stats: sum / max / mean of the masked bets, sum / max / mean / median of the
+    normalised weights, no sort and no host sync) against what the reference's own calc_log_metrics source produced
+    (train_net.py:1089-1124) -- from the flat step and from the step on the head's per-level layout."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    from oracle import dense_oracle as orc
+
+    g = gu.load("log_metrics")
+    cid, N, H, W, K, M = [int(v) for v in g["params"]]
+    lam_reg, kappa, lam_out = [float(v) for v in g["lambdas"]]
+    inp = synthetic.train_inputs(cid, N, H, W, K, M=M)
+    cfg = fsg.DenseLossConfig(num_classes=K)
+    gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+    anchors = inp["anchors"].to(cuda)
+    if native:
+        A, grids = inp["A"], inp["grids"]
+        def lv(flat, C):     # (N, R, C) -> list[(N, A*C, H, W)], the inverse of retinanet.py:24-33
+            out, off = [], 0
+            for h, w in grids:
+                n_l = h * w * A
+                out.append(flat[:, off:off + n_l].reshape(N, h, w, A, C).permute(0, 3, 4, 1, 2)
+                           .reshape(N, A * C, h, w).contiguous().to(cuda))
+                off += n_l
+            return out
+
+        xs, ds = lv(inp["logits"], K), lv(inp["deltas"], 4)
+        bs = [t.to(cuda) for t in orc.flat_to_nahw(inp["bets"], grids, A)]
+        bs = [t.contiguous() for t in bs]
+        res = fsg.dense_train_step_levels(xs, ds, bs, anchors, gt, cfg)
+        got = res.log_metrics(bs, cfg, lam_reg, kappa, lam_out)
+    else:
+        b = inp["bets"].to(cuda)
+        res = fsg.dense_train_step(inp["logits"].to(cuda), inp["deltas"].to(cuda), b, anchors, gt, cfg)
+        got = res.log_metrics(b, cfg, lam_reg, kappa, lam_out)
+    for name, want in zip([str(n) for n in g["names"]], g["values"].tolist()):
+        assert_close_scalar(float(got[name]), want, name, rtol=2e-5 if "loss" in name else 1e-5)
+
+
+def test_log_metrics_median_is_exact_rank(cuda):
+    """The 3-pass radix select returns exactly the element torch.median picks (lower median) of the device-computed
+    weights, for odd and even counts, with ties and with the GT-free image's mask = K quirk in play."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    for N, H, W in ((3, 128, 160), (2, 96, 96)):
+        inp = synthetic.train_inputs(63, N, H, W, 80, M=4)
+        cfg = fsg.DenseLossConfig(num_classes=80)
+        b = inp["bets"].clone()
+        b[0, ::3] = b[0, 0]                                   # many exact ties
+        b = b.to(cuda)
+        gt = fsg.ops.PackedGT.from_lists(inp["gt_boxes"], inp["gt_classes"], cuda)
+        res = fsg.dense_train_step(inp["logits"].to(cuda), inp["deltas"].to(cuda), b, inp["anchors"].to(cuda), gt, cfg,
+                                   want_weights=True)
+        got = res.log_metrics(b, cfg)
+        w = res.weights.flatten()
+        assert float(got["visualized weights/median"]) == float(torch.median(w))
+        assert float(got["visualized weights/max"]) == float(w.max())
+        assert_close_scalar(float(got["visualized weights/sum"]), float(w.double().sum()), "sum", rtol=1e-9)
+        bm = (b * res.mask).flatten()
+        assert float(got["gambler_bets/max"]) == float(bm.max())
+        assert_close_scalar(float(got["gambler_bets/sum"]), float(bm.double().sum()), "bets sum", rtol=1e-9)
+
+
 def test_matcher_vs_reference(cuda):
     fsg = _fsg()
     from full_scale_gambler_for_object_detection_b200 import synthetic

@@ -239,3 +239,21 @@ def test_two_stage_callers_golden():
         assert torch.equal(ob, g["frcnn%d_boxes" % ci]) and torch.equal(os_, g["frcnn%d_scores" % ci])
         assert_equal_int(oc, g["frcnn%d_classes" % ci], "classes")
         assert_equal_int(orow, g["frcnn%d_rows" % ci], "rows")
+
+
+def test_log_metrics_golden():
+    """GANTrainer.calc_log_metrics (train_net.py:1089-1124): the oracle restatement against the values the
+    reference's own function source produced (tests/golden/log_metrics.npz)."""
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+
+    g = gu.load("log_metrics")
+    cid, N, H, W, K, M = [int(v) for v in g["params"]]
+    lam_reg, kappa, lam_out = [float(v) for v in g["lambdas"]]
+    inp = synthetic.train_inputs(cid, N, H, W, K, M=M)
+    out = orc.train_step(inp["anchors"], inp["gt_boxes"], inp["gt_classes"], inp["logits"], inp["deltas"],
+                         inp["bets"], K, 1.0, 1.0, -1.0, need_grad=False)
+    masked = orc.flat_to_nahw(inp["bets"] * out["mask"], inp["grids"], inp["A"])
+    got = orc.calc_log_metrics(masked, out["weights"], out["loss_cls"], out["loss_box_reg"], out["gambler_loss"],
+                               out["loss_before_weighting"], lam_reg, kappa, lam_out)
+    for name, want in zip([str(n) for n in g["names"]], g["values"].tolist()):
+        assert_close_scalar(float(got[name]), want, name)
