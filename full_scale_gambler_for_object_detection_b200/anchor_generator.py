@@ -108,6 +108,6 @@ class DefaultAnchorGenerator:
         return [flat[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
 
     def __call__(self, features):
-        from .structures import Boxes
-        per_level = [Boxes(t) for t in self.grid_anchors([f.shape[-2:] for f in features])]
+        from .structures import make_boxes
+        per_level = [make_boxes(t) for t in self.grid_anchors([f.shape[-2:] for f in features])]
         return [per_level for _ in range(len(features[0]))]

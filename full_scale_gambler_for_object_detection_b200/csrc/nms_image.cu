@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const NmsArgs
   unsigned char* dead = smem_raw + (size_t)kNmsCap * 26;                        // kNmsCap
   __shared__ int s_pref[kMaxLevels + 1];
   __shared__ int s_warp[kNmsThreads / 32];
-  __shared__ int s_nseg, s_next, s_nkeep, s_mine, s_nbatch;
+  __shared__ int s_nseg, s_next, s_nkeep, s_mine, s_nbatch, s_bad;
   __shared__ int s_batch[32];
   __shared__ bool s_last;
 
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const NmsArgs
     } else {
       s_pref[1] = A.fixed_count;
     }
-    s_nseg = 0; s_next = 0; s_nkeep = 0; s_mine = 0;
+    s_nseg = 0; s_next = 0; s_nkeep = 0; s_mine = 0; s_bad = 0;
   }
   __syncthreads();
   const int L = A.lvl_count ? A.L : 1;
@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const NmsArgs
     if (i < nc) {
       const int s = slot_of(i);
       const int64_t craw = gcls ? gcls[s] : 0;
-      const uint64_t c = (uint64_t)(craw & 0x3ffff);
+      if (craw < 0 || craw > 0x3ffff) s_bad = 1;   // the composite key holds 18 bits of class id (every CTA sees every
+      const uint64_t c = (uint64_t)(craw & 0x3ffff);  // candidate, so the image's last CTA knows too): reported below
       mine = ((int)(c % (uint64_t)S) == part);
       if (mine) {
         const uint32_t sb = __float_as_uint(gscore[s]);
@@ -284,10 +285,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const NmsArgs
       A.out_classes[ob + t] = 0;
       if (A.keep && t < A.keep_stride) A.keep[(int64_t)n * A.keep_stride + t] = -1;
     }
-    if (tid == 0 && A.num_keep) A.num_keep[n] = total;
+    if (tid == 0 && A.num_keep) A.num_keep[n] = s_bad ? -1 : total;
     return;
   }
-  if (tid == 0 && A.num_keep) A.num_keep[n] = nk;
+  if (tid == 0 && A.num_keep) A.num_keep[n] = s_bad ? -1 : nk;   // -1: a class id outside [0, 2^18)
   const int out_rows = (A.max_out > 0) ? A.max_out : nk;
   for (int t = tid; t < out_rows; t += kNmsThreads) {
     if (t < nk) {

@@ -3,6 +3,7 @@
 //
 // Reference: detectron2/modeling/proposal_generator/rpn_outputs.py:52-151; roi_heads/fast_rcnn.py:76-118.
 #include "nms_kernel.cuh"
+#include "nms_large.cuh"
 #include "sort_utils.cuh"
 
 namespace fsg {
@@ -17,7 +18,7 @@ namespace fsg {
 // ------------------------------------------------------------------------------------------
 constexpr int kRpnThreads = 1024;
 constexpr int kRpnBins = 2048;          // 11-bit digits
-constexpr int kRpnMaxK = 8192;
+constexpr int kRpnMaxK = 16384;        // pre_nms_topk per level (128 KB of keys); C4 models train with 12000
 
 struct RpnArgs {
   const float* logits[kMaxLevels];      // level l: (N, hwa[l])
@@ -32,6 +33,7 @@ struct RpnArgs {
   float* cand_score;
   int64_t* cand_class;
   int* lvl_count;                       // (N, L)
+  int fill_tail;                        // large path: unused slots of a level get score -inf and an empty box
 };
 
 __device__ __forceinline__ uint64_t rpn_key(float v, uint32_t idx) {
@@ -173,6 +175,49 @@ __global__ void __launch_bounds__(kRpnThreads) rpn_select_kernel(const RpnArgs A
     __syncthreads();
   }
   if (tid == 0) A.lvl_count[n * A.num_levels + l] = s_base;
+  if (A.fill_tail) {
+    // the general-n NMS behind this kernel takes a fixed number of boxes: pad with boxes that sort last (score -inf)
+    // and never suppress or get suppressed (zero area: IoU 0 or NaN)
+    const int cnt = s_base;
+    for (int j = cnt + tid; j < A.topk; j += kRpnThreads) {
+      A.cand_box[slot0 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      A.cand_score[slot0 + j] = -INFINITY;
+      A.cand_class[slot0 + j] = l;
+    }
+  }
+}
+
+// large path epilogue: keep[] of the general-n NMS (score order; the padding sorts last) -> the post_nms_topk best
+// real survivors of image n
+__global__ void __launch_bounds__(256) rpn_gather_kernel(const float4* __restrict__ cand_box,
+                                                         const float* __restrict__ cand_score,
+                                                         const int64_t* __restrict__ cand_class,
+                                                         const int* __restrict__ lvl_count, int L, int64_t slots,
+                                                         const int64_t* __restrict__ keep,
+                                                         const int32_t* __restrict__ num_keep, int post,
+                                                         float4* __restrict__ out_boxes, float* __restrict__ out_logits,
+                                                         int64_t* __restrict__ out_levels, int32_t* __restrict__ out_count) {
+  const int n = blockIdx.x;
+  int real = 0;
+  for (int l = 0; l < L; ++l) real += lvl_count[n * L + l];
+  int kept = num_keep[n] - (int)(slots - real);   // every padded slot is "kept" and sits behind the real ones
+  if (kept < 0) kept = 0;
+  if (kept > post) kept = post;
+  for (int t = threadIdx.x; t < post; t += 256) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = 0.f;
+    int64_t lv = 0;
+    if (t < kept) {
+      const int64_t i = keep[(int64_t)n * slots + t];
+      b = cand_box[(int64_t)n * slots + i];
+      sc = cand_score[(int64_t)n * slots + i];
+      lv = cand_class[(int64_t)n * slots + i];
+    }
+    out_boxes[(int64_t)n * post + t] = b;
+    out_logits[(int64_t)n * post + t] = sc;
+    if (out_levels) out_levels[(int64_t)n * post + t] = lv;
+  }
+  if (threadIdx.x == 0) out_count[n] = kept;
 }
 
 struct RpnWs {
@@ -275,8 +320,11 @@ __global__ void __launch_bounds__(1024) score_filter_kernel(const float4* __rest
 
 using namespace fsg;
 
+// -> FSG_OK and *large_out = 0: everything fits the shared-memory NMS kernel (<= 8192 candidates per split CTA);
+//    *large_out = 1: more candidates per image (e.g. RPN.PRE_NMS_TOPK_TRAIN = 12000 of the C4 models,
+//    config/defaults.py:219): same select kernel, then the general-n NMS (nms_large.cu) per image.
 static int rpn_plan(const int64_t* h_level_sizes, int num_levels, int pre_nms_topk, int post_nms_topk, int N,
-                    int* k, int* topk_out, int* split_out) {
+                    int* k, int* topk_out, int* split_out, int* large_out) {
   if (!h_level_sizes || num_levels <= 0 || num_levels > kMaxLevels || pre_nms_topk <= 0 || post_nms_topk <= 0 || N <= 0)
     return FSG_ERR_INVALID_ARG;
   int topk = 0;
@@ -287,20 +335,42 @@ static int rpn_plan(const int64_t* h_level_sizes, int num_levels, int pre_nms_to
     if (k[l] > topk) topk = k[l];
     total += k[l];
   }
-  if (topk > kRpnMaxK || total >= (1 << 14) || post_nms_topk > kNmsCap || N > 65535) return FSG_ERR_UNSUPPORTED;
+  if (topk > kRpnMaxK || N > 65535) return FSG_ERR_UNSUPPORTED;
   if (topk < 1) topk = 1;
-  const int split = rpn_split_for(N, k, num_levels, post_nms_topk);
-  if (split == 0) return FSG_ERR_UNSUPPORTED;
   *topk_out = topk;
+  *large_out = 0;
+  int split = 0;
+  if (topk <= kNmsCap && total < (1 << 14) && post_nms_topk <= kNmsCap)
+    split = rpn_split_for(N, k, num_levels, post_nms_topk);
+  if (split == 0) {
+    if ((int64_t)num_levels * topk > kNmsLargeMax) return FSG_ERR_UNSUPPORTED;
+    *large_out = 1;
+    split = 1;
+  }
   *split_out = split;
   return FSG_OK;
 }
 
+struct RpnLargeWs {
+  size_t off_keep, off_numkeep, off_nms, total;
+};
+static RpnLargeWs rpn_large_ws_layout(int N, int64_t slots, size_t base) {
+  RpnLargeWs w;
+  size_t o = base;
+  w.off_keep = o;    o += align_up(sizeof(int64_t) * (size_t)N * (size_t)slots, 16);
+  w.off_numkeep = o; o += align_up(sizeof(int32_t) * (size_t)N, 16);
+  w.off_nms = o;     o += nms_large_ws_layout(slots).total;
+  w.total = o;
+  return w;
+}
+
 extern "C" size_t fsg_rpn_proposals_workspace_bytes(int N, const int64_t* h_level_sizes, int num_levels,
                                                     int pre_nms_topk, int post_nms_topk) {
-  int k[kMaxLevels], topk, split;
-  if (rpn_plan(h_level_sizes, num_levels, pre_nms_topk, post_nms_topk, N, k, &topk, &split) != FSG_OK) return 0;
-  return rpn_ws_layout(N, num_levels, topk, post_nms_topk, split).total;
+  int k[kMaxLevels], topk, split, large;
+  if (rpn_plan(h_level_sizes, num_levels, pre_nms_topk, post_nms_topk, N, k, &topk, &split, &large) != FSG_OK) return 0;
+  const RpnWs w = rpn_ws_layout(N, num_levels, topk, post_nms_topk, split);
+  if (!large) return w.total;
+  return rpn_large_ws_layout(N, (int64_t)num_levels * topk, w.off_nms).total;
 }
 
 extern "C" int fsg_rpn_proposals(const float* const* h_level_proposals, const float* const* h_level_logits,
@@ -308,14 +378,17 @@ extern "C" int fsg_rpn_proposals(const float* const* h_level_proposals, const fl
                                  int pre_nms_topk, int post_nms_topk, double nms_threshold, float min_box_side_len,
                                  float* out_boxes, float* out_logits, int64_t* out_levels, int32_t* out_count,
                                  void* workspace, size_t workspace_bytes, fsg_stream_t stream) {
-  int k[kMaxLevels], topk, split;
-  const int st = rpn_plan(h_level_sizes, num_levels, pre_nms_topk, post_nms_topk, N, k, &topk, &split);
+  int k[kMaxLevels], topk, split, large;
+  const int st = rpn_plan(h_level_sizes, num_levels, pre_nms_topk, post_nms_topk, N, k, &topk, &split, &large);
   if (st != FSG_OK) return st;
   if (!h_level_proposals || !h_level_logits || !image_sizes || !out_boxes || !out_logits || !out_count)
     return FSG_ERR_INVALID_ARG;
   if (((uintptr_t)out_boxes) & 15) return FSG_ERR_INVALID_ARG;
   const RpnWs w = rpn_ws_layout(N, num_levels, topk, post_nms_topk, split);
-  if (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  const int64_t slots = (int64_t)num_levels * topk;
+  const RpnLargeWs lw = rpn_large_ws_layout(N, slots, w.off_nms);
+  const size_t need = large ? lw.total : w.total;
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
   char* ws = (char*)workspace;
   cudaStream_t s = (cudaStream_t)stream;
 
@@ -329,12 +402,32 @@ extern "C" int fsg_rpn_proposals(const float* const* h_level_proposals, const fl
   ra.topk = topk; ra.num_levels = num_levels; ra.image_sizes = image_sizes; ra.min_size = min_box_side_len;
   ra.cand_box = (float4*)(ws + w.off_cbox); ra.cand_score = (float*)(ws + w.off_cscore);
   ra.cand_class = (int64_t*)(ws + w.off_ccls); ra.lvl_count = (int*)(ws + w.off_lvl);
+  ra.fill_tail = large;
   int m = 1;
   while (m < topk) m <<= 1;
   const size_t smem = sizeof(uint64_t) * (size_t)m;
   FSG_CUDA_TRY(cudaFuncSetAttribute(rpn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rpn_select_kernel<<<dim3((unsigned)num_levels, (unsigned)N), kRpnThreads, smem, s>>>(ra);
   FSG_LAUNCH_CHECK();
+
+  if (large) {
+    // general-n NMS per image on its L*topk slots (class id = level => per-level batched_nms), one workspace reused
+    // in stream order; then the gather of the post_nms_topk best real survivors
+    int64_t* keep = (int64_t*)(ws + lw.off_keep);
+    int32_t* numkeep = (int32_t*)(ws + lw.off_numkeep);
+    const float thr = threshold_floor(nms_threshold);
+    for (int n = 0; n < N; ++n) {
+      const int rc = nms_large((const float*)(ra.cand_box + (int64_t)n * slots), ra.cand_score + (int64_t)n * slots,
+                               ra.cand_class + (int64_t)n * slots, slots, thr, keep + (int64_t)n * slots, numkeep + n,
+                               ws + lw.off_nms, lw.total - lw.off_nms, s);
+      if (rc != FSG_OK) return rc;
+    }
+    rpn_gather_kernel<<<(unsigned)N, 256, 0, s>>>(ra.cand_box, ra.cand_score, ra.cand_class, ra.lvl_count, num_levels,
+                                                  slots, keep, numkeep, post_nms_topk, (float4*)out_boxes, out_logits,
+                                                  out_levels, out_count);
+    FSG_LAUNCH_CHECK();
+    return FSG_OK;
+  }
 
   NmsArgs a = {};
   a.boxes = ra.cand_box; a.scores = ra.cand_score; a.classes = ra.cand_class;

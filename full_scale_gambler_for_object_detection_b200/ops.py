@@ -668,13 +668,13 @@ def rpn_proposals(level_proposals, level_logits, image_sizes, nms_thresh, pre_nm
     L = lib()
     need = L.fsg_rpn_proposals_workspace_bytes(N, sizes, nl, int(pre_nms_topk), int(post_nms_topk))
     if need == 0:
-        raise RuntimeError("fsg_rpn_proposals: shape outside what the kernels cover (pre_nms_topk <= 8192 per "
-                           "level, < 16384 candidates per image, post_nms_topk <= 8192)")
+        raise RuntimeError("fsg_rpn_proposals: shape outside what the kernels cover (pre_nms_topk <= 16384 per "
+                           "level, num_levels * pre_nms_topk <= 262144)")
     ws = _ws(need, dev)
     check(L.fsg_rpn_proposals(pp, lp, sizes, nl, N, ptr(isz), int(pre_nms_topk), int(post_nms_topk),
                               float(nms_thresh), float(min_box_side_len), ptr(out["boxes"]), ptr(out["logits"]),
                               ptr(out["levels"]), ptr(out["count"]), ptr(ws), ws.numel(), stream()))
-    count_launches(2)
+    count_launches(2)   # (+ 3 per image and a gather on the general-n path)
     return out
 
 

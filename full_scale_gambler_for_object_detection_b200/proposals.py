@@ -13,7 +13,7 @@ import torch
 
 from . import ops
 from .nms import batched_nms
-from .structures import Boxes, Instances
+from .structures import as_tensor, make_boxes, make_instances
 
 
 def _image_sizes(images):
@@ -21,20 +21,19 @@ def _image_sizes(images):
 
 
 def find_top_rpn_proposals(proposals, pred_objectness_logits, images, nms_thresh, pre_nms_topk, post_nms_topk,
-                           min_box_side_len, training=False):
+                           min_box_side_len, training):
     """proposals list[(N, Hi*Wi*A, 4)], pred_objectness_logits list[(N, Hi*Wi*A)], images: ImageList or a list of
     (h, w) -> list[Instances] with ``proposal_boxes`` / ``objectness_logits``.  The whole batch runs in two kernel
-    launches (the reference loops over images with a host sync per image, rpn_outputs.py:123-131)."""
+    launches (the reference loops over images with a host sync per image, rpn_outputs.py:123-131).  ``training``
+    only matters to the reference's NaN filter (:106-116), which is a host-synchronising debug aid not kept here."""
     sizes = _image_sizes(images)
     res = ops.rpn_proposals(proposals, pred_objectness_logits, sizes, nms_thresh, pre_nms_topk, post_nms_topk,
                             min_box_side_len)
     counts = res["count"].tolist()
     out = []
     for n, size in enumerate(sizes):
-        inst = Instances(tuple(size))
-        inst.proposal_boxes = Boxes(res["boxes"][n, :counts[n]])
-        inst.objectness_logits = res["logits"][n, :counts[n]]
-        out.append(inst)
+        out.append(make_instances(tuple(size), proposal_boxes=make_boxes(res["boxes"][n, :counts[n]]),
+                                  objectness_logits=res["logits"][n, :counts[n]]))
     return out
 
 
@@ -43,7 +42,7 @@ def rpn_ground_truth(anchors, gt_boxes, iou_thresholds=(0.3, 0.7), iou_labels=(0
     """RPNOutputs._get_ground_truth.  anchors: (R,4) tensor shared by the images (or (N,R,4)); gt_boxes: list of
     Boxes / (M_i,4) tensors.  -> (gt_objectness_logits list[(R) int8 in {-1,0,1}], gt_anchor_deltas list[(R,4)]).
     Matcher(allow_low_quality_matches=True) as rpn.py builds it; images without GT: labels 0, deltas 0."""
-    boxes = [b.tensor if isinstance(b, Boxes) else b for b in gt_boxes]
+    boxes = [as_tensor(b) for b in gt_boxes]
     dev = anchors.device
     gt = ops.PackedGT.from_lists(boxes, [torch.zeros(b.shape[0], dtype=torch.int64) for b in boxes], dev)
     out = ops.match_anchors(anchors, gt, 1, iou_thresholds, iou_labels, None, None, box_weights,
@@ -73,8 +72,7 @@ def label_proposals(proposal_boxes, gt_boxes, gt_classes, num_classes, iou_thres
     low-quality pass) + the relabelling of _sample_proposals (roi_heads.py:178-186), without the (M, P) matrix.
     -> (matched_idxs (P) int64, matched_labels (P) int8, gt_classes (P) int64 with background = num_classes and
     ignored = -1)."""
-    p = proposal_boxes.tensor if isinstance(proposal_boxes, Boxes) else proposal_boxes
-    g = gt_boxes.tensor if isinstance(gt_boxes, Boxes) else gt_boxes
+    p, g = as_tensor(proposal_boxes), as_tensor(gt_boxes)
     gt = ops.PackedGT.from_lists([g], [gt_classes], p.device)
     out = ops.match_anchors(p.contiguous(), gt, num_classes, iou_thresholds, iou_labels, None, None,
                             want=("matches", "match_labels", "gt_classes"), allow_low_quality_matches=False)
@@ -87,10 +85,8 @@ def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, n
     keep = batched_nms(cb, cs, cc, nms_thresh)
     if topk_per_image >= 0:
         keep = keep[:topk_per_image]
-    result = Instances(tuple(image_shape))
-    result.pred_boxes = Boxes(cb[keep])
-    result.scores = cs[keep]
-    result.pred_classes = cc[keep]
+    result = make_instances(tuple(image_shape), pred_boxes=make_boxes(cb[keep]), scores=cs[keep],
+                            pred_classes=cc[keep])
     return result, cr[keep]
 
 

@@ -16,7 +16,7 @@ import torch
 from . import _lib, ops
 from .box_regression import Box2BoxTransform
 from .matcher import Matcher
-from .structures import Boxes, Instances
+from .structures import as_tensor, cat_tensors, make_boxes, make_instances
 
 
 class _LevelsToFlat(torch.autograd.Function):
@@ -107,6 +107,7 @@ class RetinaNetDensePath:
         self.box2box_transform = Box2BoxTransform(weights=tuple(bbox_reg_weights))
         self.matcher = Matcher(list(iou_thresholds), list(iou_labels), allow_low_quality_matches=True)
         self.picky_matcher = Matcher([0.4, 0.9], list(iou_labels), allow_low_quality_matches=True)
+        self._match_cache = None
 
     @classmethod
     def from_config(cfg_cls, cfg):
@@ -118,36 +119,50 @@ class RetinaNetDensePath:
 
     # ---------------------------------------------------------------------------------------------
     @staticmethod
-    def _anchor_tensor(anchors: List[List[Boxes]]):
-        """list[list[Boxes]] (per image, per level) -> (R,4) if every image carries the same anchors
-        (the reference deep-copies one set per image, anchor_generator.py:188), else (N,R,4)."""
-        per_image = [Boxes.cat(a).tensor for a in anchors]  # retinanet.py:339
+    def _anchor_tensor(anchors):
+        """list[list[Boxes]] (per image, per level) -> (R,4) if every image carries the SAME anchor objects or
+        storage (what ``DefaultAnchorGenerator`` of this package hands out), else (N,R,4).  The reference deep-copies
+        one anchor set per image (anchor_generator.py:188): equal contents in different storage -- telling that apart
+        would take a device-side compare and a host sync per image, so copies are simply stacked (17 MB at config 2)."""
+        first_list = anchors[0]
+        if all(a is first_list for a in anchors[1:]):
+            return cat_tensors(first_list).contiguous()
+        per_image = [cat_tensors(a) for a in anchors]  # retinanet.py:339
         first = per_image[0]
-        same = all(t.shape == first.shape and (t.data_ptr() == first.data_ptr() or torch.equal(t, first))
-                   for t in per_image[1:])
-        if same:
+        if all(t.shape == first.shape and t.data_ptr() == first.data_ptr() for t in per_image[1:]):
             return first.contiguous()
         return torch.stack(per_image).contiguous()
 
-    def _match(self, anchors, targets, want):
+    def _match(self, anchors, targets):
+        """One K1 run yields gt_classes, gt_anchors_deltas AND the picky mask; the reference calls get_ground_truth and
+        get_picky_ground_truth back to back on the same (anchors, targets) (train_net.py:1142-1150), so the result is
+        kept for the second call.  The key holds storage pointers and tensor versions: an in-place edit of the ground
+        truth or the anchors between the two calls invalidates it."""
         a = self._anchor_tensor(anchors)
-        dev = a.device
-        gt = ops.PackedGT.from_lists([t.gt_boxes.tensor for t in targets], [t.gt_classes for t in targets], dev)
-        return ops.match_anchors(a, gt, self.num_classes, self.matcher.thresholds[1:-1], self.matcher.labels,
-                                 self.picky_matcher.thresholds[1:-1], self.picky_matcher.labels,
-                                 self.box2box_transform.weights, want=want)
+        gtb = [as_tensor(t.gt_boxes) for t in targets]
+        gtc = [t.gt_classes for t in targets]
+        key = ((a.data_ptr(), a._version, tuple(a.shape)),
+               tuple((b.data_ptr(), b._version, c.data_ptr(), c._version, b.shape[0]) for b, c in zip(gtb, gtc)))
+        if self._match_cache is not None and self._match_cache[0] == key:
+            return self._match_cache[1]
+        gt = ops.PackedGT.from_lists(gtb, gtc, a.device)
+        out = ops.match_anchors(a, gt, self.num_classes, self.matcher.thresholds[1:-1], self.matcher.labels,
+                                self.picky_matcher.thresholds[1:-1], self.picky_matcher.labels,
+                                self.box2box_transform.weights, want=("gt_classes", "gt_deltas", "mask"))
+        self._match_cache = (key, out)
+        return out
 
     @torch.no_grad()
     def get_ground_truth(self, anchors, targets):
         """-> gt_classes (N,R) int64 in {-1, 0..K-1, K}, gt_anchors_deltas (N,R,4)."""
-        out = self._match(anchors, targets, ("gt_classes", "gt_deltas"))
+        out = self._match(anchors, targets)
         return out["gt_classes"], out["gt_deltas"]
 
     @torch.no_grad()
     def get_picky_ground_truth(self, anchors, targets):
         """-> mask (N,R) int64: 1 where the [0.4,0.9] matcher labels the anchor positive (IoU >= 0.9 or a
         ground truth's best anchor), else 0; all K for an image without ground truth (retinanet.py:425)."""
-        return self._match(anchors, targets, ("mask",))["mask"]
+        return self._match(anchors, targets)["mask"]
 
     def losses(self, gt_classes, gt_anchors_deltas, pred_class_logits, pred_anchor_deltas):
         """-> {"loss_cls", "loss_box_reg"} (differentiable wrt the per-level head outputs)."""
@@ -177,11 +192,8 @@ class RetinaNetDensePath:
     @staticmethod
     def _to_instances(res, n, image_size, count=None):
         c = int(res["count"][n].item()) if count is None else count
-        r = Instances(tuple(image_size))
-        r.pred_boxes = Boxes(res["boxes"][n, :c])
-        r.scores = res["scores"][n, :c]
-        r.pred_classes = res["classes"][n, :c]
-        return r
+        return make_instances(tuple(image_size), pred_boxes=make_boxes(res["boxes"][n, :c]),
+                              scores=res["scores"][n, :c], pred_classes=res["classes"][n, :c])
 
     @staticmethod
     def _to_instances_batch(res, image_sizes):
@@ -191,12 +203,14 @@ class RetinaNetDensePath:
         return [RetinaNetDensePath._to_instances(res, n, image_sizes[n], counts[n]) for n in range(len(counts))]
 
     @torch.no_grad()
-    def inference(self, box_cls, box_delta, anchors, image_sizes, output_sizes=None):
-        """box_cls/box_delta: list over levels of (N, A*K|A*4, H, W); anchors: list[list[Boxes]];
-        image_sizes: list of (h, w).  All images go through one batched launch pair.
-        output_sizes: optional list of (height, width) -- ``detector_postprocess`` (postprocessing.py:8-52,
-        what RetinaNet.forward applies to every result, retinanet.py:150-157) is then fused into the NMS
-        epilogue and the returned Instances are at the output resolution."""
+    def inference(self, box_cls, box_delta, anchors, images, *, output_sizes=None):
+        """retinanet.py:431-458.  box_cls/box_delta: list over levels of (N, A*K|A*4, H, W); anchors:
+        list[list[Boxes]]; images: an ``ImageList`` (anything with ``.image_sizes``) or a list of (h, w).  All images
+        go through one batched launch sequence.
+        output_sizes (extension, keyword only): list of (height, width) -- ``detector_postprocess``
+        (postprocessing.py:8-52, what RetinaNet.forward applies to every result, retinanet.py:150-157) is then fused
+        into the NMS epilogue and the returned Instances are at the output resolution."""
+        image_sizes = list(images.image_sizes) if hasattr(images, "image_sizes") else list(images)
         assert len(anchors) == len(image_sizes)
         post = None
         if output_sizes is not None:
@@ -226,5 +240,5 @@ class RetinaNetDensePath:
         offs = [0]
         for a in anchors:
             offs.append(offs[-1] + len(a))
-        res = self._detect(x, d, Boxes.cat(list(anchors)).tensor.contiguous(), offs)
+        res = self._detect(x, d, cat_tensors(list(anchors)).contiguous(), offs)
         return self._to_instances(res, 0, image_size)

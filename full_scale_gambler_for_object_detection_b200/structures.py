@@ -1,47 +1,44 @@
-"""``Boxes`` / ``Instances`` argument types and ``pairwise_iou`` (detectron2/structures/boxes.py,
-instances.py).  Only what the hot path touches: containers are thin; the arithmetic is in the CUDA library."""
-from typing import Any, Dict, List, Tuple, Union
+"""Argument / return containers at the boundary and ``pairwise_iou`` (detectron2/structures/boxes.py:243-275).
+
+The drop-ins are duck-typed: every function of this package accepts the reference's own ``Boxes`` / ``Instances``
+(anything with ``.tensor``, respectively ``get_fields()`` / attribute access / ``image_size``), and a maintainer who
+wants the results in the reference's own classes says so once::
+
+    fsg.structures.use_containers(detectron2.structures.Boxes, detectron2.structures.Instances)
+
+Without that call the results come back in the two small stand-ins below, which carry just what the return path
+needs (a tensor with a length; named per-instance fields with a common length, indexing, ``.to``)."""
+from typing import Any, Dict, Tuple
 
 import torch
 
 from . import ops
 
 
+def as_tensor(boxes) -> torch.Tensor:
+    """``Boxes``-like (has ``.tensor``) or a tensor -> the (n,4) tensor."""
+    return boxes.tensor if hasattr(boxes, "tensor") else boxes
+
+
+def cat_tensors(boxes_list) -> torch.Tensor:
+    """``Boxes.cat`` (boxes.py:212-228) for any mix of Boxes-likes / tensors, single-element shortcut included."""
+    ts = [as_tensor(b) for b in boxes_list]
+    return ts[0] if len(ts) == 1 else torch.cat(ts, dim=0)
+
+
 class Boxes:
-    """(N,4) fp32 XYXY wrapper (boxes.py:72-238)."""
+    """(n,4) fp32 XYXY tensor with a length (boxes.py:72-110: fp32 cast, empty input -> (0,4))."""
 
     def __init__(self, tensor: torch.Tensor):
         device = tensor.device if isinstance(tensor, torch.Tensor) else torch.device("cpu")
         tensor = torch.as_tensor(tensor, dtype=torch.float32, device=device)
         if tensor.numel() == 0:
-            tensor = tensor.reshape((0, 4))  # boxes.py:91-95
+            tensor = tensor.reshape((0, 4))
         assert tensor.dim() == 2 and tensor.size(-1) == 4, tensor.size()
         self.tensor = tensor
 
-    def clone(self) -> "Boxes":
-        return Boxes(self.tensor.clone())
-
     def to(self, device) -> "Boxes":
         return Boxes(self.tensor.to(device))
-
-    def area(self) -> torch.Tensor:
-        b = self.tensor
-        return (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
-
-    def clip(self, box_size: Tuple[int, int]) -> None:
-        h, w = box_size
-        self.tensor[:, 0].clamp_(min=0, max=w)
-        self.tensor[:, 1].clamp_(min=0, max=h)
-        self.tensor[:, 2].clamp_(min=0, max=w)
-        self.tensor[:, 3].clamp_(min=0, max=h)
-
-    def nonempty(self, threshold: float = 0) -> torch.Tensor:
-        b = self.tensor
-        return ((b[:, 2] - b[:, 0]) > threshold) & ((b[:, 3] - b[:, 1]) > threshold)
-
-    def scale(self, scale_x: float, scale_y: float) -> None:
-        self.tensor[:, 0::2] *= scale_x
-        self.tensor[:, 1::2] *= scale_y
 
     def __getitem__(self, item) -> "Boxes":
         if isinstance(item, int):
@@ -53,37 +50,17 @@ class Boxes:
     def __len__(self) -> int:
         return self.tensor.shape[0]
 
-    def __repr__(self) -> str:
-        return "Boxes(" + str(self.tensor) + ")"
-
-    @staticmethod
-    def cat(boxes_list: List["Boxes"]) -> "Boxes":
-        assert isinstance(boxes_list, (list, tuple)) and len(boxes_list) > 0
-        assert all(isinstance(b, Boxes) for b in boxes_list)
-        if len(boxes_list) == 1:  # layers/wrappers.py:15-22 single-element shortcut
-            return Boxes(boxes_list[0].tensor)
-        return Boxes(torch.cat([b.tensor for b in boxes_list], dim=0))
-
     @property
     def device(self):
         return self.tensor.device
 
-    def __iter__(self):
-        yield from self.tensor
-
-
-def pairwise_iou(boxes1: Boxes, boxes2: Boxes) -> torch.Tensor:
-    """IoU of all N x M pairs (boxes.py:243-275), materialised; bit-exact with the reference's fp32 result.
-    The fused training path (``ops.match_anchors``) never builds this matrix."""
-    return ops.pairwise_iou(boxes1.tensor, boxes2.tensor)
-
 
 class Instances:
-    """Per-image field container (structures/instances.py), the argument/return type at the boundary."""
+    """Named per-instance fields of one image (structures/instances.py): what the drop-ins return."""
 
     def __init__(self, image_size: Tuple[int, int], **kwargs: Any):
-        self._image_size = image_size
-        self._fields: Dict[str, Any] = {}
+        object.__setattr__(self, "_image_size", image_size)
+        object.__setattr__(self, "_fields", {})
         for k, v in kwargs.items():
             self.set(k, v)
 
@@ -92,21 +69,18 @@ class Instances:
         return self._image_size
 
     def __setattr__(self, name: str, val: Any) -> None:
-        if name.startswith("_"):
-            super().__setattr__(name, val)
-        else:
-            self.set(name, val)
+        self.set(name, val)
 
     def __getattr__(self, name: str) -> Any:
-        if name == "_fields" or name not in self._fields:
+        fields = object.__getattribute__(self, "_fields")
+        if name not in fields:
             raise AttributeError("Cannot find field '{}' in the given Instances!".format(name))
-        return self._fields[name]
+        return fields[name]
 
     def set(self, name: str, value: Any) -> None:
-        data_len = len(value)
         if len(self._fields):
-            assert len(self) == data_len, "Adding a field of length {} to a Instances of length {}".format(
-                data_len, len(self))
+            assert len(self) == len(value), "Adding a field of length {} to a Instances of length {}".format(
+                len(value), len(self))
         self._fields[name] = value
 
     def has(self, name: str) -> bool:
@@ -119,20 +93,38 @@ class Instances:
         return self._fields
 
     def to(self, device) -> "Instances":
-        ret = Instances(self._image_size)
-        for k, v in self._fields.items():
-            if hasattr(v, "to"):
-                v = v.to(device)
-            ret.set(k, v)
-        return ret
+        return type(self)(self._image_size, **{k: (v.to(device) if hasattr(v, "to") else v)
+                                               for k, v in self._fields.items()})
 
-    def __getitem__(self, item: Union[int, slice, torch.Tensor]) -> "Instances":
-        ret = Instances(self._image_size)
-        for k, v in self._fields.items():
-            ret.set(k, v[item])
-        return ret
+    def __getitem__(self, item) -> "Instances":
+        return type(self)(self._image_size, **{k: v[item] for k, v in self._fields.items()})
 
     def __len__(self) -> int:
         for v in self._fields.values():
             return len(v)
         raise NotImplementedError("Empty Instances does not support __len__!")
+
+
+_BOXES, _INSTANCES = Boxes, Instances
+
+
+def use_containers(boxes_cls=None, instances_cls=None):
+    """Classes the drop-ins build their results with (default: the stand-ins above).  ``boxes_cls(tensor)`` and
+    ``instances_cls(image_size, **fields)`` are the only constructor forms used."""
+    global _BOXES, _INSTANCES
+    _BOXES = boxes_cls if boxes_cls is not None else Boxes
+    _INSTANCES = instances_cls if instances_cls is not None else Instances
+
+
+def make_boxes(tensor):
+    return _BOXES(tensor)
+
+
+def make_instances(image_size, **fields):
+    return _INSTANCES(image_size, **fields)
+
+
+def pairwise_iou(boxes1, boxes2) -> torch.Tensor:
+    """IoU of all N x M pairs (boxes.py:243-275), materialised; bit-exact with the reference's fp32 result.
+    The fused training path (``ops.match_anchors``) never builds this matrix."""
+    return ops.pairwise_iou(as_tensor(boxes1), as_tensor(boxes2))

@@ -440,7 +440,10 @@ FSG_API int fsg_postprocess_boxes(const float* boxes, int64_t n, float scale_x, 
  * un-offset per-class algorithm) and the post_nms_topk best survivors by logit.
  * Outputs: out_boxes (N, post_nms_topk, 4), out_logits (N, post_nms_topk), out_levels (N, post_nms_topk) int64
  * (may be NULL), out_count (N) int32; rows >= out_count[n] are zero-filled.
- * Limits: pre_nms_topk <= 8192 per level, fewer than 16384 candidates per image, post_nms_topk <= 8192. */
+ * Up to 8192 candidates per NMS CTA (every FPN setting) the per-level NMS runs in shared memory: two launches for
+ * the batch.  Beyond that -- pre_nms_topk up to 16384 per level, e.g. RPN.PRE_NMS_TOPK_TRAIN = 12000 of the C4
+ * models (config/defaults.py:219) -- the same select kernel is followed by the general-n NMS per image (3 launches
+ * each) and a gather.  Limits: pre_nms_topk <= 16384 per level, num_levels * pre_nms_topk <= 262144. */
 FSG_API size_t fsg_rpn_proposals_workspace_bytes(int N, const int64_t* h_level_sizes, int num_levels,
                                          int pre_nms_topk, int post_nms_topk);
 FSG_API int fsg_rpn_proposals(const float* const* h_level_proposals, const float* const* h_level_logits,

@@ -423,6 +423,51 @@ def make_log_metrics(ref):
     print("[log_metrics] oracle == reference (calc_log_metrics source executed): %d scalars" % len(names))
 
 
+def reference_callables(ref):
+    """The reference callables whose signatures the drop-ins must keep (tests/test_signatures.py)."""
+    import sys as _sys
+    smp = _sys.modules["detectron2.modeling.sampling"]
+    return {
+        "structures.Boxes.__init__": ref.Boxes.__init__,
+        "structures.Instances.__init__": ref.Instances.__init__,
+        "structures.pairwise_iou": ref.pairwise_iou,
+        "modeling.matcher.Matcher.__init__": ref.Matcher.__init__,
+        "modeling.matcher.Matcher.__call__": ref.Matcher.__call__,
+        "modeling.box_regression.Box2BoxTransform.__init__": ref.Box2BoxTransform.__init__,
+        "modeling.box_regression.Box2BoxTransform.get_deltas": ref.Box2BoxTransform.get_deltas,
+        "modeling.box_regression.Box2BoxTransform.apply_deltas": ref.Box2BoxTransform.apply_deltas,
+        "layers.nms.batched_nms": ref.batched_nms,
+        "layers.nms.nms": ref.nms,                      # = torchvision.ops.nms (layers/nms.py:6)
+        "meta_arch.retinanet.RetinaNet.losses": ref.RetinaNet.losses,
+        "meta_arch.retinanet.RetinaNet.get_ground_truth": ref.RetinaNet.get_ground_truth,
+        "meta_arch.retinanet.RetinaNet.get_picky_ground_truth": ref.RetinaNet.get_picky_ground_truth,
+        "meta_arch.retinanet.RetinaNet.inference": ref.RetinaNet.inference,
+        "meta_arch.retinanet.RetinaNet.inference_single_image": ref.RetinaNet.inference_single_image,
+        "gambler_heads.LayeredUnetGambler.gambler_loss": ref.LayeredUnetGambler.gambler_loss,
+        "gambler_heads.get_loss_upper_bound": ref.gambler_heads.get_loss_upper_bound,
+        "proposal_generator.rpn_outputs.find_top_rpn_proposals": ref.rpn_outputs.find_top_rpn_proposals,
+        "modeling.sampling.subsample_labels": smp.subsample_labels,
+        "modeling.postprocessing.detector_postprocess": ref.detector_postprocess,
+        "roi_heads.fast_rcnn.fast_rcnn_inference": ref.fast_rcnn.fast_rcnn_inference,
+        "roi_heads.fast_rcnn.fast_rcnn_inference_single_image": ref.fast_rcnn.fast_rcnn_inference_single_image,
+        "modeling.anchor_generator.DefaultAnchorGenerator.grid_anchors":
+            ref.anchor_generator.DefaultAnchorGenerator.grid_anchors,
+    }
+
+
+def make_signatures(ref):
+    import inspect
+    import json
+
+    out = {}
+    for name, fn in reference_callables(ref).items():
+        out[name] = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default), p.kind.name]
+                     for p in inspect.signature(fn).parameters.values()]
+    with open(os.path.join(OUT, "signatures.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("[signatures] %d reference callables pinned" % len(out))
+
+
 class _AttrNS(dict):
     def __getattr__(self, k):
         return self[k]
@@ -443,6 +488,7 @@ def main():
     make_inference(ref)
     make_train(ref)
     make_log_metrics(ref)
+    make_signatures(ref)
 
 
 if __name__ == "__main__":

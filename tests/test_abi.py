@@ -107,7 +107,8 @@ def test_argument_validation_needs_no_device(lib_path):
     sizes = _lib.host_i64([100, 50])
     assert L.fsg_rpn_proposals_workspace_bytes(2, sizes, 2, 9000, 1000) > 0      # k clipped to the level sizes
     big = _lib.host_i64([20000, 20000])
-    assert L.fsg_rpn_proposals_workspace_bytes(2, big, 2, 9000, 1000) == 0       # pre_nms_topk > 8192 per level
+    assert L.fsg_rpn_proposals_workspace_bytes(2, big, 2, 12000, 2000) > 0       # general-n NMS path (C4 RPN setting)
+    assert L.fsg_rpn_proposals_workspace_bytes(2, big, 2, 17000, 2000) == 0      # pre_nms_topk > 16384 per level
     hl = (_lib.HeadLevel * 1)()
     hl[0].H, hl[0].W = 0, 4
     assert L.fsg_loss_main_levels_workspace_bytes(2, hl, 1, 3) == 0

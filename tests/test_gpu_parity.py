@@ -577,6 +577,20 @@ def test_batched_nms_large_n_bit_exact(cuda, n, ncls, thr):
     assert_equal_int(got, want, "batched_nms keep (large n)")
 
 
+def test_batched_nms_rejects_class_ids_outside_the_key_range(cuda):
+    fsg = _fsg()
+    b, s_, c = _nms_inputs(100, 5, 3)
+    c = c.clone()
+    c[7] = 1 << 18
+    with pytest.raises(ValueError, match="class ids"):
+        fsg.batched_nms(b.to(cuda), s_.to(cuda), c.to(cuda), 0.5)
+    c[7] = -1
+    with pytest.raises(ValueError, match="class ids"):
+        fsg.batched_nms(b.to(cuda), s_.to(cuda), c.to(cuda), 0.5)
+    c[7] = (1 << 18) - 1
+    assert fsg.batched_nms(b.to(cuda), s_.to(cuda), c.to(cuda), 0.5).numel() > 0
+
+
 def test_nms_threshold_compare_is_in_double(cuda):
     """IoU float(1/3) against threshold 1/3 (double): float(1/3) > 1/3 -> suppressed."""
     fsg = _fsg()
@@ -859,6 +873,22 @@ def test_find_top_rpn_proposals(cuda, N, counts, pre, post, thr, min_side):
     got = P.find_top_rpn_proposals([t.to(cuda) for t in inp["proposals"]], [t.to(cuda) for t in inp["logits"]],
                                    inp["image_sizes"], thr, pre, post, min_side, training=True)
     assert all(len(got[n]) == want[n][0].shape[0] for n in range(N))
+
+
+def test_find_top_rpn_proposals_c4_setting(cuda):
+    """RPN.PRE_NMS_TOPK_TRAIN = 12000 / POST 2000 on one feature level (the reference's default for C4 models,
+    config/defaults.py:219-224): more candidates than the shared-memory NMS holds -> general-n NMS path."""
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    inp = synthetic.rpn_inputs(78, 2, [50 * 84 * 15], ties=True)
+    want = orc.find_top_rpn_proposals(inp["proposals"], inp["logits"], inp["image_sizes"], 0.7, 12000, 2000, 0.0)
+    res = _fsg().ops.rpn_proposals([t.to(cuda) for t in inp["proposals"]], [t.to(cuda) for t in inp["logits"]],
+                                   inp["image_sizes"], 0.7, 12000, 2000, 0.0)
+    for n in range(2):
+        c = int(res["count"][n].item())
+        assert c == want[n][0].shape[0], "image %d: %d vs %d proposals" % (n, c, want[n][0].shape[0])
+        assert torch.equal(res["boxes"][n, :c].cpu(), want[n][0])
+        assert torch.equal(res["logits"][n, :c].cpu(), want[n][1])
+        assert float(res["boxes"][n, c:].abs().sum()) == 0.0
 
 
 def test_rpn_topk_all_equal_logits(cuda):

@@ -7,16 +7,41 @@ from full_scale_gambler_for_object_detection_b200 import _lib, anchor_generator,
 
 
 def test_boxes_container_semantics():
+    from full_scale_gambler_for_object_detection_b200 import structures as st
+
     b = fsg.Boxes(torch.tensor([[0.0, 0.0, 2.0, 3.0], [1.0, 1.0, 2.0, 2.0]], dtype=torch.float64))
     assert b.tensor.dtype == torch.float32 and len(b) == 2           # boxes.py:91-95
-    assert torch.equal(b.area(), torch.tensor([6.0, 1.0]))
     assert fsg.Boxes(torch.zeros(0)).tensor.shape == (0, 4)
     assert len(b[0]) == 1 and len(b[torch.tensor([True, False])]) == 1
-    one = fsg.Boxes.cat([b])
-    assert one.tensor.data_ptr() == b.tensor.data_ptr()               # single-element shortcut (wrappers.py:15-22)
-    assert len(fsg.Boxes.cat([b, b])) == 4
+    assert st.cat_tensors([b]).data_ptr() == b.tensor.data_ptr()      # single-element shortcut (wrappers.py:15-22)
+    assert st.cat_tensors([b, b.tensor]).shape == (4, 4)              # Boxes-likes and tensors mix
     with pytest.raises(AssertionError):
         fsg.Boxes(torch.zeros(3, 5))
+
+
+def test_containers_are_duck_typed_and_pluggable():
+    """Anything with ``.tensor`` is a Boxes, results are built with whatever classes the integrator registers."""
+    from full_scale_gambler_for_object_detection_b200 import structures as st
+
+    class TheirBoxes:
+        def __init__(self, tensor):
+            self.tensor = tensor
+
+        def __len__(self):
+            return self.tensor.shape[0]
+
+    class TheirInstances(fsg.Instances):
+        pass
+
+    t = torch.zeros(3, 4)
+    assert st.as_tensor(TheirBoxes(t)) is t and st.as_tensor(t) is t
+    try:
+        st.use_containers(TheirBoxes, TheirInstances)
+        inst = st.make_instances((4, 5), pred_boxes=st.make_boxes(t), scores=torch.zeros(3))
+        assert isinstance(inst, TheirInstances) and isinstance(inst.pred_boxes, TheirBoxes) and len(inst) == 3
+    finally:
+        st.use_containers()
+    assert isinstance(st.make_boxes(t), fsg.Boxes)
 
 
 def test_instances_container():
