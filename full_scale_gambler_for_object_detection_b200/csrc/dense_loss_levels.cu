@@ -91,61 +91,60 @@ __device__ __forceinline__ void level_body(const LevelLossArgs& A, const LevelTa
   for (int b = 0; b < BATCH; ++b)
     if (EXACT || b < K) x[b].load(xcol + (int64_t)b * HW);
 
+  // Per-anchor state that must live through the element loop is kept to the minimum (class id, the two gradient
+  // coefficients, the running sums); the normalised weight is cheap to recompute afterwards from the same two
+  // L1-resident loads, and not holding it across the loop is what keeps this kernel at 64 registers without spills.
+  auto weight_of = [&](int v, int64_t o) -> float {
+    if (!(A.bets || LT.bets[l])) return 0.f;
+    const float m = A.mask ? (float)A.mask[o] : 1.f;
+    const float b = LT.bets[l] ? LT.bets[l][((int64_t)n * LT.A + a) * HW + hw0 + v] : A.bets[o];
+    return __fadd_rn(__fmul_rn(b, m), A.T) * inv_S;              // gambler_heads.py:569,304 and :308-311
+  };
   int cls[VEC];
-  float wg[VEC], w_hat[VEC], cf[VEC], cfr[VEC], cb[VEC], sum_f[VEC], sum_b[VEC];
-  bool valid[VEC];
+  float cf[VEC], cb[VEC], sum_f[VEC], sum_b[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     const bool in = (VEC == 1) || (hw0 + v < HW);   // HW % VEC == 0 whenever VEC > 1, kept for clarity
     const int64_t o = o0 + (int64_t)v * LT.A;
     cls[v] = in ? (int)A.gt_classes[o] : -1;
-    w_hat[v] = 0.f;
-    if ((A.bets || LT.bets[l]) && in) {
-      const float m = A.mask ? (float)A.mask[o] : 1.f;
-      const float b = LT.bets[l] ? LT.bets[l][((int64_t)n * LT.A + a) * HW + hw0 + v] : A.bets[o];
-      const float w = __fadd_rn(__fmul_rn(b, m), A.T);           // gambler_heads.py:569,304
-      w_hat[v] = w * inv_S;                                      // :308-311
-    }
-    valid[v] = cls[v] >= 0;
-    wg[v] = (A.ggamma == 1.f) ? w_hat[v] : powf(w_hat[v], A.ggamma);
+    const float w_hat = in ? weight_of(v, o) : 0.f;
+    const float wg = (A.ggamma == 1.f) ? w_hat : powf(w_hat, A.ggamma);
     float coef_f = 0.f, coef_b = 0.f;
-    if (valid[v]) {
+    if (cls[v] >= 0) {
       coef_f = A.c_cls * inv_nf;
-      if (A.gmode == FSG_CLS_FOCAL) coef_f = fmaf(-A.c_gam, wg[v], coef_f);
-      else coef_b = -A.c_gam * wg[v];
+      if (A.gmode == FSG_CLS_FOCAL) coef_f = fmaf(-A.c_gam, wg, coef_f);
+      else coef_b = -A.c_gam * wg;
     }
     cf[v] = FAST ? coef_f * A.a0 : coef_f;   // ignored anchors: zero coefficient -> zero gradient
-    cfr[v] = coef_f;
     cb[v] = coef_b;
     sum_f[v] = 0.f;
     sum_b[v] = 0.f;
   }
 
+  // Rotating pipeline: slot b is re-loaded with plane k + BATCH as soon as plane k has been taken out of it, so
+  // BATCH planes stay in flight with ONE set of buffer registers (a second set for the "next batch" cost 20
+  // registers and pushed this kernel into spills at 64 registers / 4 CTAs per SM).
 #pragma unroll 1
   for (int k0 = 0; k0 < K; k0 += BATCH) {
-    Vec<VEC> y[BATCH];
-    const int k1 = k0 + BATCH;
-    if (k1 < K) {
-#pragma unroll
-      for (int b = 0; b < BATCH; ++b)
-        if (EXACT || k1 + b < K) y[b].load(xcol + (int64_t)(k1 + b) * HW);
-    }
+    const bool more = k0 + BATCH < K;
 #pragma unroll
     for (int b = 0; b < BATCH; ++b) {
       const int k = k0 + b;
       if (EXACT || k < K) {
+        const Vec<VEC> cur = x[b];
+        if (more && (EXACT || k + BATCH < K)) x[b].load(xcol + (int64_t)(k + BATCH) * HW);
         Vec<VEC> g;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           if (FAST) {
             float lo, d;
-            focal_neg_g2(x[b].v[v], lo, d);
+            focal_neg_g2(cur.v[v], lo, d);
             sum_f[v] += lo;
             g.v[v] = d * cf[v];
           } else {
             const bool t = (k == cls[v]);   // cls == K (background) or -1 (ignored) never matches
             float f, fgd, bc, bgd;
-            cls_elem_general(x[b].v[v], t, A.gamma, f, fgd, bc, bgd);
+            cls_elem_general(cur.v[v], t, A.gamma, f, fgd, bc, bgd);
             const float at = t ? A.a1 : A.a0;
             sum_f[v] += f * at;
             sum_b[v] += bc;
@@ -155,16 +154,15 @@ __device__ __forceinline__ void level_body(const LevelLossArgs& A, const LevelTa
         if (WRITE) g.store(gcol + (int64_t)k * HW);
       }
     }
-    if (k1 < K) {
-#pragma unroll
-      for (int b = 0; b < BATCH; ++b) x[b] = y[b];
-    }
   }
 
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     const int64_t o = o0 + (int64_t)v * LT.A;
-    const bool fgc = valid[v] && cls[v] != K;
+    const bool valid = cls[v] >= 0;
+    const bool fgc = valid && cls[v] != K;
+    const float w_hat = ((VEC == 1) || (hw0 + v < HW)) ? weight_of(v, o) : 0.f;
+    const float wg = (A.ggamma == 1.f) ? w_hat : powf(w_hat, A.ggamma);
     if (FAST) {
       sum_f[v] *= A.a0;
       if (fgc) {   // patch the single positive class of a foreground anchor
@@ -173,16 +171,17 @@ __device__ __forceinline__ void level_body(const LevelLossArgs& A, const LevelTa
         focal_neg_g2(xv, l0, d0);
         cls_elem_general(xv, true, 2.f, f1, fg1, b1, bg1);
         sum_f[v] += f1 * A.a1 - l0 * A.a0;
-        if (WRITE) gcol[(int64_t)cls[v] * HW + v] = fg1 * (cfr[v] * A.a1);
+        const float coef_f = fmaf(-A.c_gam, wg, A.c_cls * inv_nf);   // (FAST implies the focal gambler mode)
+        if (WRITE) gcol[(int64_t)cls[v] * HW + v] = fg1 * (coef_f * A.a1);
       }
     }
-    const float lf = valid[v] ? sum_f[v] : 0.f;                                   // gambler_heads.py:554-555
-    const float lg = (A.gmode == FSG_CLS_FOCAL) ? lf : (valid[v] ? sum_b[v] : 0.f);
+    const float lf = valid ? sum_f[v] : 0.f;                                   // gambler_heads.py:554-555
+    const float lg = (A.gmode == FSG_CLS_FOCAL) ? lf : (valid ? sum_b[v] : 0.f);
     if (LT.ell[l]) LT.ell[l][((int64_t)n * LT.A + a) * HW + hw0 + v] = lg;
     else if (A.ell) A.ell[o] = lg;
-    if (A.wout) A.wout[o] = w_hat[v];
+    if (A.wout) A.wout[o] = w_hat;
     S.cls += lf;
-    S.wl = fmaf(wg[v], lg, S.wl);
+    S.wl = fmaf(wg, lg, S.wl);
     S.l += lg;
     S.mx = fmaxf(S.mx, lg);
   }
@@ -199,7 +198,7 @@ __device__ __forceinline__ void level_body(const LevelLossArgs& A, const LevelTa
     const float sc = A.c_reg * inv_nf;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      if (valid[v] && cls[v] != K) {
+      if (cls[v] >= 0 && cls[v] != K) {
         const int64_t o = o0 + (int64_t)v * LT.A;
         float4 gd;
         if (A.gt_deltas) gd = reinterpret_cast<const float4*>(A.gt_deltas)[o];
@@ -351,8 +350,13 @@ static void launch_levels2(bool fast, bool write, dim3 grid, cudaStream_t s, con
 }
 static void launch_levels(int K, bool fast, bool write, dim3 grid, cudaStream_t s, const LevelLossArgs& a,
                           const LevelTable& t) {
+#ifdef LV_PREFER10
   if (K % 10 == 0) launch_levels2<10, true>(fast, write, grid, s, a, t);
   else if (K % 8 == 0) launch_levels2<8, true>(fast, write, grid, s, a, t);
+#else
+  if (K % 8 == 0) launch_levels2<8, true>(fast, write, grid, s, a, t);      // K = 80: 64 registers, no spills
+  else if (K % 10 == 0) launch_levels2<10, true>(fast, write, grid, s, a, t);  // K = 1230
+#endif
   else launch_levels2<8, false>(fast, write, grid, s, a, t);
 }
 
