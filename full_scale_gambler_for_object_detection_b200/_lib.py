@@ -88,6 +88,14 @@ class StepIO(ctypes.Structure):
                 ("per_anchor_loss", c_ptr), ("weights_out", c_ptr)]
 
 
+class StepLevelsIO(ctypes.Structure):
+    """``struct fsg_step_levels_io``."""
+
+    _fields_ = [("anchors", c_ptr), ("anchor_image_stride", c_i64), ("gt_boxes", c_ptr), ("gt_class_ids", c_ptr),
+                ("gt_offsets", c_ptr), ("sum_M", c_i64), ("gt_classes", c_ptr), ("mask", c_ptr),
+                ("matched_idx32", c_ptr), ("stats", c_ptr), ("scalars", c_ptr), ("weights_out", c_ptr)]
+
+
 class MatchConfig(ctypes.Structure):
     """``struct fsg_match_config``."""
 
@@ -141,6 +149,11 @@ PROTOTYPES = {
     "fsg_dense_step_workspace_bytes": (c_size, [c_i32, c_i64, c_i32, c_i64]),
     "fsg_dense_step": (c_i32, [ctypes.POINTER(StepIO), c_i32, c_i64, ctypes.POINTER(MatchConfig),
                                ctypes.POINTER(LossParams), ctypes.POINTER(PeerCtx), c_ptr, c_size, c_ptr]),
+    "fsg_dense_step_levels_workspace_bytes": (c_size, [c_i32, ctypes.POINTER(HeadLevel), c_i32, c_i32, c_i64]),
+    "fsg_dense_step_levels": (c_i32, [ctypes.POINTER(StepLevelsIO), ctypes.POINTER(HeadLevel),
+                                      ctypes.POINTER(PostLevel), c_i32, c_i32, c_i32, c_i64,
+                                      ctypes.POINTER(MatchConfig), ctypes.POINTER(LossParams),
+                                      ctypes.POINTER(PeerCtx), c_ptr, c_size, c_ptr]),
     "fsg_bet_stats_workspace_bytes": (c_size, []),
     "fsg_bet_stats": (c_i32, [c_ptr, ctypes.POINTER(BetLevels), c_ptr, c_i32, c_i64, ctypes.POINTER(LossParams), c_ptr,
                               c_ptr, c_ptr, c_size, c_ptr]),

@@ -11,6 +11,7 @@
 // r = level_offset + hw*A + a of the rest of the library.
 #include "common.cuh"
 #include "loss_math.cuh"
+#include "step_internal.cuh"
 
 namespace fsg {
 
@@ -66,6 +67,7 @@ struct LevelLossArgs {
   float* partials;
   unsigned* counter;
   double* scalars;
+  PeerPoll peer;   // sharded batch, fsg_dense_step_levels: the exchange is polled here (see dense_loss.cu)
 };
 
 struct TileSums {
@@ -233,11 +235,19 @@ __global__ void __launch_bounds__(kLvBlock, LV_MINB) loss_main_levels_kernel(con
   const int vec = LT.vec[l];
   const int hw0 = ((local - a * LT.chunks[l]) * kLvBlock + tid) * vec;
 
-  const double nf_d = A.stats[0];
+  grid_launch_dependents();   // the post pass may be scheduled as this grid's CTAs retire; it waits for the whole grid
+  grid_dependency_sync();     // everything K1 produced is read from here on
+  double nf_d = A.stats[0];
+  float s_batch = (A.nmode == FSG_NORM_BATCH) ? (float)A.stats[1] : 1.f;
+  if (A.peer.world > 1) {
+    double sb;
+    peer_poll_sum(A.peer, nf_d, sb);
+    s_batch = (float)sb;
+  }
   const float inv_nf = __frcp_rn(fmaxf((float)nf_d, 1.f));
   float inv_S = 1.f;
   if (A.nmode == FSG_NORM_IMAGE) inv_S = __frcp_rn((float)A.stats[FSG_STATS_HEADER + n]);
-  else if (A.nmode == FSG_NORM_BATCH) inv_S = __frcp_rn((float)A.stats[1]);
+  else if (A.nmode == FSG_NORM_BATCH) inv_S = __frcp_rn(s_batch);
 
   TileSums S = {0.f, 0.f, 0.f, 0.f, 0.f};
   if (hw0 < LT.HW[l]) {
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(kLvBlock, LV_MINB) loss_main_levels_kernel(con
   S.cls = warp_sum(S.cls); S.reg = warp_sum(S.reg); S.wl = warp_sum(S.wl);
   S.l = warp_sum(S.l); S.mx = warp_max(S.mx);
   finish_tile<kLvBlock>(S.cls, S.reg, S.wl, S.l, S.mx, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
-                        A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam);
+                        A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam, A.peer);
 }
 
 // d(c_gam * G)/d bets on the gambler's own layout (see fsg_loss_post for the formula): thread = one (n, a, hw).
@@ -270,6 +280,7 @@ __global__ void __launch_bounds__(256) loss_post_levels_kernel(const PostTable P
                                                                const double* __restrict__ stats,
                                                                const double* __restrict__ scalars) {
   const int n = blockIdx.y;
+  grid_dependency_sync();   // (programmatic dependent launch behind the main pass)
   int l = 0;
   while (l + 1 < PT.num_levels && (int)blockIdx.x >= PT.tile_base[l + 1]) ++l;
   const int local = (int)blockIdx.x - PT.tile_base[l];
@@ -339,25 +350,26 @@ static int build_table(const fsg_head_level* h, int num_levels, int A, LevelTabl
 
 template <int BATCH, bool EXACT>
 static void launch_levels2(bool fast, bool write, dim3 grid, cudaStream_t s, const LevelLossArgs& a,
-                           const LevelTable& t) {
+                           const LevelTable& t, bool pdl) {
+  const dim3 blk(kLvBlock);
   if (fast) {
-    if (write) loss_main_levels_kernel<BATCH, EXACT, true, true><<<grid, kLvBlock, 0, s>>>(a, t);
-    else loss_main_levels_kernel<BATCH, EXACT, true, false><<<grid, kLvBlock, 0, s>>>(a, t);
+    if (write) launch_pdl(loss_main_levels_kernel<BATCH, EXACT, true, true>, grid, blk, 0, s, pdl, a, t);
+    else launch_pdl(loss_main_levels_kernel<BATCH, EXACT, true, false>, grid, blk, 0, s, pdl, a, t);
   } else {
-    if (write) loss_main_levels_kernel<BATCH, EXACT, false, true><<<grid, kLvBlock, 0, s>>>(a, t);
-    else loss_main_levels_kernel<BATCH, EXACT, false, false><<<grid, kLvBlock, 0, s>>>(a, t);
+    if (write) launch_pdl(loss_main_levels_kernel<BATCH, EXACT, false, true>, grid, blk, 0, s, pdl, a, t);
+    else launch_pdl(loss_main_levels_kernel<BATCH, EXACT, false, false>, grid, blk, 0, s, pdl, a, t);
   }
 }
 static void launch_levels(int K, bool fast, bool write, dim3 grid, cudaStream_t s, const LevelLossArgs& a,
-                          const LevelTable& t) {
+                          const LevelTable& t, bool pdl) {
 #ifdef LV_PREFER10
-  if (K % 10 == 0) launch_levels2<10, true>(fast, write, grid, s, a, t);
-  else if (K % 8 == 0) launch_levels2<8, true>(fast, write, grid, s, a, t);
+  if (K % 10 == 0) launch_levels2<10, true>(fast, write, grid, s, a, t, pdl);
+  else if (K % 8 == 0) launch_levels2<8, true>(fast, write, grid, s, a, t, pdl);
 #else
-  if (K % 8 == 0) launch_levels2<8, true>(fast, write, grid, s, a, t);      // K = 80: 64 registers, no spills
-  else if (K % 10 == 0) launch_levels2<10, true>(fast, write, grid, s, a, t);  // K = 1230
+  if (K % 8 == 0) launch_levels2<8, true>(fast, write, grid, s, a, t, pdl);      // K = 80: 64 registers, no spills
+  else if (K % 10 == 0) launch_levels2<10, true>(fast, write, grid, s, a, t, pdl);  // K = 1230
 #endif
-  else launch_levels2<8, false>(fast, write, grid, s, a, t);
+  else launch_levels2<8, false>(fast, write, grid, s, a, t, pdl);
 }
 
 }  // namespace fsg
@@ -372,13 +384,14 @@ extern "C" size_t fsg_loss_main_levels_workspace_bytes(int N, const fsg_head_lev
   return 16 + align_up(sizeof(float) * kPartialStride * (size_t)N * t.tile_base[kLvMax], 16);
 }
 
-extern "C" int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_levels, int A, const float* gt_deltas,
-                                    const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
-                                    const int32_t* gt_offsets, const int32_t* matched_idx32,
-                                    const int64_t* gt_classes, const int64_t* mask, const float* bets, int N,
-                                    int64_t R, const fsg_loss_params* hp, const double* stats,
-                                    float* per_anchor_loss, float* weights_out, double* scalars, void* workspace,
-                                    size_t workspace_bytes, fsg_stream_t stream) {
+namespace fsg {
+int loss_main_levels_enqueue(const fsg_head_level* h_levels, int num_levels, int A, const float* gt_deltas,
+                             const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
+                             const int32_t* gt_offsets, const int32_t* matched_idx32,
+                             const int64_t* gt_classes, const int64_t* mask, const float* bets, int N,
+                             int64_t R, const fsg_loss_params* hp, double* stats,
+                             float* per_anchor_loss, float* weights_out, double* scalars, void* workspace,
+                             size_t workspace_bytes, const fsg_peer_ctx* h_peer, int flags, fsg_stream_t stream) {
   if (!hp || N <= 0 || R <= 0 || hp->num_classes <= 0) return FSG_ERR_INVALID_ARG;
   if (!gt_classes || !stats || !scalars) return FSG_ERR_INVALID_ARG;
   if (N > 65535) return FSG_ERR_UNSUPPORTED;
@@ -420,22 +433,42 @@ extern "C" int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_leve
   a.wx = hp->box_weights[0]; a.wy = hp->box_weights[1]; a.ww = hp->box_weights[2]; a.wh = hp->box_weights[3];
   a.stats = stats; a.ell = per_anchor_loss; a.wout = weights_out;
   a.partials = (float*)(ws + 16); a.counter = (unsigned*)ws; a.scalars = scalars;
+  a.peer = make_peer_poll(h_peer, stats);
 
-  FSG_CUDA_TRY(cudaMemsetAsync(a.counter, 0, 16, s));
+  if (!(flags & kLossCounterZeroed)) FSG_CUDA_TRY(cudaMemsetAsync(a.counter, 0, 16, s));
   const bool fast = (hp->focal_gamma == 2.f) && (hp->gambler_mode == FSG_CLS_FOCAL);
   dim3 grid((unsigned)t.tile_base[kLvMax], (unsigned)N);
   bool write = false;
   for (int l = 0; l < num_levels; ++l) write = write || t.grad_logits[l];
   for (int l = 0; l < num_levels; ++l)
     if (write && !t.grad_logits[l]) return FSG_ERR_INVALID_ARG;   // gradients for all levels or for none
-  launch_levels(a.K, fast, write, grid, s, a, t);
+  launch_levels(a.K, fast, write, grid, s, a, t, (flags & kLossPdl) != 0);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }
 
-extern "C" int fsg_loss_post_levels(const fsg_post_level* h_levels, int num_levels, int A, const int64_t* mask, int N,
-                                    int64_t R, const fsg_loss_params* hp, const double* stats, const double* scalars,
-                                    fsg_stream_t stream) {
+size_t loss_main_levels_ws_bytes(int N, const fsg_head_level* h_levels, int num_levels, int A) {
+  return fsg_loss_main_levels_workspace_bytes(N, h_levels, num_levels, A);
+}
+}  // namespace fsg
+
+extern "C" int fsg_loss_main_levels(const fsg_head_level* h_levels, int num_levels, int A, const float* gt_deltas,
+                                    const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
+                                    const int32_t* gt_offsets, const int32_t* matched_idx32,
+                                    const int64_t* gt_classes, const int64_t* mask, const float* bets, int N,
+                                    int64_t R, const fsg_loss_params* hp, const double* stats,
+                                    float* per_anchor_loss, float* weights_out, double* scalars, void* workspace,
+                                    size_t workspace_bytes, fsg_stream_t stream) {
+  return loss_main_levels_enqueue(h_levels, num_levels, A, gt_deltas, anchors, anchor_image_stride, gt_boxes,
+                                  gt_offsets, matched_idx32, gt_classes, mask, bets, N, R, hp,
+                                  const_cast<double*>(stats), per_anchor_loss, weights_out, scalars, workspace,
+                                  workspace_bytes, nullptr, 0, stream);
+}
+
+namespace fsg {
+int loss_post_levels_enqueue(const fsg_post_level* h_levels, int num_levels, int A, const int64_t* mask, int N,
+                             int64_t R, const fsg_loss_params* hp, const double* stats, const double* scalars,
+                             int flags, fsg_stream_t stream) {
   if (!hp || !h_levels || num_levels <= 0 || num_levels > kLvMax || A <= 0 || N <= 0 || !stats || !scalars)
     return FSG_ERR_INVALID_ARG;
   if (N > 65535) return FSG_ERR_UNSUPPORTED;
@@ -460,8 +493,16 @@ extern "C" int fsg_loss_post_levels(const fsg_post_level* h_levels, int num_leve
   t.off[kLvMax] = off; t.tile_base[kLvMax] = tiles;
   t.num_levels = num_levels; t.A = A;
   if (off != R) return FSG_ERR_INVALID_ARG;
-  loss_post_levels_kernel<<<dim3((unsigned)tiles, (unsigned)N), 256, 0, (cudaStream_t)stream>>>(
-      t, mask, R, hp->temperature, hp->gambler_gamma, hp->norm_mode, hp->c_gam, stats, scalars);
+  launch_pdl(loss_post_levels_kernel, dim3((unsigned)tiles, (unsigned)N), dim3(256), 0, (cudaStream_t)stream,
+             (flags & kLossPdl) != 0, t, mask, R, hp->temperature, hp->gambler_gamma, (int)hp->norm_mode, hp->c_gam,
+             stats, scalars);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
+}
+}  // namespace fsg
+
+extern "C" int fsg_loss_post_levels(const fsg_post_level* h_levels, int num_levels, int A, const int64_t* mask, int N,
+                                    int64_t R, const fsg_loss_params* hp, const double* stats, const double* scalars,
+                                    fsg_stream_t stream) {
+  return loss_post_levels_enqueue(h_levels, num_levels, A, mask, N, R, hp, stats, scalars, 0, stream);
 }

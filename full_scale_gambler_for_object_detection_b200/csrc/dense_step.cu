@@ -73,3 +73,60 @@ extern "C" int fsg_dense_step(const fsg_step_io* io, int N, int64_t R, const fsg
   return loss_post_enqueue(io->bets, io->mask, io->per_anchor_loss, N, R, hp, io->stats, io->scalars, io->grad_bets,
                            pdl, stream);
 }
+
+extern "C" size_t fsg_dense_step_levels_workspace_bytes(int N, const fsg_head_level* h_levels, int num_levels, int A,
+                                                        int64_t sum_M) {
+  if (N <= 0 || !h_levels || num_levels <= 0 || num_levels > FSG_MAX_LEVELS || A <= 0 || sum_M < 0) return 0;
+  int64_t R = 0;
+  for (int l = 0; l < num_levels; ++l) R += (int64_t)h_levels[l].H * h_levels[l].W * A;
+  const size_t lw = loss_main_levels_ws_bytes(N, h_levels, num_levels, A);
+  if (R <= 0 || lw == 0) return 0;
+  return align_up(fsg_match_workspace_bytes(N, R, sum_M), 256) + lw;
+}
+
+extern "C" int fsg_dense_step_levels(const fsg_step_levels_io* io, const fsg_head_level* h_levels,
+                                     const fsg_post_level* h_post, int num_levels, int A, int N, int64_t R,
+                                     const fsg_match_config* mc, const fsg_loss_params* hp,
+                                     const fsg_peer_ctx* h_peer, void* workspace, size_t workspace_bytes,
+                                     fsg_stream_t stream) {
+  if (!io || !h_levels || !h_post || !mc || !hp || N <= 0 || R <= 0 || num_levels <= 0 || num_levels > FSG_MAX_LEVELS)
+    return FSG_ERR_INVALID_ARG;
+  if (!io->anchors || !io->gt_offsets || !io->gt_classes || !io->mask || !io->matched_idx32 || !io->stats ||
+      !io->scalars)
+    return FSG_ERR_INVALID_ARG;
+  if (mc->num_thresholds < 1 || mc->num_thresholds > 4 || mc->num_picky_thresholds < 1 || mc->num_picky_thresholds > 4)
+    return FSG_ERR_INVALID_ARG;
+  const bool sharded = h_peer && h_peer->world > 1;
+  if (sharded && hp->norm_mode == FSG_NORM_BATCH) return FSG_ERR_UNSUPPORTED;
+  fsg_bet_levels bl = {};
+  bl.num_levels = num_levels;
+  bl.A = A;
+  for (int l = 0; l < num_levels; ++l) {
+    if (!h_levels[l].bets) return FSG_ERR_INVALID_ARG;   // this entry point is for the all-native form
+    bl.bets[l] = h_levels[l].bets;
+    bl.H[l] = h_levels[l].H;
+    bl.W[l] = h_levels[l].W;
+  }
+  const size_t off_loss = align_up(fsg_match_workspace_bytes(N, R, io->sum_M), 256);
+  const size_t lw = loss_main_levels_ws_bytes(N, h_levels, num_levels, A);
+  if (lw == 0) return FSG_ERR_INVALID_ARG;
+  if (!workspace || workspace_bytes < off_loss + lw || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  FSG_CUDA_TRY(cudaMemsetAsync(ws + off_loss, 0, 16, s));
+  const int pdl = step_no_pdl() ? 0 : kLossPdl;
+  int st = match_enqueue(io->anchors, R, io->anchor_image_stride, io->gt_boxes, io->gt_class_ids, io->gt_offsets, N,
+                         io->sum_M, hp->num_classes, mc->thresholds, mc->labels, mc->num_thresholds,
+                         mc->allow_low_quality_matches, mc->picky_thresholds, mc->picky_labels,
+                         mc->num_picky_thresholds, hp->box_weights, nullptr, nullptr, nullptr, io->gt_classes, io->mask,
+                         nullptr, io->matched_idx32, nullptr, &bl, hp->temperature, io->stats,
+                         sharded ? h_peer : nullptr, ws, off_loss, 3,
+                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl), nullptr, 0, stream);
+  if (st != FSG_OK) return st;
+  st = loss_main_levels_enqueue(h_levels, num_levels, A, nullptr, io->anchors, io->anchor_image_stride, io->gt_boxes,
+                                io->gt_offsets, io->matched_idx32, io->gt_classes, io->mask, nullptr, N, R, hp,
+                                io->stats, nullptr, io->weights_out, io->scalars, ws + off_loss, lw,
+                                sharded ? h_peer : nullptr, pdl | kLossCounterZeroed, stream);
+  if (st != FSG_OK) return st;
+  return loss_post_levels_enqueue(h_post, num_levels, A, io->mask, N, R, hp, io->stats, io->scalars, pdl, stream);
+}

@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(kSelThreads, SEL_CTAS) detect_select_kernel(co
   __shared__ uint64_t s_red64[kSelThreads / 32];
 
   const int tid = threadIdx.x;
+  grid_launch_dependents();   // (programmatic dependent launch: the NMS kernel behind may be scheduled early)
+  grid_dependency_sync();
   const int n = blockIdx.y;
   int l = 0;
   while (l + 1 < LV.num_levels && (int)blockIdx.x >= LV.part_base[l + 1]) ++l;
@@ -657,6 +659,7 @@ __global__ void __launch_bounds__(kBarThreads, 2) detect_bar_kernel(const Select
   uint16_t* skey = reinterpret_cast<uint16_t*>(smem_raw);   // kBarKeys
   __shared__ BarSmem sm;
   const int tid = threadIdx.x;
+  grid_launch_dependents();
   const int p = blockIdx.x, l = blockIdx.y, n = blockIdx.z;
   const int P = LV.bar_parts[l];
   if (p >= P) return;
@@ -818,6 +821,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) detect_scan_kernel(const Sele
                                                                       const DetectSrc S) {
   __shared__ uint64_t s_stage[kScanThreads / 32][kScanStage];
   const int tid = threadIdx.x;
+  grid_launch_dependents();
+  grid_dependency_sync();     // the bars come from detect_bar_kernel
   const int n = blockIdx.y;
   int l = 0;
   while (l + 1 < LV.num_levels && (int)blockIdx.x >= LV.scan_base[l + 1]) ++l;
@@ -898,6 +903,8 @@ __global__ void __launch_bounds__(kFinThreads) detect_finalize_kernel(const Sele
   __shared__ int s_count, s_count2;
   __shared__ uint64_t s_red64[kFinThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31;
+  grid_launch_dependents();
+  grid_dependency_sync();     // the candidate lists come from detect_scan_kernel
   const int l = blockIdx.x, n = blockIdx.y;
   const int slab_id = n * LV.num_levels + l;
   const int64_t E = (LV.off[l + 1] - LV.off[l]) * A.K;
@@ -1174,6 +1181,11 @@ static int detect_run(const DetectCall& c, const DetectSrc& src, cudaStream_t s)
   sa.cand_cap = kCandCap;
 
   const bool legacy = detect_legacy_mode();
+  // all memsets first, so that the kernels form one chain under programmatic dependent launch (each kernel is
+  // scheduled while its predecessor drains and waits on the device before it reads what that one wrote)
+  const int nms_split = nms_split_for(N);
+  const NmsWs nms_w = nms_ws_layout(N, nms_split, max_det);
+  FSG_CUDA_TRY(cudaMemsetAsync(ws + w.off_nms + nms_w.off_done, 0, nms_w.off_cnt - nms_w.off_done, s));
   if (!legacy) {
     int pmax = 1;
     for (int l = 0; l < num_levels; ++l) pmax = lv.bar_parts[l] > pmax ? lv.bar_parts[l] : pmax;
@@ -1181,18 +1193,20 @@ static int detect_run(const DetectCall& c, const DetectSrc& src, cudaStream_t s)
     detect_bar_kernel<<<dim3((unsigned)pmax, (unsigned)num_levels, (unsigned)N), kBarThreads, kBarSmem, s>>>(sa, lv, src);
     FSG_LAUNCH_CHECK();
     if (lv.scan_base[num_levels] > 0) {
-      detect_scan_kernel<<<dim3((unsigned)lv.scan_base[num_levels], (unsigned)N), kScanThreads, 0, s>>>(sa, lv, src);
+      launch_pdl(detect_scan_kernel, dim3((unsigned)lv.scan_base[num_levels], (unsigned)N), dim3(kScanThreads), 0, s,
+                 true, sa, lv, src);
       FSG_LAUNCH_CHECK();
     }
     FSG_CUDA_TRY(cudaFuncSetAttribute(detect_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmem));
-    detect_finalize_kernel<<<dim3((unsigned)num_levels, (unsigned)N), kFinThreads, kFinSmem, s>>>(sa, lv, src);
+    launch_pdl(detect_finalize_kernel, dim3((unsigned)num_levels, (unsigned)N), dim3(kFinThreads), kFinSmem, s, true,
+               sa, lv, src);
     FSG_LAUNCH_CHECK();
   } else {
     sa.status = nullptr;
   }
   FSG_CUDA_TRY(cudaFuncSetAttribute(detect_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmem));
-  dim3 grid((unsigned)lv.total_parts, (unsigned)N);
-  detect_select_kernel<<<grid, kSelThreads, kSelSmem, s>>>(sa, lv, src);
+  launch_pdl(detect_select_kernel, dim3((unsigned)lv.total_parts, (unsigned)N), dim3(kSelThreads), kSelSmem, s, !legacy,
+             sa, lv, src);
   FSG_LAUNCH_CHECK();
 
   NmsArgs a = {};
@@ -1200,20 +1214,17 @@ static int detect_run(const DetectCall& c, const DetectSrc& src, cudaStream_t s)
   a.slots_per_image = (int64_t)num_levels * topk; a.lvl_count = sa.lvl_count; a.L = num_levels; a.topk = topk;
   a.fixed_count = 0; a.thr = threshold_floor(c.nms_threshold); a.max_out = max_det;
   {
-    const int split = nms_split_for(N);
-    const NmsWs nw = nms_ws_layout(N, split, max_det);
     char* nws = ws + w.off_nms;
-    FSG_CUDA_TRY(cudaMemsetAsync(nws + nw.off_done, 0, nw.off_cnt - nw.off_done, s));
-    a.split = split; a.part_cap = max_det;
-    a.part_keys = (uint64_t*)(nws + nw.off_keys); a.part_cnt = (int*)(nws + nw.off_cnt);
-    a.done = (unsigned*)(nws + nw.off_done);
+    a.split = nms_split; a.part_cap = max_det;
+    a.part_keys = (uint64_t*)(nws + nms_w.off_keys); a.part_cnt = (int*)(nws + nms_w.off_cnt);
+    a.done = (unsigned*)(nws + nms_w.off_done);
   }
   a.keep = c.keep_idx; a.keep_stride = max_det; a.num_keep = c.out_count;
   a.out_boxes = (float4*)c.out_boxes; a.out_scores = c.out_scores; a.out_classes = c.out_classes;
   a.post = (const float4*)c.postprocess;
   a.exp_boxes = (float4*)c.cand_boxes; a.exp_scores = c.cand_scores; a.exp_classes = c.cand_classes;
   a.exp_count = c.cand_count;
-  return launch_nms_image(a, N, s);
+  return launch_nms_image(a, N, s, true);
 }
 
 }  // namespace fsg

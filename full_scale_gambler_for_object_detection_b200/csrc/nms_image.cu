@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const NmsArgs
   const int part = blockIdx.x;
   const int n = blockIdx.y;
   const int S = A.split;
+  grid_dependency_sync();   // (no-op unless launched under programmatic dependent launch behind the select stage)
   if (tid == 0) {
     s_pref[0] = 0;
     if (A.lvl_count) {
@@ -321,9 +322,9 @@ __global__ void __launch_bounds__(256) postprocess_boxes_kernel(const float4* __
   keep[i] = ((__fsub_rn(b.z, b.x) > 0.f) && (__fsub_rn(b.w, b.y) > 0.f)) ? 1 : 0;
 }
 
-int launch_nms_image(const NmsArgs& a, int N, cudaStream_t s) {
+int launch_nms_image(const NmsArgs& a, int N, cudaStream_t s, bool pdl) {
   FSG_CUDA_TRY(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmem));
-  nms_image_kernel<<<dim3((unsigned)a.split, (unsigned)N), kNmsThreads, kNmsSmem, s>>>(a);
+  launch_pdl(nms_image_kernel, dim3((unsigned)a.split, (unsigned)N), dim3(kNmsThreads), kNmsSmem, s, pdl, a);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }

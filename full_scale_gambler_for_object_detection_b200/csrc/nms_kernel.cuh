@@ -76,6 +76,7 @@ inline float threshold_floor(double thr) {
 constexpr size_t kNmsSmem = (size_t)kNmsCap * 27;
 
 // enqueue nms_image_kernel for N images (grid: a.split x N); returns an fsg_status
-int launch_nms_image(const NmsArgs& a, int N, cudaStream_t s);
+// pdl: launch under programmatic dependent launch (the kernel waits on the device for its predecessor)
+int launch_nms_image(const NmsArgs& a, int N, cudaStream_t s, bool pdl = false);
 
 }  // namespace fsg

@@ -34,4 +34,17 @@ int loss_post_enqueue(const float* bets, const int64_t* mask, const float* per_a
                       int flags, fsg_stream_t stream);
 size_t loss_main_ws_bytes(int N, int64_t R, int K);
 
+// the same on the head's native per-level layout (dense_loss_levels.cu)
+int loss_main_levels_enqueue(const fsg_head_level* h_levels, int num_levels, int A, const float* gt_deltas,
+                             const float* anchors, int64_t anchor_image_stride, const float* gt_boxes,
+                             const int32_t* gt_offsets, const int32_t* matched_idx32, const int64_t* gt_classes,
+                             const int64_t* mask, const float* bets, int N, int64_t R, const fsg_loss_params* hp,
+                             double* stats, float* per_anchor_loss, float* weights_out, double* scalars,
+                             void* workspace, size_t workspace_bytes, const fsg_peer_ctx* h_peer, int flags,
+                             fsg_stream_t stream);
+int loss_post_levels_enqueue(const fsg_post_level* h_levels, int num_levels, int A, const int64_t* mask, int N,
+                             int64_t R, const fsg_loss_params* hp, const double* stats, const double* scalars,
+                             int flags, fsg_stream_t stream);
+size_t loss_main_levels_ws_bytes(int N, const fsg_head_level* h_levels, int num_levels, int A);
+
 }  // namespace fsg

@@ -136,6 +136,20 @@ class StepResult:
         return out
 
 
+def _match_config(cfg):
+    mc = _lib.MatchConfig()
+    mc.num_thresholds, mc.num_picky_thresholds = len(cfg.iou_thresholds), len(cfg.picky_thresholds)
+    mc.allow_low_quality_matches = 1
+    for i, v in enumerate(cfg.iou_thresholds):
+        mc.thresholds[i] = float(v)
+    for i, v in enumerate(cfg.picky_thresholds):
+        mc.picky_thresholds[i] = float(v)
+    for i, v in enumerate(cfg.iou_labels):
+        mc.labels[i] = int(v)
+        mc.picky_labels[i] = int(v)
+    return mc
+
+
 class DenseStepPlan:
     """Pre-allocated buffers, cached host-side arguments and (optionally) a CUDA graph for the fused step
     at fixed shapes (N images, R anchors, K classes).  ``run`` enqueues the four kernels with no allocation
@@ -186,17 +200,7 @@ class DenseStepPlan:
             group is None or (self.peer is not None and cfg.norm_mode != _lib.NORM_BATCH))
         self.ws_step = torch.empty(max(16, L.fsg_dense_step_workspace_bytes(N, R, K, self.max_total_gt)),
                                    dtype=torch.uint8, device=dev) if self.one_call else None
-        mc = _lib.MatchConfig()
-        mc.num_thresholds, mc.num_picky_thresholds = len(cfg.iou_thresholds), len(cfg.picky_thresholds)
-        mc.allow_low_quality_matches = 1
-        for i, v in enumerate(cfg.iou_thresholds):
-            mc.thresholds[i] = float(v)
-        for i, v in enumerate(cfg.picky_thresholds):
-            mc.picky_thresholds[i] = float(v)
-        for i, v in enumerate(cfg.iou_labels):
-            mc.labels[i] = int(v)
-            mc.picky_labels[i] = int(v)
-        self._mc = mc
+        self._mc = _match_config(cfg)
 
     def _check(self, logits, deltas, bets, anchors, gt):
         N, R, K = self.N, self.R, self.K
@@ -219,7 +223,7 @@ class DenseStepPlan:
             self._bw, None, None, None, P(self.gt_classes), P(self.mask), None, P(self.matched), P(bets), None,
             float(cfg.gambler_temperature), P(self.stats), self.peer.ctx if self.peer is not None else None,
             P(self.ws_match), self.ws_match.numel(), _lib.stream()))
-        _lib.count_launches(2)
+        _lib.count_launches(3)
 
     def stage_main(self, logits, deltas, bets, anchors, gt):
         L, N, R, P = self.L, self.N, self.R, _lib.ptr
@@ -251,7 +255,7 @@ class DenseStepPlan:
         _lib.check(self.L.fsg_dense_step(io, self.N, self.R, self._mc, self.params,
                                          self.peer.ctx if self.peer is not None else None, P(self.ws_step),
                                          self.ws_step.numel(), _lib.stream()))
-        _lib.count_launches(3)
+        _lib.count_launches(5)
 
     def run(self, logits, deltas, bets, anchors, gt):
         """Enqueue the step on the current stream.  Inputs: detached contiguous CUDA fp32 tensors."""
@@ -323,7 +327,7 @@ class DenseStepPlan:
             if len(g) == 3:
                 sharded.all_reduce_batch_weighted_sum(self.scalars, self.group)
                 g[2].replay()
-        _lib.count_launches(3 if self.one_call else 4)
+        _lib.count_launches(5)
         return self.result()
 
     def release_graphs(self):
@@ -551,6 +555,48 @@ class DenseStepPlanLevels:
         self.ws_match = torch.empty(max(16, L.fsg_match_workspace_bytes(N, R, self.max_total_gt)), dtype=torch.uint8,
                                     device=dev)
         self.graph, self._static, self._last = None, None, None
+        # one-call form (fsg_dense_step_levels: K1 -> K2 native -> post under programmatic dependent launch, the peer
+        # exchange polled by K2); a sharded run that needs an NCCL collective in the middle keeps the staged form
+        self.one_call = (os.environ.get("FSG_STEP_STAGED", "0") != "1") and (
+            group is None or (self.peer is not None and cfg.norm_mode != _lib.NORM_BATCH))
+        self._mc = _match_config(cfg)
+        self.ws_step = None
+        self.L = L
+
+    def step_one_call(self, logit_levels, delta_levels, bet_levels, anchors, gt):
+        P = _lib.ptr
+        nl, N, A, K = len(self.shapes), self.N, self.A, self.K
+        hl = (_lib.HeadLevel * nl)()
+        pl = (_lib.PostLevel * nl)()
+        for i, (h, w) in enumerate(self.shapes):
+            x, d, b = logit_levels[i], delta_levels[i], bet_levels[i]
+            for t, c in ((x, A * K), (d, A * 4), (b, A)):
+                if tuple(t.shape) != (N, c, h, w) or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError("DenseStepPlanLevels: level %d expects contiguous fp32 (N=%d, %d, %d, %d)"
+                                       % (i, N, c, h, w))
+            hl[i].logits, hl[i].pred_deltas, hl[i].bets = P(x), P(d), P(b)
+            hl[i].grad_logits = P(self.grad_logits[i]) if self.need_gl else None
+            hl[i].grad_deltas = P(self.grad_deltas[i]) if self.need_gd else None
+            hl[i].per_anchor_loss = P(self.nakhw_loss[i])
+            hl[i].H, hl[i].W = h, w
+            pl[i].bets, pl[i].per_anchor_loss, pl[i].grad_bets = P(b), P(self.nakhw_loss[i]), P(self.grad_bets[i])
+            pl[i].H, pl[i].W = h, w
+        if gt.total > self.max_total_gt:
+            raise RuntimeError("DenseStepPlanLevels: %d GT boxes > max_total_gt %d" % (gt.total, self.max_total_gt))
+        if self.ws_step is None:
+            need = self.L.fsg_dense_step_levels_workspace_bytes(N, hl, nl, A, self.max_total_gt)
+            self.ws_step = torch.empty(max(16, need), dtype=torch.uint8, device=self.device)
+        io = _lib.StepLevelsIO()
+        io.anchors = P(anchors)
+        io.anchor_image_stride = self.R * 4 if anchors.dim() == 3 else 0
+        io.gt_boxes, io.gt_class_ids, io.gt_offsets, io.sum_M = P(gt.boxes), P(gt.classes), P(gt.offsets), gt.total
+        m = self.m
+        io.gt_classes, io.mask, io.matched_idx32 = P(m["gt_classes"]), P(m["mask"]), P(m["matched_idx32"])
+        io.stats, io.scalars, io.weights_out = P(m["stats"]), P(self.scalars), None
+        _lib.check(self.L.fsg_dense_step_levels(io, hl, pl, nl, A, N, self.R, self._mc, self.params,
+                                                self.peer.ctx if self.peer is not None else None, P(self.ws_step),
+                                                self.ws_step.numel(), _lib.stream()))
+        _lib.count_launches(5)
 
     # ---- stages ---------------------------------------------------------------------------------------
     def stage_match(self, bet_levels, anchors, gt):
@@ -583,6 +629,9 @@ class DenseStepPlanLevels:
         return self._last
 
     def run(self, logit_levels, delta_levels, bet_levels, anchors, gt):
+        if self.one_call:
+            self.step_one_call(logit_levels, delta_levels, bet_levels, anchors, gt)
+            return self.result()
         self.stage_match(bet_levels, anchors, gt)
         if self.group is not None and self.peer is None:
             sharded.all_reduce_stats(self.m["stats"], self.group)
@@ -611,7 +660,7 @@ class DenseStepPlanLevels:
             return g
 
         batch_norm = self.cfg.norm_mode == _lib.NORM_BATCH
-        if self.group is None or (self.peer is not None and not batch_norm):
+        if self.one_call or self.group is None or (self.peer is not None and not batch_norm):
             self.graph = [cap(lambda: self.run(*self._static))]
         else:
             g1 = cap(lambda: self.stage_match(bs, anchors, gt))
@@ -632,7 +681,7 @@ class DenseStepPlanLevels:
             if len(g) == 3:
                 sharded.all_reduce_batch_weighted_sum(self.scalars, self.group)
                 g[2].replay()
-        _lib.count_launches(4)
+        _lib.count_launches(5)
         return self._last
 
     def release_graphs(self):

@@ -145,7 +145,7 @@ def match_anchors(anchors, gt, num_classes, thresholds=(0.4, 0.5), labels=(0, -1
             ptr(out.get("picky_labels")), ptr(out.get("gt_classes")), ptr(out.get("mask")),
             ptr(out.get("gt_deltas")), ptr(out.get("matched_idx32")), ptr(bets), lv, float(temperature), ptr(stats),
             peer.ctx if peer is not None else None, ptr(ws), ws.numel(), int(phases), stream()))
-        count_launches(2 if phases == 3 else 1)
+        count_launches(3 if phases == 3 else (1 if phases == 1 else 2))   # pass A, pass B (patch), fold
     if stats is not None:
         out["stats"] = stats
     if phases != 3:

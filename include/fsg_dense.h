@@ -359,6 +359,30 @@ FSG_API int fsg_bet_stats(const float* bets, const fsg_bet_levels* h_bet_levels,
                   const fsg_loss_params* h_params, const double* stats, double* out /* 8 */, void* workspace,
                   size_t workspace_bytes, fsg_stream_t stream);
 
+/* fsg_dense_step on the head's NATIVE layout: logits / deltas / betting maps and their gradients, and the NAKHW_loss,
+ * all per level as the heads and the gambler produce them (h_levels: logits, grad_logits, pred_deltas, grad_deltas,
+ * bets, per_anchor_loss; h_post: bets, per_anchor_loss, grad_bets).  Same kernel chain and peer handling. */
+typedef struct fsg_step_levels_io {
+  const float* anchors;     /* (R,4), or (N,R,4) with anchor_image_stride = R*4 */
+  int64_t anchor_image_stride;
+  const float* gt_boxes;
+  const int64_t* gt_class_ids;
+  const int32_t* gt_offsets;
+  int64_t sum_M;
+  int64_t* gt_classes;      /* (N,R) */
+  int64_t* mask;            /* (N,R) */
+  int32_t* matched_idx32;   /* (N,R) */
+  double* stats;            /* [2+N] */
+  double* scalars;          /* [10+N] */
+  float* weights_out;       /* (N,R) or NULL */
+} fsg_step_levels_io;
+FSG_API size_t fsg_dense_step_levels_workspace_bytes(int N, const fsg_head_level* h_levels, int num_levels, int A,
+                                             int64_t sum_M);
+FSG_API int fsg_dense_step_levels(const fsg_step_levels_io* h_io, const fsg_head_level* h_levels,
+                          const fsg_post_level* h_post, int num_levels, int A, int N, int64_t R,
+                          const fsg_match_config* h_match, const fsg_loss_params* h_params,
+                          const fsg_peer_ctx* h_peer, void* workspace, size_t workspace_bytes, fsg_stream_t stream);
+
 /* in-place x *= *scale_dev or x *= scale_host (backward with a non-unit upstream gradient) */
 FSG_API int fsg_scale_inplace(float* x, int64_t n, const float* scale_dev, float scale_host,
                       fsg_stream_t stream);
