@@ -1218,6 +1218,8 @@ static int detect_run(const DetectCall& c, const DetectSrc& src, cudaStream_t s)
     a.split = nms_split; a.part_cap = max_det;
     a.part_keys = (uint64_t*)(nws + nms_w.off_keys); a.part_cnt = (int*)(nws + nms_w.off_cnt);
     a.done = (unsigned*)(nws + nms_w.off_done);
+    a.sorted_runs = 1;   // every level's candidates leave the select stage sorted by (score, index)
+    a.alive = (unsigned*)(nws + nms_w.off_alive); a.rank2cand = (uint16_t*)(nws + nms_w.off_r2c);
   }
   a.keep = c.keep_idx; a.keep_stride = max_det; a.num_keep = c.out_count;
   a.out_boxes = (float4*)c.out_boxes; a.out_scores = c.out_scores; a.out_classes = c.out_classes;

@@ -2,6 +2,8 @@
 // detector_postprocess epilogue; nms / batched_nms entry points (n <= 8192 here, larger n in nms_large.cu).
 //
 // Reference: detectron2/layers/nms.py:6,9-26; detectron2/modeling/postprocessing.py:8-52.
+#include <stdlib.h>
+
 #include "nms_kernel.cuh"
 #include "nms_large.cuh"
 #include "sort_utils.cuh"
@@ -16,7 +18,156 @@ __device__ __forceinline__ float4 postprocess_box(float4 b, float4 pp) {
   return b;
 }
 
-// ascending bitonic sort of m (power of two) keys in shared memory, block-wide
+// Final detections of image n: the nk best survivors in score order, `ci_of(t)` = concatenation index of the t-th.
+// Optional detector_postprocess (modeling/postprocessing.py:8-52): Boxes.scale, Boxes.clip, drop boxes that became
+// empty (Boxes.nonempty), stable compaction.  Called by all kNmsThreads threads of the image's last CTA.
+template <typename CiOf>
+__device__ __forceinline__ void nms_emit(const NmsArgs& A, int n, int nk, bool bad, int L, const int* s_pref,
+                                         int* s_warp, CiOf ci_of) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float4* gbox = A.boxes + (int64_t)n * A.slots_per_image;
+  const float* gscore = A.scores + (int64_t)n * A.slots_per_image;
+  const int64_t* gcls = A.classes ? A.classes + (int64_t)n * A.slots_per_image : nullptr;
+  auto slot_of = [&](int i) -> int {
+    int l = 0;
+    while (l + 1 < L && i >= s_pref[l + 1]) ++l;
+    return l * A.topk + (i - s_pref[l]);
+  };
+  if (A.post && A.out_boxes) {
+    // max_out <= kNmsThreads: one row per thread
+    const float4 pp = A.post[n];
+    const int t = tid;
+    bool ok = false;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = 0.f;
+    int64_t cl = 0;
+    int ci = -1;
+    if (t < nk) {
+      ci = ci_of(t);
+      const int s = slot_of(ci);
+      b = postprocess_box(gbox[s], pp);
+      sc = gscore[s];
+      cl = gcls ? gcls[s] : 0;
+      ok = (__fsub_rn(b.z, b.x) > 0.f) && (__fsub_rn(b.w, b.y) > 0.f);
+    }
+    const unsigned bm = __ballot_sync(kFull, ok);
+    if (lane == 0) s_warp[wid] = __popc(bm);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kNmsThreads / 32; ++w) {
+      const int c = s_warp[w];
+      if (w < wid) before += c;
+      total += c;
+    }
+    const int pos = before + __popc(bm & ((1u << lane) - 1u));
+    const int64_t ob = (int64_t)n * A.max_out;
+    if (ok) {
+      A.out_boxes[ob + pos] = b;
+      A.out_scores[ob + pos] = sc;
+      A.out_classes[ob + pos] = cl;
+      if (A.keep) A.keep[(int64_t)n * A.keep_stride + pos] = ci;
+    }
+    if (t >= total && t < A.max_out) {
+      A.out_boxes[ob + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      A.out_scores[ob + t] = 0.f;
+      A.out_classes[ob + t] = 0;
+      if (A.keep && t < A.keep_stride) A.keep[(int64_t)n * A.keep_stride + t] = -1;
+    }
+    if (tid == 0 && A.num_keep) A.num_keep[n] = bad ? -1 : total;
+    return;
+  }
+  if (tid == 0 && A.num_keep) A.num_keep[n] = bad ? -1 : nk;   // -1: a class id outside [0, 2^18)
+  const int out_rows = (A.max_out > 0) ? A.max_out : nk;
+  for (int t = tid; t < out_rows; t += kNmsThreads) {
+    if (t < nk) {
+      const int ci = ci_of(t);
+      const int s = slot_of(ci);
+      if (A.keep) A.keep[(int64_t)n * A.keep_stride + t] = ci;
+      if (A.out_boxes) {
+        A.out_boxes[(int64_t)n * A.max_out + t] = gbox[s];
+        A.out_scores[(int64_t)n * A.max_out + t] = gscore[s];
+        if (A.out_classes) A.out_classes[(int64_t)n * A.max_out + t] = gcls ? gcls[s] : 0;
+      }
+    } else {
+      if (A.keep && t < A.keep_stride) A.keep[(int64_t)n * A.keep_stride + t] = -1;
+      if (A.out_boxes) {
+        A.out_boxes[(int64_t)n * A.max_out + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        A.out_scores[(int64_t)n * A.max_out + t] = 0.f;
+        if (A.out_classes) A.out_classes[(int64_t)n * A.max_out + t] = 0;
+      }
+    }
+  }
+}
+
+// Greedy suppression over the class segments of `mc` boxes sorted by (class, score descending) in shared memory
+// (torchvision nms_kernel semantics).  Big segments: the whole CTA, batches of 32 boxes in score order -- warp 0 runs
+// the greedy pass inside the batch, then every thread tests the boxes behind the batch against the batch's survivors
+// (same result as the sequential pass, two barriers per 32 boxes).  Small segments: one warp each.
+struct NmsSuppressShared {
+  int next, nbatch;
+  int batch[32];
+};
+__device__ __forceinline__ void nms_suppress(const float4* sbox, unsigned char* dead, const uint16_t* seg, int nseg,
+                                             int mc, float thr, NmsSuppressShared& sh) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int s = 0; s < nseg; ++s) {
+    const int b = seg[s];
+    const int e = (s + 1 < nseg) ? (int)seg[s + 1] : mc;
+    if (e - b <= kNmsBigSeg) continue;   // uniform
+    for (int i0 = b; i0 < e; i0 += 32) {
+      const int i1 = min(i0 + 32, e);
+      if (wid == 0) {
+        for (int i = i0; i < i1; ++i) {
+          if (dead[i]) continue;   // warp-uniform
+          const float4 bi = sbox[i];
+          const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+          const int j = i + 1 + lane;
+          if (j < i1 && !dead[j] && nms_suppresses(bi, ai, sbox[j], thr)) dead[j] = 1;
+          __syncwarp();
+        }
+        const bool alive = (i0 + lane < i1) && !dead[i0 + lane];
+        const unsigned bm = __ballot_sync(kFull, alive);
+        if (alive) sh.batch[__popc(bm & ((1u << lane) - 1u))] = i0 + lane;
+        if (lane == 0) sh.nbatch = __popc(bm);
+      }
+      __syncthreads();
+      const int nk = sh.nbatch;
+      if (nk > 0) {
+        for (int j = i1 + tid; j < e; j += kNmsThreads) {
+          if (dead[j]) continue;
+          const float4 bj = sbox[j];
+          for (int q = 0; q < nk; ++q) {
+            const float4 bi = sbox[sh.batch[q]];
+            const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+            if (nms_suppresses(bi, ai, bj, thr)) { dead[j] = 1; break; }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (;;) {
+    int s = 0;
+    if (lane == 0) s = atomicAdd(&sh.next, 1);
+    s = __shfl_sync(kFull, s, 0);
+    if (s >= nseg) break;
+    const int b = seg[s];
+    const int e = (s + 1 < nseg) ? (int)seg[s + 1] : mc;
+    if (e - b > kNmsBigSeg) continue;    // done above
+    for (int i = b; i < e; ++i) {
+      if (dead[i]) continue;   // warp-uniform (shared memory, synchronised below)
+      const float4 bi = sbox[i];
+      const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+      for (int j = i + 1 + lane; j < e; j += 32) {
+        if (dead[j]) continue;
+        if (nms_suppresses(bi, ai, sbox[j], thr)) dead[j] = 1;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const NmsArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                      // kNmsCap * 8
@@ -245,71 +396,193 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_image_kernel(const NmsArgs
   if (S > 1) bitonic_asc<kNmsThreads>(keys, m2);
   int nk = tot;
   if (A.max_out > 0 && nk > A.max_out) nk = A.max_out;
-  if (A.post && A.out_boxes) {
-    // detector_postprocess (modeling/postprocessing.py:8-52) on the final detections: Boxes.scale, Boxes.clip,
-    // drop boxes that became empty (Boxes.nonempty), stable compaction.  max_out <= kNmsThreads: one row per thread.
-    const float4 pp = A.post[n];
-    const int t = tid;
-    bool ok = false;
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sc = 0.f;
-    int64_t cl = 0;
-    int ci = -1;
-    if (t < nk) {
-      ci = (int)(keys[t] & 0x3fff);
-      const int s = slot_of(ci);
-      b = postprocess_box(gbox[s], pp);
-      sc = gscore[s];
-      cl = gcls ? gcls[s] : 0;
-      ok = (__fsub_rn(b.z, b.x) > 0.f) && (__fsub_rn(b.w, b.y) > 0.f);
+  nms_emit(A, n, nk, s_bad != 0, L, s_pref, s_warp, [&](int t) { return (int)(keys[t] & 0x3fff); });
+}
+
+// ------------------------------------------------------------------------------------------
+// The same per-class NMS for candidates that arrive as L runs (the FPN levels), each already sorted by
+// (score descending, position ascending) -- what the select stage of fsg_detect and the RPN select emit.
+// The order by score of the concatenation is then a merge, not a sort: a candidate's rank is its position in its
+// own run plus, for every other run, the number of entries that go before it (two binary searches per run; equal
+// scores: the lower level first, i.e. the lower concatenation index -- the reference's stable sort).  With the
+// merged rank in hand
+//   * the (class, score) order needs only a 32-bit key (class << 13 | rank): half the shuffle traffic of the
+//     64-bit composite key;
+//   * the survivors need no second sort and the split CTAs no merge: each sets the bits of its survivors' ranks in
+//     a per-image bitmap, and the image's last CTA turns the bitmap into positions with one prefix popcount.
+// ------------------------------------------------------------------------------------------
+constexpr size_t kRunsSmem = (size_t)kNmsCap * (4 + 2 + 4 + 16);   // scores|seg+dead, rank->cand, keys, boxes
+
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_runs_kernel(const NmsArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* sbox = reinterpret_cast<float4*>(smem_raw);                                   // kNmsCap * 16
+  uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kNmsCap * 16);        // kNmsCap * 4
+  float* s_score = reinterpret_cast<float*>(smem_raw + (size_t)kNmsCap * 20);           // kNmsCap * 4 (phase A/B)
+  uint16_t* seg = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kNmsCap * 20);         //   reused: kNmsCap * 2
+  unsigned char* dead = smem_raw + (size_t)kNmsCap * 22;                                //   reused: kNmsCap
+  uint16_t* cand_of = reinterpret_cast<uint16_t*>(smem_raw + (size_t)kNmsCap * 24);     // kNmsCap * 2
+  __shared__ int s_pref[kMaxLevels + 1];
+  __shared__ int s_warp[kNmsThreads / 32];
+  __shared__ int s_nseg, s_mine, s_bad;
+  __shared__ NmsSuppressShared s_sup;
+  __shared__ bool s_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int part = blockIdx.x;
+  const int n = blockIdx.y;
+  const int S = A.split;
+  grid_dependency_sync();   // (no-op unless launched under programmatic dependent launch behind the select stage)
+  if (tid == 0) {
+    s_pref[0] = 0;
+    for (int l = 0; l < A.L; ++l) s_pref[l + 1] = s_pref[l] + A.lvl_count[n * A.L + l];
+    s_nseg = 0; s_mine = 0; s_bad = 0; s_sup.next = 0;
+  }
+  __syncthreads();
+  const int L = A.L;
+  const int nc = s_pref[L];
+  const float4* gbox = A.boxes + (int64_t)n * A.slots_per_image;
+  const float* gscore = A.scores + (int64_t)n * A.slots_per_image;
+  const int64_t* gcls = A.classes + (int64_t)n * A.slots_per_image;
+  auto slot_of = [&](int i) -> int {
+    int l = 0;
+    while (l + 1 < L && i >= s_pref[l + 1]) ++l;
+    return l * A.topk + (i - s_pref[l]);
+  };
+
+  // ---- A. every candidate's score (all runs are needed for the merge ranks), the optional candidate export
+  for (int i = tid; i < nc; i += kNmsThreads) {
+    const int s = slot_of(i);
+    s_score[i] = gscore[s];
+    if (A.exp_boxes && part == 0) {
+      const int64_t eo = (int64_t)n * A.L * A.topk + i;
+      A.exp_boxes[eo] = gbox[s];
+      A.exp_scores[eo] = gscore[s];
+      A.exp_classes[eo] = gcls[s];
     }
-    const unsigned bm = __ballot_sync(kFull, ok);
+  }
+  if (tid == 0 && part == 0 && A.exp_count) A.exp_count[n] = nc;
+  __syncthreads();
+
+  // ---- B. merged rank of this CTA's candidates; key = class << 13 | rank
+  uint16_t* g_r2c = A.rank2cand + (int64_t)n * kNmsCap;
+  for (int i0 = 0; i0 < nc; i0 += kNmsThreads) {
+    const int i = i0 + tid;
+    bool mine = false;
+    uint32_t key = 0u;
+    if (i < nc) {
+      int l0 = 0;
+      while (l0 + 1 < L && i >= s_pref[l0 + 1]) ++l0;
+      const int64_t craw = gcls[l0 * A.topk + (i - s_pref[l0])];
+      if (craw < 0 || craw > 0x3ffff) s_bad = 1;
+      const uint32_t c = (uint32_t)(craw & 0x3ffff);
+      mine = ((int)(c % (uint32_t)S) == part);
+      if (mine) {
+        const float sc = s_score[i];
+        int rank = i - s_pref[l0];
+        for (int l = 0; l < L; ++l) {
+          if (l == l0) continue;
+          // entries of run l that go before candidate i: score greater, or equal and the run is an earlier level
+          const float* run = s_score + s_pref[l];
+          int lo = 0, hi = s_pref[l + 1] - s_pref[l];
+          if (l < l0) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (run[mid] >= sc) lo = mid + 1; else hi = mid; } }
+          else        { while (lo < hi) { const int mid = (lo + hi) >> 1; if (run[mid] > sc) lo = mid + 1; else hi = mid; } }
+          rank += lo;
+        }
+        key = (c << 13) | (uint32_t)rank;
+        cand_of[rank] = (uint16_t)i;
+        g_r2c[rank] = (uint16_t)i;
+      }
+    }
+    const unsigned bm = __ballot_sync(kFull, mine);
+    if (bm != 0u) {
+      int base = 0;
+      const int leader = __ffs(bm) - 1;
+      if (lane == leader) base = atomicAdd(&s_mine, __popc(bm));
+      base = __shfl_sync(kFull, base, leader);
+      if (mine) keys[base + __popc(bm & ((1u << lane) - 1u))] = key;
+    }
+  }
+  __syncthreads();
+  const int mc = s_mine;
+  int m = 1;
+  while (m < mc) m <<= 1;
+  for (int i = mc + tid; i < m; i += kNmsThreads) keys[i] = ~0u;
+  __syncthreads();
+  bitonic_asc_u32<kNmsThreads>(keys, m);
+
+  // ---- C. boxes in (class, score) order, segment starts (s_score is dead from here on: seg / dead reuse it)
+  for (int i = tid; i < mc; i += kNmsThreads) {
+    sbox[i] = gbox[slot_of((int)cand_of[keys[i] & 0x1fff])];
+    dead[i] = 0;
+  }
+  __syncthreads();
+  for (int i0 = 0; i0 < mc; i0 += kNmsThreads) {
+    const int i = i0 + tid;
+    const bool start = (i < mc) && (i == 0 || (keys[i] >> 13) != (keys[i - 1] >> 13));
+    const unsigned bm = __ballot_sync(kFull, start);
     if (lane == 0) s_warp[wid] = __popc(bm);
     __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < kNmsThreads / 32; ++w) {
-      const int c = s_warp[w];
-      if (w < wid) before += c;
-      total += c;
-    }
-    const int pos = before + __popc(bm & ((1u << lane) - 1u));
-    const int64_t ob = (int64_t)n * A.max_out;
-    if (ok) {
-      A.out_boxes[ob + pos] = b;
-      A.out_scores[ob + pos] = sc;
-      A.out_classes[ob + pos] = cl;
-      if (A.keep) A.keep[(int64_t)n * A.keep_stride + pos] = ci;
-    }
-    if (t >= total && t < A.max_out) {
-      A.out_boxes[ob + t] = make_float4(0.f, 0.f, 0.f, 0.f);
-      A.out_scores[ob + t] = 0.f;
-      A.out_classes[ob + t] = 0;
-      if (A.keep && t < A.keep_stride) A.keep[(int64_t)n * A.keep_stride + t] = -1;
-    }
-    if (tid == 0 && A.num_keep) A.num_keep[n] = s_bad ? -1 : total;
-    return;
+    int before = s_nseg;
+    for (int w = 0; w < wid; ++w) before += s_warp[w];
+    if (start) seg[before + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)i;
+    int tot = 0;
+    if (tid == 0)
+      for (int w = 0; w < kNmsThreads / 32; ++w) tot += s_warp[w];
+    __syncthreads();
+    if (tid == 0) s_nseg += tot;
+    __syncthreads();
   }
-  if (tid == 0 && A.num_keep) A.num_keep[n] = s_bad ? -1 : nk;   // -1: a class id outside [0, 2^18)
-  const int out_rows = (A.max_out > 0) ? A.max_out : nk;
-  for (int t = tid; t < out_rows; t += kNmsThreads) {
-    if (t < nk) {
-      const int ci = (int)(keys[t] & 0x3fff);
-      const int s = slot_of(ci);
-      if (A.keep) A.keep[(int64_t)n * A.keep_stride + t] = ci;
-      if (A.out_boxes) {
-        A.out_boxes[(int64_t)n * A.max_out + t] = gbox[s];
-        A.out_scores[(int64_t)n * A.max_out + t] = gscore[s];
-        if (A.out_classes) A.out_classes[(int64_t)n * A.max_out + t] = gcls ? gcls[s] : 0;
-      }
-    } else {
-      if (A.keep && t < A.keep_stride) A.keep[(int64_t)n * A.keep_stride + t] = -1;
-      if (A.out_boxes) {
-        A.out_boxes[(int64_t)n * A.max_out + t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        A.out_scores[(int64_t)n * A.max_out + t] = 0.f;
-        if (A.out_classes) A.out_classes[(int64_t)n * A.max_out + t] = 0;
-      }
+
+  // ---- D. greedy suppression per class segment
+  nms_suppress(sbox, dead, seg, s_nseg, mc, A.thr, s_sup);
+
+  // ---- E. survivors -> bits of the image's rank bitmap
+  unsigned* g_alive = A.alive + (int64_t)n * (kNmsCap / 32);
+  for (int i = tid; i < mc; i += kNmsThreads)
+    if (!dead[i]) {
+      const uint32_t r = keys[i] & 0x1fff;
+      atomicOr(&g_alive[r >> 5], 1u << (r & 31));
+    }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&A.done[n], 1u) == (unsigned)S - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // ---- F. last CTA of the image: ranks of all survivors in order = prefix popcount over the bitmap
+  if (tid == 0) A.done[n] = 0u;
+  constexpr int kWords = kNmsCap / 32;          // 256
+  uint16_t* sel = cand_of;                      // the first max_out survivors' concatenation indices, in score order
+  unsigned word = 0u;
+  if (tid < kWords) word = __ldcg(&g_alive[tid]);
+  int cnt = __popc(word), incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int before = 0, total = 0;
+  for (int w = 0; w < kWords / 32; ++w) {
+    if (w < wid) before += s_warp[w];
+    total += s_warp[w];
+  }
+  const int limit = (A.max_out > 0 && A.max_out < total) ? A.max_out : total;
+  __syncthreads();   // cand_of (this CTA's own ranks) is overwritten below; everybody is past phase C
+  if (tid < kWords) {
+    int pos = before + incl - cnt;
+    while (word != 0u && pos < limit) {
+      const int bit = __ffs(word) - 1;
+      word &= word - 1u;
+      sel[pos++] = __ldcg(&g_r2c[tid * 32 + bit]);
     }
   }
+  __syncthreads();
+  nms_emit(A, n, limit, s_bad != 0, L, s_pref, s_warp, [&](int t) { return (int)sel[t]; });
 }
 
 // stand-alone detector_postprocess on any (n,4) box list: scaled + clipped boxes and a keep flag per box
@@ -322,7 +595,25 @@ __global__ void __launch_bounds__(256) postprocess_boxes_kernel(const float4* __
   keep[i] = ((__fsub_rn(b.z, b.x) > 0.f) && (__fsub_rn(b.w, b.y) > 0.f)) ? 1 : 0;
 }
 
+// FSG_NMS_SORT=1: always the sorting kernel (A/B timing of the merge-rank kernel)
+static bool nms_force_sort() {
+  static const int v = [] {
+    const char* e = getenv("FSG_NMS_SORT");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return v != 0;
+}
+
 int launch_nms_image(const NmsArgs& a, int N, cudaStream_t s, bool pdl) {
+  // the merge-rank kernel holds every run's scores of an image in one CTA and packs ranks into 13 bits: all
+  // L * topk slots must fit kNmsCap (config 4: 5 x 1000; the FPN RPN's 5 x 2000 does not and keeps the sort kernel)
+  if (a.sorted_runs && a.lvl_count && a.classes && a.alive && a.rank2cand && (int64_t)a.L * a.topk <= kNmsCap &&
+      !nms_force_sort()) {
+    FSG_CUDA_TRY(cudaFuncSetAttribute(nms_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRunsSmem));
+    launch_pdl(nms_runs_kernel, dim3((unsigned)a.split, (unsigned)N), dim3(kNmsThreads), kRunsSmem, s, pdl, a);
+    FSG_LAUNCH_CHECK();
+    return FSG_OK;
+  }
   FSG_CUDA_TRY(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmem));
   launch_pdl(nms_image_kernel, dim3((unsigned)a.split, (unsigned)N), dim3(kNmsThreads), kNmsSmem, s, pdl, a);
   FSG_LAUNCH_CHECK();

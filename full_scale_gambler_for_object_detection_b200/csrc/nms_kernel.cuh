@@ -26,11 +26,15 @@ struct NmsArgs {
   int fixed_count;
   float thr;                // largest float <= the double threshold (strict > compare, see fsg_nms)
   int max_out;              // truncate to this many (DETECTIONS_PER_IMAGE); <= 0: all
+  int sorted_runs;          // the L levels of an image are runs sorted by (score descending, position ascending):
+                            // nms_runs_kernel ranks by merging instead of sorting (needs lvl_count and classes)
   int split;                // CTAs per image; CTA c owns the classes with class % split == c
   int part_cap;             // survivors each CTA hands to the merge (max_out, or the candidate count)
   uint64_t* part_keys;      // (N, split, part_cap) scratch
   int* part_cnt;            // (N, split)
   unsigned* done;           // (N)
+  unsigned* alive;          // (N, kNmsCap / 32) survivor bits by merged rank, zero-initialised (sorted_runs only)
+  uint16_t* rank2cand;      // (N, kNmsCap) candidate (concatenation index) of every merged rank (sorted_runs only)
   // outputs
   int64_t* keep;            // (N, keep_stride) candidate indices in concatenation order
   int64_t keep_stride;
@@ -54,14 +58,16 @@ inline int nms_split_for(int N) {
   return s;
 }
 struct NmsWs {
-  size_t off_done, off_cnt, off_keys, total;
+  size_t off_done, off_alive, off_cnt, off_keys, off_r2c, total;   // [off_done, off_cnt) is zeroed before every call
 };
 inline NmsWs nms_ws_layout(int N, int split, int part_cap) {
   NmsWs w;
   size_t o = 0;
-  w.off_done = o; o += align_up(sizeof(unsigned) * (size_t)N, 16);
-  w.off_cnt = o;  o += align_up(sizeof(int) * (size_t)N * split, 16);
-  w.off_keys = o; o += align_up(sizeof(uint64_t) * (size_t)N * split * part_cap, 16);
+  w.off_done = o;  o += align_up(sizeof(unsigned) * (size_t)N, 16);
+  w.off_alive = o; o += align_up(sizeof(unsigned) * (size_t)N * (kNmsCap / 32), 16);
+  w.off_cnt = o;   o += align_up(sizeof(int) * (size_t)N * split, 16);
+  w.off_keys = o;  o += align_up(sizeof(uint64_t) * (size_t)N * split * part_cap, 16);
+  w.off_r2c = o;   o += align_up(sizeof(uint16_t) * (size_t)N * kNmsCap, 16);
   w.total = o;
   return w;
 }

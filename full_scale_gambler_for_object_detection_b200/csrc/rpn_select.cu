@@ -439,6 +439,9 @@ extern "C" int fsg_rpn_proposals(const float* const* h_level_proposals, const fl
   a.split = split; a.part_cap = post_nms_topk;
   a.part_keys = (uint64_t*)(nws + nw.off_keys); a.part_cnt = (int*)(nws + nw.off_cnt);
   a.done = (unsigned*)(nws + nw.off_done);
+  a.sorted_runs = 1;   // each level's proposals leave the select kernel sorted by (logit, index); the min-size filter
+                       // is a stable compaction
+  a.alive = (unsigned*)(nws + nw.off_alive); a.rank2cand = (uint16_t*)(nws + nw.off_r2c);
   a.keep = nullptr; a.keep_stride = post_nms_topk; a.num_keep = out_count;
   a.out_boxes = (float4*)out_boxes; a.out_scores = out_logits; a.out_classes = out_levels;
   return launch_nms_image(a, N, s);

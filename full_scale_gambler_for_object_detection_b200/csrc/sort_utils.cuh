@@ -82,6 +82,61 @@ __device__ void bitonic_asc(uint64_t* a, int m) {
   __syncthreads();
 }
 
+// 32-bit keys, ascending, block-wide; same scheme as bitonic_asc (two keys per thread in registers, shuffles below
+// stride 64) for 64 <= m <= 2*NT, plain shared-memory network otherwise.
+template <int NT>
+__device__ void bitonic_asc_u32(uint32_t* a, int m) {
+  if (m < 64 || m > 2 * NT) {
+    for (int size = 2; size <= m; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = threadIdx.x; t < (m >> 1); t += NT) {
+          const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+          const int hi = lo + stride;
+          const bool asc = ((lo & size) == 0);
+          const uint32_t x = a[lo], y = a[hi];
+          if (asc ? (x > y) : (x < y)) { a[lo] = y; a[hi] = x; }
+        }
+        __syncthreads();
+      }
+    }
+    return;
+  }
+  const int t = threadIdx.x;
+  const bool act = t < (m >> 1);
+  const int i0 = 2 * t;
+  uint32_t v0 = act ? a[i0] : 0u, v1 = act ? a[i0 + 1] : 0u;
+  for (int size = 2; size <= m; size <<= 1) {
+    const bool asc = ((i0 & size) == 0);
+    int stride = size >> 1;
+    if (stride >= 64) {
+      if (act) { a[i0] = v0; a[i0 + 1] = v1; }
+      __syncthreads();
+      for (; stride >= 64; stride >>= 1) {
+        if (act) {
+          const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+          const int hi = lo + stride;
+          const bool up = ((lo & size) == 0);
+          const uint32_t x = a[lo], y = a[hi];
+          if (up ? (x > y) : (x < y)) { a[lo] = y; a[hi] = x; }
+        }
+        __syncthreads();
+      }
+      if (act) { v0 = a[i0]; v1 = a[i0 + 1]; }
+    }
+    for (; stride >= 2; stride >>= 1) {
+      const int pl = stride >> 1;
+      const uint32_t p0 = __shfl_xor_sync(kFull, v0, pl);
+      const uint32_t p1 = __shfl_xor_sync(kFull, v1, pl);
+      const bool keep_min = (((i0 & stride) == 0) == asc);
+      v0 = keep_min ? min(v0, p0) : max(v0, p0);
+      v1 = keep_min ? min(v1, p1) : max(v1, p1);
+    }
+    if ((v0 > v1) == asc) { const uint32_t tmp = v0; v0 = v1; v1 = tmp; }
+  }
+  if (act) { a[i0] = v0; a[i0 + 1] = v1; }
+  __syncthreads();
+}
+
 // Per-class NMS is independent across classes, so an image is split over `split` CTAs by class id; each
 // sorts and suppresses only its own candidates (4x fewer keys per bitonic network at split = 4) and hands
 // its best survivors to the last CTA of the image, which merges them by score.
