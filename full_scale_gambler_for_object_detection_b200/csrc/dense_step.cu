@@ -62,7 +62,7 @@ extern "C" int fsg_dense_step(const fsg_step_io* io, int N, int64_t R, const fsg
                          mc->num_picky_thresholds, hp->box_weights, nullptr, nullptr, nullptr, io->gt_classes, io->mask,
                          nullptr, io->matched_idx32, io->bets, nullptr, hp->temperature, io->stats,
                          sharded ? h_peer : nullptr, ws, off_loss, 3,
-                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl), nullptr, 0, stream);
+                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl), stream);
   if (st != FSG_OK) return st;
   const int pdl = step_no_pdl() ? 0 : kLossPdl;
   st = loss_main_enqueue(io->logits, io->pred_deltas, nullptr, io->anchors, io->anchor_image_stride, io->gt_boxes,
@@ -121,7 +121,7 @@ extern "C" int fsg_dense_step_levels(const fsg_step_levels_io* io, const fsg_hea
                          mc->num_picky_thresholds, hp->box_weights, nullptr, nullptr, nullptr, io->gt_classes, io->mask,
                          nullptr, io->matched_idx32, nullptr, &bl, hp->temperature, io->stats,
                          sharded ? h_peer : nullptr, ws, off_loss, 3,
-                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl), nullptr, 0, stream);
+                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl), stream);
   if (st != FSG_OK) return st;
   st = loss_main_levels_enqueue(h_levels, num_levels, A, nullptr, io->anchors, io->anchor_image_stride, io->gt_boxes,
                                 io->gt_offsets, io->matched_idx32, io->gt_classes, io->mask, nullptr, N, R, hp,

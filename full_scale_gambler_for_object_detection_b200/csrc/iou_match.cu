@@ -260,6 +260,13 @@ struct PassAEpi {
   float* part_s;
 };
 
+// order-preserving float <-> int (its own inverse), so that redux.sync reduces a float min/max in one instruction
+__device__ __forceinline__ int float_key(float f) {
+  const int k = __float_as_int(f);
+  return k ^ ((k >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
 template <int U>
 __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
     const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
@@ -271,13 +278,13 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
   __shared__ unsigned s_max[kGtChunk];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int64_t s_cls[kSmallM];
-  grid_launch_dependents();   // pass B may be scheduled as this grid's CTAs retire (it waits for the whole grid)
+  grid_launch_dependents();   // the next kernel may be scheduled as this grid's CTAs retire (it waits for the whole grid)
 
   const int n = blockIdx.y;
   const int m0 = gt_offsets[n];
   const int M = gt_offsets[n + 1] - m0;
   const int tid = threadIdx.x;
-  const int lane = tid & 31, wid = tid >> 5;
+  const int lane = tid & 31;
   const int64_t base = (int64_t)blockIdx.x * (kMatchBlock * U);
   const float4* a_img = anchors + (int64_t)n * anchor_stride4;
 
@@ -295,40 +302,44 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
     bi[u] = 0;     // and strict '>' keeps the lowest GT index among ties (matcher.py:86)
   }
 
-  if (M <= kSmallM) {
-    // ---- few GT (the detection-training case).  The M boxes and areas arrive by one parallel load (M broadcast
-    //      loads inside the loop would each expose a full L2 latency); per-GT maxima are merged per CTA in shared
-    //      memory first, because same-address atomics serialise in L2 (~27 cycles each).
+  unsigned live = 0xffffffffu;   // few-GT images: the GT whose box reaches into this warp's anchors
+  const bool small = M <= kSmallM;
+  if (small) {
+    // ---- few GT (the detection-training case).  Lane g holds GT g (one parallel load; M broadcast loads inside
+    //      the loop would each expose a full L2 latency) and hands it out by shuffles; per-GT maxima are merged per
+    //      CTA in shared memory first, because same-address atomics serialise in L2 (~27 cycles each).
+    const bool has_g = lane < M;
+    float4 myG = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_g) myG = gt_boxes[m0 + lane];
     if (tid < kSmallM) {
       s_max[tid] = 0u;
-      if (tid < M) {
-        const float4 G = gt_boxes[m0 + tid];
-        s_gt[tid] = G;
-        s_area[tid] = box_area(G);
-        s_cls[tid] = E.gt_class_ids ? E.gt_class_ids[m0 + tid] : 0;
-      }
+      if (tid < M) s_cls[tid] = E.gt_class_ids ? E.gt_class_ids[m0 + tid] : 0;
     }
     // warp-level culling: consecutive anchors are neighbouring cells of one pyramid level, so the warp's anchors
     // span a small rectangle, and a ground truth that does not reach into it has IoU exactly 0 with every lane --
     // it can neither beat a running best (which starts at 0) nor raise a per-GT maximum.  Exact, not a heuristic.
-    float bx0 = __int_as_float(0x7f800000), by0 = bx0, bx1 = -bx0, by1 = -bx0;
+    // All GT are tested at once (lane g tests GT g) and only the survivors are walked.
+    int kx0 = 0x7fffffff, ky0 = 0x7fffffff, kx1 = (int)0x80000000, ky1 = (int)0x80000000;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (base + u * kMatchBlock + tid < R) {
-        bx0 = fminf(bx0, a[u].x); by0 = fminf(by0, a[u].y);
-        bx1 = fmaxf(bx1, a[u].z); by1 = fmaxf(by1, a[u].w);
+        kx0 = min(kx0, float_key(a[u].x)); ky0 = min(ky0, float_key(a[u].y));
+        kx1 = max(kx1, float_key(a[u].z)); ky1 = max(ky1, float_key(a[u].w));
       }
     }
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) {
-      bx0 = fminf(bx0, __shfl_xor_sync(kFull, bx0, sft)); by0 = fminf(by0, __shfl_xor_sync(kFull, by0, sft));
-      bx1 = fmaxf(bx1, __shfl_xor_sync(kFull, bx1, sft)); by1 = fmaxf(by1, __shfl_xor_sync(kFull, by1, sft));
-    }
+    const float bx0 = key_float(__reduce_min_sync(kFull, kx0)), by0 = key_float(__reduce_min_sync(kFull, ky0));
+    const float bx1 = key_float(__reduce_max_sync(kFull, kx1)), by1 = key_float(__reduce_max_sync(kFull, ky1));
+    const float my_ga = box_area(myG);
+    // (NaN never culls; a warp without a valid anchor has a NaN rectangle and culls nothing, harmlessly)
+    const bool hit = has_g && !(myG.z <= bx0 || myG.x >= bx1 || myG.w <= by0 || myG.y >= by1);
+    live = __ballot_sync(kFull, hit);
     __syncthreads();
-    for (int g = 0; g < M; ++g) {
-      const float4 G = s_gt[g];
-      if (G.z <= bx0 || G.x >= bx1 || G.w <= by0 || G.y >= by1) continue;   // warp-uniform; NaN never culls
-      const float ga = s_area[g];
+    for (unsigned rem = live; rem != 0u; rem &= rem - 1u) {   // ascending g: ties keep the lowest GT index
+      const int g = __ffs(rem) - 1;
+      float4 G;
+      G.x = __shfl_sync(kFull, myG.x, g); G.y = __shfl_sync(kFull, myG.y, g);
+      G.z = __shfl_sync(kFull, myG.z, g); G.w = __shfl_sync(kFull, myG.w, g);
+      const float ga = __shfl_sync(kFull, my_ga, g);
       const float known = __uint_as_float(s_max[g]);  // what this CTA found so far: only makes the filter looser
       float m = 0.f;
 #pragma unroll
@@ -396,6 +407,8 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
   const bool has_ids = E.gt_class_ids != nullptr, has_bets = E.bets != nullptr;
   int fg = 0;
   float w_part = 0.f;
+  int8_t l1 = 0, l2 = 0;
+  int64_t cls = 0, msk = 0;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int64_t r = base + u * kMatchBlock + tid;
@@ -404,17 +417,18 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
     const float val = (M > 0) ? bv[u] : 0.f;
     best_val[o] = val;
     best_idx[o] = bi[u];
-    int8_t l1, l2 = 0;
-    int64_t cls, msk = 0;
     int id = bi[u];
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     if (M > 0) {
-      l1 = band_label_reg(E.br, val);
-      if (E.has_picky) l2 = band_label_reg(E.pbr, val);
-      cls = (M <= kSmallM) ? s_cls[id] : (has_ids ? E.gt_class_ids[m0 + id] : 0);
-      if (l1 == 0) cls = E.num_classes;   // retinanet.py:356
-      if (l1 == -1) cls = -1;             // :360
-      msk = (l2 == 1) ? 1 : 0;            // :417-423
+      // a warp no ground truth reaches into (most of them) has IoU 0 / argmax 0 everywhere: classify once
+      if (u == 0 || live != 0u) {
+        l1 = band_label_reg(E.br, val);
+        l2 = E.has_picky ? band_label_reg(E.pbr, val) : (int8_t)0;
+        cls = small ? s_cls[id] : (has_ids ? E.gt_class_ids[m0 + id] : 0);
+        if (l1 == 0) cls = E.num_classes;   // retinanet.py:356
+        if (l1 == -1) cls = -1;             // :360
+        msk = (l2 == 1) ? 1 : 0;            // :417-423
+      }
       if (need_deltas) d = encode_deltas(a[u], gt_boxes[m0 + id], E.wx, E.wy, E.ww, E.wh);
     } else {                              // matcher.py:70-80, retinanet.py:362-363, :425
       l1 = E.lab0;
@@ -434,9 +448,8 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
     if (has_bets) w_part += __fadd_rn(__fmul_rn(bet[u], (float)msk), E.temperature);  // gambler_heads.py:569,304
     else if (lv.num_levels > 0 && msk != 0) w_part += __fmul_rn(bet_at(lv, n, r), (float)msk);  // + R*T at the fold
   }
-  if (E.part_cnt == nullptr) return;
-  // one partial per CTA in a fixed slot; the fold kernel sums the slots in a fixed order => run-to-run deterministic
-  block_partial(fg, w_part, E.part_cnt, E.part_s, (int64_t)n * gridDim.x + blockIdx.x);
+  // one partial per CTA in a fixed slot; the finish kernel sums the slots in a fixed order => run-to-run deterministic
+  if (E.part_cnt != nullptr) block_partial(fg, w_part, E.part_cnt, E.part_s, (int64_t)n * gridDim.x + blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -652,37 +665,61 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
   }
 
   if (part_cnt == nullptr) return;
-  // corrections of this CTA in its fixed slot (zero for almost every CTA); folded by match_fold_kernel
-  block_partial(dfg, dw, part_cnt, part_s, (int64_t)n * gridDim.x + blockIdx.x);
+  // corrections of this WARP in its own slot, written only where there is something to add (the slots are zeroed by
+  // the memset in front of pass A): almost every warp retires here without a barrier; folded by match_fold_kernel
+  const int cw = __reduce_add_sync(kFull, dfg);
+  const float sw = warp_sum(dw);
+  if (lane == 0 && (cw != 0 || sw != 0.f)) {
+    const int64_t slot = ((int64_t)n * gridDim.x + blockIdx.x) * kWarpsPerBlock + wid;
+    part_cnt[slot] = cw;
+    part_s[slot] = sw;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // Fold of the loss pre-pass sums: num_foreground and S[n] = sum_r (bet*mask + T).  One CTA per image adds pass A's
-// per-warp partials and pass B's corrections in a fixed order (run-to-run deterministic); the last CTA to finish
-// adds the images up in image order and runs the peer exchange.  A kernel of its own because 1000+ CTAs each
+// per-CTA partials and pass B's per-warp corrections in a fixed order (run-to-run deterministic); the last CTA to
+// finish adds the images up in image order and runs the peer exchange.  A kernel of its own because 1000+ CTAs each
 // ending in fence + atomic + barrier cost pass B more than all of its real work.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMatchBlock) match_fold_kernel(
-    int N, int64_t R, const int* __restrict__ part_cnt_a, const float* __restrict__ part_s_a, int slots_a,
-    const int* __restrict__ part_cnt_b, const float* __restrict__ part_s_b, int slots_b, float temperature,
-    int levels_mode, double* __restrict__ img_cnt, unsigned* __restrict__ done_counter, double* __restrict__ stats,
-    const fsg_peer_ctx peer, const int peer_wait) {
+struct FoldArgs {
+  int N;
+  int64_t R;
+  int nb_a;
+  const int* part_cnt_a;       // pass A (N, nb_a)
+  const float* part_s_a;
+  const int* part_cnt_b;       // pass B (N, slots_b) or NULL: not launched
+  const float* part_s_b;
+  int slots_b, levels_mode;
+  float temperature;
+  double* img_cnt;
+  unsigned* done_counter;
+  double* stats;
+  int peer_wait;
+};
+
+__global__ void __launch_bounds__(kMatchBlock) match_fold_kernel(const FoldArgs F, const fsg_peer_ctx peer) {
   grid_launch_dependents();
   grid_dependency_sync();
   __shared__ double s_tc[kWarpsPerBlock], s_ts[kWarpsPerBlock];
   __shared__ bool s_last;
   const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t R = F.R;
+  double* stats = F.stats;
+  double* img_cnt = F.img_cnt;
+  unsigned* done_counter = F.done_counter;
+  const int N = F.N;
   {
     double c = 0.0, sacc = 0.0;
-    for (int b = tid; b < slots_a; b += kMatchBlock) {
-      c += (double)part_cnt_a[(int64_t)n * slots_a + b];
-      sacc += (double)part_s_a[(int64_t)n * slots_a + b];
+    for (int b = tid; b < F.nb_a; b += kMatchBlock) {
+      c += (double)F.part_cnt_a[(int64_t)n * F.nb_a + b];
+      sacc += (double)F.part_s_a[(int64_t)n * F.nb_a + b];
     }
-    if (part_cnt_b != nullptr) {
-      for (int b = tid; b < slots_b; b += kMatchBlock) {
-        c += (double)part_cnt_b[(int64_t)n * slots_b + b];
-        sacc += (double)part_s_b[(int64_t)n * slots_b + b];
+    if (F.part_cnt_b != nullptr) {
+      for (int b = tid; b < F.slots_b; b += kMatchBlock) {
+        c += (double)F.part_cnt_b[(int64_t)n * F.slots_b + b];
+        sacc += (double)F.part_s_b[(int64_t)n * F.slots_b + b];
       }
     }
     c = warp_sum_d(c);
@@ -693,7 +730,7 @@ __global__ void __launch_bounds__(kMatchBlock) match_fold_kernel(
   if (tid == 0) {
     double c = 0.0, sacc = 0.0;
     for (int w = 0; w < kWarpsPerBlock; ++w) { c += s_tc[w]; sacc += s_ts[w]; }
-    if (levels_mode) sacc += (double)R * (double)temperature;   // per-level bets: S[n] = R*T + sum bet*mask
+    if (F.levels_mode) sacc += (double)R * (double)F.temperature;   // per-level bets: S[n] = R*T + sum bet*mask
     stats[FSG_STATS_HEADER + n] = sacc;
     img_cnt[n] = c;
     __threadfence();
@@ -742,7 +779,7 @@ __global__ void __launch_bounds__(kMatchBlock) match_fold_kernel(
     unsigned long long* fl = reinterpret_cast<unsigned long long*>(dst + 2);
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(ep) : "memory");
   }
-  if (!peer_wait) {
+  if (!F.peer_wait) {
     // fsg_dense_step: the sums are only POSTED here; every CTA of the loss main pass polls this rank's mailbox
     // (stats[0..1] stay local until that kernel's last CTA stores the global sums)
     __syncthreads();
@@ -872,22 +909,22 @@ extern "C" int fsg_matcher(const float* mqm, int64_t M, int64_t N, const float* 
 
 namespace {
 struct MatchWs {
-  size_t off_counter, off_gtmax, off_val, off_idx, off_pcnt, off_ps, off_pcnt_a, off_ps_a, off_icnt, total;
+  size_t off_counter, off_gtmax, off_pcnt, off_ps, off_val, off_idx, off_pcnt_a, off_ps_a, off_icnt, total;
   int nb;
 };
 MatchWs match_ws_layout(int N, int64_t R, int64_t sum_M) {
   MatchWs w;
   w.nb = (int)ceil_div(R > 0 ? R : 1, kMatchBlock * kPassBU);
   // per-CTA partial-sum slots of pass B and of pass A (at most: 2 anchors per thread)
-  const size_t slots = (size_t)N * w.nb;
+  const size_t slots = (size_t)N * w.nb * kWarpsPerBlock;
   const size_t slots_a = (size_t)N * (size_t)ceil_div(R > 0 ? R : 1, kMatchBlock * 2);
   size_t o = 0;
   w.off_counter = o; o += align_up(sizeof(unsigned) * (size_t)(N + 1), 16);
   w.off_gtmax = o;   o += align_up(sizeof(unsigned) * (size_t)(sum_M > 0 ? sum_M : 1), 16);
+  w.off_pcnt = o;    o += align_up(sizeof(int) * slots, 16);       // pass B's slots: written only where non-zero,
+  w.off_ps = o;      o += align_up(sizeof(float) * slots, 16);     // [0, off_val) is zeroed before pass A
   w.off_val = o;     o += align_up(sizeof(float) * (size_t)N * (size_t)R, 16);
   w.off_idx = o;     o += align_up(sizeof(int32_t) * (size_t)N * (size_t)R, 16);
-  w.off_pcnt = o;    o += align_up(sizeof(int) * slots, 16);
-  w.off_ps = o;      o += align_up(sizeof(float) * slots, 16);
   w.off_pcnt_a = o;  o += align_up(sizeof(int) * slots_a, 16);
   w.off_ps_a = o;    o += align_up(sizeof(float) * slots_a, 16);
   w.off_icnt = o;    o += align_up(sizeof(double) * (size_t)N, 16);
@@ -913,8 +950,7 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
                   float* gt_deltas, int32_t* matched_idx32, const float* bets,
                   const fsg_bet_levels* h_bet_levels, float temperature,
                   double* stats, const fsg_peer_ctx* h_peer, void* workspace,
-                  size_t workspace_bytes, int phases, int flags, const void* prefetch, size_t prefetch_bytes,
-                  fsg_stream_t stream) {
+                  size_t workspace_bytes, int phases, int flags, fsg_stream_t stream) {
   if (N <= 0 || R < 0 || sum_M < 0 || !gt_offsets) return FSG_ERR_INVALID_ARG;
   if (phases < 1 || phases > 3) return FSG_ERR_INVALID_ARG;
   BetLevels lv = {};
@@ -979,7 +1015,6 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
   const float wx = h_box_weights ? h_box_weights[0] : 1.f, wy = h_box_weights ? h_box_weights[1] : 1.f;
   const float ww = h_box_weights ? h_box_weights[2] : 1.f, wh = h_box_weights ? h_box_weights[3] : 1.f;
 
-  (void)prefetch; (void)prefetch_bytes;
   // anchors per thread in pass A: 2 for the few-GT training case (more CTAs in flight), 4 when the batch is crowded
   // (each staged GT box is reused more); the same choice sizes pass A's partial-sum slots in both phases
   const bool few_gt = sum_M <= (int64_t)N * kSmallM;
@@ -1021,11 +1056,14 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
     FSG_LAUNCH_CHECK();
   }
   if (!stats) return FSG_OK;
-  launch_pdl(match_fold_kernel, dim3((unsigned)N), dim3(kMatchBlock), 0, s, pdl, N, R,
-             (const int*)(ws + w.off_pcnt_a), (const float*)(ws + w.off_ps_a), nb_a,
-             patch ? (const int*)(ws + w.off_pcnt) : (const int*)nullptr, (const float*)(ws + w.off_ps),
-             nb_b, temperature, lv.num_levels > 0 ? 1 : 0, (double*)(ws + w.off_icnt), counter, stats,
-             peer, (flags & kMatchPeerPolled) ? 0 : 1);
+  FoldArgs f = {};
+  f.N = N; f.R = R; f.nb_a = nb_a;
+  f.part_cnt_a = (const int*)(ws + w.off_pcnt_a); f.part_s_a = (const float*)(ws + w.off_ps_a);
+  f.part_cnt_b = patch ? (const int*)(ws + w.off_pcnt) : nullptr; f.part_s_b = (const float*)(ws + w.off_ps);
+  f.slots_b = nb_b * kWarpsPerBlock; f.levels_mode = lv.num_levels > 0 ? 1 : 0; f.temperature = temperature;
+  f.img_cnt = (double*)(ws + w.off_icnt); f.done_counter = counter; f.stats = stats;
+  f.peer_wait = (flags & kMatchPeerPolled) ? 0 : 1;
+  launch_pdl(match_fold_kernel, dim3((unsigned)N), dim3(kMatchBlock), 0, s, pdl, f, peer);
   FSG_LAUNCH_CHECK();
   return FSG_OK;
 }
@@ -1047,7 +1085,7 @@ extern "C" int fsg_match_anchors_ex(const float* anchors, int64_t R, int64_t anc
                        h_thresholds, h_labels, num_thresholds, allow_lq, h_picky_thresholds, h_picky_labels,
                        num_picky_thresholds, h_box_weights, matches, match_labels, picky_labels, gt_classes_out,
                        mask_out, gt_deltas, matched_idx32, bets, h_bet_levels, temperature, stats, h_peer, workspace,
-                       workspace_bytes, phases, 0, nullptr, 0, stream);
+                       workspace_bytes, phases, 0, stream);
 }
 
 extern "C" int fsg_box2box_get_deltas(const float* src_boxes, const float* target_boxes, int64_t n,

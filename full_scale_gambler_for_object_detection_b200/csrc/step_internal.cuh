@@ -6,7 +6,7 @@
 namespace fsg {
 
 constexpr int kMatchPeerPolled = 1;   // match_enqueue flag: post the peer exchange, the consumer kernel polls it
-constexpr int kMatchPdl = 2;          // launch pass B under programmatic dependent launch
+constexpr int kMatchPdl = 2;          // launch pass B and the fold under programmatic dependent launch
 
 int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride, const float* gt_boxes,
                   const int64_t* gt_class_ids, const int32_t* gt_offsets, int N, int64_t sum_M, int num_classes,
@@ -16,8 +16,7 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride, 
                   int64_t* gt_classes_out, int64_t* mask_out, float* gt_deltas, int32_t* matched_idx32,
                   const float* bets, const fsg_bet_levels* h_bet_levels, float temperature, double* stats,
                   const fsg_peer_ctx* h_peer, void* workspace, size_t workspace_bytes, int phases, int flags,
-                  const void* prefetch, size_t prefetch_bytes, fsg_stream_t stream);
-// prefetch / prefetch_bytes: pass A pulls this memory (the head of the next kernel's input) into L2 while it runs
+                  fsg_stream_t stream);
 
 constexpr int kLossPdl = 1;            // launch under programmatic dependent launch (the kernel waits on-device)
 constexpr int kLossCounterZeroed = 2;  // the caller already zeroed the first 16 bytes of the loss workspace
