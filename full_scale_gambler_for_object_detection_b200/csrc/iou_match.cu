@@ -63,12 +63,13 @@ __device__ __forceinline__ bool may_reach(float inter, float uni, float bound) {
 // "both extents positive" test (a clamped extent of 0 gives inter == 0 -> IoU exactly 0, which can never
 // beat a running best that starts at 0 nor raise a per-GT maximum).
 __device__ __forceinline__ void pair_update(float4 G, float ga, float4 a, float aa, float known, int gidx,
-                                            float& bv, int& bi, float& m) {
+                                            float& bv, int& bi, float& m, int& ov) {
   const float w = __fsub_rn(fminf(G.z, a.z), fmaxf(G.x, a.x));
   const float h = __fsub_rn(fminf(G.w, a.w), fmaxf(G.y, a.y));
   if (w > 0.f && h > 0.f) {
     const float inter = __fmul_rn(w, h);
     if (inter > 0.f) {   // the product of two tiny positives can underflow to 0
+      ++ov;              // ground truth with IoU > 0: pass B needs no second look at an anchor that has only one
       const float uni = __fsub_rn(__fadd_rn(ga, aa), inter);
       if (may_reach(inter, uni, fminf(bv, known))) {
         const float v = __fdiv_rn(inter, uni);
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(256) matrix_match_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------
 // Fused path, pass A: per-anchor max/argmax over the image's GT + per-GT max over anchors
 // ------------------------------------------------------------------------------------------
+constexpr int kMultiOverlap = 1 << 30;   // best_idx flag: the anchor has IoU > 0 with two or more ground truth
 constexpr int kSmallM = 32;  // images with at most this many GT: boxes staged by one parallel load, warp-level culling
 
 struct MatchOut {
@@ -290,9 +292,10 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
 
   float4 a[U];
   float aa[U], bv[U], bet[U];
-  int bi[U];
+  int bi[U], ov[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
+    ov[u] = 0;
     int64_t r = base + u * kMatchBlock + tid;
     a[u] = (r < R) ? a_img[r] : make_float4(0.f, 0.f, 0.f, 0.f);
     // the bet is only needed by the epilogue; loading it now hides its HBM latency behind the GT loop
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
       const float known = __uint_as_float(s_max[g]);  // what this CTA found so far: only makes the filter looser
       float m = 0.f;
 #pragma unroll
-      for (int u = 0; u < U; ++u) pair_update(G, ga, a[u], aa[u], known, g, bv[u], bi[u], m);
+      for (int u = 0; u < U; ++u) pair_update(G, ga, a[u], aa[u], known, g, bv[u], bi[u], m, ov[u]);
       if (__any_sync(kFull, m > known)) {
         const unsigned wm = __reduce_max_sync(kFull, __float_as_uint(m));
         if (lane == 0) atomicMax(&s_max[g], wm);
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
         const float known = __uint_as_float(s_max[g]);
         float m = 0.f;
 #pragma unroll
-        for (int u = 0; u < U; ++u) pair_update(G, ga, a[u], aa[u], known, c + g, bv[u], bi[u], m);
+        for (int u = 0; u < U; ++u) pair_update(G, ga, a[u], aa[u], known, c + g, bv[u], bi[u], m, ov[u]);
         // padding lanes (r >= R) hold a zero box: no overlap, harmless for the max
         if (__any_sync(kFull, m > known)) {
           const unsigned wm = __reduce_max_sync(kFull, __float_as_uint(m));
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
     const int64_t o = (int64_t)n * R + r;
     const float val = (M > 0) ? bv[u] : 0.f;
     best_val[o] = val;
-    best_idx[o] = bi[u];
+    best_idx[o] = bi[u] | (ov[u] >= 2 ? kMultiOverlap : 0);
     int id = bi[u];
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     if (M > 0) {
@@ -509,9 +512,20 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
 #pragma unroll
   for (int u = 0; u < U; ++u) lq[u] = false;
 
+  int dfg = 0;       // what the promotions do to num_foreground and to the bet normaliser
+  float dw = 0.f;
   if (allow_lq && M > 0 && M <= kSmallM) {
-    // ---- few GT: lane g holds GT g's maximum and box (one parallel load, then shuffles), warp-level control flow
-    const float my_gm = (lane < M) ? __uint_as_float(gt_max[m0 + lane]) : __int_as_float(0x7f800000);
+    // ---- few GT: lane g holds GT g's maximum, box and class (one parallel load, then shuffles), warp-level control
+    //      flow, and every load issued as early as its address is known: the warps that do find candidates are the
+    //      critical path of the whole kernel (a CTA's slot is held until its slowest warp retires).
+    float my_gm = __int_as_float(0x7f800000);
+    float4 myG = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t my_cls = 0;
+    if (lane < M) {
+      my_gm = __uint_as_float(gt_max[m0 + lane]);
+      myG = gt_boxes[m0 + lane];
+      my_cls = gt_class_ids ? gt_class_ids[m0 + lane] : 0;
+    }
     float mn = my_gm;
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, sft));
@@ -523,20 +537,66 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
       any_cand |= cand[u];
     }
     if (__any_sync(kFull, any_cand)) {
-      float4 myG = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane < M) myG = gt_boxes[m0 + lane];
-      // candidates are rare: one anchor slot at a time keeps a single box live instead of U of them
+      // the candidates' argmax (+ overlap flag), box and bet: independent loads, all in flight together
+      int bix[U];
+      float4 a[U];
+      float betv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (!__any_sync(kFull, cand[u])) continue;
-        const float4 a = cand[u] ? a_img[r_of(u)] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float aa = box_area(a);
-        for (int g = 0; g < M; ++g) {
-          const float gm = __shfl_sync(kFull, my_gm, g);
-          float4 G;
-          G.x = __shfl_sync(kFull, myG.x, g); G.y = __shfl_sync(kFull, myG.y, g);
-          G.z = __shfl_sync(kFull, myG.z, g); G.w = __shfl_sync(kFull, myG.w, g);
-          if (cand[u] && gm <= val[u] && iou_exact(G, box_area(G), a, aa) == gm) lq[u] = true;  // matcher.py:114-116
+        const int64_t r = r_of(u);
+        bix[u] = cand[u] ? best_idx[img + r] : 0;
+        a[u] = cand[u] ? a_img[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+        betv[u] = (cand[u] && bets != nullptr) ? bets[img + r] : 0.f;
+      }
+      if (mn == 0.f) {
+        // a GT that overlaps no anchor: every anchor has IoU 0 == its maximum 0 and is promoted (matcher.py:114-116)
+#pragma unroll
+        for (int u = 0; u < U; ++u) lq[u] = cand[u];
+      } else {
+        // IoU(g, a) <= best(a), so GT g can promote a only if max(g) <= best(a).  For g = argmax(a) that is the
+        // test best(a) == max(g), no recomputation; any other g needs IoU(g, a) > 0, i.e. an anchor that pass A
+        // flagged as overlapping two or more GT -- only those (a fraction of the candidates) are looked at again.
+        bool hard[U];
+        bool any_hard = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float gmb = __shfl_sync(kFull, my_gm, bix[u] & 31);
+          lq[u] = cand[u] && val[u] == gmb;
+          hard[u] = cand[u] && !lq[u] && (bix[u] & kMultiOverlap) != 0;
+          any_hard |= hard[u];
+        }
+        if (__any_sync(kFull, any_hard)) {
+          const float my_ga = box_area(myG);
+          for (int g = 0; g < M; ++g) {
+            const float gm = __shfl_sync(kFull, my_gm, g);
+            float4 G;
+            G.x = __shfl_sync(kFull, myG.x, g); G.y = __shfl_sync(kFull, myG.y, g);
+            G.z = __shfl_sync(kFull, myG.z, g); G.w = __shfl_sync(kFull, myG.w, g);
+            const float ga = __shfl_sync(kFull, my_ga, g);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (hard[u] && gm <= val[u] && iou_exact(G, ga, a[u], box_area(a[u])) == gm) lq[u] = true;  // :114-116
+          }
+        }
+      }
+      // patch (label 1 whatever the band said; `matches` is never changed, matcher.py:131-132)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t cls = __shfl_sync(kFull, my_cls, bix[u] & 31);
+        if (!lq[u]) continue;   // (lq implies live)
+        lq[u] = false;          // done here, not by the generic loop below
+        const int64_t r = r_of(u);
+        const int64_t o = img + r;
+        if (band_label_reg(br, val[u]) != 1) {
+          if (out.match_labels) out.match_labels[o] = 1;
+          if (out.gt_classes) out.gt_classes[o] = cls;
+          dfg += 1;             // was background or ignored, is foreground now
+        }
+        if (has_picky && band_label_reg(pbr, val[u]) != 1) {
+          if (out.picky_labels) out.picky_labels[o] = 1;
+          if (out.mask) out.mask[o] = 1;
+          if (bets) dw += __fadd_rn(betv[u], temperature) - temperature;   // (bet*1 + T) - (bet*0 + T)
+          else if (lv.num_levels > 0) dw += bet_at(lv, n, r);
         }
       }
     }
@@ -644,8 +704,6 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
 
   // ---- patch the anchors the low-quality rule promotes (label 1 whatever their band said; `matches` is never
   //      changed, matcher.py:131-132) and note what that does to num_foreground and to the bet normaliser
-  int dfg = 0;
-  float dw = 0.f;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (!lq[u]) continue;   // (lq implies live)
@@ -653,7 +711,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     const int64_t o = img + r;
     if (band_label_reg(br, val[u]) != 1) {
       if (out.match_labels) out.match_labels[o] = 1;
-      if (out.gt_classes) out.gt_classes[o] = gt_class_ids ? gt_class_ids[m0 + best_idx[o]] : 0;
+      if (out.gt_classes) out.gt_classes[o] = gt_class_ids ? gt_class_ids[m0 + (best_idx[o] & (kMultiOverlap - 1))] : 0;
       dfg += 1;             // was background or ignored, is foreground now
     }
     if (has_picky && band_label_reg(pbr, val[u]) != 1) {

@@ -56,3 +56,9 @@ print("floor (y += 1 on N*R floats) %.1f us" % graph_us(lambda: y.add_(1.0)))
 print("K1 pass A            %.1f us" % graph_us(k1(1)))
 print("K1 pass B + fold     %.1f us" % graph_us(k1(2)))
 print("K1 A + B + fold      %.1f us" % graph_us(k1(3)))
+nobets = lambda ph, lq: (lambda: fsg.ops.match_anchors(anchors, gt, K, phases=ph, workspace=ws, out=out,
+                                                       allow_low_quality_matches=lq))
+print("K1 pass B alone      %.1f us   (no pre-pass sums: no fold)" % graph_us(nobets(2, True)))
+print("K1 fold alone        %.1f us   (allow_low_quality_matches=False: no pass B)" % graph_us(
+    lambda: fsg.ops.match_anchors(anchors, gt, K, bets=bets, temperature=0.1, phases=2, workspace=ws, out=out,
+                                  allow_low_quality_matches=False)))
