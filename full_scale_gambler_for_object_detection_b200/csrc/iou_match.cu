@@ -472,7 +472,6 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     const BandsReg br, const BandsReg pbr, const BetLevels lv) {
   static_assert(U % 4 == 0, "runs of 4 consecutive anchors per thread");
   grid_launch_dependents();
-  grid_dependency_sync();     // (programmatic dependent launch behind pass A in fsg_dense_step)
   __shared__ __align__(16) float4 s_gt[kGtChunk];
   __shared__ float s_area[kGtChunk];
   __shared__ float s_max[kGtChunk];
@@ -488,6 +487,15 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
   const int64_t base = (int64_t)blockIdx.x * (kMatchBlock * U);
   const int64_t img = (int64_t)n * R;
   const float4* a_img = anchors + (int64_t)n * anchor_stride4;
+  // few GT: lane g holds GT g's box and class.  These are inputs of the step, not results of pass A, so under
+  // programmatic dependent launch they are fetched while pass A still drains.
+  float4 myG = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t my_cls = 0;
+  if (allow_lq && M <= kSmallM && lane < M) {
+    myG = gt_boxes[m0 + lane];
+    my_cls = gt_class_ids ? gt_class_ids[m0 + lane] : 0;
+  }
+  grid_dependency_sync();     // (programmatic dependent launch behind pass A in fsg_dense_step)
 
   // thread t owns two runs of 4 consecutive anchors: base + j*1024 + 4t .. +3 (16-byte loads of the best IoUs)
   auto r_of = [&](int u) -> int64_t { return base + (int64_t)(u >> 2) * (kMatchBlock * 4) + tid * 4 + (u & 3); };
@@ -519,13 +527,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     //      flow, and every load issued as early as its address is known: the warps that do find candidates are the
     //      critical path of the whole kernel (a CTA's slot is held until its slowest warp retires).
     float my_gm = __int_as_float(0x7f800000);
-    float4 myG = make_float4(0.f, 0.f, 0.f, 0.f);
-    int64_t my_cls = 0;
-    if (lane < M) {
-      my_gm = __uint_as_float(gt_max[m0 + lane]);
-      myG = gt_boxes[m0 + lane];
-      my_cls = gt_class_ids ? gt_class_ids[m0 + lane] : 0;
-    }
+    if (lane < M) my_gm = __uint_as_float(gt_max[m0 + lane]);
     float mn = my_gm;
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, sft));
