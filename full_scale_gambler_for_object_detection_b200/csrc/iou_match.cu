@@ -225,24 +225,6 @@ __device__ __forceinline__ float bet_at(const BetLevels& lv, int n, int64_t r) {
 
 constexpr int kWarpsPerBlock = kMatchBlock / 32;
 
-// (count, sum) of the CTA into slot `slot`: warp shuffles, one barrier, warps summed in a fixed order
-__device__ __forceinline__ void block_partial(int cnt, float sum, int* part_cnt, float* part_s, int64_t slot) {
-  __shared__ int s_pi[kWarpsPerBlock];
-  __shared__ float s_pf[kWarpsPerBlock];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int cw = __reduce_add_sync(kFull, cnt);
-  const float sw = warp_sum(sum);
-  if (lane == 0) { s_pi[wid] = cw; s_pf[wid] = sw; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int ci = 0;
-    float cs = 0.f;
-    for (int w = 0; w < kWarpsPerBlock; ++w) { ci += s_pi[w]; cs += s_pf[w]; }
-    part_cnt[slot] = ci;
-    part_s[slot] = cs;
-  }
-}
-
 // Every thread of pass A has seen ALL ground truth of its image when its loop ends, so its best IoU / argmax are
 // final and the threshold bands (matcher.py:88-92), the class relabel (retinanet.py:354-360), the picky mask
 // (:417-425), get_deltas and the loss pre-pass sums can be produced right there.  What pass A cannot know is the
@@ -269,7 +251,9 @@ __device__ __forceinline__ int float_key(float f) {
 }
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
 
-template <int U>
+// STEP: the output set of the fused training step (gt_classes, mask, matched_idx32; class ids given) known at compile
+// time -- the per-anchor tests of seven output pointers were 11 % of the kernel's instructions.
+template <int U, bool STEP>
 __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
     const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
     const float4* __restrict__ gt_boxes, const int32_t* __restrict__ gt_offsets,
@@ -405,11 +389,11 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
 
 
   // ---- epilogue: everything that depends only on this anchor's own best IoU
-  const bool need_deltas = (E.out.gt_deltas != nullptr);
-  const bool o_matches = E.out.matches != nullptr, o_labels = E.out.match_labels != nullptr;
-  const bool o_picky = E.out.picky_labels != nullptr, o_cls = E.out.gt_classes != nullptr;
-  const bool o_mask = E.out.mask != nullptr, o_idx32 = E.out.matched_idx32 != nullptr;
-  const bool has_ids = E.gt_class_ids != nullptr, has_bets = E.bets != nullptr;
+  const bool need_deltas = !STEP && (E.out.gt_deltas != nullptr);
+  const bool o_matches = !STEP && E.out.matches != nullptr, o_labels = !STEP && E.out.match_labels != nullptr;
+  const bool o_picky = !STEP && E.out.picky_labels != nullptr, o_cls = STEP || E.out.gt_classes != nullptr;
+  const bool o_mask = STEP || E.out.mask != nullptr, o_idx32 = STEP || E.out.matched_idx32 != nullptr;
+  const bool has_ids = STEP || E.gt_class_ids != nullptr, has_bets = E.bets != nullptr;
   int fg = 0;
   float w_part = 0.f;
   int8_t l1 = 0, l2 = 0;
@@ -453,8 +437,17 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
     if (has_bets) w_part += __fadd_rn(__fmul_rn(bet[u], (float)msk), E.temperature);  // gambler_heads.py:569,304
     else if (lv.num_levels > 0 && msk != 0) w_part += __fmul_rn(bet_at(lv, n, r), (float)msk);  // + R*T at the fold
   }
-  // one partial per CTA in a fixed slot; the finish kernel sums the slots in a fixed order => run-to-run deterministic
-  if (E.part_cnt != nullptr) block_partial(fg, w_part, E.part_cnt, E.part_s, (int64_t)n * gridDim.x + blockIdx.x);
+  // one partial per WARP in a fixed slot (no barrier, no serial tail in any of the 2000 CTAs); the fold kernel sums
+  // the slots in a fixed order => run-to-run deterministic
+  if (E.part_cnt != nullptr) {
+    const int cw = __reduce_add_sync(kFull, fg);
+    const float sw = warp_sum(w_part);
+    if (lane == 0) {
+      const int64_t slot = ((int64_t)n * gridDim.x + blockIdx.x) * kWarpsPerBlock + (tid >> 5);
+      E.part_cnt[slot] = cw;
+      E.part_s[slot] = sw;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -979,7 +972,7 @@ MatchWs match_ws_layout(int N, int64_t R, int64_t sum_M) {
   w.nb = (int)ceil_div(R > 0 ? R : 1, kMatchBlock * kPassBU);
   // per-CTA partial-sum slots of pass B and of pass A (at most: 2 anchors per thread)
   const size_t slots = (size_t)N * w.nb * kWarpsPerBlock;
-  const size_t slots_a = (size_t)N * (size_t)ceil_div(R > 0 ? R : 1, kMatchBlock * 2);
+  const size_t slots_a = (size_t)N * (size_t)ceil_div(R > 0 ? R : 1, kMatchBlock * 2) * kWarpsPerBlock;
   size_t o = 0;
   w.off_counter = o; o += align_up(sizeof(unsigned) * (size_t)(N + 1), 16);
   w.off_gtmax = o;   o += align_up(sizeof(unsigned) * (size_t)(sum_M > 0 ? sum_M : 1), 16);
@@ -1092,12 +1085,14 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
     e.part_cnt = stats ? (int*)(ws + w.off_pcnt_a) : nullptr;
     e.part_s = (float*)(ws + w.off_ps_a);
     dim3 grid_a((unsigned)nb_a, (unsigned)N);
-    if (few_gt)
-      match_pass_a_kernel<2><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
-                                                            (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax, e, lv);
-    else
-      match_pass_a_kernel<4><<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4,
-                                                            (const float4*)gt_boxes, gt_offsets, bval, bidx, gtmax, e, lv);
+    const bool step_set = !matches && !match_labels && !picky_labels && !gt_deltas && gt_classes_out && mask_out &&
+                          matched_idx32 && gt_class_ids && pmb.n != 0;
+    auto go_a = [&](auto kern) {
+      kern<<<grid_a, kMatchBlock, 0, s>>>((const float4*)anchors, R, anchor_image_stride / 4, (const float4*)gt_boxes,
+                                          gt_offsets, bval, bidx, gtmax, e, lv);
+    };
+    if (few_gt) { if (step_set) go_a(match_pass_a_kernel<2, true>); else go_a(match_pass_a_kernel<2, false>); }
+    else        { if (step_set) go_a(match_pass_a_kernel<4, true>); else go_a(match_pass_a_kernel<4, false>); }
     FSG_LAUNCH_CHECK();
   }
   if (!(phases & 2)) return FSG_OK;
@@ -1119,7 +1114,7 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
   }
   if (!stats) return FSG_OK;
   FoldArgs f = {};
-  f.N = N; f.R = R; f.nb_a = nb_a;
+  f.N = N; f.R = R; f.nb_a = nb_a * kWarpsPerBlock;   // (pass A leaves one slot per warp)
   f.part_cnt_a = (const int*)(ws + w.off_pcnt_a); f.part_s_a = (const float*)(ws + w.off_ps_a);
   f.part_cnt_b = patch ? (const int*)(ws + w.off_pcnt) : nullptr; f.part_s_b = (const float*)(ws + w.off_ps);
   f.slots_b = nb_b * kWarpsPerBlock; f.levels_mode = lv.num_levels > 0 ? 1 : 0; f.temperature = temperature;
