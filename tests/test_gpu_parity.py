@@ -94,6 +94,54 @@ def test_fused_match_vs_oracle(cuda, N, H, W, M):
         assert int((want["match_labels"] == 1).sum()) > 0
 
 
+@pytest.mark.parametrize("case", ["nested", "untouched", "duplicates"])
+def test_fused_match_few_gt_low_quality_corner_cases(cuda, case):
+    """Few-GT path (lane-held GT, ballot cull, argmax shortcut of pass B) on the cases that shortcut must get right:
+    nested ground truth (an anchor whose argmax is the outer box is the best anchor of the inner one: promoted through a
+    GT that is NOT its argmax), a GT that touches no anchor (maximum 0: every anchor of that image is promoted),
+    duplicated GT and duplicated anchors (ties: lowest GT index wins, every tied anchor is promoted), IoU exactly 1.
+    Labels / classes / mask bit-exact and the loss pre-pass sums against the oracle."""
+    fsg = _fsg()
+    inp = _train_inputs(4, 3, 384, 512, 80, 6)
+    anchors = inp["anchors"].clone()
+    gt_boxes = [b.clone() for b in inp["gt_boxes"]]
+    gt_classes = [c.clone() for c in inp["gt_classes"]]
+    if case == "nested":
+        for b in gt_boxes:
+            if b.shape[0] >= 4:
+                b[0] = torch.tensor([40.0, 40.0, 360.0, 300.0])
+                b[1] = torch.tensor([150.0, 120.0, 200.0, 170.0])     # inside GT 0
+                b[2] = torch.tensor([140.0, 110.0, 230.0, 200.0])     # around GT 1, inside GT 0
+                b[3] = torch.tensor([41.0, 41.0, 359.0, 299.0])       # almost GT 0
+    elif case == "untouched":
+        for n, b in enumerate(gt_boxes):
+            if b.shape[0] >= 2 and n == 0:
+                b[1] = torch.tensor([9000.0, 9000.0, 9100.0, 9050.0])
+    else:
+        for b in gt_boxes:
+            if b.shape[0] >= 4:
+                b[3] = b[1]                                           # duplicated GT
+        anchors[101] = anchors[100]                                   # duplicated anchors
+        anchors[102] = anchors[100]
+        anchors[200] = gt_boxes[0][2] if gt_boxes[0].shape[0] > 2 else anchors[200]   # IoU exactly 1
+    want = orc.ground_truth(anchors, gt_boxes, gt_classes, 80)
+    gt = fsg.ops.PackedGT.from_lists(gt_boxes, gt_classes, cuda)
+    R = anchors.shape[0]
+    bets = torch.sigmoid(torch.randn((len(gt_boxes), R), generator=torch.Generator().manual_seed(3)) - 2.0)
+    got = fsg.ops.match_anchors(anchors.to(cuda), gt, 80, bets=bets.to(cuda), temperature=0.1,
+                                want=("matches", "match_labels", "picky_labels", "gt_classes", "mask"))
+    for k in ("matches", "match_labels", "picky_labels", "gt_classes", "mask"):
+        assert_equal_int(got[k], want[k], k)
+    if case == "untouched":
+        assert bool((want["match_labels"][0] == 1).all())
+    stats = got["stats"].cpu()
+    fgm = (want["gt_classes"] >= 0) & (want["gt_classes"] != 80)
+    assert int(stats[0]) == int(fgm.sum())
+    S = (bets.double() * want["mask"].double() + 0.1).sum(dim=1)
+    assert_close_tensor(stats[2:2 + len(gt_boxes)].float(), S.float(), "S[n]")
+    assert abs(float(stats[1]) - float(S.sum())) <= 1e-6 * float(S.sum())
+
+
 def test_fused_match_stress_slice(cuda):
     """Config 5 shape at a size the oracle finishes in seconds: 200 GT x 50k free-form anchors, 2 images
     with per-image anchors, > kGtChunk not needed; exercises ties through duplicated anchors."""
