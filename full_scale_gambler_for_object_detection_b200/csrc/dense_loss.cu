@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) 
   // Sharded run: this CTA is about to wait for the peers' sums to cross NVLink.  The logits are not produced by K1,
   // so it pulls its tile's rows into L2 first and the HBM latency of the first wave hides behind the exchange.
   // (Not done on one GPU: with nothing to hide, the extra L2 requests cost the main pass 2 %.)
-  if (A.peer.world > 1) {
+  // Only the first wave of CTAs waits (the later ones find the sums published), so only it prefetches.
+  if (A.peer.world > 1 && blockIdx.y * gridDim.x + blockIdx.x < 148 * 4) {
     const char* rows = reinterpret_cast<const char*>(A.logits + ((int64_t)n * A.R + tile_base) * A.K);
     int64_t bytes = (min((int64_t)A.anchors_per_tile, A.R - tile_base)) * A.K * (int64_t)sizeof(float);
     if (bytes > 96 * 1024) bytes = 96 * 1024;

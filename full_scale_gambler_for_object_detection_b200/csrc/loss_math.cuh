@@ -136,7 +136,8 @@ __device__ __forceinline__ void smooth_l1_elem(float pd, float gd, float beta, f
 
 // ---- peer exchange polled by the consumer ------------------------------------------------------------
 struct PeerPoll {
-  const double* mailbox;              // this rank's own mailbox (2 parities x 8 senders x {v0, v1, flag, pad})
+  const double* mailbox;              // this rank's own mailbox (2 parities x 8 senders x {v0, v1, flag, pad} in the
+                                      // first 512 bytes; bytes 512..535: {v0, v1, epoch} published by the first CTA)
   const unsigned long long* epoch;    // written by K1's last CTA: the epoch of this step
   int* error;
   double* stats_out;                  // stats[0..1] receive the global sums (written once, by the last CTA)
@@ -159,11 +160,34 @@ inline PeerPoll make_peer_poll(const fsg_peer_ctx* h, double* stats) {
 // All threads of the CTA call this (it contains a barrier).  v0 / v1 come back as the sums over the ranks, in rank
 // order (identical on every rank and in every CTA).  A peer that does not arrive within the time-out poisons the
 // result with NaN (the step's losses and gradients become NaN: it cannot be used silently) and raises *error.
+// Only the CTAs that start before the peers have arrived (the first wave) pay for the system-scope poll: the first
+// one through publishes {v0, v1, epoch} in the unused upper half of this rank's own mailbox, and every later CTA
+// takes the sums from there with one device-scope acquire (4000+ CTAs each polling eight system-scope flags cost
+// the main pass ~10 us at N > 1).
 __device__ __forceinline__ void peer_poll_sum(const PeerPoll& P, double& v0, double& v1) {
   __shared__ double s_p0[8], s_p1[8];
+  __shared__ int s_fast;
   const int tid = threadIdx.x;
+  unsigned long long* pub = reinterpret_cast<unsigned long long*>(const_cast<double*>(P.mailbox)) + 64;
+  const unsigned long long ep = *reinterpret_cast<const volatile unsigned long long*>(P.epoch);
+  if (tid == 0) {
+    unsigned long long seen;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(pub + 2) : "memory");
+    const bool fast = seen == ep;
+    if (fast) {
+      s_p0[0] = __longlong_as_double((long long)*reinterpret_cast<const volatile unsigned long long*>(pub));
+      s_p1[0] = __longlong_as_double((long long)*reinterpret_cast<const volatile unsigned long long*>(pub + 1));
+    }
+    s_fast = fast ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_fast) {
+    v0 = s_p0[0];
+    v1 = s_p1[0];
+    return;
+  }
+  __syncthreads();   // (s_p0 / s_p1 are rewritten below)
   if (tid < P.world) {
-    const unsigned long long ep = *reinterpret_cast<const volatile unsigned long long*>(P.epoch);
     const double* src = P.mailbox + ((int)(ep & 1ull) * 8 + tid) * 4;
     const unsigned long long* fin = reinterpret_cast<const unsigned long long*>(src + 2);
     const long long t0 = clock64();
@@ -188,6 +212,12 @@ __device__ __forceinline__ void peer_poll_sum(const PeerPoll& P, double& v0, dou
   for (int p = 0; p < P.world; ++p) { a += s_p0[p]; b += s_p1[p]; }
   v0 = a;
   v1 = b;
+  if (tid == 0) {   // (several CTAs may publish at once: the same values; a poisoned result is published as well,
+                    //  so that the rest of the grid does not wait for the time-out again)
+    *reinterpret_cast<volatile unsigned long long*>(pub) = (unsigned long long)__double_as_longlong(a);
+    *reinterpret_cast<volatile unsigned long long*>(pub + 1) = (unsigned long long)__double_as_longlong(b);
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(pub + 2), "l"(ep) : "memory");
+  }
 }
 
 // ---- per-tile partials -> scalars --------------------------------------------------------------

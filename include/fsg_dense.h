@@ -78,7 +78,8 @@ FSG_API int fsg_matcher(const float* mqm, int64_t M, int64_t N, const float* h_t
                 int64_t* matches, int8_t* match_labels, float* ws_rowmax, fsg_stream_t stream);
 
 /* Peer-memory exchange context for a batch sharded by image over the GPUs of one NVLink/NVSwitch box.
- * mailbox[p] is rank p's mailbox (1 KiB of symmetric, zero-initialised device memory) as mapped in THIS
+ * mailbox[p] is rank p's mailbox (1 KiB of symmetric, zero-initialised device memory; the upper 512 bytes are
+ * scratch of the owning rank: the first CTA of the loss kernel that has all peers' sums publishes them there) as mapped in THIS
  * process (its own mailbox included).  When a context is passed to fsg_match_anchors, the last CTA of its
  * second kernel all-reduces stats[0..1] = [num_foreground, S_batch] itself: it stores its two partial sums
  * and a release flag (a per-launch epoch) into every peer's mailbox with plain st.global over NVLink, spins
