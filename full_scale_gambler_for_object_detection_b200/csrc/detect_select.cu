@@ -1081,12 +1081,18 @@ static DetectWs detect_ws_layout(int N, int num_levels, int topk, int max_parts,
   DetectWs w;
   size_t o = 0;
   const size_t slabs = (size_t)N * num_levels;
-  // zero-initialised by one memset: done, lvl_count, cand_count, pool_done
+  // zero-initialised by ONE memset: done, lvl_count, cand_count, pool_done and the head of the NMS workspace (its
+  // completion counters and survivor bitmaps), which is why that workspace sits here and not at the end
   w.off_done = o;     o += align_up(sizeof(unsigned) * slabs, 16);
   w.off_lvl = o;      o += align_up(sizeof(int) * slabs, 16);
   w.off_ccount = o;   o += align_up(sizeof(unsigned) * slabs, 16);
   w.off_pooldone = o; o += align_up(sizeof(unsigned) * slabs, 16);
-  w.off_zero_end = o;
+  {
+    const NmsWs nw = nms_ws_layout(N, 8, max_det > 0 ? max_det : 1024);
+    w.off_nms = o;
+    w.off_zero_end = o + nw.off_cnt;   // (nw.off_done == 0: the zeroed part of the NMS workspace comes first)
+    o += align_up(nw.total, 16);
+  }
   w.off_bar = o;      o += align_up(sizeof(unsigned) * slabs, 16);
   w.off_status = o;   o += align_up(sizeof(int) * slabs, 16);
   w.off_pcount = o; o += align_up(sizeof(int) * slabs * max_parts, 16);
@@ -1096,7 +1102,6 @@ static DetectWs detect_ws_layout(int N, int num_levels, int topk, int max_parts,
   w.off_ccls = o;   o += align_up(sizeof(int64_t) * slabs * topk, 16);
   w.off_pool = o;   o += align_up(sizeof(uint16_t) * slabs * kBarPoolParts * kBarPoolKeys, 16);
   w.off_clist = o;  o += align_up(sizeof(uint64_t) * slabs * kCandCap, 16);
-  w.off_nms = o;    o += nms_ws_layout(N, 8, max_det > 0 ? max_det : 1024).total;
   w.total = o;
   return w;
 }
@@ -1184,8 +1189,7 @@ static int detect_run(const DetectCall& c, const DetectSrc& src, cudaStream_t s)
   // all memsets first, so that the kernels form one chain under programmatic dependent launch (each kernel is
   // scheduled while its predecessor drains and waits on the device before it reads what that one wrote)
   const int nms_split = nms_split_for(N);
-  const NmsWs nms_w = nms_ws_layout(N, nms_split, max_det);
-  FSG_CUDA_TRY(cudaMemsetAsync(ws + w.off_nms + nms_w.off_done, 0, nms_w.off_cnt - nms_w.off_done, s));
+  const NmsWs nms_w = nms_ws_layout(N, nms_split, max_det);   // (its zeroed head is part of the memset above)
   if (!legacy) {
     int pmax = 1;
     for (int l = 0; l < num_levels; ++l) pmax = lv.bar_parts[l] > pmax ? lv.bar_parts[l] : pmax;
