@@ -101,7 +101,7 @@ class MatchConfig(ctypes.Structure):
 
     _fields_ = [("thresholds", c_f32 * 4), ("picky_thresholds", c_f32 * 4), ("labels", ctypes.c_int8 * 8),
                 ("picky_labels", ctypes.c_int8 * 8), ("num_thresholds", c_i32), ("num_picky_thresholds", c_i32),
-                ("allow_low_quality_matches", c_i32), ("reserved", c_i32)]
+                ("allow_low_quality_matches", c_i32), ("workspace_is_clean", c_i32)]
 
 
 CLS_MODES = {"focal": 0, "sigmoid": 1}

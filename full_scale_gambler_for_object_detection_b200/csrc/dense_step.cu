@@ -48,21 +48,26 @@ extern "C" int fsg_dense_step(const fsg_step_io* io, int N, int64_t R, const fsg
   const bool sharded = h_peer && h_peer->world > 1;
   if (sharded && hp->norm_mode == FSG_NORM_BATCH) return FSG_ERR_UNSUPPORTED;
   const int K = hp->num_classes;
-  const size_t off_loss = align_up(fsg_match_workspace_bytes(N, R, io->sum_M), 256);
-  const size_t need = off_loss + loss_main_ws_bytes(N, R, K);
-  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  // K1's workspace in front, the loss kernel's at the very END of the buffer: its position then depends on the buffer
+  // and not on this call's GT count, which a workspace that is kept clean across calls (workspace_is_clean) needs
+  const size_t match_bytes = fsg_match_workspace_bytes(N, R, io->sum_M);
+  const size_t loss_bytes = loss_main_ws_bytes(N, R, K);
+  if (!workspace || ((uintptr_t)workspace & 15) || workspace_bytes < align_up(match_bytes, 256) + loss_bytes)
+    return FSG_ERR_WORKSPACE;
+  const size_t off_loss = (workspace_bytes - loss_bytes) & ~(size_t)255;
+  const size_t need = off_loss + loss_bytes;
   char* ws = (char*)workspace;
-  cudaStream_t s = (cudaStream_t)stream;
-  // the loss kernel's completion counter; K1 zeroes its own workspace head (one more memset node) -- both sit in
-  // front of K1, so nothing separates K1 from the main pass
-  FSG_CUDA_TRY(cudaMemsetAsync(ws + off_loss, 0, 16, s));
+  // ONE memset node in front of K1 clears the zero-initialised tail of K1's workspace and, with it, the loss
+  // kernel's completion counter at the head of the workspace that follows
+  const size_t zero_tail = off_loss - match_bytes + 16;
   int st = match_enqueue(io->anchors, R, io->anchor_image_stride, io->gt_boxes, io->gt_class_ids, io->gt_offsets, N,
                          io->sum_M, K, mc->thresholds, mc->labels, mc->num_thresholds,
                          mc->allow_low_quality_matches, mc->picky_thresholds, mc->picky_labels,
                          mc->num_picky_thresholds, hp->box_weights, nullptr, nullptr, nullptr, io->gt_classes, io->mask,
                          nullptr, io->matched_idx32, io->bets, nullptr, hp->temperature, io->stats,
                          sharded ? h_peer : nullptr, ws, off_loss, 3,
-                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl), stream);
+                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl) | (mc->workspace_is_clean ? kMatchSelfClean : 0), zero_tail,
+                         stream);
   if (st != FSG_OK) return st;
   const int pdl = step_no_pdl() ? 0 : kLossPdl;
   st = loss_main_enqueue(io->logits, io->pred_deltas, nullptr, io->anchors, io->anchor_image_stride, io->gt_boxes,
@@ -107,13 +112,14 @@ extern "C" int fsg_dense_step_levels(const fsg_step_levels_io* io, const fsg_hea
     bl.H[l] = h_levels[l].H;
     bl.W[l] = h_levels[l].W;
   }
-  const size_t off_loss = align_up(fsg_match_workspace_bytes(N, R, io->sum_M), 256);
+  const size_t match_bytes = fsg_match_workspace_bytes(N, R, io->sum_M);
   const size_t lw = loss_main_levels_ws_bytes(N, h_levels, num_levels, A);
   if (lw == 0) return FSG_ERR_INVALID_ARG;
-  if (!workspace || workspace_bytes < off_loss + lw || ((uintptr_t)workspace & 15)) return FSG_ERR_WORKSPACE;
+  if (!workspace || ((uintptr_t)workspace & 15) || workspace_bytes < align_up(match_bytes, 256) + lw)
+    return FSG_ERR_WORKSPACE;
+  const size_t off_loss = (workspace_bytes - lw) & ~(size_t)255;   // (see fsg_dense_step)
   char* ws = (char*)workspace;
-  cudaStream_t s = (cudaStream_t)stream;
-  FSG_CUDA_TRY(cudaMemsetAsync(ws + off_loss, 0, 16, s));
+  const size_t zero_tail = off_loss - match_bytes + 16;
   const int pdl = step_no_pdl() ? 0 : kLossPdl;
   int st = match_enqueue(io->anchors, R, io->anchor_image_stride, io->gt_boxes, io->gt_class_ids, io->gt_offsets, N,
                          io->sum_M, hp->num_classes, mc->thresholds, mc->labels, mc->num_thresholds,
@@ -121,7 +127,8 @@ extern "C" int fsg_dense_step_levels(const fsg_step_levels_io* io, const fsg_hea
                          mc->num_picky_thresholds, hp->box_weights, nullptr, nullptr, nullptr, io->gt_classes, io->mask,
                          nullptr, io->matched_idx32, nullptr, &bl, hp->temperature, io->stats,
                          sharded ? h_peer : nullptr, ws, off_loss, 3,
-                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl), stream);
+                         kMatchPeerPolled | (step_no_pdl() ? 0 : kMatchPdl) | (mc->workspace_is_clean ? kMatchSelfClean : 0), zero_tail,
+                         stream);
   if (st != FSG_OK) return st;
   st = loss_main_levels_enqueue(h_levels, num_levels, A, nullptr, io->anchors, io->anchor_image_stride, io->gt_boxes,
                                 io->gt_offsets, io->matched_idx32, io->gt_classes, io->mask, nullptr, N, R, hp,

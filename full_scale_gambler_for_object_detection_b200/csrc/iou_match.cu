@@ -738,6 +738,10 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
 // ending in fence + atomic + barrier cost pass B more than all of its real work.
 // ------------------------------------------------------------------------------------------
 struct FoldArgs {
+  const int32_t* gt_offsets;   // with gt_max: self-cleaning call, the fold zeroes what pass A / pass B dirtied
+  unsigned* gt_max;
+  int* clean_cnt_b;            // pass B's slots, writable (NULL: leave them)
+  float* clean_s_b;
   int N;
   int64_t R;
   int nb_a;
@@ -773,9 +777,19 @@ __global__ void __launch_bounds__(kMatchBlock) match_fold_kernel(const FoldArgs 
     }
     if (F.part_cnt_b != nullptr) {
       for (int b = tid; b < F.slots_b; b += kMatchBlock) {
-        c += (double)F.part_cnt_b[(int64_t)n * F.slots_b + b];
-        sacc += (double)F.part_s_b[(int64_t)n * F.slots_b + b];
+        const int pc = F.part_cnt_b[(int64_t)n * F.slots_b + b];
+        const float ps = F.part_s_b[(int64_t)n * F.slots_b + b];
+        c += (double)pc;
+        sacc += (double)ps;
+        if (F.clean_cnt_b != nullptr && (pc != 0 || ps != 0.f)) {
+          F.clean_cnt_b[(int64_t)n * F.slots_b + b] = 0;
+          F.clean_s_b[(int64_t)n * F.slots_b + b] = 0.f;
+        }
       }
+    }
+    if (F.gt_max != nullptr) {
+      const int m0 = F.gt_offsets[n], m1 = F.gt_offsets[n + 1];
+      for (int g = m0 + tid; g < m1; g += kMatchBlock) F.gt_max[g] = 0u;
     }
     c = warp_sum_d(c);
     sacc = warp_sum_d(sacc);
@@ -964,7 +978,7 @@ extern "C" int fsg_matcher(const float* mqm, int64_t M, int64_t N, const float* 
 
 namespace {
 struct MatchWs {
-  size_t off_counter, off_gtmax, off_pcnt, off_ps, off_val, off_idx, off_pcnt_a, off_ps_a, off_icnt, total;
+  size_t off_counter, off_gtmax, off_pcnt, off_ps, off_val, off_idx, off_pcnt_a, off_ps_a, off_icnt, off_zero, total;
   int nb;
 };
 MatchWs match_ws_layout(int N, int64_t R, int64_t sum_M) {
@@ -974,15 +988,20 @@ MatchWs match_ws_layout(int N, int64_t R, int64_t sum_M) {
   const size_t slots = (size_t)N * w.nb * kWarpsPerBlock;
   const size_t slots_a = (size_t)N * (size_t)ceil_div(R > 0 ? R : 1, kMatchBlock * 2) * kWarpsPerBlock;
   size_t o = 0;
-  w.off_counter = o; o += align_up(sizeof(unsigned) * (size_t)(N + 1), 16);
-  w.off_gtmax = o;   o += align_up(sizeof(unsigned) * (size_t)(sum_M > 0 ? sum_M : 1), 16);
-  w.off_pcnt = o;    o += align_up(sizeof(int) * slots, 16);       // pass B's slots: written only where non-zero,
-  w.off_ps = o;      o += align_up(sizeof(float) * slots, 16);     // [0, off_val) is zeroed before pass A
   w.off_val = o;     o += align_up(sizeof(float) * (size_t)N * (size_t)R, 16);
   w.off_idx = o;     o += align_up(sizeof(int32_t) * (size_t)N * (size_t)R, 16);
   w.off_pcnt_a = o;  o += align_up(sizeof(int) * slots_a, 16);
   w.off_ps_a = o;    o += align_up(sizeof(float) * slots_a, 16);
   w.off_icnt = o;    o += align_up(sizeof(double) * (size_t)N, 16);
+  // [off_zero, total) is zeroed by one memset before pass A.  It is the TAIL of the workspace so that the fused step
+  // can extend that memset over the counter of the loss kernel, which follows in its own workspace.
+  // (The per-GT maxima come last: every other offset is independent of the number of GT, so a workspace that a step
+  //  left clean -- kMatchSelfClean -- is clean for the next step's GT count as well.)
+  w.off_zero = o;
+  w.off_counter = o; o += align_up(sizeof(unsigned) * (size_t)(N + 1), 16);
+  w.off_pcnt = o;    o += align_up(sizeof(int) * slots, 16);       // pass B's slots: written only where non-zero
+  w.off_ps = o;      o += align_up(sizeof(float) * slots, 16);
+  w.off_gtmax = o;   o += align_up(sizeof(unsigned) * (size_t)(sum_M > 0 ? sum_M : 1), 16);
   w.total = o;
   return w;
 }
@@ -1005,7 +1024,7 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
                   float* gt_deltas, int32_t* matched_idx32, const float* bets,
                   const fsg_bet_levels* h_bet_levels, float temperature,
                   double* stats, const fsg_peer_ctx* h_peer, void* workspace,
-                  size_t workspace_bytes, int phases, int flags, fsg_stream_t stream) {
+                  size_t workspace_bytes, int phases, int flags, size_t zero_tail_bytes, fsg_stream_t stream) {
   if (N <= 0 || R < 0 || sum_M < 0 || !gt_offsets) return FSG_ERR_INVALID_ARG;
   if (phases < 1 || phases > 3) return FSG_ERR_INVALID_ARG;
   BetLevels lv = {};
@@ -1064,9 +1083,15 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
   unsigned* gtmax = (unsigned*)(ws + w.off_gtmax);
   float* bval = (float*)(ws + w.off_val);
   int32_t* bidx = (int32_t*)(ws + w.off_idx);
-  // counter + gt_max are contiguous: one memset node (phase 1 only: phase 2 consumes the -- possibly all-reduced --
-  // per-GT maxima that phase 1 left in the workspace)
-  if (phases & 1) FSG_CUDA_TRY(cudaMemsetAsync(ws, 0, w.off_val, s));
+  // counter + gt_max + pass B's slots are contiguous: one memset node (phase 1 only: phase 2 consumes the --
+  // possibly all-reduced -- per-GT maxima that phase 1 left in the workspace); zero_tail_bytes more bytes behind the
+  // workspace belong to the caller (fsg_dense_step: up to and including the loss kernel's completion counter)
+  // kMatchSelfClean: no memset at all -- the caller vouches that this region is zero (freshly zeroed, or left by a
+  // previous self-cleaning call), and the fold kernel zeroes again what this call dirties.  A memset NODE in a CUDA
+  // graph costs ~4 us of the step.
+  const bool self_clean = (flags & kMatchSelfClean) != 0 && stats != nullptr && phases == 3;
+  if ((phases & 1) && !self_clean)
+    FSG_CUDA_TRY(cudaMemsetAsync(ws + w.off_zero, 0, w.total - w.off_zero + zero_tail_bytes, s));
   const float wx = h_box_weights ? h_box_weights[0] : 1.f, wy = h_box_weights ? h_box_weights[1] : 1.f;
   const float ww = h_box_weights ? h_box_weights[2] : 1.f, wh = h_box_weights ? h_box_weights[3] : 1.f;
 
@@ -1114,6 +1139,10 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
   }
   if (!stats) return FSG_OK;
   FoldArgs f = {};
+  if (self_clean) {
+    f.gt_offsets = gt_offsets; f.gt_max = gtmax;
+    if (patch) { f.clean_cnt_b = (int*)(ws + w.off_pcnt); f.clean_s_b = (float*)(ws + w.off_ps); }
+  }
   f.N = N; f.R = R; f.nb_a = nb_a * kWarpsPerBlock;   // (pass A leaves one slot per warp)
   f.part_cnt_a = (const int*)(ws + w.off_pcnt_a); f.part_s_a = (const float*)(ws + w.off_ps_a);
   f.part_cnt_b = patch ? (const int*)(ws + w.off_pcnt) : nullptr; f.part_s_b = (const float*)(ws + w.off_ps);
@@ -1142,7 +1171,7 @@ extern "C" int fsg_match_anchors_ex(const float* anchors, int64_t R, int64_t anc
                        h_thresholds, h_labels, num_thresholds, allow_lq, h_picky_thresholds, h_picky_labels,
                        num_picky_thresholds, h_box_weights, matches, match_labels, picky_labels, gt_classes_out,
                        mask_out, gt_deltas, matched_idx32, bets, h_bet_levels, temperature, stats, h_peer, workspace,
-                       workspace_bytes, phases, 0, stream);
+                       workspace_bytes, phases, 0, 0, stream);
 }
 
 extern "C" int fsg_box2box_get_deltas(const float* src_boxes, const float* target_boxes, int64_t n,

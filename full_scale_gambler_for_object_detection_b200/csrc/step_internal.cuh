@@ -6,6 +6,7 @@
 namespace fsg {
 
 constexpr int kMatchPeerPolled = 1;   // match_enqueue flag: post the peer exchange, the consumer kernel polls it
+constexpr int kMatchSelfClean = 4;    // no memset: the zero-initialised part of the workspace is clean and is left clean
 constexpr int kMatchPdl = 2;          // launch pass B and the fold under programmatic dependent launch
 
 int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride, const float* gt_boxes,
@@ -16,7 +17,8 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride, 
                   int64_t* gt_classes_out, int64_t* mask_out, float* gt_deltas, int32_t* matched_idx32,
                   const float* bets, const fsg_bet_levels* h_bet_levels, float temperature, double* stats,
                   const fsg_peer_ctx* h_peer, void* workspace, size_t workspace_bytes, int phases, int flags,
-                  fsg_stream_t stream);
+                  size_t zero_tail_bytes, fsg_stream_t stream);
+// zero_tail_bytes: bytes right behind fsg_match_workspace_bytes() that the memset in front of pass A clears as well
 
 constexpr int kLossPdl = 1;            // launch under programmatic dependent launch (the kernel waits on-device)
 constexpr int kLossCounterZeroed = 2;  // the caller already zeroed the first 16 bytes of the loss workspace

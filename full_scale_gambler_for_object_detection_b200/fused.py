@@ -198,9 +198,12 @@ class DenseStepPlan:
         # exchange polled by K2): everything except a sharded run that still needs an NCCL collective in the middle
         self.one_call = (os.environ.get("FSG_STEP_STAGED", "0") != "1") and (
             group is None or (self.peer is not None and cfg.norm_mode != _lib.NORM_BATCH))
-        self.ws_step = torch.empty(max(16, L.fsg_dense_step_workspace_bytes(N, R, K, self.max_total_gt)),
+        # zero-filled once and owned by this plan: every fsg_dense_step call leaves it clean again, so no memset node
+        # is enqueued (fsg_match_config.workspace_is_clean; a memset node costs ~4 us of the step inside a graph)
+        self.ws_step = torch.zeros(max(16, L.fsg_dense_step_workspace_bytes(N, R, K, self.max_total_gt)),
                                    dtype=torch.uint8, device=dev) if self.one_call else None
         self._mc = _match_config(cfg)
+        self._mc.workspace_is_clean = 1
 
     def _check(self, logits, deltas, bets, anchors, gt):
         N, R, K = self.N, self.R, self.K
@@ -242,7 +245,7 @@ class DenseStepPlan:
         _lib.count_launches(1)
 
     def step_one_call(self, logits, deltas, bets, anchors, gt):
-        """The whole step through ``fsg_dense_step`` (one ctypes call, 2 memset nodes + 3 kernels)."""
+        """The whole step through ``fsg_dense_step`` (one ctypes call, five kernels, no memset)."""
         P = _lib.ptr
         io = _lib.StepIO()
         io.logits, io.pred_deltas, io.bets, io.anchors = P(logits), P(deltas), P(bets), P(anchors)
@@ -283,7 +286,7 @@ class DenseStepPlan:
         """Capture the step reading from exactly these tensors (their storage must stay alive and is
         refreshed in place by the caller between replays).
 
-        Single process: one graph (4 kernels + 2 memset nodes).  Sharded (``group`` set): the collectives stay
+        Single process: one graph (the five kernels of the step).  Sharded (``group`` set): the collectives stay
         *outside* the graphs -- graph 1 = K1, eager all-reduce of the two scalars, graph 2 = K2 main (+ post);
         for ``L_BAHW_extendtobatch`` the post pass is a third graph after the second all-reduce."""
         self._check(logits, deltas, bets, anchors, gt)
@@ -585,7 +588,8 @@ class DenseStepPlanLevels:
             raise RuntimeError("DenseStepPlanLevels: %d GT boxes > max_total_gt %d" % (gt.total, self.max_total_gt))
         if self.ws_step is None:
             need = self.L.fsg_dense_step_levels_workspace_bytes(N, hl, nl, A, self.max_total_gt)
-            self.ws_step = torch.empty(max(16, need), dtype=torch.uint8, device=self.device)
+            self.ws_step = torch.zeros(max(16, need), dtype=torch.uint8, device=self.device)   # kept clean, see above
+            self._mc.workspace_is_clean = 1
         io = _lib.StepLevelsIO()
         io.anchors = P(anchors)
         io.anchor_image_stride = self.R * 4 if anchors.dim() == 3 else 0

@@ -363,6 +363,44 @@ def test_one_call_step_equals_staged_step(cuda):
         a.release_graphs()
 
 
+def test_step_workspace_stays_clean_across_changing_ground_truth(cuda):
+    """The plan's one-call step enqueues no memset (fsg_match_config.workspace_is_clean): K1's fold kernel zeroes what
+    the call dirtied.  Steps with a growing and shrinking number of GT (the per-GT maxima move inside the workspace), a
+    GT that touches no anchor (every anchor promoted) and a GT-free batch must each equal the same step on a plan
+    whose call clears its workspace itself -- bit for bit."""
+    fsg = _fsg()
+    N, K = 3, 80
+    base = _train_inputs(63, N, 256, 320, K, M=12)
+    R = base["R"]
+    x, d, b = (base[k].to(cuda) for k in ("logits", "deltas", "bets"))
+    anchors = base["anchors"].to(cuda)
+    cfg = fsg.DenseLossConfig(num_classes=K)
+    clean = fsg.DenseStepPlan(N, R, K, cfg, cuda, (1.0, 0.5, -2.0), max_total_gt=256)
+    assert clean.one_call and clean._mc.workspace_is_clean == 1
+    boxes, classes = base["gt_boxes"], base["gt_classes"]
+    far = torch.tensor([[9000.0, 9000.0, 9100.0, 9050.0]])
+    rounds = [
+        ([bx[:2] for bx in boxes], [c[:2] for c in classes]),
+        (boxes, classes),
+        ([torch.cat((bx[:1], far)) if bx.shape[0] else bx for bx in boxes],
+         [torch.cat((c[:1], c[:1])) if c.shape[0] else c for c in classes]),
+        ([bx[:0] for bx in boxes], [c[:0] for c in classes]),
+        ([bx[:5] for bx in boxes], [c[:5] for c in classes]),
+        (boxes, classes),
+    ]
+    for i, (gb, gc) in enumerate(rounds):
+        gt = fsg.ops.PackedGT.from_lists(gb, gc, cuda)
+        fresh = fsg.DenseStepPlan(N, R, K, cfg, cuda, (1.0, 0.5, -2.0), max_total_gt=256)
+        fresh._mc.workspace_is_clean = 0
+        fresh.ws_step.fill_(0xAB)          # the self-clearing call must not depend on the buffer's content
+        rc, rf = clean.run(x, d, b, anchors, gt), fresh.run(x, d, b, anchors, gt)
+        for name in ("gt_classes", "mask", "stats", "scalars"):
+            assert torch.equal(getattr(rc, name), getattr(rf, name)), "round %d: %s" % (i, name)
+        assert torch.equal(clean.matched, fresh.matched)
+        assert torch.equal(clean.grad_logits, fresh.grad_logits) and torch.equal(clean.grad_bets, fresh.grad_bets)
+        assert torch.equal(clean.grad_deltas, fresh.grad_deltas)
+
+
 def test_backward_is_single_use(cuda):
     fsg = _fsg()
     inp = _train_inputs(62, 2, 128, 128, 80, M=3)
