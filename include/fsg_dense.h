@@ -343,8 +343,9 @@ typedef struct fsg_match_config {
   int32_t allow_low_quality_matches;
   int32_t workspace_is_clean; /* 0: the call clears what it needs (one memset node, ~4 us of the step inside a CUDA
                                * graph).  1: the caller vouches that `workspace` was zero-filled once after allocation
-                               * and since then only used by fsg_dense_step / fsg_dense_step_levels calls of the same
-                               * (N, R, levels): every call leaves it clean again, and no memset is enqueued. */
+                               * and since then only used by fsg_dense_step / fsg_dense_step_levels calls with the same
+                               * (N, R, levels, workspace_bytes) -- the number of GT may change: every call leaves it
+                               * clean again, and no memset is enqueued. */
 } fsg_match_config;
 FSG_API size_t fsg_dense_step_workspace_bytes(int N, int64_t R, int K, int64_t sum_M);
 FSG_API int fsg_dense_step(const fsg_step_io* h_io, int N, int64_t R, const fsg_match_config* h_match,
