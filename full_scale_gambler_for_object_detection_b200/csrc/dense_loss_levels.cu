@@ -239,10 +239,12 @@ __global__ void __launch_bounds__(kLvBlock, LV_MINB) loss_main_levels_kernel(con
   grid_dependency_sync();     // everything K1 produced is read from here on
   double nf_d = A.stats[0];
   float s_batch = (A.nmode == FSG_NORM_BATCH) ? (float)A.stats[1] : 1.f;
-  if (A.peer.world > 1) {
-    double sb;
-    peer_poll_sum(A.peer, nf_d, sb);
-    s_batch = (float)sb;
+  if (A.peer.world > 1) {   // sharded batch: num_foreground of the whole batch arrives through the peer mailboxes
+    const double nf_local = nf_d, sb_local = A.stats[1];
+    peer_poll_nf(A.peer, nf_d);
+    // (S_batch is not a normaliser of a sharded step -- FSG_NORM_BATCH is refused there; the ranks' complete records
+    //  are for the step's statistics and are posted off the critical path, by one CTA, after its own wait)
+    if (blockIdx.x == 0 && blockIdx.y == 0) peer_post_full(A.peer, nf_local, sb_local);
   }
   const float inv_nf = __frcp_rn(fmaxf((float)nf_d, 1.f));
   float inv_S = 1.f;

@@ -834,11 +834,27 @@ __global__ void __launch_bounds__(kMatchBlock) match_fold_kernel(const FoldArgs 
   if (peer.world <= 1) return;
 
   // ---- fused exchange over peer memory: all-reduce(SUM) of [num_foreground, S_batch] across the ranks.
-  //      Mailbox of a rank: 2 (epoch parity) x 8 (sender) slots of {double v0, double v1, u64 flag, pad}.
+  //      Mailbox of a rank: 2 (epoch parity) x 8 (sender) slots of {double v0, double v1, u64 flag, u64 fast word}.
   __shared__ double s_px[8], s_py[8];
   __syncthreads();
   unsigned long long* epoch_ptr = reinterpret_cast<unsigned long long*>(peer.epoch);
   const unsigned long long ep = *epoch_ptr + 1ull;
+  if (!F.peer_wait) {
+    // fsg_dense_step: what the loss kernel has to wait for is one number, num_foreground (the batch normaliser S is
+    // not used when the batch is sharded).  It travels together with the epoch in ONE 8-byte word per peer -- an
+    // aligned 8-byte store is atomic, so there is no payload / fence / flag sequence and no NVLink round trip on this
+    // kernel's way out.  The complete record {num_foreground, S_batch} for the step's statistics is posted later, by
+    // one CTA of the loss kernel (stats[0..1] stay local until that kernel's last CTA stores the global sums).
+    if (tid < peer.world) {
+      const int slot_out = (int)(ep & 1ull) * 8 + peer.rank;
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(peer.mailbox[tid]) + slot_out * 4 + 3;
+      const unsigned long long word = (ep << 32) | (unsigned long long)(unsigned)(long long)s_loc[0];
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+    }
+    __syncthreads();
+    if (tid == 0) *epoch_ptr = ep;
+    return;
+  }
   if (tid < peer.world) {
     const int slot_out = (int)(ep & 1ull) * 8 + peer.rank;
     double* dst = reinterpret_cast<double*>(peer.mailbox[tid]) + slot_out * 4;
@@ -847,13 +863,6 @@ __global__ void __launch_bounds__(kMatchBlock) match_fold_kernel(const FoldArgs 
     __threadfence_system();
     unsigned long long* fl = reinterpret_cast<unsigned long long*>(dst + 2);
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(ep) : "memory");
-  }
-  if (!F.peer_wait) {
-    // fsg_dense_step: the sums are only POSTED here; every CTA of the loss main pass polls this rank's mailbox
-    // (stats[0..1] stay local until that kernel's last CTA stores the global sums)
-    __syncthreads();
-    if (tid == 0) *epoch_ptr = ep;
-    return;
   }
   if (tid < peer.world) {
     const int slot_in = (int)(ep & 1ull) * 8 + tid;

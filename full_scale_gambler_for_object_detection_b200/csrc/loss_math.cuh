@@ -135,14 +135,21 @@ __device__ __forceinline__ void smooth_l1_elem(float pd, float gd, float beta, f
 }
 
 // ---- peer exchange polled by the consumer ------------------------------------------------------------
+// Mailbox of a rank (1 KiB): 2 (epoch parity) x 8 (sender) slots of {double v0, double v1, u64 flag, u64 fast word}
+// in the first 512 bytes; bytes 512..519 are scratch of the owning rank: epoch << 32 | global num_foreground, published
+// by the first CTA that has collected every peer's fast word.
+//   fast word  = epoch << 32 | num_foreground (one atomic 8-byte store, posted by K1's fold kernel): all the loss
+//                kernel waits for before it can scale a gradient
+//   full record {v0 = num_foreground, v1 = S_batch, flag = epoch}: posted by CTA (0,0) of the loss kernel, read by its
+//                last CTA for the step's statistics (stats[0..1])
 struct PeerPoll {
-  const double* mailbox;              // this rank's own mailbox (2 parities x 8 senders x {v0, v1, flag, pad} in the
-                                      // first 512 bytes; bytes 512..535: {v0, v1, epoch} published by the first CTA)
+  const double* mailbox;              // this rank's own mailbox
   const unsigned long long* epoch;    // written by K1's last CTA: the epoch of this step
   int* error;
   double* stats_out;                  // stats[0..1] receive the global sums (written once, by the last CTA)
   long long timeout_cycles;
-  int world;
+  double* peer_mailbox[8];            // every rank's mailbox as mapped here (for the full record)
+  int world, rank;
 };
 inline PeerPoll make_peer_poll(const fsg_peer_ctx* h, double* stats) {
   PeerPoll p = {};
@@ -154,41 +161,80 @@ inline PeerPoll make_peer_poll(const fsg_peer_ctx* h, double* stats) {
     p.stats_out = stats;
     p.timeout_cycles = h->timeout_cycles > 0 ? (long long)h->timeout_cycles : 120000000000ll;   // ~60 s
     p.world = h->world;
+    p.rank = h->rank;
+    for (int q = 0; q < h->world; ++q) p.peer_mailbox[q] = reinterpret_cast<double*>(h->mailbox[q]);
   }
   return p;
 }
-// All threads of the CTA call this (it contains a barrier).  v0 / v1 come back as the sums over the ranks, in rank
-// order (identical on every rank and in every CTA).  A peer that does not arrive within the time-out poisons the
-// result with NaN (the step's losses and gradients become NaN: it cannot be used silently) and raises *error.
+// All threads of the CTA call this (it contains a barrier).  nf comes back as the sum of num_foreground over the
+// ranks (integers: the same on every rank and in every CTA).  A peer that does not arrive within the time-out poisons
+// the result with NaN (the step's losses and gradients become NaN: it cannot be used silently) and raises *error.
 // Only the CTAs that start before the peers have arrived (the first wave) pay for the system-scope poll: the first
-// one through publishes {v0, v1, epoch} in the unused upper half of this rank's own mailbox, and every later CTA
-// takes the sums from there with one device-scope acquire (4000+ CTAs each polling eight system-scope flags cost
-// the main pass ~10 us at N > 1).
-__device__ __forceinline__ void peer_poll_sum(const PeerPoll& P, double& v0, double& v1) {
-  __shared__ double s_p0[8], s_p1[8];
-  __shared__ int s_fast;
+// one through publishes the sum in the scratch half of this rank's own mailbox, and every later CTA takes it from
+// there with one device-scope acquire.
+__device__ __forceinline__ void peer_poll_nf(const PeerPoll& P, double& nf) {
+  __shared__ double s_p0[8];
   const int tid = threadIdx.x;
   unsigned long long* pub = reinterpret_cast<unsigned long long*>(const_cast<double*>(P.mailbox)) + 64;
+  // fast path (every CTA after the first wave): two independent loads per thread, one barrier.  The published word
+  // carries its own validity (epoch << 32 | sum; 0xffffffff = poisoned), so no acquire / dependent second load.
   const unsigned long long ep = *reinterpret_cast<const volatile unsigned long long*>(P.epoch);
-  if (tid == 0) {
-    unsigned long long seen;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(pub + 2) : "memory");
-    const bool fast = seen == ep;
-    if (fast) {
-      s_p0[0] = __longlong_as_double((long long)*reinterpret_cast<const volatile unsigned long long*>(pub));
-      s_p1[0] = __longlong_as_double((long long)*reinterpret_cast<const volatile unsigned long long*>(pub + 1));
-    }
-    s_fast = fast ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_fast) {
-    v0 = s_p0[0];
-    v1 = s_p1[0];
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(pub) : "memory");
+  const bool fast = (w >> 32) == (ep & 0xffffffffull);
+  if (!__syncthreads_or(fast ? 0 : 1)) {   // (CTA-uniform: warps may have read the word at different times)
+    const unsigned v = (unsigned)(w & 0xffffffffull);
+    nf = (v == 0xffffffffu) ? __longlong_as_double(0x7ff8000000000000ll) : (double)v;
     return;
   }
-  __syncthreads();   // (s_p0 / s_p1 are rewritten below)
   if (tid < P.world) {
-    const double* src = P.mailbox + ((int)(ep & 1ull) * 8 + tid) * 4;
+    const unsigned long long* src =
+        reinterpret_cast<const unsigned long long*>(P.mailbox) + ((int)(ep & 1ull) * 8 + tid) * 4 + 3;
+    const long long t0 = clock64();
+    unsigned long long word = 0ull;
+    bool ok = true;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
+      if ((word >> 32) == (ep & 0xffffffffull)) break;
+      if (clock64() - t0 > P.timeout_cycles) { ok = false; break; }
+    }
+    if (ok) {
+      s_p0[tid] = (double)(unsigned)(word & 0xffffffffull);
+    } else {
+      *P.error = 1;
+      s_p0[tid] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+  }
+  __syncthreads();
+  double a = 0.0;
+  for (int p = 0; p < P.world; ++p) a += s_p0[p];
+  nf = a;
+  if (tid == 0) {   // (several CTAs may publish at once: the same word; a poisoned result is published as well, so
+                    //  that the rest of the grid does not wait for the time-out again)
+    const unsigned long long lo = (a == a) ? (unsigned long long)(unsigned)(long long)a : 0xffffffffull;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(pub), "l"((ep << 32) | lo) : "memory");
+  }
+}
+// One CTA of the loss kernel (the caller picks it) posts this rank's complete record to every peer; threads
+// 0..world-1 each serve one peer.  Not on anybody's critical path: the record is read at the END of the peers' kernels.
+__device__ __forceinline__ void peer_post_full(const PeerPoll& P, double v0, double v1) {
+  const int tid = threadIdx.x;
+  if (tid < P.world) {
+    const unsigned long long ep = *reinterpret_cast<const volatile unsigned long long*>(P.epoch);
+    double* dst = P.peer_mailbox[tid] + ((int)(ep & 1ull) * 8 + P.rank) * 4;
+    dst[0] = v0;
+    dst[1] = v1;
+    __threadfence_system();
+    unsigned long long* fl = reinterpret_cast<unsigned long long*>(dst + 2);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(ep) : "memory");
+  }
+}
+// The last CTA's thread 0: the sum of v1 (S_batch) over the ranks' complete records, in rank order.
+__device__ __forceinline__ double peer_sum_v1(const PeerPoll& P) {
+  const unsigned long long ep = *reinterpret_cast<const volatile unsigned long long*>(P.epoch);
+  double sb = 0.0;
+  for (int p = 0; p < P.world; ++p) {
+    const double* src = P.mailbox + ((int)(ep & 1ull) * 8 + p) * 4;
     const unsigned long long* fin = reinterpret_cast<const unsigned long long*>(src + 2);
     const long long t0 = clock64();
     unsigned long long seen = 0ull;
@@ -198,26 +244,10 @@ __device__ __forceinline__ void peer_poll_sum(const PeerPoll& P, double& v0, dou
       if (seen == ep) break;
       if (clock64() - t0 > P.timeout_cycles) { ok = false; break; }
     }
-    if (ok) {
-      s_p0[tid] = *reinterpret_cast<const volatile double*>(src);
-      s_p1[tid] = *reinterpret_cast<const volatile double*>(src + 1);
-    } else {
-      *P.error = 1;
-      s_p0[tid] = __longlong_as_double(0x7ff8000000000000ll);
-      s_p1[tid] = __longlong_as_double(0x7ff8000000000000ll);
-    }
+    if (!ok) *P.error = 1;
+    sb += ok ? *reinterpret_cast<const volatile double*>(src + 1) : __longlong_as_double(0x7ff8000000000000ll);
   }
-  __syncthreads();
-  double a = 0.0, b = 0.0;
-  for (int p = 0; p < P.world; ++p) { a += s_p0[p]; b += s_p1[p]; }
-  v0 = a;
-  v1 = b;
-  if (tid == 0) {   // (several CTAs may publish at once: the same values; a poisoned result is published as well,
-                    //  so that the rest of the grid does not wait for the time-out again)
-    *reinterpret_cast<volatile unsigned long long*>(pub) = (unsigned long long)__double_as_longlong(a);
-    *reinterpret_cast<volatile unsigned long long*>(pub + 1) = (unsigned long long)__double_as_longlong(b);
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(pub + 2), "l"(ep) : "memory");
-  }
+  return sb;
 }
 
 // ---- per-tile partials -> scalars --------------------------------------------------------------
@@ -228,7 +258,7 @@ template <int NT = kLossBlock>
 __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float acc_wl, float acc_l, float max_l,
                                             int n, int tile, int T, int N, float* partials, unsigned* counter,
                                             double* scalars, double nf_d, float c_cls, float c_reg, float c_gam,
-                                            const PeerPoll peer = PeerPoll{nullptr, nullptr, nullptr, nullptr, 0, 1}) {
+                                            const PeerPoll peer = PeerPoll{}) {
   __shared__ float s_part[NT / 32][5];
   __shared__ double s_tot[NT / 32][5];
   __shared__ bool s_last;
@@ -283,13 +313,9 @@ __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float 
     scalars[7] = -v[2];
     scalars[8] = (double)c_cls * scalars[5] + (double)c_reg * scalars[6] + (double)c_gam * scalars[7];
     scalars[9] = nf_d;
-    if (peer.world > 1) {   // the polled global sums become stats[0..1] (every peer has arrived: no waiting here)
-      const unsigned long long ep = *reinterpret_cast<const volatile unsigned long long*>(peer.epoch);
-      double sb = 0.0;
-      for (int p = 0; p < peer.world; ++p)
-        sb += *reinterpret_cast<const volatile double*>(peer.mailbox + ((int)(ep & 1ull) * 8 + p) * 4 + 1);
+    if (peer.world > 1) {   // the global sums become stats[0..1] (the peers posted their records long ago)
+      peer.stats_out[1] = peer_sum_v1(peer);
       peer.stats_out[0] = nf_d;
-      peer.stats_out[1] = sb;
     }
     *counter = 0u;
   }

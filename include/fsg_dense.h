@@ -85,7 +85,11 @@ FSG_API int fsg_matcher(const float* mqm, int64_t M, int64_t N, const float* h_t
  * and a release flag (a per-launch epoch) into every peer's mailbox with plain st.global over NVLink, spins
  * (acquire loads, with a clock time-out that raises *error) until every peer's flag shows the same epoch,
  * and sums the slots in rank order (identical result on every rank).  No NCCL launch, capturable in a CUDA
- * graph; every rank must enqueue the same sequence of calls. */
+ * graph; every rank must enqueue the same sequence of calls.
+ * fsg_dense_step / fsg_dense_step_levels shorten that to what the loss kernel really has to wait for: K1's fold
+ * kernel posts one 8-byte word per peer (epoch << 32 | num_foreground, an atomic store: no payload / fence / flag
+ * sequence), the first CTAs of the loss kernel poll those words, and the complete records for stats[0..1] are posted
+ * by one CTA of the loss kernel and read by its last one. */
 typedef struct fsg_peer_ctx {
   uint64_t mailbox[8]; /* device pointers */
   uint64_t epoch;      /* device pointer to a local uint64 counter, zero-initialised                */
