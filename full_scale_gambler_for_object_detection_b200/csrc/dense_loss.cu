@@ -130,7 +130,9 @@ __global__ void __launch_bounds__(256) loss_prepass_kernel(const int64_t* __rest
 // ------------------------------------------------------------------------------------------
 // main pass
 // ------------------------------------------------------------------------------------------
-template <int V, int BATCH, int VARIANT, int GT>
+// PEER: the sharded form (fsg_dense_step with a peer context).  A separate instantiation, because even dead peer code
+// in the prologue and in finish_tile cost the single-GPU kernel 1.6 us (133.6 -> 135.2 us) through register allocation.
+template <int V, int BATCH, int VARIANT, int GT, bool PEER = false>
 __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) loss_main_kernel(const LossArgs A) {
   // GT > 0: "exact" instantiation, G == GT lanes per anchor and K == V*GT*BATCH (no predication in the
   // element loop); GT == 0: G and K are run-time values.
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) 
   // so it pulls its tile's rows into L2 first and the HBM latency of the first wave hides behind the exchange.
   // (Not done on one GPU: with nothing to hide, the extra L2 requests cost the main pass 2 %.)
   // Only the first wave of CTAs waits (the later ones find the sums published), so only it prefetches.
-  if (A.peer.world > 1 && blockIdx.y * gridDim.x + blockIdx.x < 148 * 4) {
+  if (PEER && A.peer.world > 1 && blockIdx.y * gridDim.x + blockIdx.x < 148 * 4) {
     const char* rows = reinterpret_cast<const char*>(A.logits + ((int64_t)n * A.R + tile_base) * A.K);
     int64_t bytes = (min((int64_t)A.anchors_per_tile, A.R - tile_base)) * A.K * (int64_t)sizeof(float);
     if (bytes > 96 * 1024) bytes = 96 * 1024;
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) 
   // reference's own fp32 division; S[n] is rounded to fp32 like the reference's fp32 sum.
   double nf_d = A.stats[0];
   float s_batch = (A.nmode == FSG_NORM_BATCH) ? (float)A.stats[1] : 1.f;
-  if (A.peer.world > 1) {   // sharded batch: num_foreground of the whole batch arrives through the peer mailboxes
+  if (PEER && A.peer.world > 1) {   // sharded batch: num_foreground of the whole batch arrives through the peer mailboxes
     const double nf_local = nf_d, sb_local = A.stats[1];
     peer_poll_nf(A.peer, nf_d);
     // (S_batch is not a normaliser of a sharded step -- FSG_NORM_BATCH is refused there; the ranks' complete records
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(kLossBlock, (GT > 0 ? 4 : LOSS_GENERIC_MINB)) 
   // ---- tile partials -> scalars (deterministic: one slot per tile, fixed reduction order)
   acc_cls = warp_sum(acc_cls); acc_reg = warp_sum(acc_reg); acc_wl = warp_sum(acc_wl);
   acc_l = warp_sum(acc_l); max_l = warp_max(max_l);
-  finish_tile(acc_cls, acc_reg, acc_wl, acc_l, max_l, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
+  finish_tile<kLossBlock, PEER>(acc_cls, acc_reg, acc_wl, acc_l, max_l, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
               A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam, A.peer);
 }
 
@@ -522,6 +524,12 @@ static LossWs loss_ws_layout(int N, const LossPlan& p) {
 
 template <int V, int BATCH, int GT>
 static void launch_main(int variant, dim3 grid, cudaStream_t s, const LossArgs& a, bool pdl) {
+  if (a.peer.world > 1) {
+    if (variant == kFastWrite) launch_pdl(loss_main_kernel<V, BATCH, kFastWrite, GT, true>, grid, dim3(kLossBlock), 0, s, pdl, a);
+    else if (variant == kFastNoWrite) launch_pdl(loss_main_kernel<V, BATCH, kFastNoWrite, GT, true>, grid, dim3(kLossBlock), 0, s, pdl, a);
+    else launch_pdl(loss_main_kernel<V, BATCH, kGeneric, GT, true>, grid, dim3(kLossBlock), 0, s, pdl, a);
+    return;
+  }
   if (variant == kFastWrite) launch_pdl(loss_main_kernel<V, BATCH, kFastWrite, GT>, grid, dim3(kLossBlock), 0, s, pdl, a);
   else if (variant == kFastNoWrite) launch_pdl(loss_main_kernel<V, BATCH, kFastNoWrite, GT>, grid, dim3(kLossBlock), 0, s, pdl, a);
   else launch_pdl(loss_main_kernel<V, BATCH, kGeneric, GT>, grid, dim3(kLossBlock), 0, s, pdl, a);

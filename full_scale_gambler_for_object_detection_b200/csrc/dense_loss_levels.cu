@@ -224,7 +224,7 @@ __device__ __forceinline__ void level_body(const LevelLossArgs& A, const LevelTa
   }
 }
 
-template <int BATCH, bool EXACT, bool FAST, bool WRITE>
+template <int BATCH, bool EXACT, bool FAST, bool WRITE, bool PEER = false>   // PEER: see loss_main_kernel
 __global__ void __launch_bounds__(kLvBlock, LV_MINB) loss_main_levels_kernel(const LevelLossArgs A, const LevelTable LT) {
   const int tid = threadIdx.x;
   const int n = blockIdx.y;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kLvBlock, LV_MINB) loss_main_levels_kernel(con
   grid_dependency_sync();     // everything K1 produced is read from here on
   double nf_d = A.stats[0];
   float s_batch = (A.nmode == FSG_NORM_BATCH) ? (float)A.stats[1] : 1.f;
-  if (A.peer.world > 1) {   // sharded batch: num_foreground of the whole batch arrives through the peer mailboxes
+  if (PEER && A.peer.world > 1) {   // sharded batch: num_foreground of the whole batch arrives through the peer mailboxes
     const double nf_local = nf_d, sb_local = A.stats[1];
     peer_poll_nf(A.peer, nf_d);
     // (S_batch is not a normaliser of a sharded step -- FSG_NORM_BATCH is refused there; the ranks' complete records
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kLvBlock, LV_MINB) loss_main_levels_kernel(con
   }
   S.cls = warp_sum(S.cls); S.reg = warp_sum(S.reg); S.wl = warp_sum(S.wl);
   S.l = warp_sum(S.l); S.mx = warp_max(S.mx);
-  finish_tile<kLvBlock>(S.cls, S.reg, S.wl, S.l, S.mx, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
+  finish_tile<kLvBlock, PEER>(S.cls, S.reg, S.wl, S.l, S.mx, n, blockIdx.x, A.tiles_per_image, A.N, A.partials, A.counter,
                         A.scalars, nf_d, A.c_cls, A.c_reg, A.c_gam, A.peer);
 }
 
@@ -354,6 +354,16 @@ template <int BATCH, bool EXACT>
 static void launch_levels2(bool fast, bool write, dim3 grid, cudaStream_t s, const LevelLossArgs& a,
                            const LevelTable& t, bool pdl) {
   const dim3 blk(kLvBlock);
+  if (a.peer.world > 1) {
+    if (fast) {
+      if (write) launch_pdl(loss_main_levels_kernel<BATCH, EXACT, true, true, true>, grid, blk, 0, s, pdl, a, t);
+      else launch_pdl(loss_main_levels_kernel<BATCH, EXACT, true, false, true>, grid, blk, 0, s, pdl, a, t);
+    } else {
+      if (write) launch_pdl(loss_main_levels_kernel<BATCH, EXACT, false, true, true>, grid, blk, 0, s, pdl, a, t);
+      else launch_pdl(loss_main_levels_kernel<BATCH, EXACT, false, false, true>, grid, blk, 0, s, pdl, a, t);
+    }
+    return;
+  }
   if (fast) {
     if (write) launch_pdl(loss_main_levels_kernel<BATCH, EXACT, true, true>, grid, blk, 0, s, pdl, a, t);
     else launch_pdl(loss_main_levels_kernel<BATCH, EXACT, true, false>, grid, blk, 0, s, pdl, a, t);

@@ -254,7 +254,7 @@ __device__ __forceinline__ double peer_sum_v1(const PeerPoll& P) {
 // Called by every thread of an NT-thread CTA after it has reduced its own five sums into registers of
 // warp lane 0 (acc_* already warp-reduced).  Writes the tile's slot, elects the last CTA of the grid and lets it
 // fold all slots in a fixed order (run-to-run deterministic), producing the scalars of include/fsg_dense.h.
-template <int NT = kLossBlock>
+template <int NT = kLossBlock, bool PEER = false>
 __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float acc_wl, float acc_l, float max_l,
                                             int n, int tile, int T, int N, float* partials, unsigned* counter,
                                             double* scalars, double nf_d, float c_cls, float c_reg, float c_gam,
@@ -313,7 +313,7 @@ __device__ __forceinline__ void finish_tile(float acc_cls, float acc_reg, float 
     scalars[7] = -v[2];
     scalars[8] = (double)c_cls * scalars[5] + (double)c_reg * scalars[6] + (double)c_gam * scalars[7];
     scalars[9] = nf_d;
-    if (peer.world > 1) {   // the global sums become stats[0..1] (the peers posted their records long ago)
+    if (PEER && peer.world > 1) {   // the global sums become stats[0..1] (the peers posted their records long ago)
       peer.stats_out[1] = peer_sum_v1(peer);
       peer.stats_out[0] = nf_d;
     }
