@@ -126,6 +126,18 @@ __device__ __forceinline__ void grid_launch_dependents() {
 #endif
 }
 
+// Pointers to what the PRECEDING kernel of a programmatic-dependent-launch chain produced go through this right after
+// grid_dependency_sync().  nvcc treats loads through `const __restrict__` pointers as invariant for the kernel's
+// lifetime (ld.global.nc) and is free to hoist them above griddepcontrol.wait -- seen in SASS as an LDG of pass A's
+// best IoUs in front of ACQBULK, i.e. read while pass A was still running.  The empty volatile asm makes the pointer
+// value opaque until the wait has executed (volatile asm statements keep their order); profiles/pdl_audit.py lists
+// the global loads every kernel of the library issues before its wait.
+template <typename T>
+__device__ __forceinline__ T* produced_by_dependency(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
 // L2 prefetch of one 128-byte line (fire and forget: no register, no scoreboard entry)
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));

@@ -451,29 +451,308 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
+// Pass A for CROWDED batches (more than kSmallM ground truth per image on average; BASELINE config 5: 200 GT x 1 M
+// free-form anchors).  Same results as match_pass_a_kernel's generic branch, bit for bit; different schedule.
+//
+// The brute-force loop spends its time in divergence: ~6 % of the (anchor, GT) pairs overlap, so with 32 lanes nearly
+// every warp-level step enters the expensive branch (exact IEEE division, max / argmax, per-GT maximum) for one or two
+// active lanes -- 33 issued instructions per pair where a non-overlapping pair needs under ten.  Here the two kinds of
+// work are separated:
+//   * screen: one anchor per lane against the staged GT, four ordered compares per pair (a superset test of
+//     "both extents positive": fl(p - q) > 0 <=> p > q without flush-to-zero), hits are appended to the lane's own
+//     queue column in shared memory (ascending GT index);
+//   * drain: when some lane's column is nearly full (and after the last GT) every lane takes its pending pairs in
+//     FIFO order and does the exact arithmetic of pair_update -- dense: all lanes with work run the same code.
+// Ascending GT order per anchor is preserved, so strict '>' keeps the lowest GT index among ties (matcher.py:86).
+// ------------------------------------------------------------------------------------------
+// The queue is written and read through explicit 32-bit shared-window addresses: nvcc re-derives the window base
+// (S2R CgaCtaId, LEA) inside every predicated store otherwise, which doubles the cost of a push.  Both accessors are
+// volatile asm, so they keep their program order with respect to each other.
+__device__ __forceinline__ void queue_push(uint32_t addr, int v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
+}
+__device__ __forceinline__ int queue_at(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return (int)v;
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void reds_max_u32(uint32_t addr, unsigned v) {
+  asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+constexpr int kCrU = 4;      // anchors per thread, one after the other (same grid as match_pass_a_kernel<4, *>)
+constexpr int kCrQ = 32;     // pending pairs per lane
+constexpr int kCrStep = 4;   // GT screened between two fill checks (kGtChunk % kCrStep == 0)
+
+template <bool STEP>
+__global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
+    const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
+    const float4* __restrict__ gt_boxes, const int32_t* __restrict__ gt_offsets,
+    float* __restrict__ best_val, int32_t* __restrict__ best_idx, unsigned* __restrict__ gt_max,
+    const PassAEpi E, const BetLevels lv) {
+  static_assert(kGtChunk % kCrStep == 0 && kGtChunk <= 65536, "queue entries are 16-bit chunk-local GT indices");
+  __shared__ __align__(16) float4 s_gt[kGtChunk];
+  __shared__ float s_area[kGtChunk];
+  __shared__ unsigned s_max[kGtChunk];
+  __shared__ unsigned short s_q[kCrQ * kMatchBlock];   // [slot][thread]: a lane's column, conflict-free per slot
+  __shared__ __align__(8) uint64_t s_bar;
+  grid_launch_dependents();
+
+  const int n = blockIdx.y;
+  const int m0 = gt_offsets[n];
+  const int M = gt_offsets[n + 1] - m0;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int64_t base = (int64_t)blockIdx.x * (kMatchBlock * kCrU);
+  const float4* a_img = anchors + (int64_t)n * anchor_stride4;
+  const float inf = __int_as_float(0x7f800000);
+
+  float4 a[kCrU];
+  float bv[kCrU];
+  int bi[kCrU], ov[kCrU];
+#pragma unroll
+  for (int u = 0; u < kCrU; ++u) {
+    const int64_t r = base + u * kMatchBlock + tid;
+    // a lane without an anchor screens an inverted box: no ground truth passes
+    a[u] = (r < R) ? a_img[r] : make_float4(inf, inf, -inf, -inf);
+    bv[u] = 0.f;   // (IoU 0, GT 0): torch's argmax of an all-zero column
+    bi[u] = 0;
+    ov[u] = 0;
+  }
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(s_q + tid);   // the lane's queue column
+  constexpr uint32_t kSlot = kMatchBlock * 2;                              // bytes between two slots of a column
+  const uint32_t gt0 = (uint32_t)__cvta_generic_to_shared(s_gt), area0 = (uint32_t)__cvta_generic_to_shared(s_area);
+  const uint32_t max0 = (uint32_t)__cvta_generic_to_shared(s_max);
+  uint32_t phase = 0;
+  for (int c = 0; c < M; c += kGtChunk) {
+    const int cnt = min(kGtChunk, M - c);
+    const int cnt_up = (cnt + kCrStep - 1) / kCrStep * kCrStep;
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&s_bar, (uint32_t)cnt * 16u);
+      tma_bulk_g2s(s_gt, gt_boxes + m0 + c, (uint32_t)cnt * 16u, &s_bar);
+    }
+    mbar_wait(&s_bar, phase);
+    phase ^= 1u;
+    for (int g = tid; g < cnt_up; g += kMatchBlock) {
+      if (g < cnt) {
+        s_area[g] = box_area(s_gt[g]);
+        s_max[g] = gt_max[m0 + c + g];   // what other CTAs found so far (stale is fine)
+      } else {
+        s_gt[g] = make_float4(inf, inf, -inf, -inf);   // padding of the unrolled screen: never hit
+      }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int u = 0; u < kCrU; ++u) {
+      const float4 au = a[u];
+      const float aa = box_area(au);
+      float bvu = bv[u];
+      int biu = bi[u], ovu = ov[u];
+      uint32_t qp = q0;   // the lane's next free queue slot
+      // the exact per-pair arithmetic of pair_update, for the pairs the screen let through
+      auto drain = [&]() {
+        const uint32_t most = __reduce_max_sync(kFull, qp);
+        for (uint32_t qr = q0; qr < most; qr += kSlot) {
+          if (qr < qp) {
+            const int g = queue_at(qr);
+            const float4 G = lds_f4(gt0 + 16u * g);
+            const float w = __fsub_rn(fminf(G.z, au.z), fmaxf(G.x, au.x));
+            const float h = __fsub_rn(fminf(G.w, au.w), fmaxf(G.y, au.y));
+            if (w > 0.f && h > 0.f) {   // (the screen is a superset test: degenerate boxes pass it and stop here)
+              const float inter = __fmul_rn(w, h);
+              if (inter > 0.f) {
+                ++ovu;
+                const float uni = __fsub_rn(__fadd_rn(lds_f32(area0 + 4u * g), aa), inter);
+                const float known = lds_f32(max0 + 4u * g);
+                if (may_reach(inter, uni, fminf(bvu, known))) {
+                  const float v = __fdiv_rn(inter, uni);
+                  if (v > bvu) { bvu = v; biu = c + g; }
+                  if (v > known) reds_max_u32(max0 + 4u * g, __float_as_uint(v));   // (IoU >= 0: bits order like uints)
+                }
+              }
+            }
+          }
+        }
+        qp = q0;
+      };
+      for (int g0 = 0; g0 < cnt_up; g0 += kCrStep) {
+        float4 G[kCrStep];
+#pragma unroll
+        for (int i = 0; i < kCrStep; ++i) G[i] = s_gt[g0 + i];
+#pragma unroll
+        for (int i = 0; i < kCrStep; ++i) {
+          if (G[i].z > au.x && au.z > G[i].x && G[i].w > au.y && au.w > G[i].y) {
+            queue_push(qp, g0 + i);
+            qp += kSlot;
+          }
+        }
+        if (__any_sync(kFull, qp > q0 + (kCrQ - kCrStep) * kSlot)) drain();
+      }
+      drain();
+      bv[u] = bvu; bi[u] = biu; ov[u] = ovu;
+    }
+    __syncthreads();
+    for (int g = tid; g < cnt; g += kMatchBlock) {
+      const unsigned v = s_max[g];
+      if (v > 0u) atomicMax(&gt_max[m0 + c + g], v);
+    }
+    __syncthreads();  // s_gt / s_max are rewritten by the next chunk
+  }
+
+  // ---- epilogue: as in match_pass_a_kernel
+  const bool need_deltas = !STEP && (E.out.gt_deltas != nullptr);
+  const bool o_matches = !STEP && E.out.matches != nullptr, o_labels = !STEP && E.out.match_labels != nullptr;
+  const bool o_picky = !STEP && E.out.picky_labels != nullptr, o_cls = STEP || E.out.gt_classes != nullptr;
+  const bool o_mask = STEP || E.out.mask != nullptr, o_idx32 = STEP || E.out.matched_idx32 != nullptr;
+  const bool has_ids = STEP || E.gt_class_ids != nullptr, has_bets = E.bets != nullptr;
+  int fg = 0;
+  float w_part = 0.f;
+#pragma unroll
+  for (int u = 0; u < kCrU; ++u) {
+    const int64_t r = base + u * kMatchBlock + tid;
+    if (r >= R) continue;
+    const int64_t o = (int64_t)n * R + r;
+    const float val = (M > 0) ? bv[u] : 0.f;
+    best_val[o] = val;
+    best_idx[o] = bi[u] | (ov[u] >= 2 ? kMultiOverlap : 0);
+    int id = bi[u];
+    int8_t l1, l2;
+    int64_t cls, msk;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (M > 0) {
+      l1 = band_label_reg(E.br, val);
+      l2 = E.has_picky ? band_label_reg(E.pbr, val) : (int8_t)0;
+      cls = has_ids ? E.gt_class_ids[m0 + id] : 0;
+      if (l1 == 0) cls = E.num_classes;   // retinanet.py:356
+      if (l1 == -1) cls = -1;             // :360
+      msk = (l2 == 1) ? 1 : 0;            // :417-423
+      if (need_deltas) d = encode_deltas(a[u], gt_boxes[m0 + id], E.wx, E.wy, E.ww, E.wh);
+    } else {                              // matcher.py:70-80, retinanet.py:362-363, :425
+      l1 = E.lab0;
+      l2 = E.plab0;
+      cls = E.num_classes;
+      msk = E.num_classes;
+      id = 0;
+    }
+    if (o_matches) E.out.matches[o] = id;
+    if (o_labels) E.out.match_labels[o] = l1;
+    if (o_picky) E.out.picky_labels[o] = l2;
+    if (o_cls) E.out.gt_classes[o] = cls;
+    if (o_mask) E.out.mask[o] = msk;
+    if (need_deltas) E.out.gt_deltas[o] = d;
+    if (o_idx32) E.out.matched_idx32[o] = id;
+    fg += (cls >= 0 && cls != E.num_classes) ? 1 : 0;
+    if (has_bets) w_part += __fadd_rn(__fmul_rn(E.bets[o], (float)msk), E.temperature);  // gambler_heads.py:569,304
+    else if (lv.num_levels > 0 && msk != 0) w_part += __fmul_rn(bet_at(lv, n, r), (float)msk);  // + R*T at the fold
+  }
+  if (E.part_cnt != nullptr) {   // one partial per warp in a fixed slot (see match_pass_a_kernel)
+    const int cw = __reduce_add_sync(kFull, fg);
+    const float sw = warp_sum(w_part);
+    if (lane == 0) {
+      const int64_t slot = ((int64_t)n * gridDim.x + blockIdx.x) * kWarpsPerBlock + (tid >> 5);
+      E.part_cnt[slot] = cw;
+      E.part_s[slot] = sw;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused path, pass B: the low-quality rule (matcher.py:99-132) as a patch pass, and the fold of the pre-pass sums.
 // An anchor can equal some GT's maximum only if its own best IoU reaches the smallest per-GT maximum of its image
 // (IoU(g,a) <= best(a)), so all but a handful of anchors are dismissed after one 4-byte load.
 // ------------------------------------------------------------------------------------------
+// Pass B for one run of 4 consecutive anchors per thread in a CROWDED image (more than kSmallM ground truth),
+// warp-level and barrier-free.  Only a small share of the anchors reaches the smallest per-GT maximum; for each of them
+// the roles flip -- the candidate is broadcast and the LANES hold the ground truth (32 at a time), testing
+// IoU(g, a) == max(g) for the GT whose maximum the anchor's own best IoU reaches (IoU(g, a) <= best(a)).  Nothing is
+// staged or sorted.  Kept out of line so that its registers do not weigh on the few-GT path of the kernel.
+// a_warp0: the image's anchors offset so that thread t's run starts at a_warp0[4 * t]; gt_boxes / gt_max: this image's.
+// Returns the 4-bit mask of promoted anchors; live4: which of the 4 exist.
+__device__ __noinline__ unsigned pass_b_crowded_run(float4 val4, unsigned live4, const float4* a_run0,
+                                                    const float4* gt_boxes, const unsigned* gt_max, int M) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  // lane l keeps the maxima of GT l, l + 32, ... (the first kLaneGt * 32 of the image) in registers: the same values
+  // serve the minimum below and the test of every candidate
+  constexpr int kLaneGt = 8;
+  const float inf = __int_as_float(0x7f800000);
+  float gmr[kLaneGt];
+#pragma unroll
+  for (int k = 0; k < kLaneGt; ++k) {
+    const int g = lane + 32 * k;
+    gmr[k] = (g < M) ? __uint_as_float(gt_max[g]) : inf;
+  }
+  float mn = inf;
+#pragma unroll
+  for (int k = 0; k < kLaneGt; ++k) mn = fminf(mn, gmr[k]);
+  for (int g = lane + 32 * kLaneGt; g < M; g += 32) mn = fminf(mn, __uint_as_float(gt_max[g]));
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, sft));
+  const float val[4] = {val4.x, val4.y, val4.z, val4.w};
+  unsigned lq4 = 0u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const bool cand = ((live4 >> q) & 1u) && val[q] >= mn;
+    if (mn == 0.f) {   // a GT that overlaps no anchor promotes every anchor (matcher.py:114-116)
+      lq4 |= cand ? (1u << q) : 0u;
+      continue;
+    }
+    for (unsigned rem = __ballot_sync(kFull, cand); rem != 0u; rem &= rem - 1u) {
+      const int src = __ffs(rem) - 1;
+      const float cval = __shfl_sync(kFull, val[q], src);
+      const float4 ac = a_run0[((tid & ~31) + src) * 4 + q];   // lane src's anchor: one address for the whole warp
+      const float aac = box_area(ac);
+      bool hit = false;
+#pragma unroll
+      for (int k = 0; k < kLaneGt; ++k) {
+        if (gmr[k] <= cval) {        // (padding entries are +inf)
+          const float4 G = gt_boxes[lane + 32 * k];
+          hit = hit || (iou_exact(G, box_area(G), ac, aac) == gmr[k]);
+        }
+      }
+      for (int g = lane + 32 * kLaneGt; g < M; g += 32) {
+        const float gm = __uint_as_float(gt_max[g]);
+        if (gm <= cval) {
+          const float4 G = gt_boxes[g];
+          hit = hit || (iou_exact(G, box_area(G), ac, aac) == gm);
+        }
+      }
+      if (__any_sync(kFull, hit) && lane == src) lq4 |= 1u << q;
+    }
+  }
+  return lq4;
+}
+
 constexpr int kPassBU = 4;  // anchors per thread in pass B (8 was measured slower: 17 vs 13 us on config 2)
 
 template <int U>
 __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     const float4* __restrict__ anchors, int64_t R, int64_t anchor_stride4,
     const float4* __restrict__ gt_boxes, const int64_t* __restrict__ gt_class_ids,
-    const int32_t* __restrict__ gt_offsets, int N, int allow_lq, int has_picky, const float* __restrict__ best_val,
-    const int32_t* __restrict__ best_idx, const unsigned* __restrict__ gt_max, MatchOut out,
+    const int32_t* __restrict__ gt_offsets, int N, int allow_lq, int has_picky, const float* best_val,
+    const int32_t* best_idx, const unsigned* gt_max, MatchOut out,
     const float* __restrict__ bets, float temperature, int* __restrict__ part_cnt, float* __restrict__ part_s,
     const BandsReg br, const BandsReg pbr, const BetLevels lv) {
   static_assert(U % 4 == 0, "runs of 4 consecutive anchors per thread");
   grid_launch_dependents();
-  __shared__ __align__(16) float4 s_gt[kGtChunk];
-  __shared__ float s_area[kGtChunk];
-  __shared__ float s_max[kGtChunk];
-  __shared__ __align__(8) uint64_t s_key[kGtChunk];   // (gt max bits << 32 | gt index), sorted ascending
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ float s_red[kWarpsPerBlock];
-  __shared__ float s_min;
 
   const int n = blockIdx.y;
   const int m0 = gt_offsets[n];
@@ -491,6 +770,9 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
     my_cls = gt_class_ids ? gt_class_ids[m0 + lane] : 0;
   }
   grid_dependency_sync();     // (programmatic dependent launch behind pass A in fsg_dense_step)
+  best_val = produced_by_dependency(best_val);   // pass A's results: no load of these may move above the wait
+  best_idx = produced_by_dependency(best_idx);
+  gt_max = produced_by_dependency(gt_max);
 
   // thread t owns two runs of 4 consecutive anchors: base + j*1024 + 4t .. +3 (16-byte loads of the best IoUs)
   auto r_of = [&](int u) -> int64_t { return base + (int64_t)(u >> 2) * (kMatchBlock * 4) + tid * 4 + (u & 3); };
@@ -598,103 +880,16 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
       }
     }
   } else if (allow_lq && M > 0) {
-    float mn = __int_as_float(0x7f800000);
-    for (int g = tid; g < M; g += kMatchBlock) mn = fminf(mn, __uint_as_float(gt_max[m0 + g]));
+    // ---- crowded image (see pass_b_crowded_run)
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, s));
-    if (lane == 0) s_red[wid] = mn;
-    if (tid == 0) {
-      mbar_init(&s_bar, 1);
-      mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-      float v = s_red[0];
-      for (int w = 1; w < kWarpsPerBlock; ++w) v = fminf(v, s_red[w]);
-      s_min = v;
-    }
-    __syncthreads();
-    const float min_gt_max = s_min;
-    bool cand[U];
-    bool any_cand = false;
-    float vmax = -1.f;
+    for (int j = 0; j < U / 4; ++j) {
+      unsigned live4 = 0u;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      cand[u] = live[u] && val[u] >= min_gt_max;
-      any_cand |= cand[u];
-      if (cand[u]) vmax = fmaxf(vmax, val[u]);
-    }
-    if (__syncthreads_or(any_cand)) {
-      // U <= 4 (the instantiation crowded batches get): the candidates' boxes stay in registers; U = 8 (a few-GT
-      // batch with one crowded image in it): they are re-read from L1 where needed, which keeps the common path lean
-      constexpr int UA = (U <= 4) ? U : 1;
-      float4 a[UA];
-      float aa[UA];
-      if (U <= 4) {
+      for (int q = 0; q < 4; ++q) live4 |= live[4 * j + q] ? (1u << q) : 0u;
+      const unsigned lq4 = pass_b_crowded_run(make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]),
+                                              live4, a_img + r_of(4 * j) - tid * 4, gt_boxes + m0, gt_max + m0, M);
 #pragma unroll
-        for (int u = 0; u < UA; ++u) {
-          a[u] = cand[u] ? a_img[r_of(u)] : make_float4(0.f, 0.f, 0.f, 0.f);
-          aa[u] = box_area(a[u]);
-        }
-      }
-      uint32_t phase = 0;
-      for (int c = 0; c < M; c += kGtChunk) {
-        const int cnt = min(kGtChunk, M - c);
-        if (tid == 0) {
-          fence_proxy_async();
-          mbar_expect_tx(&s_bar, (uint32_t)cnt * 16u);
-          tma_bulk_g2s(s_gt, gt_boxes + m0 + c, (uint32_t)cnt * 16u, &s_bar);
-        }
-        mbar_wait(&s_bar, phase);
-        phase ^= 1u;
-        int m2 = 1;
-        while (m2 < cnt) m2 <<= 1;
-        for (int g = tid; g < m2; g += kMatchBlock) {
-          if (g < cnt) {
-            const unsigned gmb = gt_max[m0 + c + g];
-            s_area[g] = box_area(s_gt[g]);
-            s_max[g] = __uint_as_float(gmb);
-            s_key[g] = ((uint64_t)gmb << 32) | (uint64_t)g;
-          } else {
-            s_key[g] = ~0ull;
-          }
-        }
-        __syncthreads();
-        // sort the chunk's GT by their maxima (ascending) so every anchor stops at the first GT whose
-        // maximum exceeds its own best IoU
-        for (int size = 2; size <= m2; size <<= 1) {
-          for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (m2 >> 1); t += kMatchBlock) {
-              const int lo = ((t / stride) * (stride << 1)) + (t % stride);
-              const int hi = lo + stride;
-              const bool asc = ((lo & size) == 0);
-              const uint64_t x = s_key[lo], y = s_key[hi];
-              if (asc ? (x > y) : (x < y)) { s_key[lo] = y; s_key[hi] = x; }
-            }
-            __syncthreads();
-          }
-        }
-        if (__any_sync(kFull, any_cand)) {
-          const float wmax = warp_max(vmax);
-          for (int i = 0; i < cnt; ++i) {
-            const uint64_t key = s_key[i];
-            const float gm = __uint_as_float((unsigned)(key >> 32));
-            if (gm > wmax) break;   // warp-uniform: no anchor of this warp reaches the remaining GTs
-            const int g = (int)(key & 0xffffffffu);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if (cand[u] && gm <= val[u]) {
-                float4 au;
-                float aau;
-                if (U <= 4) { au = a[u < UA ? u : 0]; aau = aa[u < UA ? u : 0]; }
-                else { au = a_img[r_of(u)]; aau = box_area(au); }
-                if (iou_exact(s_gt[g], s_area[g], au, aau) == gm) lq[u] = true;
-              }
-            }
-          }
-        }
-        __syncthreads();
-      }
+      for (int q = 0; q < 4; ++q) lq[4 * j + q] = (lq4 >> q) & 1u;
     }
   }
 
@@ -1107,6 +1302,7 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
   // anchors per thread in pass A: 2 for the few-GT training case (more CTAs in flight), 4 when the batch is crowded
   // (each staged GT box is reused more); the same choice sizes pass A's partial-sum slots in both phases
   const bool few_gt = sum_M <= (int64_t)N * kSmallM;
+  static const bool crowded_queue = getenv("FSG_MATCH_CROWDED_BRUTE") == nullptr;   // (diagnostic switch for A/B timing)
   const int nb_a = (int)ceil_div(R, kMatchBlock * (few_gt ? 2 : 4));
   MatchOut out{matches, match_labels, picky_labels, gt_classes_out, mask_out, (float4*)gt_deltas, matched_idx32};
   if (phases & 1) {
@@ -1126,7 +1322,10 @@ int match_enqueue(const float* anchors, int64_t R, int64_t anchor_image_stride,
                                           gt_offsets, bval, bidx, gtmax, e, lv);
     };
     if (few_gt) { if (step_set) go_a(match_pass_a_kernel<2, true>); else go_a(match_pass_a_kernel<2, false>); }
-    else        { if (step_set) go_a(match_pass_a_kernel<4, true>); else go_a(match_pass_a_kernel<4, false>); }
+    else if (crowded_queue) {
+      static_assert(kCrU == 4, "pass A's partial-sum slots are sized for 4 anchors per thread in crowded batches");
+      if (step_set) go_a(match_pass_a_crowded_kernel<true>); else go_a(match_pass_a_crowded_kernel<false>);
+    } else      { if (step_set) go_a(match_pass_a_kernel<4, true>); else go_a(match_pass_a_kernel<4, false>); }
     FSG_LAUNCH_CHECK();
   }
   if (!(phases & 2)) return FSG_OK;
