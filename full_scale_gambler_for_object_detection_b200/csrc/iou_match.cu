@@ -509,18 +509,28 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
   __shared__ __align__(8) uint64_t s_bar;
   grid_launch_dependents();
 
-  const int n = blockIdx.y;
+  // CTAs are dealt out round-robin over the images (the hardware starts them in linear order): the CTAs that run
+  // first -- with no per-GT maxima to start from, so that every pair looks like a new maximum -- are then a thin
+  // slice of every image instead of most of the first one
+  const unsigned linear = blockIdx.y * gridDim.x + blockIdx.x;
+  const int n = (int)(linear % gridDim.y);
+  const unsigned bx = linear / gridDim.y;
   const int m0 = gt_offsets[n];
   const int M = gt_offsets[n + 1] - m0;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int64_t base = (int64_t)blockIdx.x * (kMatchBlock * kCrU);
+  const int64_t base = (int64_t)bx * (kMatchBlock * kCrU);
   const float4* a_img = anchors + (int64_t)n * anchor_stride4;
   const float inf = __int_as_float(0x7f800000);
 
   float4 a[kCrU];
   float bv[kCrU];
-  int bi[kCrU], ov[kCrU];
+  int bi[kCrU];
+  // bit 0: the pair that currently holds the anchor's best IoU reached its GT's running maximum when it was evaluated;
+  // bit 1: some OTHER evaluated pair of the anchor did.  IoU(g, a) can equal the final maximum of g only if it reached
+  // the running one, so bit 1 is what pass B needs to know whether a GT other than the argmax can promote the anchor
+  // (it takes the place of the "overlaps two or more GT" flag of match_pass_a_kernel: same meaning, far fewer hits).
+  int tops[kCrU];
 #pragma unroll
   for (int u = 0; u < kCrU; ++u) {
     const int64_t r = base + u * kMatchBlock + tid;
@@ -528,7 +538,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
     a[u] = (r < R) ? a_img[r] : make_float4(inf, inf, -inf, -inf);
     bv[u] = 0.f;   // (IoU 0, GT 0): torch's argmax of an all-zero column
     bi[u] = 0;
-    ov[u] = 0;
+    tops[u] = 0;
   }
 
   if (tid == 0) {
@@ -566,7 +576,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
       const float4 au = a[u];
       const float aa = box_area(au);
       float bvu = bv[u];
-      int biu = bi[u], ovu = ov[u];
+      int biu = bi[u], tpu = tops[u];
       uint32_t qp = q0;   // the lane's next free queue slot
       // the exact per-pair arithmetic of pair_update, for the pairs the screen let through
       auto drain = [&]() {
@@ -580,12 +590,14 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
             if (w > 0.f && h > 0.f) {   // (the screen is a superset test: degenerate boxes pass it and stop here)
               const float inter = __fmul_rn(w, h);
               if (inter > 0.f) {
-                ++ovu;
                 const float uni = __fsub_rn(__fadd_rn(lds_f32(area0 + 4u * g), aa), inter);
                 const float known = lds_f32(max0 + 4u * g);
+                // (a pair the filter rejects is strictly below both the anchor's best and the GT's running maximum)
                 if (may_reach(inter, uni, fminf(bvu, known))) {
                   const float v = __fdiv_rn(inter, uni);
-                  if (v > bvu) { bvu = v; biu = c + g; }
+                  const int top = (v >= known) ? 1 : 0;
+                  if (v > bvu) { bvu = v; biu = c + g; tpu = ((tpu & 1) << 1) | (tpu & 2) | top; }
+                  else tpu |= top << 1;
                   if (v > known) reds_max_u32(max0 + 4u * g, __float_as_uint(v));   // (IoU >= 0: bits order like uints)
                 }
               }
@@ -608,7 +620,16 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
         if (__any_sync(kFull, qp > q0 + (kCrQ - kCrStep) * kSlot)) drain();
       }
       drain();
-      bv[u] = bvu; bi[u] = biu; ov[u] = ovu;
+      bv[u] = bvu; bi[u] = biu; tops[u] = tpu;
+      if (u + 1 < kCrU) {
+        // exchange the per-GT maxima with the other CTAs before the next anchor (no barrier: every step is a max).
+        // Fresher maxima make may_reach reject more pairs and keep the "reached the running maximum" flag rare.
+        for (int g = tid; g < cnt; g += kMatchBlock) {
+          const unsigned mine = s_max[g], seen = __ldcg(&gt_max[m0 + c + g]);
+          if (mine > seen) atomicMax(&gt_max[m0 + c + g], mine);
+          else if (seen > mine) atomicMax(&s_max[g], seen);
+        }
+      }
     }
     __syncthreads();
     for (int g = tid; g < cnt; g += kMatchBlock) {
@@ -633,7 +654,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
     const int64_t o = (int64_t)n * R + r;
     const float val = (M > 0) ? bv[u] : 0.f;
     best_val[o] = val;
-    best_idx[o] = bi[u] | (ov[u] >= 2 ? kMultiOverlap : 0);
+    best_idx[o] = bi[u] | ((tops[u] & 2) ? kMultiOverlap : 0);
     int id = bi[u];
     int8_t l1, l2;
     int64_t cls, msk;
@@ -668,7 +689,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
     const int cw = __reduce_add_sync(kFull, fg);
     const float sw = warp_sum(w_part);
     if (lane == 0) {
-      const int64_t slot = ((int64_t)n * gridDim.x + blockIdx.x) * kWarpsPerBlock + (tid >> 5);
+      const int64_t slot = ((int64_t)n * gridDim.x + bx) * kWarpsPerBlock + (tid >> 5);
       E.part_cnt[slot] = cw;
       E.part_s[slot] = sw;
     }
@@ -681,41 +702,58 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
 // (IoU(g,a) <= best(a)), so all but a handful of anchors are dismissed after one 4-byte load.
 // ------------------------------------------------------------------------------------------
 // Pass B for one run of 4 consecutive anchors per thread in a CROWDED image (more than kSmallM ground truth),
-// warp-level and barrier-free.  Only a small share of the anchors reaches the smallest per-GT maximum; for each of them
-// the roles flip -- the candidate is broadcast and the LANES hold the ground truth (32 at a time), testing
-// IoU(g, a) == max(g) for the GT whose maximum the anchor's own best IoU reaches (IoU(g, a) <= best(a)).  Nothing is
-// staged or sorted.  Kept out of line so that its registers do not weigh on the few-GT path of the kernel.
-// a_warp0: the image's anchors offset so that thread t's run starts at a_warp0[4 * t]; gt_boxes / gt_max: this image's.
-// Returns the 4-bit mask of promoted anchors; live4: which of the 4 exist.
+// warp-level and barrier-free.  An anchor is a candidate when its best IoU reaches the smallest per-GT maximum of the
+// image.  Its own argmax GT promotes it iff best(a) == max(argmax) -- two loads, no arithmetic.  Any other GT g needs
+// IoU(g, a) == max(g), which pass A rules out for all but the anchors it flagged (kMultiOverlap); for those few the
+// roles flip: the candidate is broadcast and the LANES hold the ground truth (32 at a time), each testing the GT
+// whose maximum the anchor's best IoU reaches (IoU(g, a) <= best(a)).  Nothing is staged or sorted.  Kept out of line
+// so that its registers do not weigh on the few-GT path of the kernel.
+// a_run0 / idx_run0: the image's anchors / pass A's argmax words, offset so that thread t's run starts at [4 * t];
+// gt_boxes / gt_max: this image's.  Returns the 4-bit mask of promoted anchors; live4: which of the 4 exist.
 __device__ __noinline__ unsigned pass_b_crowded_run(float4 val4, unsigned live4, const float4* a_run0,
-                                                    const float4* gt_boxes, const unsigned* gt_max, int M) {
+                                                    const int32_t* idx_run0, const float4* gt_boxes,
+                                                    const unsigned* gt_max, int M) {
   const int tid = threadIdx.x, lane = tid & 31;
-  // lane l keeps the maxima of GT l, l + 32, ... (the first kLaneGt * 32 of the image) in registers: the same values
-  // serve the minimum below and the test of every candidate
-  constexpr int kLaneGt = 8;
   const float inf = __int_as_float(0x7f800000);
+  float mn = inf;
+  for (int g = lane; g < M; g += 32) mn = fminf(mn, __uint_as_float(gt_max[g]));
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, sft));
+  const float val[4] = {val4.x, val4.y, val4.z, val4.w};
+  unsigned lq4 = 0u;
+  if (mn == 0.f) {   // a GT that overlaps no anchor promotes every anchor (matcher.py:114-116)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lq4 |= (((live4 >> q) & 1u) && val[q] >= 0.f) ? (1u << q) : 0u;
+    return lq4;
+  }
+  bool hard[4];
+  int bix[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const bool cand = ((live4 >> q) & 1u) && val[q] >= mn;
+    bix[q] = cand ? idx_run0[tid * 4 + q] : 0;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const bool cand = ((live4 >> q) & 1u) && val[q] >= mn;
+    const float gmb = cand ? __uint_as_float(gt_max[bix[q] & (kMultiOverlap - 1)]) : inf;
+    const bool own = cand && val[q] == gmb;
+    lq4 |= own ? (1u << q) : 0u;
+    hard[q] = cand && !own && (bix[q] & kMultiOverlap) != 0;
+  }
+  if (!__any_sync(kFull, hard[0] || hard[1] || hard[2] || hard[3])) return lq4;
+  // lane l keeps the maxima of GT l, l + 32, ... (the first kLaneGt * 32 of the image) in registers for all the
+  // candidates of the warp: a candidate then costs kLaneGt compares, and loads only for the GT it can reach
+  constexpr int kLaneGt = 8;
   float gmr[kLaneGt];
 #pragma unroll
   for (int k = 0; k < kLaneGt; ++k) {
     const int g = lane + 32 * k;
     gmr[k] = (g < M) ? __uint_as_float(gt_max[g]) : inf;
   }
-  float mn = inf;
-#pragma unroll
-  for (int k = 0; k < kLaneGt; ++k) mn = fminf(mn, gmr[k]);
-  for (int g = lane + 32 * kLaneGt; g < M; g += 32) mn = fminf(mn, __uint_as_float(gt_max[g]));
-#pragma unroll
-  for (int sft = 16; sft > 0; sft >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, sft));
-  const float val[4] = {val4.x, val4.y, val4.z, val4.w};
-  unsigned lq4 = 0u;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const bool cand = ((live4 >> q) & 1u) && val[q] >= mn;
-    if (mn == 0.f) {   // a GT that overlaps no anchor promotes every anchor (matcher.py:114-116)
-      lq4 |= cand ? (1u << q) : 0u;
-      continue;
-    }
-    for (unsigned rem = __ballot_sync(kFull, cand); rem != 0u; rem &= rem - 1u) {
+    for (unsigned rem = __ballot_sync(kFull, hard[q]); rem != 0u; rem &= rem - 1u) {
       const int src = __ffs(rem) - 1;
       const float cval = __shfl_sync(kFull, val[q], src);
       const float4 ac = a_run0[((tid & ~31) + src) * 4 + q];   // lane src's anchor: one address for the whole warp
@@ -887,7 +925,8 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
 #pragma unroll
       for (int q = 0; q < 4; ++q) live4 |= live[4 * j + q] ? (1u << q) : 0u;
       const unsigned lq4 = pass_b_crowded_run(make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]),
-                                              live4, a_img + r_of(4 * j) - tid * 4, gt_boxes + m0, gt_max + m0, M);
+                                              live4, a_img + r_of(4 * j) - tid * 4,
+                                              best_idx + img + r_of(4 * j) - tid * 4, gt_boxes + m0, gt_max + m0, M);
 #pragma unroll
       for (int q = 0; q < 4; ++q) lq[4 * j + q] = (lq4 >> q) & 1u;
     }
