@@ -482,6 +482,17 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// (the screen's loads: no "memory" clobber, so that a group of them can be scheduled together; volatile keeps them
+//  behind the barrier that follows the staging of the chunk)
+__device__ __forceinline__ float4 lds_f4_screen(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {   // keeps nvcc from re-deriving a shared-window base per use
+  asm volatile("" : "+r"(v));
+  return v;
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -493,7 +504,7 @@ __device__ __forceinline__ void reds_max_u32(uint32_t addr, unsigned v) {
 
 constexpr int kCrU = 4;      // anchors per thread, one after the other (same grid as match_pass_a_kernel<4, *>)
 constexpr int kCrQ = 32;     // pending pairs per lane
-constexpr int kCrStep = 4;   // GT screened between two fill checks (kGtChunk % kCrStep == 0)
+constexpr int kCrStep = 8;   // GT screened between two fill checks (kGtChunk % kCrStep == 0)
 
 template <bool STEP>
 __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
@@ -546,10 +557,11 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
     mbar_fence_init();
   }
   __syncthreads();
-  const uint32_t q0 = (uint32_t)__cvta_generic_to_shared(s_q + tid);   // the lane's queue column
-  constexpr uint32_t kSlot = kMatchBlock * 2;                              // bytes between two slots of a column
-  const uint32_t gt0 = (uint32_t)__cvta_generic_to_shared(s_gt), area0 = (uint32_t)__cvta_generic_to_shared(s_area);
-  const uint32_t max0 = (uint32_t)__cvta_generic_to_shared(s_max);
+  const uint32_t q0 = opaque((uint32_t)__cvta_generic_to_shared(s_q + tid));   // the lane's queue column
+  constexpr uint32_t kSlot = kMatchBlock * 2;                                      // bytes between two slots of a column
+  const uint32_t gt0 = opaque((uint32_t)__cvta_generic_to_shared(s_gt));
+  const uint32_t area0 = opaque((uint32_t)__cvta_generic_to_shared(s_area));
+  const uint32_t max0 = opaque((uint32_t)__cvta_generic_to_shared(s_max));
   uint32_t phase = 0;
   for (int c = 0; c < M; c += kGtChunk) {
     const int cnt = min(kGtChunk, M - c);
@@ -607,14 +619,17 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
         qp = q0;
       };
       for (int g0 = 0; g0 < cnt_up; g0 += kCrStep) {
-        float4 G[kCrStep];
 #pragma unroll
-        for (int i = 0; i < kCrStep; ++i) G[i] = s_gt[g0 + i];
+        for (int h = 0; h < kCrStep; h += 4) {
+          float4 G[4];
 #pragma unroll
-        for (int i = 0; i < kCrStep; ++i) {
-          if (G[i].z > au.x && au.z > G[i].x && G[i].w > au.y && au.w > G[i].y) {
-            queue_push(qp, g0 + i);
-            qp += kSlot;
+          for (int i = 0; i < 4; ++i) G[i] = lds_f4_screen(gt0 + 16u * (g0 + h + i));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (G[i].z > au.x && au.z > G[i].x && G[i].w > au.y && au.w > G[i].y) {
+              queue_push(qp, g0 + h + i);
+              qp += kSlot;
+            }
           }
         }
         if (__any_sync(kFull, qp > q0 + (kCrQ - kCrStep) * kSlot)) drain();
