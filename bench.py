@@ -287,7 +287,8 @@ def secondary_metrics(ctx, fsg, with_cpu=True):
                             "hbm_frac": 25.0 * 8e6 / (ms5 * 1e-3) / (hbm * 1e9),
                             # SURVEY 8d model: ~16 fp32 instructions + 1 IEEE divide per pair
                             "fp32_issue_frac_model": pairs * 17.0 / fp32_peak,
-                            "bound": "fp32 issue (ncu: 90% of issue slots busy in pass A, 33 instr/pair)"}
+                            "bound": "instruction issue (ncu, profiles/r2_match_crowded_ncu_summary.txt: pass A 17.8 "
+                                     "instr/pair = 9.1 screen + deferred exact pairs, 78% of issue slots, ALU pipe 63%)"}
     if with_cpu:
         from oracle import dense_oracle as orc
         a_cpu, g_cpu, c_cpu = inp5["anchors"][0][:100000], inp5["gt_boxes"][:1], inp5["gt_classes"][:1]

@@ -503,8 +503,9 @@ __device__ __forceinline__ void reds_max_u32(uint32_t addr, unsigned v) {
 }
 
 constexpr int kCrU = 4;      // anchors per thread, one after the other (same grid as match_pass_a_kernel<4, *>)
-constexpr int kCrQ = 32;     // pending pairs per lane
-constexpr int kCrStep = 8;   // GT screened between two fill checks (kGtChunk % kCrStep == 0)
+constexpr int kCrQ = 48;     // pending pairs per lane
+constexpr int kCrChunk = 512;   // GT staged per shared-memory chunk
+constexpr int kCrStep = 8;   // GT screened between two fill checks (kCrChunk % kCrStep == 0)
 
 template <bool STEP>
 __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
@@ -512,10 +513,10 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
     const float4* __restrict__ gt_boxes, const int32_t* __restrict__ gt_offsets,
     float* __restrict__ best_val, int32_t* __restrict__ best_idx, unsigned* __restrict__ gt_max,
     const PassAEpi E, const BetLevels lv) {
-  static_assert(kGtChunk % kCrStep == 0 && kGtChunk <= 65536, "queue entries are 16-bit chunk-local GT indices");
-  __shared__ __align__(16) float4 s_gt[kGtChunk];
-  __shared__ float s_area[kGtChunk];
-  __shared__ unsigned s_max[kGtChunk];
+  static_assert(kCrChunk % kCrStep == 0 && kCrChunk <= 65536, "queue entries are 16-bit chunk-local GT indices");
+  __shared__ __align__(16) float4 s_gt[kCrChunk];
+  __shared__ float s_area[kCrChunk];
+  __shared__ unsigned s_max[kCrChunk];
   __shared__ unsigned short s_q[kCrQ * kMatchBlock];   // [slot][thread]: a lane's column, conflict-free per slot
   __shared__ __align__(8) uint64_t s_bar;
   grid_launch_dependents();
@@ -563,8 +564,8 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
   const uint32_t area0 = opaque((uint32_t)__cvta_generic_to_shared(s_area));
   const uint32_t max0 = opaque((uint32_t)__cvta_generic_to_shared(s_max));
   uint32_t phase = 0;
-  for (int c = 0; c < M; c += kGtChunk) {
-    const int cnt = min(kGtChunk, M - c);
+  for (int c = 0; c < M; c += kCrChunk) {
+    const int cnt = min(kCrChunk, M - c);
     const int cnt_up = (cnt + kCrStep - 1) / kCrStep * kCrStep;
     if (tid == 0) {
       fence_proxy_async();

@@ -120,3 +120,22 @@ def test_argument_validation_needs_no_device(lib_path):
                         null, null, null, null, null, null, null, null, 0, null) == INVALID
     assert b"invalid" in L.fsg_status_string(INVALID).lower() or b"argument" in L.fsg_status_string(INVALID).lower()
     assert L.fsg_status_string(UNSUPPORTED) and L.fsg_status_string(WORKSPACE)
+
+
+def test_no_dependent_loads_before_pdl_wait(lib_path):
+    """Kernels launched under programmatic dependent launch may read only the step's INPUTS before
+    griddepcontrol.wait (SASS: ACQBULK).  nvcc hoists loads through `const __restrict__` pointers above the wait
+    (common.cuh: produced_by_dependency), which reads the preceding kernel's results while it is still running.
+    The built library is disassembled: the only kernel with global loads in front of its wait is pass B of the
+    matcher -- gt_offsets[n], gt_offsets[n + 1], its GT box and GT class (all inputs) -- and nothing stores there."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "pdl_audit.py")
+    out = subprocess.run(["python", script, lib_path], capture_output=True, text=True, check=True).stdout
+    kernels = [l for l in out.splitlines() if re.match(r"\s*\d+  ", l)]
+    assert len(kernels) >= 10, out[-2000:]           # every kernel of the PDL chains is in the list
+    offenders = {l.split(None, 1)[1].split("(")[0]: int(l.split()[0]) for l in kernels if int(l.split()[0]) > 0}
+    assert list(offenders) == ["void fsg::match_pass_b_kernel<4>"], offenders
+    pre = [l.strip() for l in out.splitlines() if l.startswith("        ")]
+    assert len(pre) == 4 and all(re.match(r"(@!?P\d+ )?LDG\.E(\.\d+)?\.CONSTANT ", l) for l in pre), pre
