@@ -159,9 +159,12 @@ def test_fused_match_stress_slice(cuda):
         assert_equal_int(got[k], want[k], k)
 
 
-@pytest.mark.parametrize("Ms", [(65, 256), (130, 200), (256, 65), (257, 64), (100, 0, 180)])
+@pytest.mark.parametrize("Ms", [(65, 256), (130, 200), (256, 65), (257, 64), (100, 0, 180), (200, 8, 20),
+                                (90, 3, 2, 1, 0)])
 def test_fused_match_crowded_images_spatial_prefilter(cuda, Ms):
-    """Crowded images (64..257 GT per image, mixed with a GT-free one) on the shared-memory GT path.  Includes: anchors far outside the GT extent,
+    """Crowded images (64..257 GT per image, mixed with a GT-free one) on the shared-memory GT path; (200, 8, 20):
+    few-GT images inside a crowded batch (the crowded pass A kernel with pass B's few-GT path); (90, 3, 2, 1, 0): a
+    crowded image inside a few-GT batch (the few-GT pass A kernel with pass B's crowded path).  Includes: anchors far outside the GT extent,
     anchors covering the whole extent, GT that touch nothing (zero maximum: every anchor becomes a low-quality
     match), duplicated anchors and GT (ties -> lowest GT index), degenerate and identical GT boxes."""
     fsg = _fsg()
