@@ -374,7 +374,11 @@ static void launch_levels2(bool fast, bool write, dim3 grid, cudaStream_t s, con
 }
 static void launch_levels(int K, bool fast, bool write, dim3 grid, cudaStream_t s, const LevelLossArgs& a,
                           const LevelTable& t, bool pdl) {
-#ifdef LV_PREFER10
+#if defined(LV_BATCH16)
+  if (K % 16 == 0) launch_levels2<16, true>(fast, write, grid, s, a, t, pdl);
+  else if (K % 8 == 0) launch_levels2<8, true>(fast, write, grid, s, a, t, pdl);
+  else if (K % 10 == 0) launch_levels2<10, true>(fast, write, grid, s, a, t, pdl);
+#elif defined(LV_PREFER10)
   if (K % 10 == 0) launch_levels2<10, true>(fast, write, grid, s, a, t, pdl);
   else if (K % 8 == 0) launch_levels2<8, true>(fast, write, grid, s, a, t, pdl);
 #else

@@ -458,9 +458,10 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
 // every warp-level step enters the expensive branch (exact IEEE division, max / argmax, per-GT maximum) for one or two
 // active lanes -- 33 issued instructions per pair where a non-overlapping pair needs under ten.  Here the two kinds of
 // work are separated:
-//   * screen: one anchor per lane against the staged GT, four ordered compares per pair (a superset test of
-//     "both extents positive": fl(p - q) > 0 <=> p > q without flush-to-zero), hits are appended to the lane's own
-//     queue column in shared memory (ascending GT index);
+//   * screen: one anchor per lane against the staged GT, a superset test of "both extents positive"
+//     (fl(p - q) > 0 <=> p > q without flush-to-zero) done in packed half precision with outward rounding -- two
+//     2-wide compares per pair -- and hits are appended to the lane's own queue column in shared memory (ascending
+//     GT index);
 //   * drain: when some lane's column is nearly full (and after the last GT) every lane takes its pending pairs in
 //     FIFO order and does the exact arithmetic of pair_update -- dense: all lanes with work run the same code.
 // Ascending GT order per anchor is preserved, so strict '>' keeps the lowest GT index among ties (matcher.py:86).
@@ -502,6 +503,42 @@ __device__ __forceinline__ void reds_max_u32(uint32_t addr, unsigned v) {
   asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// ---- the screen in packed half precision.  A box is kept as two f16x2 words, lo = (x1, y1) rounded DOWN and
+// hi = (x2, y2) rounded UP, so that "G.hi > a.lo && a.hi > G.lo" (two HSETP2 + one PLOP3 per pair, on the fp16 pipe
+// instead of four FSETP on the ALU pipe that bounds this kernel) holds whenever the fp32 test does: a superset, and
+// the drain repeats the test exactly.  Out-of-range coordinates saturate towards the permissive side (+-inf / +-65504).
+__device__ __forceinline__ uint32_t pack_half2_rd(float x, float y) {
+  unsigned short hx, hy;
+  asm("cvt.rm.f16.f32 %0, %1;" : "=h"(hx) : "f"(x));
+  asm("cvt.rm.f16.f32 %0, %1;" : "=h"(hy) : "f"(y));
+  return (uint32_t)hx | ((uint32_t)hy << 16);
+}
+__device__ __forceinline__ uint32_t pack_half2_ru(float x, float y) {
+  unsigned short hx, hy;
+  asm("cvt.rp.f16.f32 %0, %1;" : "=h"(hx) : "f"(x));
+  asm("cvt.rp.f16.f32 %0, %1;" : "=h"(hy) : "f"(y));
+  return (uint32_t)hx | ((uint32_t)hy << 16);
+}
+// if the boxes (glo, ghi) and (alo, ahi) may overlap: append entry `g` to the queue column at qp and advance it
+__device__ __forceinline__ void screen_push(uint32_t& qp, int g, uint32_t glo, uint32_t ghi, uint32_t alo, uint32_t ahi,
+                                            uint32_t slot_bytes) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, r, s;\n\t"
+      "setp.gt.f16x2 p|q, %2, %3;\n\t"
+      "setp.gt.and.f16x2 r|s, %4, %5, p;\n\t"
+      "and.pred r, r, s;\n\t"
+      "and.pred r, r, q;\n\t"
+      "@r st.shared.u16 [%0], %1;\n\t"
+      "@r add.u32 %0, %0, %6;\n\t}"
+      : "+r"(qp)
+      : "h"((unsigned short)g), "r"(ghi), "r"(alo), "r"(ahi), "r"(glo), "r"(slot_bytes));
+}
+__device__ __forceinline__ uint4 lds_u4_screen(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
 constexpr int kCrU = 4;      // anchors per thread, one after the other (same grid as match_pass_a_kernel<4, *>)
 constexpr int kCrQ = 48;     // pending pairs per lane
 constexpr int kCrChunk = 512;   // GT staged per shared-memory chunk
@@ -518,6 +555,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
   __shared__ float s_area[kCrChunk];
   __shared__ unsigned s_max[kCrChunk];
   __shared__ unsigned short s_q[kCrQ * kMatchBlock];   // [slot][thread]: a lane's column, conflict-free per slot
+  __shared__ __align__(16) uint2 s_gth[kCrChunk];      // the staged GT for the screen: (lo, hi) f16x2 words
   __shared__ __align__(8) uint64_t s_bar;
   grid_launch_dependents();
 
@@ -561,6 +599,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
   const uint32_t q0 = opaque((uint32_t)__cvta_generic_to_shared(s_q + tid));   // the lane's queue column
   constexpr uint32_t kSlot = kMatchBlock * 2;                                      // bytes between two slots of a column
   const uint32_t gt0 = opaque((uint32_t)__cvta_generic_to_shared(s_gt));
+  const uint32_t gth0 = opaque((uint32_t)__cvta_generic_to_shared(s_gth));
   const uint32_t area0 = opaque((uint32_t)__cvta_generic_to_shared(s_area));
   const uint32_t max0 = opaque((uint32_t)__cvta_generic_to_shared(s_max));
   uint32_t phase = 0;
@@ -576,10 +615,12 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
     phase ^= 1u;
     for (int g = tid; g < cnt_up; g += kMatchBlock) {
       if (g < cnt) {
-        s_area[g] = box_area(s_gt[g]);
+        const float4 G = s_gt[g];
+        s_area[g] = box_area(G);
         s_max[g] = gt_max[m0 + c + g];   // what other CTAs found so far (stale is fine)
+        s_gth[g] = make_uint2(pack_half2_rd(G.x, G.y), pack_half2_ru(G.z, G.w));
       } else {
-        s_gt[g] = make_float4(inf, inf, -inf, -inf);   // padding of the unrolled screen: never hit
+        s_gth[g] = make_uint2(pack_half2_rd(inf, inf), pack_half2_ru(-inf, -inf));   // padding of the unrolled screen: never hit
       }
     }
     __syncthreads();
@@ -588,6 +629,7 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
     for (int u = 0; u < kCrU; ++u) {
       const float4 au = a[u];
       const float aa = box_area(au);
+      const uint32_t alo = pack_half2_rd(au.x, au.y), ahi = pack_half2_ru(au.z, au.w);
       float bvu = bv[u];
       int biu = bi[u], tpu = tops[u];
       uint32_t qp = q0;   // the lane's next free queue slot
@@ -620,18 +662,13 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_crowded_kernel(
         qp = q0;
       };
       for (int g0 = 0; g0 < cnt_up; g0 += kCrStep) {
+        uint4 G2[kCrStep / 2];   // two GT per 16-byte load
 #pragma unroll
-        for (int h = 0; h < kCrStep; h += 4) {
-          float4 G[4];
+        for (int i = 0; i < kCrStep / 2; ++i) G2[i] = lds_u4_screen(gth0 + 8u * g0 + 16u * i);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) G[i] = lds_f4_screen(gt0 + 16u * (g0 + h + i));
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (G[i].z > au.x && au.z > G[i].x && G[i].w > au.y && au.w > G[i].y) {
-              queue_push(qp, g0 + h + i);
-              qp += kSlot;
-            }
-          }
+        for (int i = 0; i < kCrStep / 2; ++i) {
+          screen_push(qp, g0 + 2 * i, G2[i].x, G2[i].y, alo, ahi, kSlot);
+          screen_push(qp, g0 + 2 * i + 1, G2[i].z, G2[i].w, alo, ahi, kSlot);
         }
         if (__any_sync(kFull, qp > q0 + (kCrQ - kCrStep) * kSlot)) drain();
       }
