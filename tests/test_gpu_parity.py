@@ -215,6 +215,27 @@ def test_fused_match_crowded_identical_gt(cuda):
         assert_equal_int(got[k], want[k], k)
 
 
+def test_fused_match_crowded_coordinates_beyond_half_range(cuda):
+    """The crowded pass A screens pairs in half precision with outward rounding; coordinates beyond the half range
+    (65504) saturate towards "may overlap" and the exact drain decides.  Image 1 is image 0 scaled by 100 (up to
+    1.5e5) and shifted, image 2 has tiny boxes (subnormal halves)."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    base = synthetic.matcher_stress_inputs(9, 3, 20000, 100)
+    anchors = base["anchors"].clone()
+    gt_boxes = [b.clone() for b in base["gt_boxes"]]
+    anchors[1] = anchors[0] * 100.0 - 40000.0
+    gt_boxes[1] = gt_boxes[0] * 100.0 - 40000.0
+    anchors[2] = anchors[0] * 1e-7
+    gt_boxes[2] = gt_boxes[0] * 1e-7
+    want = orc.ground_truth([anchors[n] for n in range(3)], gt_boxes, base["gt_classes"], 80)
+    gt = fsg.ops.PackedGT.from_lists(gt_boxes, base["gt_classes"], cuda)
+    got = fsg.ops.match_anchors(anchors.to(cuda), gt, 80, want=("matches", "match_labels", "gt_classes", "mask"))
+    for k in ("matches", "match_labels", "gt_classes", "mask"):
+        assert_equal_int(got[k], want[k], k)
+    assert int((want["match_labels"][1] == 1).sum()) > 0 and int((want["match_labels"][2] == 1).sum()) > 0
+
+
 def test_fused_match_many_gt_chunks(cuda):
     """More GT than one shared-memory chunk (1024)."""
     fsg = _fsg()
