@@ -273,7 +273,7 @@ struct PostTable {
   float* grad[kLvMax];
   int64_t off[kLvMax + 1];
   int HW[kLvMax];
-  int tile_base[kLvMax + 1];   // tiles of 256 hw positions, A slots each
+  int tile_base[kLvMax + 1];   // tiles of 256 cells (all A anchor slots of a cell in one thread)
   int num_levels, A;
 };
 
@@ -281,14 +281,13 @@ __global__ void __launch_bounds__(256) loss_post_levels_kernel(const PostTable P
                                                                int64_t R, float T, float ggamma, int nmode, float c_gam,
                                                                const double* __restrict__ stats,
                                                                const double* __restrict__ scalars) {
+  // thread = one cell (n, level, hw), all A anchor slots of it: the A mask entries of a cell are adjacent in the
+  // (N, R) order, so a warp reads them as one contiguous piece, and each of the A planes is walked coalesced
   const int n = blockIdx.y;
   grid_dependency_sync();   // (programmatic dependent launch behind the main pass)
   int l = 0;
   while (l + 1 < PT.num_levels && (int)blockIdx.x >= PT.tile_base[l + 1]) ++l;
-  const int local = (int)blockIdx.x - PT.tile_base[l];
-  const int chunks = (PT.HW[l] + 255) / 256;
-  const int a = local / chunks;
-  const int hw = (local - a * chunks) * 256 + threadIdx.x;
+  const int hw = ((int)blockIdx.x - PT.tile_base[l]) * 256 + threadIdx.x;
   if (hw >= PT.HW[l]) return;
   float inv_S = 1.f, Asum = 0.f;
   if (nmode != FSG_NORM_NONE) {
@@ -297,20 +296,35 @@ __global__ void __launch_bounds__(256) loss_post_levels_kernel(const PostTable P
     inv_S = __frcp_rn((float)S);
     Asum = (float)Av;
   }
-  const int64_t i = ((int64_t)n * PT.A + a) * PT.HW[l] + hw;
-  const float m = mask ? (float)mask[(int64_t)n * R + PT.off[l] + (int64_t)hw * PT.A + a] : 1.f;
-  const float b = PT.bets[l][i], e = PT.ell[l][i];
-  const float w = __fadd_rn(__fmul_rn(b, m), T);
-  float g;
-  if (nmode == FSG_NORM_NONE) {
-    const float pw = (ggamma == 1.f) ? 1.f : powf(w, ggamma - 1.f);
-    g = -m * ggamma * pw * e;
-  } else {
-    const float w_hat = w * inv_S;
-    const float pw = (ggamma == 1.f) ? 1.f : powf(w_hat, ggamma - 1.f);
-    g = -(m * inv_S) * ggamma * (pw * e - Asum);
+  const int64_t* mrow = mask ? mask + (int64_t)n * R + PT.off[l] + (int64_t)hw * PT.A : nullptr;
+  constexpr int kG = 3;   // anchor slots per round: all loads of a round are issued before its arithmetic
+  for (int a0 = 0; a0 < PT.A; a0 += kG) {
+    float m[kG], b[kG], e[kG];
+#pragma unroll
+    for (int j = 0; j < kG; ++j) {
+      const bool in = a0 + j < PT.A;
+      const int64_t i = ((int64_t)n * PT.A + a0 + j) * PT.HW[l] + hw;
+      m[j] = (in && mrow) ? (float)mrow[a0 + j] : 1.f;
+      b[j] = in ? PT.bets[l][i] : 0.f;
+      e[j] = in ? PT.ell[l][i] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kG; ++j) {
+      if (a0 + j >= PT.A) break;
+      const int64_t i = ((int64_t)n * PT.A + a0 + j) * PT.HW[l] + hw;
+      const float w = __fadd_rn(__fmul_rn(b[j], m[j]), T);
+      float g;
+      if (nmode == FSG_NORM_NONE) {
+        const float pw = (ggamma == 1.f) ? 1.f : powf(w, ggamma - 1.f);
+        g = -m[j] * ggamma * pw * e[j];
+      } else {
+        const float w_hat = w * inv_S;
+        const float pw = (ggamma == 1.f) ? 1.f : powf(w_hat, ggamma - 1.f);
+        g = -(m[j] * inv_S) * ggamma * (pw * e[j] - Asum);
+      }
+      PT.grad[l][i] = c_gam * g;
+    }
   }
-  PT.grad[l][i] = c_gam * g;
 }
 
 static int build_table(const fsg_head_level* h, int num_levels, int A, LevelTable* t, int64_t* R_out) {
@@ -501,7 +515,7 @@ int loss_post_levels_enqueue(const fsg_post_level* h_levels, int num_levels, int
       t.bets[l] = h_levels[l].bets; t.ell[l] = h_levels[l].per_anchor_loss; t.grad[l] = h_levels[l].grad_bets;
       t.HW[l] = (int)hw;
       off += hw * A;
-      tiles += A * (int)ceil_div(hw, 256);
+      tiles += (int)ceil_div(hw, 256);
     } else {
       t.bets[l] = nullptr; t.ell[l] = nullptr; t.grad[l] = nullptr; t.HW[l] = 0;
     }
