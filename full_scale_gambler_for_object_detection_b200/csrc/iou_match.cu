@@ -69,11 +69,18 @@ __device__ __forceinline__ void pair_update(float4 G, float ga, float4 a, float 
   if (w > 0.f && h > 0.f) {
     const float inter = __fmul_rn(w, h);
     if (inter > 0.f) {   // the product of two tiny positives can underflow to 0
-      ++ov;              // ground truth with IoU > 0: pass B needs no second look at an anchor that has only one
       const float uni = __fsub_rn(__fadd_rn(ga, aa), inter);
+      // (a pair the filter rejects is strictly below both the anchor's best and the GT's running maximum)
       if (may_reach(inter, uni, fminf(bv, known))) {
         const float v = __fdiv_rn(inter, uni);
-        if (v > bv) { bv = v; bi = gidx; }
+        // ov bit 0: the pair that holds the anchor's best IoU reached its GT's running maximum when it was evaluated;
+        // bit 1: some OTHER evaluated pair of the anchor did.  IoU(g, a) can equal the final maximum of g only if it
+        // reached the running one, so bit 1 (ov >= 2) tells pass B whether a GT other than the argmax can promote the
+        // anchor at all -- for nearly every anchor it cannot, and pass B is done after the argmax test.  (Config 2:
+        // no difference to flagging "overlaps two or more GT"; a crowded image in the batch: fewer warp-serial walks.)
+        const int top = (v >= known) ? 1 : 0;
+        if (v > bv) { bv = v; bi = gidx; ov = ((ov & 1) << 1) | (ov & 2) | top; }
+        else ov |= top << 1;
         m = fmaxf(m, v);
       }
     }
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(256) matrix_match_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------
 // Fused path, pass A: per-anchor max/argmax over the image's GT + per-GT max over anchors
 // ------------------------------------------------------------------------------------------
-constexpr int kMultiOverlap = 1 << 30;   // best_idx flag: the anchor has IoU > 0 with two or more ground truth
+constexpr int kMultiOverlap = 1 << 30;   // best_idx flag: a GT other than the argmax may promote the anchor (pair_update)
 constexpr int kSmallM = 32;  // images with at most this many GT: boxes staged by one parallel load, warp-level culling
 
 struct MatchOut {
@@ -342,6 +349,20 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
       if (v > 0u) atomicMax(&gt_max[m0 + tid], v);
     }
   } else {
+    // ---- a crowded image inside a few-GT batch (a whole crowded batch goes to match_pass_a_crowded_kernel): detection
+    //      training, i.e. anchors on a regular grid, so the warp-level cull of the few-GT path applies here as well --
+    //      a staged GT that does not reach into the rectangle of the warp's anchors is skipped by the whole warp (exact:
+    //      its IoU is 0 with every lane).  At 33..100 GT on an 800 x 1333 image that leaves a handful per warp.
+    int kx0 = 0x7fffffff, ky0 = 0x7fffffff, kx1 = (int)0x80000000, ky1 = (int)0x80000000;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * kMatchBlock + tid < R) {
+        kx0 = min(kx0, float_key(a[u].x)); ky0 = min(ky0, float_key(a[u].y));
+        kx1 = max(kx1, float_key(a[u].z)); ky1 = max(ky1, float_key(a[u].w));
+      }
+    }
+    const float bx0 = key_float(__reduce_min_sync(kFull, kx0)), by0 = key_float(__reduce_min_sync(kFull, ky0));
+    const float bx1 = key_float(__reduce_max_sync(kFull, kx1)), by1 = key_float(__reduce_max_sync(kFull, ky1));
     if (tid == 0) {
       mbar_init(&s_bar, 1);
       mbar_fence_init();
@@ -364,9 +385,8 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
       __syncthreads();
 
       for (int g = 0; g < cnt; ++g) {
-        // (no warp-level cull here: with 4 strided runs per warp and hundreds of GT almost nothing is culled --
-        //  measured 2.43 vs 2.23 ms on config 5 -- the per-pair early-out in pair_update does the work)
         const float4 G = s_gt[g];
+        if (G.z <= bx0 || G.x >= bx1 || G.w <= by0 || G.y >= by1) continue;   // warp-uniform; NaN never culls
         const float ga = s_area[g];
         const float known = __uint_as_float(s_max[g]);
         float m = 0.f;
@@ -834,7 +854,33 @@ __device__ __noinline__ unsigned pass_b_crowded_run(float4 val4, unsigned live4,
     lq4 |= own ? (1u << q) : 0u;
     hard[q] = cand && !own && (bix[q] & kMultiOverlap) != 0;
   }
-  if (!__any_sync(kFull, hard[0] || hard[1] || hard[2] || hard[3])) return lq4;
+  int nhard = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) nhard += __popc(__ballot_sync(kFull, hard[q]));
+  if (nhard == 0) return lq4;
+  if (nhard * 12 > M) {   // (a walk costs about M / 12 of the scan below)
+    // Many flagged candidates in one warp (a crowded image whose pass A CTAs all started without per-GT maxima to
+    // compare against, e.g. the one crowded image of a detection batch): every lane keeps its own anchors and the
+    // warp walks the ground truth once -- one broadcast load of a maximum per GT, and the box only for a GT that some
+    // lane's candidate can reach.
+    float4 aq[4];
+    float vmax = -1.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      aq[q] = hard[q] ? a_run0[tid * 4 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hard[q]) vmax = fmaxf(vmax, val[q]);
+    }
+    for (int g = 0; g < M; ++g) {
+      const float gm = __uint_as_float(gt_max[g]);
+      if (!__any_sync(kFull, gm <= vmax)) continue;
+      const float4 G = gt_boxes[g];
+      const float ga = box_area(G);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (hard[q] && gm <= val[q] && iou_exact(G, ga, aq[q], box_area(aq[q])) == gm) lq4 |= 1u << q;
+    }
+    return lq4;
+  }
   // lane l keeps the maxima of GT l, l + 32, ... (the first kLaneGt * 32 of the image) in registers for all the
   // candidates of the warp: a candidate then costs kLaneGt compares, and loads only for the GT it can reach
   constexpr int kLaneGt = 8;

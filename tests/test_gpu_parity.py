@@ -215,6 +215,29 @@ def test_fused_match_crowded_identical_gt(cuda):
         assert_equal_int(got[k], want[k], k)
 
 
+@pytest.mark.parametrize("Ms", [(60, 8, 8, 0), (8, 33, 2, 80), (1030,) + (5,) * 40])
+def test_fused_match_crowded_image_in_a_few_gt_batch_on_the_anchor_grid(cuda, Ms):
+    """Detection training with one crowded image (COCO has images with 60..90 objects): the batch averages at most 32
+    GT per image, so the few-GT pass A runs, and the crowded image takes its staged-GT branch with the warp-level
+    cull on the regular anchor grid (1030 GT: two shared-memory chunks)."""
+    fsg = _fsg()
+    from full_scale_gambler_for_object_detection_b200 import synthetic
+    N = len(Ms)
+    assert sum(Ms) <= 32 * N
+    base = synthetic.train_inputs(71, N, 320, 448, 80, M=max(Ms), empty_image=False, logits=False)
+    gt_boxes = [base["gt_boxes"][n][:m].clone() for n, m in enumerate(Ms)]
+    gt_classes = [base["gt_classes"][n][:m].clone() for n, m in enumerate(Ms)]
+    if Ms[0] >= 60:
+        gt_boxes[0][7] = gt_boxes[0][3]                                          # duplicate: the lower index wins
+        gt_boxes[0][9] = torch.tensor([5000.0, 5000.0, 5100.0, 5100.0])          # reaches no anchor: promotes all
+    want = orc.ground_truth(base["anchors"], gt_boxes, gt_classes, 80)
+    gt = fsg.ops.PackedGT.from_lists(gt_boxes, gt_classes, cuda)
+    got = fsg.ops.match_anchors(base["anchors"].to(cuda), gt, 80,
+                                want=("matches", "match_labels", "picky_labels", "gt_classes", "mask"))
+    for k in ("matches", "match_labels", "picky_labels", "gt_classes", "mask"):
+        assert_equal_int(got[k], want[k], k)
+
+
 def test_fused_match_crowded_coordinates_beyond_half_range(cuda):
     """The crowded pass A screens pairs in half precision with outward rounding; coordinates beyond the half range
     (65504) saturate towards "may overlap" and the exact drain decides.  Image 1 is image 0 scaled by 100 (up to
