@@ -1010,8 +1010,8 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_b_kernel(
         for (int u = 0; u < U; ++u) lq[u] = cand[u];
       } else {
         // IoU(g, a) <= best(a), so GT g can promote a only if max(g) <= best(a).  For g = argmax(a) that is the
-        // test best(a) == max(g), no recomputation; any other g needs IoU(g, a) > 0, i.e. an anchor that pass A
-        // flagged as overlapping two or more GT -- only those (a fraction of the candidates) are looked at again.
+        // test best(a) == max(g), no recomputation; any other g needs IoU(g, a) == max(g), which pass A rules out
+        // unless it flagged the anchor (pair_update) -- only those (a fraction of the candidates) are looked at again.
         bool hard[U];
         bool any_hard = false;
 #pragma unroll
