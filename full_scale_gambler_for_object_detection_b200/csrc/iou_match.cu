@@ -486,12 +486,9 @@ __global__ void __launch_bounds__(kMatchBlock, 4) match_pass_a_kernel(
 //     FIFO order and does the exact arithmetic of pair_update -- dense: all lanes with work run the same code.
 // Ascending GT order per anchor is preserved, so strict '>' keeps the lowest GT index among ties (matcher.py:86).
 // ------------------------------------------------------------------------------------------
-// The queue is written and read through explicit 32-bit shared-window addresses: nvcc re-derives the window base
-// (S2R CgaCtaId, LEA) inside every predicated store otherwise, which doubles the cost of a push.  Both accessors are
-// volatile asm, so they keep their program order with respect to each other.
-__device__ __forceinline__ void queue_push(uint32_t addr, int v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
-}
+// The queue is written (screen_push) and read through explicit 32-bit shared-window addresses: nvcc re-derives the
+// window base (S2R CgaCtaId, LEA) inside every predicated store otherwise, which doubles the cost of a push.  Both
+// accessors are volatile asm, so they keep their program order with respect to each other.
 __device__ __forceinline__ int queue_at(uint32_t addr) {
   unsigned short v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
@@ -501,13 +498,6 @@ __device__ __forceinline__ int queue_at(uint32_t addr) {
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-// (the screen's loads: no "memory" clobber, so that a group of them can be scheduled together; volatile keeps them
-//  behind the barrier that follows the staging of the chunk)
-__device__ __forceinline__ float4 lds_f4_screen(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ uint32_t opaque(uint32_t v) {   // keeps nvcc from re-deriving a shared-window base per use
@@ -553,6 +543,8 @@ __device__ __forceinline__ void screen_push(uint32_t& qp, int g, uint32_t glo, u
       : "+r"(qp)
       : "h"((unsigned short)g), "r"(ghi), "r"(alo), "r"(ahi), "r"(glo), "r"(slot_bytes));
 }
+// (the screen's loads: no "memory" clobber, so that a group of them can be scheduled together; volatile keeps them
+//  behind the barrier that follows the staging of the chunk)
 __device__ __forceinline__ uint4 lds_u4_screen(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
